@@ -1,0 +1,837 @@
+// gx_abi.cu - C ABI of the graphax_b200 engine (include/graphax_b200.h).
+//
+//  * plan blob validation + upload (the flat program emitted by graphax_b200/plan.py)
+//  * the generic persistent interpreter kernel: walks the plan with the batch on the grid, live edge
+//    values in shared memory (always available, any elimination order)
+//  * dispatch to plan-specialised kernels: ahead-of-time ones registered by generated TUs
+//    (gx_skeleton.cuh) and run-time ones compiled with NVRTC and loaded through the driver API
+//  * gx_jacve_host: chunked, double-buffered H2D -> kernel -> D2H pipeline for host buffers
+//
+// No CPU fallback: every compute entry point needs a CUDA device and says so when there is none.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/graphax_b200.h"
+#include "gx_ops.h"
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+namespace {
+thread_local std::string g_error;
+
+int fail(int code, const std::string& msg) {
+  g_error = msg;
+  return code;
+}
+#define GX_CUDA(expr)                                                                          \
+  do {                                                                                         \
+    cudaError_t e__ = (expr);                                                                  \
+    if (e__ != cudaSuccess)                                                                    \
+      return fail(GX_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__) +           \
+                                   " (graphax_b200 has no CPU fallback; a CUDA device is required)"); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// AOT registry (filled by static registrars in generated translation units)
+// ------------------------------------------------------------------------------------------------
+struct GxAotKernel {
+  unsigned long long key;
+  int threads, smem_bytes, n_in, n_rows, n_cols, has_primal;
+  const void* func;
+};
+std::vector<GxAotKernel>& aot_registry() {
+  static std::vector<GxAotKernel> r;
+  return r;
+}
+}  // namespace
+
+extern "C" void gx_register_aot(const GxAotKernel* k) { aot_registry().push_back(*k); }
+
+// launch-argument block shared with gx_skeleton.cuh (must stay layout-identical)
+struct GxLaunchArgs {
+  const float* in[GX_MAX_ARRAYS];
+  float* jac;
+  float* primal;
+  long long batch;
+  long long n_bulk_tiles;
+};
+
+// ------------------------------------------------------------------------------------------------
+// generic interpreter kernel
+// ------------------------------------------------------------------------------------------------
+struct GxInterpArgs {
+  const float* in[GX_MAX_ARRAYS];
+  float* jac;
+  float* primal;
+  long long batch;
+  const gx_op* ops;      // device
+  const float* consts;   // device
+  int n_ops, n_consts, n_slots, n_in, n_rows, n_cols, n_arr, has_primal;
+  int in_size[GX_MAX_ARRAYS];
+  int in_off[GX_MAX_ARRAYS];
+};
+
+namespace {
+
+__device__ __forceinline__ float gx_apply(unsigned op, float a, float b, float c) {
+  switch (op) {
+    case GX_OP_ADD: return __fadd_rn(a, b);
+    case GX_OP_SUB: return __fsub_rn(a, b);
+    case GX_OP_MUL: return __fmul_rn(a, b);
+    case GX_OP_FMA: return __fmaf_rn(a, b, c);
+    case GX_OP_DIV: return __fdiv_rn(a, b);
+    case GX_OP_NEG: return -a;
+    case GX_OP_ABS: return fabsf(a);
+    case GX_OP_SQRT: return __fsqrt_rn(a);
+    case GX_OP_SIN: return sinf(a);
+    case GX_OP_COS: return cosf(a);
+    case GX_OP_TAN: return tanf(a);
+    case GX_OP_ATAN2: return atan2f(a, b);
+    case GX_OP_EXP: return expf(a);
+    case GX_OP_LOG: return logf(a);
+    case GX_OP_LOG1P: return log1pf(a);
+    case GX_OP_TANH: return tanhf(a);
+    case GX_OP_SINH: return sinhf(a);
+    case GX_OP_COSH: return coshf(a);
+    case GX_OP_ASIN: return asinf(a);
+    case GX_OP_ACOS: return acosf(a);
+    case GX_OP_ATAN: return atanf(a);
+    case GX_OP_ASINH: return asinhf(a);
+    case GX_OP_ACOSH: return acoshf(a);
+    case GX_OP_ATANH: return atanhf(a);
+    case GX_OP_ERF: return erff(a);
+    case GX_OP_POW: return powf(a, b);
+    case GX_OP_LOGISTIC: return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-a)));
+    default: return 0.0f;
+  }
+}
+
+// Shared memory per CTA of T samples:
+//   ops[n_ops] (3 words each) | consts[n_consts] | in_base[n_in], in_stride[n_in] |
+//   in_stage[n_in*T] | slots[n_slots*T] (slot-major: conflict free) | out[T*(tile+rows)]
+template <int T>
+__global__ void __launch_bounds__(T) gx_interp_kernel(const __grid_constant__ GxInterpArgs a) {
+  extern __shared__ __align__(16) unsigned gx_ismem[];
+  unsigned* s_ops = gx_ismem;
+  float* s_consts = reinterpret_cast<float*>(s_ops + 3 * a.n_ops);
+  int* s_in_base = reinterpret_cast<int*>(s_consts + a.n_consts);
+  int* s_in_stride = s_in_base + a.n_in;
+  float* s_in = reinterpret_cast<float*>(s_in_stride + a.n_in);
+  float* s_slots = s_in + a.n_in * T;
+  float* s_out = s_slots + a.n_slots * T;
+
+  const int tid = threadIdx.x;
+  const int tile_words = a.n_rows * a.n_cols;
+  const int out_words = tile_words + (a.has_primal ? a.n_rows : 0);
+
+  // one-time: plan into shared memory (every thread reads the same op -> broadcast LDS)
+  {
+    const unsigned* g = reinterpret_cast<const unsigned*>(a.ops);
+    for (int i = tid; i < 3 * a.n_ops; i += T) s_ops[i] = g[i];
+    for (int i = tid; i < a.n_consts; i += T) s_consts[i] = a.consts[i];
+    if (tid == 0) {
+      for (int arr = 0; arr < a.n_arr; ++arr)
+        for (int c = 0; c < a.in_size[arr]; ++c) {
+          s_in_base[a.in_off[arr] + c] = a.in_off[arr] * T + c;
+          s_in_stride[a.in_off[arr] + c] = a.in_size[arr];
+        }
+    }
+  }
+  __syncthreads();
+
+  const long long n_tiles = (a.batch + T - 1) / T;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long base = tile * T;
+    const int valid = (int)(a.batch - base < T ? a.batch - base : T);
+    // coalesced stage-in of every input array's chunk
+    for (int arr = 0; arr < a.n_arr; ++arr) {
+      const int sz = a.in_size[arr];
+      const float* src = a.in[arr] + base * sz;
+      float* dst = s_in + a.in_off[arr] * T;
+      for (int i = tid; i < T * sz; i += T) dst[i] = i < valid * sz ? __ldg(src + i) : 1.0f;
+    }
+    __syncthreads();
+
+    auto fetch = [&](unsigned o) -> float {
+      const unsigned kind = GX_OPERAND_KIND(o), idx = GX_OPERAND_INDEX(o);
+      if (kind == GX_K_SLOT) return s_slots[idx * T + tid];
+      if (kind == GX_K_CONST) return s_consts[idx];
+      return s_in[s_in_base[idx] + tid * s_in_stride[idx]];
+    };
+    float* my_out = s_out + tid * out_words;
+    for (int i = 0; i < a.n_ops; ++i) {
+      const unsigned w0 = s_ops[3 * i], w1 = s_ops[3 * i + 1], w2 = s_ops[3 * i + 2];
+      const unsigned op = w0 & 0xffffu, dst = w0 >> 16, oa = w1 & 0xffffu, ob = w1 >> 16, oc = w2 & 0xffffu;
+      if (op == GX_OP_STORE_JAC) {
+        my_out[dst] = fetch(oa);
+      } else if (op == GX_OP_STORE_PRIMAL) {
+        my_out[tile_words + dst] = fetch(oa);
+      } else {
+        const float va = fetch(oa);
+        const float vb = (op == GX_OP_ADD || op == GX_OP_SUB || op == GX_OP_MUL || op == GX_OP_DIV ||
+                          op == GX_OP_FMA || op == GX_OP_ATAN2 || op == GX_OP_POW)
+                             ? fetch(ob)
+                             : 0.0f;
+        const float vc = op == GX_OP_FMA ? fetch(oc) : 0.0f;
+        s_slots[dst * T + tid] = gx_apply(op, va, vb, vc);
+      }
+    }
+    __syncthreads();
+    // coalesced stage-out: the tile rows of `valid` consecutive samples are contiguous in HBM
+    for (int i = tid; i < valid * tile_words; i += T) {
+      const int smp = i / tile_words, w = i - smp * tile_words;
+      a.jac[base * tile_words + i] = s_out[smp * out_words + w];
+    }
+    if (a.has_primal && a.primal != nullptr)
+      for (int i = tid; i < valid * a.n_rows; i += T) {
+        const int smp = i / a.n_rows, w = i - smp * a.n_rows;
+        a.primal[base * a.n_rows + i] = s_out[smp * out_words + tile_words + w];
+      }
+    __syncthreads();
+  }
+}
+
+size_t interp_smem_bytes(const gx_blob_header& h, int T) {
+  const size_t tile = (size_t)h.n_rows * h.n_cols + ((h.flags & GX_FLAG_HAS_PRIMAL) ? h.n_rows : 0);
+  return 4 * (3 * (size_t)h.n_ops + h.n_consts + 2 * (size_t)h.n_in_scalars + (size_t)h.n_in_scalars * T +
+              (size_t)h.n_slots * T + tile * T) + 16;
+}
+
+uint64_t fnv1a64(const void* data, size_t n) {
+  const unsigned char* p = static_cast<const unsigned char*>(data);
+  uint64_t h = 0xCBF29CE484222325ull;
+  for (size_t i = 0; i < n; ++i) h = (h ^ p[i]) * 0x100000001B3ull;
+  return h;
+}
+
+// ------------------------------------------------------------------------------------------------
+// driver API through the runtime (no link-time dependency on libcuda) + NVRTC through dlopen
+// ------------------------------------------------------------------------------------------------
+struct DriverApi {
+  CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
+  CUresult (*ModuleUnload)(CUmodule) = nullptr;
+  CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+  CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
+  CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
+  CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
+  CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
+                           CUstream, void**, void**) = nullptr;
+  CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+  bool ok = false;
+};
+
+template <class F>
+bool load_entry(const char* name, F*& fn) {
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult st;
+  if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &st) != cudaSuccess || p == nullptr) return false;
+  fn = reinterpret_cast<F*>(p);
+  return true;
+}
+
+DriverApi& driver() {
+  static DriverApi d;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    d.ok = load_entry("cuModuleLoadData", d.ModuleLoadData) && load_entry("cuModuleUnload", d.ModuleUnload) &&
+           load_entry("cuModuleGetFunction", d.ModuleGetFunction) &&
+           load_entry("cuFuncSetAttribute", d.FuncSetAttribute) &&
+           load_entry("cuFuncGetAttribute", d.FuncGetAttribute) &&
+           load_entry("cuOccupancyMaxActiveBlocksPerMultiprocessor", d.OccupancyMaxActiveBlocksPerMultiprocessor) &&
+           load_entry("cuLaunchKernel", d.LaunchKernel) && load_entry("cuGetErrorString", d.GetErrorString);
+  });
+  return d;
+}
+
+std::string cu_err(CUresult r) {
+  const char* s = nullptr;
+  if (driver().GetErrorString) driver().GetErrorString(r, &s);
+  return s ? s : "unknown driver error";
+}
+
+struct Nvrtc {
+  typedef struct _nvrtcProgram* Program;
+  int (*CreateProgram)(Program*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+  int (*CompileProgram)(Program, int, const char* const*) = nullptr;
+  int (*GetProgramLogSize)(Program, size_t*) = nullptr;
+  int (*GetProgramLog)(Program, char*) = nullptr;
+  int (*GetCUBINSize)(Program, size_t*) = nullptr;
+  int (*GetCUBIN)(Program, char*) = nullptr;
+  int (*DestroyProgram)(Program*) = nullptr;
+  bool ok = false;
+  std::string why;
+};
+
+Nvrtc& nvrtc() {
+  static Nvrtc n;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char* names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12",
+                           "/usr/local/cuda/lib64/libnvrtc.so"};
+    void* h = nullptr;
+    for (const char* nm : names)
+      if ((h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL)) != nullptr) break;
+    if (!h) {
+      n.why = "libnvrtc.so.12 not found";
+      return;
+    }
+#define GX_SYM(field, sym) *(void**)(&n.field) = dlsym(h, sym)
+    GX_SYM(CreateProgram, "nvrtcCreateProgram");
+    GX_SYM(CompileProgram, "nvrtcCompileProgram");
+    GX_SYM(GetProgramLogSize, "nvrtcGetProgramLogSize");
+    GX_SYM(GetProgramLog, "nvrtcGetProgramLog");
+    GX_SYM(GetCUBINSize, "nvrtcGetCUBINSize");
+    GX_SYM(GetCUBIN, "nvrtcGetCUBIN");
+    GX_SYM(DestroyProgram, "nvrtcDestroyProgram");
+#undef GX_SYM
+    n.ok = n.CreateProgram && n.CompileProgram && n.GetProgramLogSize && n.GetProgramLog && n.GetCUBINSize &&
+           n.GetCUBIN && n.DestroyProgram;
+    if (!n.ok) n.why = "libnvrtc is missing required symbols";
+  });
+  return n;
+}
+
+constexpr int kSpecThreads = 128;
+constexpr int kSpecMinBlocks = 2;
+constexpr int kSpecOutStages = 2;
+constexpr int64_t kHostChunk = 1 << 16;  // samples per pipeline stage of gx_jacve_host
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// plan object
+// ------------------------------------------------------------------------------------------------
+struct gx_plan {
+  gx_blob_header h;
+  std::vector<unsigned> in_sizes, out_sizes, in_cols;
+  std::vector<float> consts;
+  std::vector<gx_op> ops;
+  uint64_t key = 0;
+  int device = 0;
+  int sm_count = 0;
+  gx_op* d_ops = nullptr;
+  float* d_consts = nullptr;
+
+  // interpreter configuration
+  int interp_threads = 0;
+  size_t interp_smem = 0;
+  int interp_ctas_per_sm = 1;
+  // AOT kernel
+  const GxAotKernel* aot = nullptr;
+  int aot_ctas_per_sm = 0;
+  int aot_regs = 0;
+  // JIT kernel
+  CUmodule jit_module = nullptr;
+  CUfunction jit_func = nullptr;
+  int jit_smem = 0;
+  int jit_ctas_per_sm = 0;
+  int jit_regs = 0;
+
+  int kernel_kind = GX_KERNEL_INTERPRETER;
+  std::atomic<uint64_t> launches{0};
+
+  // host pipeline resources (lazily created, guarded by host_mu)
+  std::mutex host_mu;
+  struct HostSlot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    float* d_in = nullptr;    // all input arrays of one chunk, back to back
+    float* d_jac = nullptr;
+    float* d_primal = nullptr;
+    float* h_in = nullptr;    // pinned staging (pageable callers only)
+    float* h_jac = nullptr;
+    float* h_primal = nullptr;
+  } slots[2];
+  bool host_ready = false;
+  bool host_staging = false;
+};
+
+namespace {
+
+int validate_blob(const void* blob, size_t nbytes, gx_plan* p) {
+  if (blob == nullptr) return fail(GX_ERR_BAD_ARG, "gx_plan_create: blob is NULL");
+  if (nbytes < sizeof(gx_blob_header)) return fail(GX_ERR_BAD_BLOB, "plan blob shorter than its header");
+  memcpy(&p->h, blob, sizeof(gx_blob_header));
+  const gx_blob_header& h = p->h;
+  if (h.magic != GX_BLOB_MAGIC) return fail(GX_ERR_BAD_BLOB, "plan blob: bad magic (not a graphax_b200 plan)");
+  if (h.version != GX_BLOB_VERSION) return fail(GX_ERR_BAD_BLOB, "plan blob: unsupported version");
+  if (h.total_bytes != nbytes) return fail(GX_ERR_BAD_BLOB, "plan blob: size field does not match buffer length");
+  if (h.n_in_arrays == 0 || h.n_in_arrays > GX_MAX_ARRAYS || h.n_out_arrays == 0 || h.n_out_arrays > GX_MAX_ARRAYS)
+    return fail(GX_ERR_BAD_BLOB, "plan blob: between 1 and 16 input and output arrays are supported");
+  const size_t need = sizeof(gx_blob_header) + 4ull * (2 * h.n_in_arrays + h.n_out_arrays) + 4ull * h.n_consts +
+                      sizeof(gx_op) * (size_t)h.n_ops;
+  if (need != nbytes) return fail(GX_ERR_BAD_BLOB, "plan blob: section sizes do not add up to the buffer length");
+  if (h.n_slots > 0x3fff || h.n_consts > 0x3fff || h.n_in_scalars > 0x3fff)
+    return fail(GX_ERR_BAD_BLOB, "plan blob: index space exceeds the 14-bit operand encoding");
+  if (h.n_rows == 0 || h.n_cols == 0 || (size_t)h.n_rows * h.n_cols > 0xffff)
+    return fail(GX_ERR_BAD_BLOB, "plan blob: Jacobian tile must have between 1 and 65535 entries");
+
+  const unsigned char* cur = static_cast<const unsigned char*>(blob) + sizeof(gx_blob_header);
+  auto take_u32 = [&](std::vector<unsigned>& v, size_t n) {
+    v.resize(n);
+    memcpy(v.data(), cur, 4 * n);
+    cur += 4 * n;
+  };
+  take_u32(p->in_sizes, h.n_in_arrays);
+  take_u32(p->out_sizes, h.n_out_arrays);
+  take_u32(p->in_cols, h.n_in_arrays);
+  p->consts.resize(h.n_consts);
+  memcpy(p->consts.data(), cur, 4ull * h.n_consts);
+  cur += 4ull * h.n_consts;
+  p->ops.resize(h.n_ops);
+  memcpy(p->ops.data(), cur, sizeof(gx_op) * (size_t)h.n_ops);
+
+  size_t sum_in = 0, sum_out = 0;
+  for (unsigned s : p->in_sizes) {
+    if (s == 0) return fail(GX_ERR_BAD_BLOB, "plan blob: empty input array");
+    sum_in += s;
+  }
+  for (unsigned s : p->out_sizes) sum_out += s;
+  if (sum_in != h.n_in_scalars) return fail(GX_ERR_BAD_BLOB, "plan blob: in_sizes do not sum to n_in_scalars");
+  if (sum_out != h.n_rows) return fail(GX_ERR_BAD_BLOB, "plan blob: out_sizes do not sum to n_rows");
+
+  const unsigned tile = h.n_rows * h.n_cols;
+  std::vector<unsigned char> stored(tile, 0), stored_p(h.n_rows, 0), defined(h.n_slots, 0);
+  auto check_operand = [&](unsigned o, size_t i) -> int {
+    const unsigned kind = GX_OPERAND_KIND(o), idx = GX_OPERAND_INDEX(o);
+    char buf[96];
+    if (kind == GX_K_SLOT) {
+      if (idx >= h.n_slots || !defined[idx]) {
+        snprintf(buf, sizeof buf, "plan blob: op %zu reads slot %u before it is written", i, idx);
+        return fail(GX_ERR_BAD_BLOB, buf);
+      }
+    } else if (kind == GX_K_CONST) {
+      if (idx >= h.n_consts) return fail(GX_ERR_BAD_BLOB, "plan blob: constant index out of range");
+    } else if (kind == GX_K_INPUT) {
+      if (idx >= h.n_in_scalars) return fail(GX_ERR_BAD_BLOB, "plan blob: input index out of range");
+    } else {
+      return fail(GX_ERR_BAD_BLOB, "plan blob: unknown operand kind");
+    }
+    return GX_OK;
+  };
+  for (size_t i = 0; i < p->ops.size(); ++i) {
+    const gx_op& o = p->ops[i];
+    if (o.op >= GX_OP_COUNT || o.op == GX_OP_INPUT || o.op == GX_OP_CONST)
+      return fail(GX_ERR_BAD_BLOB, "plan blob: invalid opcode in op stream");
+    int rc = check_operand(o.a, i);
+    if (rc) return rc;
+    const bool binary = o.op == GX_OP_ADD || o.op == GX_OP_SUB || o.op == GX_OP_MUL || o.op == GX_OP_DIV ||
+                        o.op == GX_OP_FMA || o.op == GX_OP_ATAN2 || o.op == GX_OP_POW;
+    if (binary && (rc = check_operand(o.b, i))) return rc;
+    if (o.op == GX_OP_FMA && (rc = check_operand(o.c, i))) return rc;
+    if (o.op == GX_OP_STORE_JAC) {
+      if (o.dst >= tile) return fail(GX_ERR_BAD_BLOB, "plan blob: store_jac outside the Jacobian tile");
+      if (stored[o.dst]++) return fail(GX_ERR_BAD_BLOB, "plan blob: Jacobian tile entry stored twice");
+    } else if (o.op == GX_OP_STORE_PRIMAL) {
+      if (!(h.flags & GX_FLAG_HAS_PRIMAL) || o.dst >= h.n_rows)
+        return fail(GX_ERR_BAD_BLOB, "plan blob: store_primal outside the output vector");
+      if (stored_p[o.dst]++) return fail(GX_ERR_BAD_BLOB, "plan blob: primal output stored twice");
+    } else {
+      if (o.dst >= h.n_slots) return fail(GX_ERR_BAD_BLOB, "plan blob: destination slot out of range");
+      defined[o.dst] = 1;
+    }
+  }
+  for (unsigned i = 0; i < tile; ++i)
+    if (!stored[i]) return fail(GX_ERR_BAD_BLOB, "plan blob: a Jacobian tile entry is never stored");
+  if (h.flags & GX_FLAG_HAS_PRIMAL)
+    for (unsigned i = 0; i < h.n_rows; ++i)
+      if (!stored_p[i]) return fail(GX_ERR_BAD_BLOB, "plan blob: a primal output is never stored");
+  p->key = fnv1a64(blob, nbytes);
+  return GX_OK;
+}
+
+template <int T>
+int config_interp(gx_plan* p, int max_smem_optin) {
+  const size_t smem = interp_smem_bytes(p->h, T);
+  if ((long long)smem > max_smem_optin) return 1;
+  GX_CUDA(cudaFuncSetAttribute(gx_interp_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int n = 0;
+  GX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gx_interp_kernel<T>, T, smem));
+  if (n < 1) return 1;
+  p->interp_threads = T;
+  p->interp_smem = smem;
+  p->interp_ctas_per_sm = n;
+  return GX_OK;
+}
+
+void fill_args(const gx_plan* p, GxLaunchArgs& a, int64_t batch, const void* const* in_ptrs, void* jac, void* primal,
+               int threads) {
+  memset(&a, 0, sizeof a);
+  bool aligned = (reinterpret_cast<uintptr_t>(jac) & 15u) == 0 &&
+                 (primal == nullptr || (reinterpret_cast<uintptr_t>(primal) & 15u) == 0);
+  for (unsigned i = 0; i < p->h.n_in_arrays; ++i) {
+    a.in[i] = static_cast<const float*>(in_ptrs[i]);
+    aligned = aligned && (reinterpret_cast<uintptr_t>(in_ptrs[i]) & 15u) == 0;
+  }
+  a.jac = static_cast<float*>(jac);
+  a.primal = static_cast<float*>(primal);
+  a.batch = batch;
+  a.n_bulk_tiles = aligned ? batch / threads : 0;
+}
+
+int launch_on(gx_plan* p, int64_t batch, const void* const* in_ptrs, void* jac, void* primal, cudaStream_t stream) {
+  if (batch == 0) return GX_OK;
+  const int kind = p->kernel_kind;
+  if (kind == GX_KERNEL_AOT && p->aot) {
+    GxLaunchArgs a;
+    fill_args(p, a, batch, in_ptrs, jac, primal, p->aot->threads);
+    const long long tiles = (batch + p->aot->threads - 1) / p->aot->threads;
+    const int grid = (int)std::min<long long>(tiles, (long long)p->sm_count * p->aot_ctas_per_sm);
+    void* params[] = {&a};
+    GX_CUDA(cudaLaunchKernel(p->aot->func, dim3(grid), dim3(p->aot->threads), params, p->aot->smem_bytes, stream));
+  } else if (kind == GX_KERNEL_JIT && p->jit_func) {
+    GxLaunchArgs a;
+    fill_args(p, a, batch, in_ptrs, jac, primal, kSpecThreads);
+    const long long tiles = (batch + kSpecThreads - 1) / kSpecThreads;
+    const int grid = (int)std::min<long long>(tiles, (long long)p->sm_count * p->jit_ctas_per_sm);
+    void* params[] = {&a};
+    CUresult r = driver().LaunchKernel(p->jit_func, grid, 1, 1, kSpecThreads, 1, 1, p->jit_smem, (CUstream)stream,
+                                       params, nullptr);
+    if (r != CUDA_SUCCESS) return fail(GX_ERR_CUDA, "cuLaunchKernel(jit): " + cu_err(r));
+  } else {
+    GxInterpArgs a;
+    memset(&a, 0, sizeof a);
+    unsigned off = 0;
+    for (unsigned i = 0; i < p->h.n_in_arrays; ++i) {
+      a.in[i] = static_cast<const float*>(in_ptrs[i]);
+      a.in_size[i] = (int)p->in_sizes[i];
+      a.in_off[i] = (int)off;
+      off += p->in_sizes[i];
+    }
+    a.jac = static_cast<float*>(jac);
+    a.primal = static_cast<float*>(primal);
+    a.batch = batch;
+    a.ops = p->d_ops;
+    a.consts = p->d_consts;
+    a.n_ops = (int)p->h.n_ops;
+    a.n_consts = (int)p->h.n_consts;
+    a.n_slots = (int)p->h.n_slots;
+    a.n_in = (int)p->h.n_in_scalars;
+    a.n_rows = (int)p->h.n_rows;
+    a.n_cols = (int)p->h.n_cols;
+    a.n_arr = (int)p->h.n_in_arrays;
+    a.has_primal = (p->h.flags & GX_FLAG_HAS_PRIMAL) ? 1 : 0;
+    const int T = p->interp_threads;
+    const long long tiles = (batch + T - 1) / T;
+    const int grid = (int)std::min<long long>(tiles, (long long)p->sm_count * p->interp_ctas_per_sm);
+    if (T == 128)
+      gx_interp_kernel<128><<<grid, 128, p->interp_smem, stream>>>(a);
+    else if (T == 64)
+      gx_interp_kernel<64><<<grid, 64, p->interp_smem, stream>>>(a);
+    else
+      gx_interp_kernel<32><<<grid, 32, p->interp_smem, stream>>>(a);
+    GX_CUDA(cudaGetLastError());
+  }
+  p->launches.fetch_add(1, std::memory_order_relaxed);
+  return GX_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// exported API
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* gx_last_error(void) { return g_error.c_str(); }
+int gx_abi_version(void) { return GX_ABI_VERSION; }
+int gx_aot_count(void) { return (int)aot_registry().size(); }
+uint64_t gx_aot_key(int index) {
+  return index >= 0 && index < (int)aot_registry().size() ? aot_registry()[index].key : 0;
+}
+uint64_t gx_hash_bytes(const void* data, size_t nbytes) { return data ? fnv1a64(data, nbytes) : 0; }
+
+int gx_plan_create(const void* blob, size_t nbytes, int device, gx_plan** out) {
+  if (out == nullptr) return fail(GX_ERR_BAD_ARG, "gx_plan_create: out is NULL");
+  *out = nullptr;
+  gx_plan* p = new gx_plan();
+  int rc = validate_blob(blob, nbytes, p);
+  if (rc != GX_OK) {
+    delete p;
+    return rc;
+  }
+  p->device = device;
+  auto cleanup = [&](int code) {
+    gx_plan_destroy(p);
+    return code;
+  };
+#define GX_CUDA_P(expr)                                                                              \
+  do {                                                                                               \
+    cudaError_t e__ = (expr);                                                                        \
+    if (e__ != cudaSuccess)                                                                          \
+      return cleanup(fail(GX_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__) +         \
+                                           " (graphax_b200 has no CPU fallback; a CUDA device is required)")); \
+  } while (0)
+  GX_CUDA_P(cudaSetDevice(device));
+  int max_optin = 0;
+  GX_CUDA_P(cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device));
+  GX_CUDA_P(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  GX_CUDA_P(cudaMalloc(&p->d_ops, std::max<size_t>(sizeof(gx_op) * p->ops.size(), 16)));
+  GX_CUDA_P(cudaMalloc(&p->d_consts, std::max<size_t>(4 * p->consts.size(), 16)));
+  if (!p->ops.empty())
+    GX_CUDA_P(cudaMemcpy(p->d_ops, p->ops.data(), sizeof(gx_op) * p->ops.size(), cudaMemcpyHostToDevice));
+  if (!p->consts.empty())
+    GX_CUDA_P(cudaMemcpy(p->d_consts, p->consts.data(), 4 * p->consts.size(), cudaMemcpyHostToDevice));
+
+  // interpreter: the largest CTA whose live-value file fits, preferring two resident CTAs per SM
+  rc = 1;
+  if (interp_smem_bytes(p->h, 128) * 2 <= (size_t)max_optin) rc = config_interp<128>(p, max_optin);
+  if (rc == 1 && interp_smem_bytes(p->h, 64) * 2 <= (size_t)max_optin) rc = config_interp<64>(p, max_optin);
+  if (rc == 1) rc = config_interp<128>(p, max_optin);
+  if (rc == 1) rc = config_interp<64>(p, max_optin);
+  if (rc == 1) rc = config_interp<32>(p, max_optin);
+  if (rc == 1) return cleanup(fail(GX_ERR_UNSUPPORTED, "plan keeps too many live values for shared memory"));
+  if (rc != GX_OK) return cleanup(rc);
+
+  // plan-specialised kernel compiled into the library for exactly this blob?
+  for (const GxAotKernel& k : aot_registry()) {
+    if (k.key != p->key) continue;
+    if (k.n_in != (int)p->h.n_in_scalars || k.n_rows != (int)p->h.n_rows || k.n_cols != (int)p->h.n_cols)
+      return cleanup(fail(GX_ERR_BAD_BLOB, "AOT kernel with the plan's key has a different shape (hash collision?)"));
+    GX_CUDA_P(cudaFuncSetAttribute(k.func, cudaFuncAttributeMaxDynamicSharedMemorySize, k.smem_bytes));
+    int n = 0;
+    GX_CUDA_P(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k.func, k.threads, k.smem_bytes));
+    if (n < 1) break;
+    cudaFuncAttributes fa;
+    GX_CUDA_P(cudaFuncGetAttributes(&fa, k.func));
+    p->aot = &k;
+    p->aot_ctas_per_sm = n;
+    p->aot_regs = fa.numRegs;
+    p->kernel_kind = GX_KERNEL_AOT;
+    break;
+  }
+#undef GX_CUDA_P
+  *out = p;
+  return GX_OK;
+}
+
+void gx_plan_destroy(gx_plan* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  for (auto& s : p->slots) {
+    if (s.stream) cudaStreamSynchronize(s.stream);
+    if (s.d_in) cudaFree(s.d_in);
+    if (s.d_jac) cudaFree(s.d_jac);
+    if (s.d_primal) cudaFree(s.d_primal);
+    if (s.h_in) cudaFreeHost(s.h_in);
+    if (s.h_jac) cudaFreeHost(s.h_jac);
+    if (s.h_primal) cudaFreeHost(s.h_primal);
+    if (s.done) cudaEventDestroy(s.done);
+    if (s.stream) cudaStreamDestroy(s.stream);
+  }
+  if (p->jit_module && driver().ok) driver().ModuleUnload(p->jit_module);
+  if (p->d_ops) cudaFree(p->d_ops);
+  if (p->d_consts) cudaFree(p->d_consts);
+  delete p;
+}
+
+int gx_plan_info(const gx_plan* p, gx_info* out) {
+  if (!p || !out) return fail(GX_ERR_BAD_ARG, "gx_plan_info: NULL argument");
+  memset(out, 0, sizeof *out);
+  out->abi_version = GX_ABI_VERSION;
+  out->n_in_arrays = p->h.n_in_arrays;
+  out->n_out_arrays = p->h.n_out_arrays;
+  out->n_in_scalars = p->h.n_in_scalars;
+  out->n_rows = p->h.n_rows;
+  out->n_cols = p->h.n_cols;
+  out->n_ops = p->h.n_ops;
+  out->n_slots = p->h.n_slots;
+  out->has_primal = (p->h.flags & GX_FLAG_HAS_PRIMAL) ? 1 : 0;
+  out->kernel_kind = (uint32_t)p->kernel_kind;
+  if (p->kernel_kind == GX_KERNEL_AOT && p->aot) {
+    out->threads = p->aot->threads;
+    out->smem_bytes = p->aot->smem_bytes;
+    out->ctas_per_sm = p->aot_ctas_per_sm;
+    out->regs_per_thread = p->aot_regs;
+  } else if (p->kernel_kind == GX_KERNEL_JIT && p->jit_func) {
+    out->threads = kSpecThreads;
+    out->smem_bytes = p->jit_smem;
+    out->ctas_per_sm = p->jit_ctas_per_sm;
+    out->regs_per_thread = p->jit_regs;
+  } else {
+    out->threads = p->interp_threads;
+    out->smem_bytes = (uint32_t)p->interp_smem;
+    out->ctas_per_sm = p->interp_ctas_per_sm;
+  }
+  for (unsigned i = 0; i < p->h.n_in_arrays; ++i) out->in_sizes[i] = p->in_sizes[i];
+  for (unsigned i = 0; i < p->h.n_out_arrays; ++i) out->out_sizes[i] = p->out_sizes[i];
+  out->plan_key = p->key;
+  out->launches = p->launches.load();
+  return GX_OK;
+}
+
+int gx_plan_select_kernel(gx_plan* p, int kind) {
+  if (!p) return fail(GX_ERR_BAD_ARG, "gx_plan_select_kernel: plan is NULL");
+  if (kind == GX_KERNEL_INTERPRETER || (kind == GX_KERNEL_AOT && p->aot) || (kind == GX_KERNEL_JIT && p->jit_func)) {
+    p->kernel_kind = kind;
+    return GX_OK;
+  }
+  return fail(GX_ERR_UNSUPPORTED, "requested kernel kind is not attached to this plan");
+}
+
+int gx_plan_specialize(gx_plan* p, const char* src, size_t nbytes, const char* arch) {
+  if (!p || !src) return fail(GX_ERR_BAD_ARG, "gx_plan_specialize: NULL argument");
+  (void)nbytes;
+  Nvrtc& rt = nvrtc();
+  if (!rt.ok) return fail(GX_ERR_JIT, "NVRTC unavailable: " + rt.why);
+  GX_CUDA(cudaSetDevice(p->device));
+  GX_CUDA(cudaFree(0));
+  if (!driver().ok) return fail(GX_ERR_JIT, "CUDA driver entry points unavailable");
+
+  Nvrtc::Program prog = nullptr;
+  if (rt.CreateProgram(&prog, src, "gx_plan.cu", 0, nullptr, nullptr) != 0)
+    return fail(GX_ERR_JIT, "nvrtcCreateProgram failed");
+  std::string archopt = std::string("--gpu-architecture=") + (arch && *arch ? arch : "sm_100a");
+  char d_threads[48], d_blocks[48], d_stages[48];
+  snprintf(d_threads, sizeof d_threads, "-DGX_THREADS=%d", kSpecThreads);
+  snprintf(d_blocks, sizeof d_blocks, "-DGX_MIN_BLOCKS=%d", kSpecMinBlocks);
+  snprintf(d_stages, sizeof d_stages, "-DGX_OUT_STAGES=%d", kSpecOutStages);
+  const char* opts[] = {archopt.c_str(), "-std=c++17", "-lineinfo", d_threads, d_blocks, d_stages};
+  const int rc = rt.CompileProgram(prog, 6, opts);
+  if (rc != 0) {
+    size_t n = 0;
+    rt.GetProgramLogSize(prog, &n);
+    std::string log(n, '\0');
+    if (n) rt.GetProgramLog(prog, &log[0]);
+    rt.DestroyProgram(&prog);
+    return fail(GX_ERR_JIT, "nvrtcCompileProgram failed:\n" + log);
+  }
+  size_t n = 0;
+  rt.GetCUBINSize(prog, &n);
+  std::vector<char> cubin(n);
+  rt.GetCUBIN(prog, cubin.data());
+  rt.DestroyProgram(&prog);
+
+  CUmodule mod = nullptr;
+  CUresult r = driver().ModuleLoadData(&mod, cubin.data());
+  if (r != CUDA_SUCCESS) return fail(GX_ERR_JIT, "cuModuleLoadData: " + cu_err(r));
+  CUfunction fn = nullptr;
+  r = driver().ModuleGetFunction(&fn, mod, "gx_jacve_kernel");
+  if (r != CUDA_SUCCESS) {
+    driver().ModuleUnload(mod);
+    return fail(GX_ERR_JIT, "cuModuleGetFunction(gx_jacve_kernel): " + cu_err(r));
+  }
+  const int tile = (int)(p->h.n_rows * p->h.n_cols + ((p->h.flags & GX_FLAG_HAS_PRIMAL) ? p->h.n_rows : 0));
+  const int smem = (2 * (int)p->h.n_in_scalars * kSpecThreads + kSpecOutStages * tile * kSpecThreads) * 4 + 64;
+  r = driver().FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, smem);
+  int occ = 0, regs = 0;
+  if (r == CUDA_SUCCESS) r = driver().OccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kSpecThreads, smem);
+  if (r == CUDA_SUCCESS) r = driver().FuncGetAttribute(&regs, CU_FUNC_ATTRIBUTE_NUM_REGS, fn);
+  if (r != CUDA_SUCCESS || occ < 1) {
+    driver().ModuleUnload(mod);
+    return fail(GX_ERR_JIT, "specialised kernel does not fit on the device: " + cu_err(r));
+  }
+  if (p->jit_module) driver().ModuleUnload(p->jit_module);
+  p->jit_module = mod;
+  p->jit_func = fn;
+  p->jit_smem = smem;
+  p->jit_ctas_per_sm = occ;
+  p->jit_regs = regs;
+  p->kernel_kind = GX_KERNEL_JIT;
+  return GX_OK;
+}
+
+int gx_jacve_launch(gx_plan* p, int64_t batch, const void* const* in_ptrs, void* jac_out, void* primal_out,
+                    void* stream) {
+  if (!p) return fail(GX_ERR_BAD_ARG, "gx_jacve_launch: plan is NULL");
+  if (batch < 0) return fail(GX_ERR_BAD_ARG, "gx_jacve_launch: negative batch");
+  if (batch == 0) return GX_OK;
+  if (!in_ptrs || !jac_out) return fail(GX_ERR_BAD_ARG, "gx_jacve_launch: NULL buffer");
+  for (unsigned i = 0; i < p->h.n_in_arrays; ++i)
+    if (!in_ptrs[i]) return fail(GX_ERR_BAD_ARG, "gx_jacve_launch: NULL input array");
+  if (primal_out && !(p->h.flags & GX_FLAG_HAS_PRIMAL))
+    return fail(GX_ERR_BAD_ARG, "gx_jacve_launch: plan was built without primal outputs");
+  GX_CUDA(cudaSetDevice(p->device));
+  return launch_on(p, batch, in_ptrs, jac_out, primal_out, static_cast<cudaStream_t>(stream));
+}
+
+int gx_jacve_host(gx_plan* p, int64_t batch, const void* const* in_ptrs, void* jac_out, void* primal_out,
+                  int pinned) {
+  if (!p) return fail(GX_ERR_BAD_ARG, "gx_jacve_host: plan is NULL");
+  if (batch < 0) return fail(GX_ERR_BAD_ARG, "gx_jacve_host: negative batch");
+  if (batch == 0) return GX_OK;
+  if (!in_ptrs || !jac_out) return fail(GX_ERR_BAD_ARG, "gx_jacve_host: NULL buffer");
+  if (primal_out && !(p->h.flags & GX_FLAG_HAS_PRIMAL))
+    return fail(GX_ERR_BAD_ARG, "gx_jacve_host: plan was built without primal outputs");
+  std::lock_guard<std::mutex> lock(p->host_mu);
+  GX_CUDA(cudaSetDevice(p->device));
+  const size_t n_in = p->h.n_in_scalars, tile = (size_t)p->h.n_rows * p->h.n_cols, rows = p->h.n_rows;
+  const bool staging = !pinned;
+  if (!p->host_ready || (staging && !p->host_staging)) {
+    for (auto& s : p->slots) {
+      if (!s.stream) GX_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+      if (!s.done) GX_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+      if (!s.d_in) GX_CUDA(cudaMalloc(&s.d_in, 4 * n_in * kHostChunk));
+      if (!s.d_jac) GX_CUDA(cudaMalloc(&s.d_jac, 4 * tile * kHostChunk));
+      if (!s.d_primal) GX_CUDA(cudaMalloc(&s.d_primal, 4 * rows * kHostChunk));
+      if (staging && !s.h_in) {
+        GX_CUDA(cudaMallocHost(&s.h_in, 4 * n_in * kHostChunk));
+        GX_CUDA(cudaMallocHost(&s.h_jac, 4 * tile * kHostChunk));
+        GX_CUDA(cudaMallocHost(&s.h_primal, 4 * rows * kHostChunk));
+      }
+    }
+    p->host_ready = true;
+    p->host_staging = p->host_staging || staging;
+  }
+  const int64_t n_chunks = (batch + kHostChunk - 1) / kHostChunk;
+  auto drain = [&](int64_t c) -> int {  // staged results of chunk c -> caller memory
+    auto& s = p->slots[c & 1];
+    GX_CUDA(cudaEventSynchronize(s.done));
+    if (staging) {
+      const int64_t b0 = c * kHostChunk, nb = std::min<int64_t>(kHostChunk, batch - b0);
+      memcpy(static_cast<float*>(jac_out) + b0 * tile, s.h_jac, 4 * tile * nb);
+      if (primal_out) memcpy(static_cast<float*>(primal_out) + b0 * rows, s.h_primal, 4 * rows * nb);
+    }
+    return GX_OK;
+  };
+  for (int64_t c = 0; c < n_chunks; ++c) {
+    auto& s = p->slots[c & 1];
+    const int64_t b0 = c * kHostChunk, nb = std::min<int64_t>(kHostChunk, batch - b0);
+    if (c >= 2) {
+      int rc = drain(c - 2);
+      if (rc) return rc;
+    }
+    const void* d_ptrs[GX_MAX_ARRAYS];
+    size_t off = 0;
+    for (unsigned i = 0; i < p->h.n_in_arrays; ++i) {
+      const size_t sz = p->in_sizes[i];
+      const float* src = static_cast<const float*>(in_ptrs[i]) + b0 * sz;
+      float* dst = s.d_in + off * kHostChunk;
+      if (staging) {
+        float* st = s.h_in + off * kHostChunk;
+        memcpy(st, src, 4 * sz * nb);
+        src = st;
+      }
+      GX_CUDA(cudaMemcpyAsync(dst, src, 4 * sz * nb, cudaMemcpyHostToDevice, s.stream));
+      d_ptrs[i] = dst;
+      off += sz;
+    }
+    int rc = launch_on(p, nb, d_ptrs, s.d_jac, primal_out ? s.d_primal : nullptr, s.stream);
+    if (rc) return rc;
+    float* hj = staging ? s.h_jac : static_cast<float*>(jac_out) + b0 * tile;
+    GX_CUDA(cudaMemcpyAsync(hj, s.d_jac, 4 * tile * nb, cudaMemcpyDeviceToHost, s.stream));
+    if (primal_out) {
+      float* hp = staging ? s.h_primal : static_cast<float*>(primal_out) + b0 * rows;
+      GX_CUDA(cudaMemcpyAsync(hp, s.d_primal, 4 * rows * nb, cudaMemcpyDeviceToHost, s.stream));
+    }
+    GX_CUDA(cudaEventRecord(s.done, s.stream));
+  }
+  for (int64_t c = std::max<int64_t>(0, n_chunks - 2); c < n_chunks; ++c) {
+    int rc = drain(c);
+    if (rc) return rc;
+  }
+  return GX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,211 @@
+// gx_skeleton.cuh - persistent, TMA-staged kernel around a plan-specialised body (sm_100a).
+//
+// One thread evaluates one sample: the whole elimination plan (primal, elemental partials, every
+// J[s,p] += J[s,v]*J[v,p] product, reference core.py:155-272) runs in registers as straight-line
+// code.  HBM is touched exactly twice per sample: the inputs (4*n_in bytes) and the dense Jacobian
+// tile (4*n_rows*n_cols bytes).  Both sides are staged through shared memory with 1-D bulk
+// asynchronous copies (cp.async.bulk = the TMA engine, SASS UBLKCP) so that
+//   * global traffic is fully coalesced although every thread owns a strided [tile] row,
+//   * the loads of tile i+1 and the stores of tile i-1 overlap the arithmetic of tile i, and
+//   * no issue slots are spent on address arithmetic / LDG / STG for the 60 words per sample.
+// CTAs are persistent (grid = SMs x resident CTAs) and stride over the batch in tiles of GX_THREADS
+// samples.  A partial last tile, or misaligned caller buffers, take a guarded non-bulk path through
+// the same body.
+//
+// The including translation unit (emitted by graphax_b200/codegen.py) defines:
+//   GX_N_ARR, GX_N_IN, GX_N_ROWS, GX_N_COLS, GX_HAS_PRIMAL, GX_THREADS, GX_MIN_BLOCKS, GX_OUT_STAGES
+//   GX_KERNEL_NAME                unique symbol of this kernel (gx_jacve_kernel for NVRTC)
+//   GX_FOREACH_ARRAY(F)           F(index, scalars_per_sample, prefix_offset) for every input array
+//   gx_body(x, jrow, prow)        __device__ __forceinline__ function: the straight-line plan; reads the
+//                                 sample's inputs x[k], writes tile entries jrow[pos] and outputs prow[row]
+#pragma once
+
+#ifndef GX_NVRTC
+#include <cuda_runtime.h>
+#include <stdint.h>
+#else
+typedef unsigned int uint32_t;
+typedef unsigned long long uint64_t;
+#endif
+
+#define GX_TILE (GX_N_ROWS * GX_N_COLS)
+#define GX_MAX_ARRAYS_K 16
+
+struct GxLaunchArgs {
+  const float* in[GX_MAX_ARRAYS_K];
+  float* jac;
+  float* primal;
+  long long batch;
+  long long n_bulk_tiles;  // leading tiles that are full and 16B-aligned on every buffer
+};
+
+namespace {
+namespace gxk {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "GX_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra GX_DONE;\n"
+      "bra GX_WAIT;\n"
+      "GX_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy, completion signalled on an mbarrier (TMA load)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// shared -> global bulk copy, tracked by bulk async-groups (TMA store)
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+constexpr int kInStageFloats = GX_N_IN * GX_THREADS;
+constexpr int kOutStageFloats = (GX_TILE + (GX_HAS_PRIMAL ? GX_N_ROWS : 0)) * GX_THREADS;
+constexpr int kSmemBytes = (2 * kInStageFloats + GX_OUT_STAGES * kOutStageFloats) * 4 + 64;
+
+}  // namespace gxk
+}  // namespace
+
+// shared memory: [ in stage 0 | in stage 1 | out stage 0 (jac tile rows, then primal rows) | out stage 1 | mbarriers ]
+extern "C" __global__ void __launch_bounds__(GX_THREADS, GX_MIN_BLOCKS)
+GX_KERNEL_NAME(const __grid_constant__ GxLaunchArgs args) {
+  using namespace gxk;
+  extern __shared__ __align__(128) float gx_smem[];
+  float* in_stage = gx_smem;
+  float* out_stage = gx_smem + 2 * kInStageFloats;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_stage + GX_OUT_STAGES * kOutStageFloats);
+
+  const int tid = threadIdx.x;
+  const long long n_tiles = (args.batch + GX_THREADS - 1) / GX_THREADS;
+  const long long n_bulk = args.n_bulk_tiles;
+
+  if (tid == 0) {
+    mbar_init(&full_bar[0], 1);
+    mbar_init(&full_bar[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  auto issue_loads = [&](long long tile, int stage) {
+    // one elected thread programs the TMA engine: GX_N_ARR contiguous chunks of this tile
+    mbar_expect_tx(&full_bar[stage], (uint32_t)(GX_N_IN * GX_THREADS * 4));
+#define GX_ISSUE(a, size, off)                                                                    \
+  bulk_g2s(in_stage + stage * kInStageFloats + (off) * GX_THREADS,                                \
+           args.in[a] + tile * (long long)(GX_THREADS * (size)), (uint32_t)((size) * GX_THREADS * 4), \
+           &full_bar[stage]);
+    GX_FOREACH_ARRAY(GX_ISSUE)
+#undef GX_ISSUE
+  };
+
+  long long tile = blockIdx.x;
+  if (tid == 0 && tile < n_bulk) issue_loads(tile, 0);
+
+  for (int it = 0; tile < n_tiles; ++it, tile += gridDim.x) {
+    const int stage = it & 1;
+    const int ostage = it % GX_OUT_STAGES;
+    const bool bulk = tile < n_bulk;
+    const long long next = tile + gridDim.x;
+    // prefetch the next tile: its stage was last read one iteration ago, before the barrier below
+    if (tid == 0 && next < n_bulk) issue_loads(next, stage ^ 1);
+
+    float x[GX_N_IN];
+    const long long sample = tile * GX_THREADS + tid;
+    if (bulk) {
+      mbar_wait(&full_bar[stage], (uint32_t)((it >> 1) & 1));
+      const float* s = in_stage + stage * kInStageFloats;
+#define GX_RD_BULK(a, size, off) \
+  _Pragma("unroll") for (int c = 0; c < (size); ++c) x[(off) + c] = s[(off) * GX_THREADS + tid * (size) + c];
+      GX_FOREACH_ARRAY(GX_RD_BULK)
+#undef GX_RD_BULK
+    } else {
+#define GX_RD_DIRECT(a, size, off)                       \
+  _Pragma("unroll") for (int c = 0; c < (size); ++c)     \
+      x[(off) + c] = sample < args.batch ? __ldg(args.in[a] + sample * (size) + c) : 1.0f;
+      GX_FOREACH_ARRAY(GX_RD_DIRECT)
+#undef GX_RD_DIRECT
+    }
+    // the out stage about to be written was handed to the TMA engine GX_OUT_STAGES iterations ago
+    if (tid == 0) bulk_wait_read<GX_OUT_STAGES - 1>();
+    __syncthreads();
+
+    float* jrow = out_stage + ostage * kOutStageFloats + tid * GX_TILE;
+    float* prow = out_stage + ostage * kOutStageFloats + GX_THREADS * GX_TILE + tid * GX_N_ROWS;
+    gx_body(x, jrow, prow);
+
+    if (bulk) {
+      fence_async_smem();  // generic-proxy writes -> visible to the async proxy
+      __syncthreads();
+      if (tid == 0) {
+        bulk_s2g(args.jac + tile * (long long)(GX_THREADS * GX_TILE), out_stage + ostage * kOutStageFloats,
+                 (uint32_t)(GX_THREADS * GX_TILE * 4));
+#if GX_HAS_PRIMAL
+        if (args.primal != nullptr)
+          bulk_s2g(args.primal + tile * (long long)(GX_THREADS * GX_N_ROWS),
+                   out_stage + ostage * kOutStageFloats + GX_THREADS * GX_TILE,
+                   (uint32_t)(GX_THREADS * GX_N_ROWS * 4));
+#endif
+        bulk_commit();
+      }
+    } else {
+      __syncthreads();
+      const long long base = tile * (long long)GX_THREADS;
+      const long long valid = args.batch - base < GX_THREADS ? args.batch - base : GX_THREADS;
+      const float* src = out_stage + ostage * kOutStageFloats;
+      for (long long i = tid; i < valid * GX_TILE; i += GX_THREADS) args.jac[base * GX_TILE + i] = src[i];
+#if GX_HAS_PRIMAL
+      if (args.primal != nullptr)
+        for (long long i = tid; i < valid * GX_N_ROWS; i += GX_THREADS)
+          args.primal[base * GX_N_ROWS + i] = src[GX_THREADS * GX_TILE + i];
+#endif
+      __syncthreads();  // the stage may be rewritten by the next iteration
+    }
+  }
+  if (tid == 0) bulk_wait_all();  // shared memory must outlive the stores that read it
+}
+
+#ifndef GX_NVRTC
+// ---- ahead-of-time registration: build() compiles one such TU per named plan into the library ----
+struct GxAotKernel {
+  unsigned long long key;
+  int threads, smem_bytes, n_in, n_rows, n_cols, has_primal;
+  const void* func;
+};
+extern "C" void gx_register_aot(const GxAotKernel* k);
+namespace {
+struct GxRegistrar {
+  GxRegistrar() {
+    static GxAotKernel k = {GX_KEY, GX_THREADS, gxk::kSmemBytes, GX_N_IN, GX_N_ROWS, GX_N_COLS, GX_HAS_PRIMAL,
+                            (const void*)GX_KERNEL_NAME};
+    gx_register_aot(&k);
+  }
+} gx_registrar_instance;
+}  // namespace
+#endif

@@ -1,0 +1,265 @@
+"""Graph builder and symbolic vertex elimination.
+
+``build_graph`` mirrors the reference's ``_build_graph`` (``core.py:314-412``):
+one pass over the equations that numbers vertices, evaluates the primal and
+stores one edge per traced operand in ``graph[src][dst]`` /
+``transpose[dst][src]`` (insertion-ordered dicts, like the reference's).
+``eliminate`` mirrors ``_eliminate_vertex`` (``core.py:155-272``): for every
+successor s (outer loop) and predecessor p (inner loop) of the vertex,
+``J[s,p] (+)= J[s,v] . J[v,p]``, then the vertex's edges are deleted.
+
+What differs from the reference is *when* the arithmetic happens: nothing is
+computed here.  Every edge carries (i) the tensor-level structure descriptor
+(``structure.Struct``) that ``count_ops`` and the sparsity classes are defined
+on, and (ii) its structurally non-zero scalar entries as nodes of the expression
+DAG.  Products append ``mul``/``fma``/``add`` nodes; the finished DAG is
+linearised into the flat plan (``plan.py``).
+
+Accumulation order (stated because fp32 results depend on it): within one
+product the contraction index runs ascending, ``t = a0*b0; t = fma(ak, bk, t)``;
+an existing edge is added last, ``new = t + old``, contracted to a single
+``fma(a0, b0, old)`` when the product has one term.  Factors that are
+structurally +-1 (add/sub/neg/slice/concatenate/reduce_sum edges) are not
+multiplied: ``x*1`` and ``fma(x, 1, c) = x + c`` are exact identities.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field, replace
+from typing import Dict, List, Optional, Sequence, Set, Tuple, Union
+
+from . import structure as st
+from .lowering import Dag, Entries, Vec, lower_eqn
+from .tracer import Jaxpr, Literal, Var
+
+Order = Union[str, Sequence[int]]
+
+
+@dataclass
+class Edge:
+    struct: st.Struct
+    entries: Entries          # (i, j) -> DAG node; i over dst components, j over src components
+
+
+@dataclass
+class Graph:
+    jaxpr: Jaxpr
+    dag: Dag
+    env: Dict[int, Vec]                                  # vertex key -> lowered primal value
+    fwd: Dict[int, Dict[int, Edge]]                      # graph[src][dst]
+    bwd: Dict[int, Dict[int, Edge]]                      # transpose_graph[dst][src]
+    vo_vertices: Set[int]                                # outputs that are consumed later (core.py:387-390)
+    elemental: List[Tuple[int, int, st.Struct]] = field(default_factory=list)
+    first_elim_node: int = 0
+
+    @staticmethod
+    def key(var: Var) -> int:
+        """Inputs are -(k+1), equation results are their 1-based vertex id."""
+        return -(var.input_index + 1) if var.input_index is not None else var.eqn_index + 1
+
+
+def build_graph(jaxpr: Jaxpr) -> Graph:
+    dag = Dag()
+    env: Dict[int, Vec] = {}
+    k = 0
+    for var in jaxpr.invars:
+        env[Graph.key(var)] = Vec(var.shape, [dag.input(k + i) for i in range(var.size)])
+        k += var.size
+    g = Graph(jaxpr, dag, env, {}, {}, set())
+    for var in jaxpr.invars:
+        g.fwd[Graph.key(var)] = {}
+        g.bwd[Graph.key(var)] = {}
+    out_keys = {Graph.key(v) for v in jaxpr.outvars if isinstance(v, Var)}
+
+    def read(atom) -> Vec:
+        if isinstance(atom, Literal):
+            return Vec((), [dag.const(atom.val)], is_literal=True)
+        return env[Graph.key(atom)]
+
+    for eqn in jaxpr.eqns:
+        v = Graph.key(eqn.outvar)
+        g.fwd.setdefault(v, {})
+        g.bwd.setdefault(v, {})
+        for a in eqn.invars:
+            if isinstance(a, Var) and Graph.key(a) in out_keys and a.eqn_index is not None:
+                g.vo_vertices.add(Graph.key(a))
+        out, edges = lower_eqn(dag, eqn, read)
+        if out.shape != eqn.outvar.shape:
+            raise AssertionError(f"shape mismatch lowering {eqn!r}: {out.shape}")
+        env[v] = out
+        n_traced = sum(isinstance(a, Var) for a in eqn.invars)
+        if len(edges) != n_traced:
+            continue                                      # core.py:409: no edge at all
+        for src_var, struct, entries in edges:
+            src = Graph.key(src_var)
+            if v in g.fwd[src]:
+                # same variable used twice by one equation (x*x): the reference overwrites the
+                # first edge (core.py:367-371); this engine accumulates
+                old = g.fwd[src][v]
+                merged = dict(old.entries)
+                for ij, n in entries.items():
+                    merged[ij] = dag.add(n, merged[ij]) if ij in merged else n
+                edge = Edge(st.add(struct, old.struct), merged)
+            else:
+                edge = Edge(struct, entries)
+            g.fwd[src][v] = edge
+            g.bwd[v][src] = edge
+            g.elemental.append((src, v, edge.struct))
+    g.first_elim_node = len(dag.op)
+    return g
+
+
+def eliminable_vertices(g: Graph) -> List[int]:
+    out_keys = {Graph.key(v) for v in g.jaxpr.outvars if isinstance(v, Var)}
+    return [i for i in range(1, len(g.jaxpr.eqns) + 1) if i not in out_keys or i in g.vo_vertices]
+
+
+def checkify_order(order: Order, g: Graph) -> List[int]:
+    """``_checkify_order`` (core.py:275-311), with strict validation of custom
+    orders: unknown ids, output vertices and duplicates raise ``ValueError``
+    instead of failing later with ``IndexError``/``KeyError``."""
+    valid = eliminable_vertices(g)
+    if isinstance(order, str):
+        if order in ("forward", "fwd"):
+            return valid
+        if order in ("reverse", "rev"):
+            return valid[::-1]
+        raise ValueError(f"{order} is not a valid order identifier!")
+    order = [int(o) for o in order]
+    missing = set(valid).difference(order)
+    if missing:
+        raise ValueError(f"Supplied order is missing vertices {missing}!")
+    extra = [o for o in order if o not in set(valid)]
+    if extra:
+        raise ValueError(f"Supplied order contains vertices that cannot be eliminated: {sorted(set(extra))}!")
+    if len(set(order)) != len(order):
+        raise ValueError("Supplied order eliminates a vertex more than once!")
+    return order
+
+
+def _strip(s: st.Struct) -> st.Struct:
+    return replace(s, pre=()) if s.pre else s
+
+
+def _product_entries(dag: Dag, post: Entries, pre: Entries, existing: Optional[Entries]) -> Entries:
+    by_k_post: Dict[int, List[Tuple[int, int]]] = {}
+    for (i, k), n in post.items():
+        by_k_post.setdefault(k, []).append((i, n))
+    terms: Dict[Tuple[int, int], List[Tuple[int, int, int]]] = {}
+    for (k, j), m in pre.items():
+        for i, n in by_k_post.get(k, ()):
+            terms.setdefault((i, j), []).append((k, n, m))
+    out: Entries = {}
+    for ij in sorted(terms):
+        ts = sorted(terms[ij])
+        old = existing.get(ij) if existing is not None else None
+        if old is not None and len(ts) == 1:
+            out[ij] = dag.fma(ts[0][1], ts[0][2], old)
+            continue
+        acc = dag.mul(ts[0][1], ts[0][2])
+        for _, n, m in ts[1:]:
+            acc = dag.fma(n, m, acc)
+        out[ij] = dag.add(acc, old) if old is not None else acc
+    if existing is not None:
+        for ij, n in existing.items():
+            out.setdefault(ij, n)
+    return out
+
+
+@dataclass
+class StepStats:
+    vertex: int
+    num_muls: int = 0
+    num_adds: int = 0
+    pairs: int = 0
+    classes: Dict[str, int] = field(default_factory=dict)
+
+
+def eliminate(g: Graph, vertex: int) -> StepStats:
+    """Eliminate one vertex (core.py:155-272). Returns the reference's op counts."""
+    stats = StepStats(vertex)
+    dag = g.dag
+    v = vertex
+    for s in list(g.fwd[v].keys()):
+        post = g.fwd[v][s]
+        for p in list(g.bwd[v].keys()):
+            pre = g.bwd[v][p]
+            stats.pairs += 1
+            pre_s = pre.struct
+            if post.struct.pre and pre.struct.has_val:
+                # unload_pre_transforms: shape-op Jacobians pending on the outgoing edge act on the incoming one
+                pre_s = _strip(pre_s)
+                for t in post.struct.pre:
+                    pre_s = st.apply_transform(t, pre_s)
+            if pre.struct.has_val and post.struct.has_val:
+                lhs, rhs = _strip(post.struct), _strip(pre_s)
+                cls = st.mul_class(lhs, rhs)
+                key = f"{post.struct.sparsity_class()}x{pre.struct.sparsity_class()}:{cls}"
+                stats.classes[key] = stats.classes.get(key, 0) + 1
+                out_s = st.mul(lhs, rhs)
+                stats.num_muls += st.num_muls(lhs, rhs)
+                pending = pre.struct.pre
+            elif pre.struct.has_val:
+                out_s, pending = _strip(pre_s), pre.struct.pre
+            else:
+                out_s, pending = _strip(post.struct), pre.struct.pre + post.struct.pre
+            out_s = replace(out_s, pre=pending)
+
+            old = g.fwd[p].get(s)
+            if old is not None:
+                # fill-in onto an existing edge: flush deferred transforms on both, then add
+                new_m, old_m = st.materialise(out_s), st.materialise(old.struct)
+                out_s = st.add(new_m, old_m)
+                stats.num_adds += st.num_adds(out_s, old_m)
+            entries = _product_entries(dag, post.entries, pre.entries, None if old is None else old.entries)
+            edge = Edge(out_s, entries)
+            g.fwd[p][s] = edge
+            g.bwd[s][p] = edge
+
+    keep_in_edges = v in g.vo_vertices
+    if not keep_in_edges:
+        for p in g.bwd[v]:
+            del g.fwd[p][v]
+    for s in g.fwd[v]:
+        del g.bwd[s][v]
+    del g.fwd[v]
+    if not keep_in_edges:
+        del g.bwd[v]
+    return stats
+
+
+@dataclass
+class Accumulated:
+    """Result of eliminating a whole order."""
+    graph: Graph
+    order: List[int]
+    steps: List[StepStats]
+    # blocks[(out_idx, arg_idx)] = (struct or None, entries) in flush-ed (dense-coordinate) form
+    blocks: Dict[Tuple[int, int], Tuple[Optional[st.Struct], Entries]]
+
+    @property
+    def num_muls(self) -> int:
+        return sum(s.num_muls for s in self.steps)
+
+    @property
+    def num_adds(self) -> int:
+        return sum(s.num_adds for s in self.steps)
+
+
+def accumulate(jaxpr: Jaxpr, order: Order, argnums: Sequence[int]) -> Accumulated:
+    """``vertex_elimination_jaxpr`` minus densification (core.py:522-562)."""
+    g = build_graph(jaxpr)
+    for o in jaxpr.outvars:
+        if not isinstance(o, Var) or o.eqn_index is None:
+            raise NotImplementedError("outputs that are inputs or constants are not supported")
+    vertices = checkify_order(order, g)
+    steps = [eliminate(g, v) for v in vertices]
+    blocks: Dict[Tuple[int, int], Tuple[Optional[st.Struct], Entries]] = {}
+    for oi, o in enumerate(jaxpr.outvars):
+        for ai, a in enumerate(argnums):
+            src, dst = Graph.key(jaxpr.invars[a]), Graph.key(o)
+            edge = g.fwd.get(src, {}).get(dst)
+            if edge is None:
+                blocks[(oi, ai)] = (None, {})
+            else:
+                blocks[(oi, ai)] = (st.materialise(edge.struct), edge.entries)
+    return Accumulated(g, vertices, steps, blocks)

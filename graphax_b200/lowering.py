@@ -1,0 +1,401 @@
+"""Scalar expression DAG and the elemental rules, lowered to scalars.
+
+The reference evaluates every equation and its local partial derivatives as
+small ``jnp`` arrays (``core.py:380-410``, ``primitives.py:113-205``).  Here the
+same formulas are recorded once, per scalar component, as nodes of a hash-consed
+expression DAG; the elimination later appends its products to the same DAG and
+the whole thing is linearised into the flat plan the CUDA kernels run.
+
+Exactness rules (they are what makes "bit-exact against the plan replay"
+possible): every node is one IEEE-754 binary32 operation with round-to-nearest;
+identical (op, operands) pairs are the same node (no CSE in the jaxpr, but equal
+expressions have equal values); operands of commutative ops are ordered;
+``x*1 -> x``, ``x*-1 -> -x``, ``fma(x, +-1, c) -> c +- x`` and all-constant
+operations are folded at plan time with the same binary32 arithmetic.
+"""
+from __future__ import annotations
+
+import math
+import warnings
+from fractions import Fraction
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import structure as st
+from .tracer import Eqn, Literal, Var
+
+# opcode table shared with csrc/gx_ops.h and oracle/replay.c (keep in sync; tests check it)
+OPCODES = [
+    "input", "const",
+    "add", "sub", "mul", "div", "fma", "neg", "abs", "sqrt",
+    "sin", "cos", "tan", "atan2", "exp", "log", "log1p", "tanh", "sinh", "cosh",
+    "asin", "acos", "atan", "asinh", "acosh", "atanh", "erf", "pow", "logistic",
+    "store_jac", "store_primal",
+]
+OP = {name: i for i, name in enumerate(OPCODES)}
+_UNARY = {"neg", "abs", "sqrt", "sin", "cos", "tan", "exp", "log", "log1p", "tanh", "sinh", "cosh",
+          "asin", "acos", "atan", "asinh", "acosh", "atanh", "erf", "logistic"}
+_COMMUTATIVE = {"add", "mul"}
+
+f32 = np.float32
+
+
+def _f32_from_fraction(x: Fraction) -> np.float32:
+    """Correctly rounded (nearest-even) binary32 value of an exact rational."""
+    approx = f32(float(x))
+    if not np.isfinite(approx):
+        return approx
+    best = approx
+    for cand in (np.nextafter(approx, f32(-np.inf)), np.nextafter(approx, f32(np.inf))):
+        if not np.isfinite(cand):
+            continue
+        db, dc = abs(Fraction(float(best)) - x), abs(Fraction(float(cand)) - x)
+        if dc < db or (dc == db and (int(np.array(cand).view(np.uint32)) & 1) == 0):
+            best = cand
+    return f32(best)
+
+
+class Dag:
+    """Hash-consed scalar expression DAG. Node ids are dense ints."""
+
+    def __init__(self) -> None:
+        self.op: List[str] = []
+        self.args: List[Tuple[int, ...]] = []
+        self.cval: List[Optional[np.float32]] = []     # value for const nodes
+        self._memo: Dict[tuple, int] = {}
+
+    # ---- node construction -------------------------------------------------
+    def _new(self, key: tuple, op: str, args: Tuple[int, ...], cval=None) -> int:
+        nid = self._memo.get(key)
+        if nid is None:
+            nid = len(self.op)
+            self.op.append(op)
+            self.args.append(args)
+            self.cval.append(cval)
+            self._memo[key] = nid
+        return nid
+
+    def const(self, v) -> int:
+        v = f32(v)
+        bits = int(np.array(v).view(np.uint32))
+        return self._new(("const", bits), "const", (), v)
+
+    def input(self, k: int) -> int:
+        return self._new(("input", k), "input", (k,))
+
+    def is_const(self, n: int) -> bool:
+        return self.op[n] == "const"
+
+    def _is(self, n: int, v: float) -> bool:
+        return self.op[n] == "const" and float(self.cval[n]) == v and not (v == 0.0)
+
+    def _fold(self, op: str, vals: Sequence[np.float32]) -> Optional[int]:
+        with warnings.catch_warnings(), np.errstate(all="ignore"):
+            warnings.simplefilter("ignore")
+            if op == "add":
+                return self.const(f32(vals[0]) + f32(vals[1]))
+            if op == "sub":
+                return self.const(f32(vals[0]) - f32(vals[1]))
+            if op == "mul":
+                return self.const(f32(vals[0]) * f32(vals[1]))
+            if op == "div":
+                if float(vals[1]) == 0.0:
+                    return None
+                return self.const(f32(vals[0]) / f32(vals[1]))
+            if op == "neg":
+                return self.const(-f32(vals[0]))
+            if op == "abs":
+                return self.const(np.abs(f32(vals[0])))
+            if op == "sqrt":
+                return self.const(np.sqrt(f32(vals[0])))
+            if op == "fma":
+                if all(np.isfinite(v) for v in vals):
+                    exact = Fraction(float(vals[0])) * Fraction(float(vals[1])) + Fraction(float(vals[2]))
+                    if exact == 0:
+                        return None   # sign of an exact zero depends on operand signs; leave to run time
+                    return self.const(_f32_from_fraction(exact))
+        return None   # transcendental constants are evaluated on the device, not by host libm
+
+    def emit(self, op: str, *a: int) -> int:
+        if op == "neg" and self.op[a[0]] == "neg":
+            return self.args[a[0]][0]
+        if op == "mul":
+            x, y = a
+            if self._is(y, 1.0):
+                return x
+            if self._is(x, 1.0):
+                return y
+            if self._is(y, -1.0):
+                return self.emit("neg", x)
+            if self._is(x, -1.0):
+                return self.emit("neg", y)
+        if op == "fma":
+            x, y, c = a
+            for p, q in ((x, y), (y, x)):
+                if self._is(q, 1.0):
+                    return self.emit("add", p, c)
+                if self._is(q, -1.0):
+                    return self.emit("sub", c, p)
+            if x > y:
+                a = (y, x, c)
+        if op in _COMMUTATIVE and a[0] > a[1]:
+            a = (a[1], a[0])
+        if all(self.op[n] == "const" for n in a):
+            folded = self._fold(op, [self.cval[n] for n in a])
+            if folded is not None:
+                return folded
+        return self._new((op,) + tuple(a), op, tuple(a))
+
+    # convenience
+    def add(self, a, b): return self.emit("add", a, b)
+    def sub(self, a, b): return self.emit("sub", a, b)
+    def mul(self, a, b): return self.emit("mul", a, b)
+    def div(self, a, b): return self.emit("div", a, b)
+    def fma(self, a, b, c): return self.emit("fma", a, b, c)
+    def neg(self, a): return self.emit("neg", a)
+
+
+class Vec:
+    """A traced value lowered to scalar nodes: shape () or (n,)."""
+    __slots__ = ("shape", "nodes", "is_literal")
+
+    def __init__(self, shape: Tuple[int, ...], nodes: Sequence[int], is_literal: bool = False):
+        if len(shape) > 1:
+            raise NotImplementedError("vertices of rank > 1 are not lowered yet (scope row (f)1)")
+        self.shape = tuple(shape)
+        self.nodes = list(nodes)
+        self.is_literal = is_literal
+        assert len(self.nodes) == self.size
+
+    @property
+    def size(self) -> int:
+        return self.shape[0] if self.shape else 1
+
+    @property
+    def ndim(self) -> int:
+        return len(self.shape)
+
+
+def _bshape(a: Tuple[int, ...], b: Tuple[int, ...]) -> Tuple[int, ...]:
+    if a == ():
+        return b
+    if b == ():
+        return a
+    return (max(a[0], b[0]),)
+
+
+class _Ew:
+    """Elementwise helpers with lax broadcasting over Vec."""
+
+    def __init__(self, dag: Dag):
+        self.dag = dag
+
+    def lit(self, v: float) -> Vec:
+        return Vec((), [self.dag.const(v)], is_literal=True)
+
+    def binary(self, op: str, a: Vec, b: Vec) -> Vec:
+        shape = _bshape(a.shape, b.shape)
+        n = shape[0] if shape else 1
+        out = [self.dag.emit(op, a.nodes[i if a.size == n else 0], b.nodes[i if b.size == n else 0])
+               for i in range(n)]
+        return Vec(shape, out)
+
+    def unary(self, op: str, a: Vec) -> Vec:
+        return Vec(a.shape, [self.dag.emit(op, x) for x in a.nodes])
+
+    def add(self, a, b): return self.binary("add", a, b)
+    def sub(self, a, b): return self.binary("sub", a, b)
+    def mul(self, a, b): return self.binary("mul", a, b)
+    def div(self, a, b): return self.binary("div", a, b)
+    def neg(self, a): return self.unary("neg", a)
+
+    def ones_like(self, a: Vec) -> Vec:
+        return Vec(a.shape, [self.dag.const(1.0)] * a.size)
+
+    def ipow(self, a: Vec, y: int) -> Vec:
+        """lax.integer_pow by repeated squaring (y=2 -> x*x, y=3 -> (x*x)*x)."""
+        if y == 0:
+            return self.ones_like(a)
+        if y < 0:
+            return self.div(self.lit(1.0), self.ipow(a, -y))
+        result, base, e = None, a, y
+        while e:
+            if e & 1:
+                result = base if result is None else self.mul(result, base)
+            e >>= 1
+            if e:
+                base = self.mul(base, base)
+        return result
+
+
+Entries = Dict[Tuple[int, int], int]
+
+
+def _parallel_jacobian(primal: Vec, out: Vec, partial: Vec, n_operands: int) -> Tuple[st.Struct, Entries]:
+    """``make_parallel_jacobian`` (reference primitives.py:42-107) for rank <= 1."""
+    n = out.size
+    if primal.ndim == 0 and out.ndim == 0:
+        return st.SCALAR, {(0, 0): partial.nodes[0]}
+    if primal.ndim == 0:
+        # rank-0 operand broadcast into a vector result
+        return st.rank0_operand(n), {(i, 0): partial.nodes[i if partial.size == n else 0] for i in range(n)}
+    if n_operands == 1:
+        return st.diag(n), {(i, i): partial.nodes[i] for i in range(n)}
+    if primal.shape != out.shape:
+        # (1,) operand stretched to (n,): dense out dim, replicated primal dim
+        return (st.bcast(n, primal.size),
+                {(i, 0): partial.nodes[i if partial.size == n else 0] for i in range(n)})
+    if partial.is_literal or partial.size == 1:
+        return st.kron_scalar(n), {(i, i): partial.nodes[0] for i in range(n)}
+    return st.diag(n), {(i, i): partial.nodes[i] for i in range(n)}
+
+
+def lower_eqn(dag: Dag, eqn: Eqn, read) -> Tuple[Vec, List[Tuple[Var, st.Struct, Entries]]]:
+    """Primal value and elemental edges of one equation.
+
+    Returns ``(out, [(operand_var, structure, entries), ...])`` with one edge per
+    non-literal operand, or no edge at all when the rule yields fewer partials
+    than traced operands (reference ``core.py:405-410``).
+    """
+    ew = _Ew(dag)
+    prim = eqn.primitive
+    ops = [read(a) for a in eqn.invars]
+    traced = [i for i, a in enumerate(eqn.invars) if isinstance(a, Var)]
+
+    def edges(out: Vec, partials: Sequence[Vec]):
+        return out, [(eqn.invars[i],) + _parallel_jacobian(ops[i], out, partials[i], len(ops)) for i in traced]
+
+    # ---- elementwise binary (primitives.py:180-205, 237-239) ----------------
+    if prim in ("add", "sub", "mul", "div", "atan2", "pow"):
+        x, y = ops
+        out = ew.binary(prim, x, y)
+        if prim == "add":
+            parts = (ew.ones_like(y), ew.ones_like(x))
+        elif prim == "sub":
+            parts = (ew.ones_like(y), ew.neg(ew.ones_like(x)))
+        elif prim == "mul":
+            parts = (y, x)
+        elif prim == "div":
+            parts = (ew.div(ew.lit(1.0), y), ew.div(ew.neg(x), ew.ipow(y, 2)))
+        elif prim == "atan2":
+            abs2 = ew.add(ew.ipow(x, 2), ew.ipow(y, 2))
+            parts = (ew.div(y, abs2), ew.div(ew.neg(x), abs2))
+        else:  # pow
+            parts = (ew.mul(y, ew.binary("pow", x, ew.sub(y, ew.lit(1.0)))), ew.mul(ew.unary("log", x), out))
+        # ones_like / other-operand partials of a literal operand are Python floats in the reference
+        parts = tuple(Vec(p.shape, p.nodes, is_literal=(prim in ("add", "sub", "mul") and ops[1 - i].is_literal))
+                      for i, p in enumerate(parts))
+        return edges(out, parts)
+
+    # ---- elementwise unary (primitives.py:150-175) ---------------------------
+    if prim == "integer_pow":
+        (x,) = ops
+        y = int(eqn.params["y"])
+        out = ew.ipow(x, y)
+        return edges(out, (ew.mul(ew.lit(float(y)), ew.ipow(x, y - 1)),))
+    if prim == "square":
+        (x,) = ops
+        return edges(ew.mul(x, x), (ew.mul(ew.lit(2.0), x),))
+    if prim in _UNARY:
+        (x,) = ops
+        out = ew.unary(prim, x)
+        one = ew.lit(1.0)
+        if prim == "neg":
+            part = ew.neg(ew.ones_like(x))
+        elif prim == "abs":
+            part = ew.div(x, out)
+        elif prim == "exp":
+            part = out
+        elif prim == "log":
+            part = ew.div(one, x)
+        elif prim == "sqrt":
+            part = ew.div(ew.lit(0.5), out)
+        elif prim == "logistic":
+            part = ew.mul(out, ew.sub(one, out))
+        elif prim == "log1p":
+            part = ew.div(one, ew.add(one, x))
+        elif prim == "sin":
+            part = ew.unary("cos", x)
+        elif prim == "asin":
+            part = ew.div(one, ew.unary("sqrt", ew.sub(one, ew.ipow(x, 2))))
+        elif prim == "cos":
+            part = ew.neg(ew.unary("sin", x))
+        elif prim == "acos":
+            part = ew.div(ew.lit(-1.0), ew.unary("sqrt", ew.sub(one, ew.ipow(x, 2))))
+        elif prim == "tan":
+            part = ew.add(one, ew.ipow(out, 2))
+        elif prim == "atan":
+            part = ew.div(one, ew.add(one, ew.ipow(x, 2)))
+        elif prim == "sinh":
+            part = ew.unary("cosh", x)
+        elif prim == "asinh":
+            # the reference has sqrt(1+x^2) here (primitives.py:169), which is not the
+            # derivative; this engine uses the correct 1/sqrt(1+x^2)
+            part = ew.div(one, ew.unary("sqrt", ew.add(one, ew.ipow(x, 2))))
+        elif prim == "cosh":
+            part = ew.unary("sinh", x)
+        elif prim == "acosh":
+            part = ew.div(one, ew.unary("sqrt", ew.sub(ew.ipow(x, 2), one)))
+        elif prim == "tanh":
+            part = ew.sub(one, ew.ipow(out, 2))
+        elif prim == "atanh":
+            part = ew.div(one, ew.sub(one, ew.ipow(x, 2)))
+        elif prim == "erf":
+            two_over_sqrt_pi = ew.div(ew.lit(2.0), ew.unary("sqrt", ew.lit(math.pi)))
+            part = ew.mul(ew.unary("exp", ew.neg(ew.ipow(x, 2))), two_over_sqrt_pi)
+        else:  # pragma: no cover
+            raise NotImplementedError(prim)
+        return edges(out, (part,))
+
+    # ---- structural rules ----------------------------------------------------
+    if prim == "reduce_sum":          # primitives.py:243-272: row of ones over the reduced axis
+        (x,) = ops
+        if x.ndim == 0:
+            return x, [(eqn.invars[0], st.SCALAR, {(0, 0): dag.const(1.0)})] if traced else []
+        acc = x.nodes[0]
+        for k in range(1, x.size):
+            acc = dag.add(acc, x.nodes[k])
+        out = Vec((), [acc])
+        e = {(0, k): dag.const(1.0) for k in range(x.size)}
+        return out, ([(eqn.invars[0], st.row(x.size), e)] if traced else [])
+    if prim == "dot_general":         # primitives.py:349-441: each operand's edge carries the other operand
+        x, y = ops
+        if x.ndim != 1 or y.ndim != 1 or x.size != y.size:
+            raise NotImplementedError("only 1-D . 1-D dot_general is lowered (scope row (f)1)")
+        acc = dag.mul(x.nodes[0], y.nodes[0])
+        for k in range(1, x.size):
+            acc = dag.fma(x.nodes[k], y.nodes[k], acc)
+        out = Vec((), [acc])
+        es = []
+        for i in traced:
+            other = ops[1 - i]
+            es.append((eqn.invars[i], st.row(x.size), {(0, k): other.nodes[k] for k in range(x.size)}))
+        return out, es
+    if prim == "slice":               # primitives.py:699-760: transform edge
+        (x,) = ops
+        (lo,), (hi,) = eqn.params["start_indices"], eqn.params["limit_indices"]
+        out = Vec((hi - lo,), x.nodes[lo:hi])
+        t = st.Transform("slice", lo, hi, x.size)
+        e = {(i, lo + i): dag.const(1.0) for i in range(hi - lo)}
+        return out, ([(eqn.invars[0], st.transform_edge(t), e)] if traced else [])
+    if prim == "concatenate":         # primitives.py:971-1233: one transform edge per operand
+        nodes, es, off = [], [], 0
+        total = sum(o.size for o in ops)
+        for a, o in zip(eqn.invars, ops):
+            if o.ndim != 1:
+                raise NotImplementedError("only 1-D concatenation is lowered")
+            nodes.extend(o.nodes)
+            if isinstance(a, Var):
+                t = st.Transform("concat", off, off + o.size, total)
+                es.append((a, st.transform_edge(t), {(off + i, i): dag.const(1.0) for i in range(o.size)}))
+            off += o.size
+        return Vec((total,), nodes), es
+    if prim == "broadcast_in_dim":    # primitives.py:763-883; only the literal-operand form (jnp.zeros)
+        (x,) = ops
+        if traced:
+            raise NotImplementedError("broadcast_in_dim of a traced operand is not lowered yet")
+        shape = tuple(eqn.params["shape"])
+        n = shape[0] if shape else 1
+        return Vec(shape, [x.nodes[0]] * n), []
+    raise NotImplementedError(f"{prim} does not have registered elemental partial.")   # core.py:398

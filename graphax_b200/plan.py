@@ -1,0 +1,277 @@
+"""Elimination plan: the flat, static program one Jacobian evaluation runs.
+
+``build_plan`` traces nothing and computes nothing: it takes the symbolic result
+of ``elimination.accumulate`` and linearises the expression DAG into
+
+* an SSA op list (used by the CUDA source emitter, ``codegen.py``), and
+* a binary blob with physical slots (consumed by ``gx_plan_create`` for the
+  generic persistent interpreter kernel and by the oracle's C replay).
+
+Blob layout (little endian, version 1)::
+
+    u32[16] header: magic 'GXPL', version, total_bytes, n_in_arrays, n_out_arrays,
+                    n_in_scalars, n_cols, n_rows, n_ops, n_slots, n_consts, flags,
+                    reserved[4]
+    u32[n_in_arrays]  in_sizes      scalars per input array, in argument order
+    u32[n_out_arrays] out_sizes     scalars per output array
+    u32[n_in_arrays]  in_cols       first Jacobian column of the array, 0xffffffff if not in argnums
+    f32[n_consts]     consts
+    op[n_ops]         {u16 opcode, dst, a, b, c, 0}
+        operand = kind<<14 | index, kind 0 slot / 1 const / 2 input scalar
+        store_jac:    dst = row*n_cols + col, a = value
+        store_primal: dst = row,              a = value
+
+The Jacobian tile is ``[n_rows, n_cols]`` row-major per sample: rows are the
+output scalars in output order, columns the scalars of the ``argnums`` inputs in
+``argnums`` order.  Every tile position is written by exactly one ``store_jac``
+(structural zeros store the constant 0).
+"""
+from __future__ import annotations
+
+import hashlib
+import struct as _struct
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .elimination import Accumulated, Graph, accumulate
+from .lowering import OP, Dag
+from .tracer import Jaxpr, Var
+
+MAGIC = 0x4C505847
+VERSION = 1
+FLAG_HAS_PRIMAL = 1
+K_SLOT, K_CONST, K_INPUT = 0, 1, 2
+MAX_INDEX = (1 << 14) - 1
+
+
+@dataclass
+class SsaOp:
+    op: str
+    dst: int                  # SSA value id (== DAG node id) or tile/row index for stores
+    args: Tuple[int, ...]     # DAG node ids
+
+
+@dataclass
+class Plan:
+    in_sizes: List[int]
+    out_sizes: List[int]
+    argnums: List[int]
+    n_rows: int
+    n_cols: int
+    order: List[int]
+    dag: Dag
+    ssa: List[SsaOp]
+    tile: List[Optional[int]]           # per tile position: DAG node or None (structural zero)
+    primal_nodes: List[int]
+    blob: bytes = b""
+    n_slots: int = 0
+    stats: Dict[str, object] = field(default_factory=dict)
+    structure: Dict[str, object] = field(default_factory=dict)
+
+    @property
+    def key(self) -> str:
+        return hashlib.sha1(self.blob).hexdigest()[:16]
+
+    @property
+    def n_in_scalars(self) -> int:
+        return sum(self.in_sizes)
+
+    @property
+    def in_cols(self) -> List[int]:
+        cols, c = [], 0
+        first = {}
+        for a in self.argnums:
+            first[a] = c
+            c += self.in_sizes[a]
+        return [first.get(i, 0xFFFFFFFF) for i in range(len(self.in_sizes))]
+
+    @property
+    def bytes_per_jacobian(self) -> int:
+        """Compulsory HBM traffic: read every input once, write the dense tile once
+        (240 B for RoeFlux_3d)."""
+        return 4 * (self.n_in_scalars + self.n_rows * self.n_cols)
+
+
+def _linearise(dag: Dag, first_elim: int, roots: Sequence[int]) -> List[int]:
+    """Topological order of the nodes reachable from ``roots``: elimination nodes in
+    the order the elimination created them, each preceded by whatever it still
+    needs (partials and primal values are emitted right before their first use)."""
+    reachable = set()
+    stack = [r for r in roots]
+    while stack:
+        n = stack.pop()
+        if n in reachable:
+            continue
+        reachable.add(n)
+        stack.extend(dag.args[n] if dag.op[n] not in ("const", "input") else ())
+    emitted, out = set(), []
+
+    def visit(root: int) -> None:
+        work = [(root, 0)]
+        while work:
+            n, i = work.pop()
+            if n in emitted:
+                continue
+            args = dag.args[n] if dag.op[n] not in ("const", "input") else ()
+            if i < len(args):
+                work.append((n, i + 1))
+                if args[i] not in emitted:
+                    work.append((args[i], 0))
+            else:
+                emitted.add(n)
+                if dag.op[n] not in ("const", "input"):
+                    out.append(n)
+
+    for n in range(first_elim, len(dag.op)):
+        if n in reachable:
+            visit(n)
+    for r in roots:
+        visit(r)
+    return out
+
+
+def build_plan(jaxpr: Jaxpr, order, argnums: Sequence[int], with_primal: bool = True) -> Plan:
+    argnums = [int(a) for a in argnums]
+    for a in argnums:
+        if not 0 <= a < len(jaxpr.invars):
+            raise ValueError(f"argnum {a} out of range for a function of {len(jaxpr.invars)} arguments")
+    acc = accumulate(jaxpr, order, argnums)
+    g, dag = acc.graph, acc.graph.dag
+
+    in_sizes = [v.size for v in jaxpr.invars]
+    out_sizes = [v.size for v in jaxpr.outvars]
+    n_rows, n_cols = sum(out_sizes), sum(in_sizes[a] for a in argnums)
+    row0 = np.concatenate([[0], np.cumsum(out_sizes)]).astype(int)
+    col0 = np.concatenate([[0], np.cumsum([in_sizes[a] for a in argnums])]).astype(int)
+
+    tile: List[Optional[int]] = [None] * (n_rows * n_cols)
+    for (oi, ai), (_, entries) in acc.blocks.items():
+        for (i, j), node in entries.items():
+            if not (0 <= i < out_sizes[oi] and 0 <= j < in_sizes[argnums[ai]]):
+                raise AssertionError("edge entry outside its block")
+            tile[(row0[oi] + i) * n_cols + col0[ai] + j] = node
+    primal_nodes = [n for o in jaxpr.outvars for n in g.env[Graph.key(o)].nodes] if with_primal else []
+
+    roots = [n for n in tile if n is not None] + primal_nodes
+    sched = _linearise(dag, g.first_elim_node, roots)
+
+    # stores directly after the value they read; constant / input / zero stores at the end
+    stores_after: Dict[int, List[SsaOp]] = {}
+    tail: List[SsaOp] = []
+    zero = dag.const(0.0)
+    for pos, node in enumerate(tile):
+        op = SsaOp("store_jac", pos, (zero if node is None else node,))
+        if node is None or dag.op[node] in ("const", "input"):
+            tail.append(op)
+        else:
+            stores_after.setdefault(node, []).append(op)
+    for r, node in enumerate(primal_nodes):
+        op = SsaOp("store_primal", r, (node,))
+        if dag.op[node] in ("const", "input"):
+            tail.append(op)
+        else:
+            stores_after.setdefault(node, []).append(op)
+    ssa: List[SsaOp] = []
+    for n in sched:
+        ssa.append(SsaOp(dag.op[n], n, dag.args[n]))
+        ssa.extend(stores_after.get(n, ()))
+    ssa.extend(tail)
+
+    plan = Plan(in_sizes, out_sizes, argnums, n_rows, n_cols, list(acc.order), dag, ssa, tile, primal_nodes)
+    _allocate_and_serialise(plan, with_primal)
+    _collect_stats(plan, acc)
+    return plan
+
+
+def _allocate_and_serialise(plan: Plan, with_primal: bool) -> None:
+    dag = plan.dag
+    last_use: Dict[int, int] = {}
+    for idx, op in enumerate(plan.ssa):
+        for a in op.args:
+            last_use[a] = idx
+    consts: Dict[int, int] = {}
+    slot_of: Dict[int, int] = {}
+    free: List[int] = []
+    n_slots = 0
+
+    def operand(node: int) -> int:
+        kind = dag.op[node]
+        if kind == "const":
+            idx = consts.setdefault(node, len(consts))
+            return (K_CONST << 14) | idx
+        if kind == "input":
+            return (K_INPUT << 14) | dag.args[node][0]
+        return (K_SLOT << 14) | slot_of[node]
+
+    records = []
+    for idx, op in enumerate(plan.ssa):
+        enc = [operand(a) for a in op.args] + [0] * (3 - len(op.args))
+        # operands whose last use is here release their slot before dst is allocated,
+        # so dst may reuse one of them (the interpreter reads all operands first)
+        for a in set(op.args):
+            if dag.op[a] not in ("const", "input") and last_use[a] == idx:
+                free.append(slot_of.pop(a))
+        if op.op in ("store_jac", "store_primal"):
+            dst = op.dst
+        else:
+            if op.dst not in last_use:
+                raise AssertionError("dead value in plan")
+            if free:
+                free.sort(reverse=True)
+                dst = free.pop()
+            else:
+                dst = n_slots
+                n_slots += 1
+            slot_of[op.dst] = dst
+        records.append((OP[op.op], dst, enc[0], enc[1], enc[2]))
+    if n_slots > MAX_INDEX or len(consts) > MAX_INDEX or plan.n_in_scalars > MAX_INDEX \
+            or plan.n_rows * plan.n_cols > 0xFFFF:
+        raise NotImplementedError("plan exceeds the 14-bit operand encoding")
+
+    const_vals = np.zeros(len(consts), dtype=np.float32)
+    for node, i in consts.items():
+        const_vals[i] = dag.cval[node]
+    flags = FLAG_HAS_PRIMAL if with_primal else 0
+    body = b"".join([
+        np.asarray(plan.in_sizes, dtype="<u4").tobytes(),
+        np.asarray(plan.out_sizes, dtype="<u4").tobytes(),
+        np.asarray(plan.in_cols, dtype="<u4").tobytes(),
+        const_vals.astype("<f4").tobytes(),
+        np.asarray([r + (0,) for r in records], dtype="<u2").reshape(-1, 6).tobytes() if records else b"",
+    ])
+    header = [MAGIC, VERSION, 64 + len(body), len(plan.in_sizes), len(plan.out_sizes), plan.n_in_scalars,
+              plan.n_cols, plan.n_rows, len(records), n_slots, len(consts), flags, 0, 0, 0, 0]
+    plan.blob = _struct.pack("<16I", *header) + body
+    plan.n_slots = n_slots
+
+
+def _collect_stats(plan: Plan, acc: Accumulated) -> None:
+    hist: Dict[str, int] = {}
+    for op in plan.ssa:
+        hist[op.op] = hist.get(op.op, 0) + 1
+    classes: Dict[str, int] = {}
+    for s in acc.steps:
+        for k, v in s.classes.items():
+            classes[k] = classes.get(k, 0) + v
+    plan.stats = {
+        "n_vertices": len(acc.graph.jaxpr.eqns),
+        "n_eliminated": len(acc.order),
+        "n_ops": len(plan.ssa),
+        "n_slots": plan.n_slots,
+        "op_histogram": hist,
+        "num_muls": acc.num_muls,                       # reference count_ops semantics
+        "num_adds": acc.num_adds,
+        "order_counts": [(s.vertex, s.num_muls) for s in acc.steps],
+        "pairs": sum(s.pairs for s in acc.steps),
+        "max_pairs_per_step": max((s.pairs for s in acc.steps), default=0),
+        "product_classes": classes,
+        "bytes_per_jacobian": plan.bytes_per_jacobian,
+    }
+    plan.structure = {
+        "elemental": [[src, dst, s.descriptor()] for src, dst, s in acc.graph.elemental],
+        "blocks": {f"{oi},{ai}": (None if s is None else s.descriptor())
+                   for (oi, ai), (s, _) in sorted(acc.blocks.items())},
+        "order": list(acc.order),
+    }

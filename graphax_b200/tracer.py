@@ -1,0 +1,387 @@
+"""Mini-jaxpr tracer.
+
+graphax numbers the vertices of the computational graph by the position of an
+equation in ``jax.make_jaxpr(f)(*xs).jaxpr.eqns`` (reference ``core.py:184``,
+``core.py:380-385``), so a caller-given elimination order only means something
+relative to how JAX lowers the Python function.  JAX is not part of this image,
+therefore this module re-creates that lowering for the ``jnp`` subset the
+workloads use (rules: SURVEY.md Appendix A.1):
+
+* one equation per array op, in Python evaluation order, no CSE;
+* Python scalars become ``Literal`` operands that keep their source position;
+* ``x**2`` -> ``integer_pow``, ``jnp.sum`` -> ``reduce_sum``, 1-D ``jnp.dot`` ->
+  ``dot_general``, static ``x[a:b]`` -> ``slice``, ``jnp.zeros(n)`` ->
+  ``broadcast_in_dim`` of a literal;
+* rank-0 / size-1 operands rely on lax broadcasting (a single binary equation).
+
+``vmap_numbering=True`` additionally records where ``jax.vmap`` would insert
+identity ``broadcast_in_dim`` equations (Appendix A.1 rule 5) so that orders
+written against ``jacve(jax.vmap(f))`` (reference ``example_test.py:150-159``)
+can be translated to the per-sample numbering this engine runs.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+Shape = Tuple[int, ...]
+
+
+class Var:
+    """A traced value: either a function input or the result of one equation."""
+    __slots__ = ("shape", "eqn_index", "input_index", "name")
+
+    def __init__(self, shape: Shape, eqn_index: Optional[int] = None,
+                 input_index: Optional[int] = None, name: str = ""):
+        self.shape = tuple(int(s) for s in shape)
+        self.eqn_index = eqn_index      # 0-based position in Jaxpr.eqns (vertex id - 1)
+        self.input_index = input_index  # position in Jaxpr.invars
+        self.name = name
+
+    @property
+    def ndim(self) -> int:
+        return len(self.shape)
+
+    @property
+    def size(self) -> int:
+        return int(np.prod(self.shape, dtype=np.int64)) if self.shape else 1
+
+    def __repr__(self) -> str:
+        tag = f"in{self.input_index}" if self.input_index is not None else f"v{self.eqn_index + 1}"
+        return f"{tag}{list(self.shape)}"
+
+
+@dataclass(frozen=True)
+class Literal:
+    """A trace-time constant operand (weak-typed Python scalar -> f32)."""
+    val: float
+
+    @property
+    def shape(self) -> Shape:
+        return ()
+
+    def __repr__(self) -> str:
+        return repr(self.val)
+
+
+Atom = Union[Var, Literal]
+
+
+@dataclass
+class Eqn:
+    primitive: str
+    invars: Tuple[Atom, ...]
+    outvar: Var
+    params: Dict[str, Any] = field(default_factory=dict)
+
+    def __repr__(self) -> str:
+        p = "" if not self.params else "[" + ",".join(f"{k}={v}" for k, v in self.params.items()) + "]"
+        return f"{self.outvar!r} = {self.primitive}{p}({', '.join(map(repr, self.invars))})"
+
+
+@dataclass
+class Jaxpr:
+    invars: List[Var]
+    eqns: List[Eqn]
+    outvars: List[Atom]
+    # vmap_pads[i] = number of identity broadcast_in_dim equations jax.vmap
+    # would insert immediately before equation i (0-based)
+    vmap_pads: List[int] = field(default_factory=list)
+    out_is_sequence: bool = True
+
+    def vertex_of(self, var: Var) -> int:
+        return var.eqn_index + 1
+
+    @property
+    def output_vertices(self) -> List[int]:
+        return [v.eqn_index + 1 for v in self.outvars if isinstance(v, Var) and v.eqn_index is not None]
+
+    def to_vmap_numbering(self) -> Tuple[Dict[int, int], List[int]]:
+        """Per-sample vertex id -> id under ``jacve(jax.vmap(f))`` and the list
+        of ids that only exist in the vmapped jaxpr (identity pads)."""
+        mapping, pads, shift = {}, [], 0
+        for i in range(len(self.eqns)):
+            for _ in range(self.vmap_pads[i] if self.vmap_pads else 0):
+                shift += 1
+                pads.append(i + shift)
+            mapping[i + 1] = i + 1 + shift
+        return mapping, pads
+
+    def translate_vmap_order(self, order: Sequence[int]) -> List[int]:
+        """Map an order written in the ``jacve(vmap(f))`` numbering onto the
+        per-sample numbering by dropping the identity pad vertices."""
+        mapping, pads = self.to_vmap_numbering()
+        inverse = {v: k for k, v in mapping.items()}
+        padset = set(pads)
+        out = []
+        for o in order:
+            o = int(o)
+            if o in padset:
+                continue
+            if o not in inverse:
+                raise ValueError(f"vertex {o} does not exist in the vmapped numbering")
+            out.append(inverse[o])
+        return out
+
+    def pretty(self) -> str:
+        lines = ["{ lambda ; " + " ".join(map(repr, self.invars)) + " . let"]
+        for i, e in enumerate(self.eqns, start=1):
+            lines.append(f"  {i:4d}: {e!r}")
+        lines.append("  in (" + ", ".join(map(repr, self.outvars)) + ") }")
+        return "\n".join(lines)
+
+
+class _Trace:
+    def __init__(self) -> None:
+        self.eqns: List[Eqn] = []
+        self.vmap_pads: List[int] = []
+
+    def emit(self, primitive: str, invars: Sequence[Atom], out_shape: Shape,
+             pads: int = 0, **params) -> "Tracer":
+        out = Var(out_shape, eqn_index=len(self.eqns))
+        self.eqns.append(Eqn(primitive, tuple(invars), out, dict(params)))
+        self.vmap_pads.append(pads)
+        return Tracer(self, out)
+
+
+_ACTIVE: List[_Trace] = []
+
+
+def _current() -> _Trace:
+    if not _ACTIVE:
+        raise RuntimeError("graphax_b200.jnp functions must be called on traced values inside jacve/make_jaxpr")
+    return _ACTIVE[-1]
+
+
+def _atom(x: Any) -> Atom:
+    if isinstance(x, Tracer):
+        return x.var
+    if isinstance(x, (bool, int, float, np.floating, np.integer)):
+        return Literal(float(x))
+    if isinstance(x, np.ndarray) and x.shape == ():
+        return Literal(float(x))
+    raise TypeError(f"cannot trace operand of type {type(x).__name__}; "
+                    "array constants must enter the function as arguments")
+
+
+def _bcast_shape(a: Shape, b: Shape) -> Shape:
+    """lax-style broadcasting: equal ranks (size-1 dims stretch) or a rank-0 operand."""
+    if a == ():
+        return b
+    if b == ():
+        return a
+    if len(a) != len(b):
+        raise NotImplementedError(
+            f"rank promotion between {a} and {b} is not lowered (jnp would insert reshape equations)")
+    out = []
+    for x, y in zip(a, b):
+        if x != y and 1 not in (x, y):
+            raise TypeError(f"incompatible shapes for broadcasting: {a} and {b}")
+        out.append(max(x, y))
+    return tuple(out)
+
+
+class Tracer:
+    """Array stand-in that records one equation per operation."""
+    __slots__ = ("trace", "var")
+    __array_priority__ = 1000
+
+    def __init__(self, trace: _Trace, var: Var):
+        self.trace = trace
+        self.var = var
+
+    shape = property(lambda self: self.var.shape)
+    ndim = property(lambda self: self.var.ndim)
+    size = property(lambda self: self.var.size)
+
+    def __repr__(self) -> str:
+        return f"Tracer<{self.var!r}>"
+
+    # ---- binary arithmetic -------------------------------------------------
+    def _binary(self, prim: str, other: Any, reflected: bool = False) -> "Tracer":
+        a, b = _atom(self), _atom(other)
+        if reflected:
+            a, b = b, a
+        shape = _bcast_shape(a.shape, b.shape)
+        # jax.vmap pads the lower-rank traced operand of a mixed-rank binary op
+        pads = 1 if (isinstance(a, Var) and isinstance(b, Var) and len(a.shape) != len(b.shape)) else 0
+        return self.trace.emit(prim, (a, b), shape, pads=pads)
+
+    __add__ = lambda s, o: s._binary("add", o)
+    __radd__ = lambda s, o: s._binary("add", o, True)
+    __sub__ = lambda s, o: s._binary("sub", o)
+    __rsub__ = lambda s, o: s._binary("sub", o, True)
+    __mul__ = lambda s, o: s._binary("mul", o)
+    __rmul__ = lambda s, o: s._binary("mul", o, True)
+    __truediv__ = lambda s, o: s._binary("div", o)
+    __rtruediv__ = lambda s, o: s._binary("div", o, True)
+
+    def __neg__(self) -> "Tracer":
+        return self.trace.emit("neg", (self.var,), self.shape)
+
+    def __pow__(self, y: Any) -> "Tracer":
+        if isinstance(y, (int, np.integer)) and not isinstance(y, bool):
+            return self.trace.emit("integer_pow", (self.var,), self.shape, y=int(y))
+        if isinstance(y, float) and float(y).is_integer():
+            # jnp.power with a Python float exponent stays `pow` against a literal
+            return self._binary("pow", y)
+        return self._binary("pow", y)
+
+    def __rpow__(self, x: Any) -> "Tracer":
+        return self._binary("pow", x, True)
+
+    # ---- static indexing ---------------------------------------------------
+    def __getitem__(self, idx: Any) -> "Tracer":
+        if self.ndim != 1 or not isinstance(idx, slice):
+            raise NotImplementedError("only static 1-D slices x[a:b] are lowered")
+        start, stop, step = idx.indices(self.shape[0])
+        if step != 1:
+            raise NotImplementedError("strided slices are not lowered")
+        return self.trace.emit("slice", (self.var,), (max(stop - start, 0),),
+                               start_indices=(start,), limit_indices=(stop,), strides=None)
+
+    def sum(self, axis=None) -> "Tracer":
+        return _reduce_sum(self, axis)
+
+    def dot(self, other) -> "Tracer":
+        return _dot(self, other)
+
+
+def _unary(prim: str):
+    def fn(x: Any) -> Tracer:
+        if not isinstance(x, Tracer):
+            raise TypeError(f"{prim} expects a traced value")
+        return x.trace.emit(prim, (x.var,), x.shape)
+    fn.__name__ = prim
+    return fn
+
+
+def _binary_fn(prim: str):
+    def fn(x: Any, y: Any) -> Tracer:
+        if isinstance(x, Tracer):
+            return x._binary(prim, y)
+        if isinstance(y, Tracer):
+            return y._binary(prim, x, True)
+        raise TypeError(f"{prim} expects at least one traced value")
+    fn.__name__ = prim
+    return fn
+
+
+def _reduce_sum(x: Tracer, axis=None) -> Tracer:
+    if axis is None:
+        axes = tuple(range(x.ndim))
+    elif isinstance(axis, int):
+        axes = (axis % max(x.ndim, 1),)
+    else:
+        axes = tuple(sorted(a % x.ndim for a in axis))
+    shape = tuple(s for i, s in enumerate(x.shape) if i not in axes)
+    return x.trace.emit("reduce_sum", (x.var,), shape, axes=axes)
+
+
+def _dot(a: Tracer, b: Tracer) -> Tracer:
+    if not (isinstance(a, Tracer) and isinstance(b, Tracer)):
+        raise TypeError("dot expects two traced values")
+    if a.ndim == 1 and b.ndim == 1:
+        if a.shape != b.shape:
+            raise TypeError(f"dot: incompatible shapes {a.shape} and {b.shape}")
+        dn = (((0,), (0,)), ((), ()))
+        return a.trace.emit("dot_general", (a.var, b.var), (), dimension_numbers=dn,
+                            pads=0)
+    raise NotImplementedError("only 1-D . 1-D dot products are lowered")
+
+
+def _square(x: Tracer) -> Tracer:
+    return x.trace.emit("square", (x.var,), x.shape)
+
+
+def _zeros(shape, dtype=None) -> Tracer:
+    shape = (int(shape),) if isinstance(shape, (int, np.integer)) else tuple(int(s) for s in shape)
+    return _current().emit("broadcast_in_dim", (Literal(0.0),), shape,
+                           shape=shape, broadcast_dimensions=())
+
+
+def _concatenate(parts: Sequence[Tracer], axis: int = 0) -> Tracer:
+    parts = list(parts)
+    if not parts or not all(isinstance(p, Tracer) for p in parts):
+        raise TypeError("concatenate expects a sequence of traced values")
+    if any(p.ndim != 1 for p in parts) or axis not in (0, -1):
+        raise NotImplementedError("only 1-D concatenation is lowered")
+    n = sum(p.shape[0] for p in parts)
+    # vmap broadcasts an un-batched operand (the literal zeros) before concatenating
+    pads = sum(1 for p in parts
+               if p.var.eqn_index is not None
+               and p.trace.eqns[p.var.eqn_index].primitive == "broadcast_in_dim"
+               and all(isinstance(a, Literal) for a in p.trace.eqns[p.var.eqn_index].invars))
+    return parts[0].trace.emit("concatenate", tuple(p.var for p in parts), (n,), pads=pads,
+                               dimension=0)
+
+
+class _JnpShim:
+    """The slice of ``jax.numpy`` the reference workloads touch, over Tracers."""
+    float32 = np.float32
+    pi = math.pi
+
+    sqrt = staticmethod(_unary("sqrt"))
+    abs = staticmethod(_unary("abs"))
+    sin = staticmethod(_unary("sin"))
+    cos = staticmethod(_unary("cos"))
+    tan = staticmethod(_unary("tan"))
+    exp = staticmethod(_unary("exp"))
+    log = staticmethod(_unary("log"))
+    log1p = staticmethod(_unary("log1p"))
+    tanh = staticmethod(_unary("tanh"))
+    sinh = staticmethod(_unary("sinh"))
+    cosh = staticmethod(_unary("cosh"))
+    arcsin = staticmethod(_unary("asin"))
+    arccos = staticmethod(_unary("acos"))
+    arctan = staticmethod(_unary("atan"))
+    arcsinh = staticmethod(_unary("asinh"))
+    arccosh = staticmethod(_unary("acosh"))
+    arctanh = staticmethod(_unary("atanh"))
+    negative = staticmethod(_unary("neg"))
+    square = staticmethod(_square)
+
+    add = staticmethod(_binary_fn("add"))
+    subtract = staticmethod(_binary_fn("sub"))
+    multiply = staticmethod(_binary_fn("mul"))
+    divide = staticmethod(_binary_fn("div"))
+    arctan2 = staticmethod(_binary_fn("atan2"))
+    power = staticmethod(_binary_fn("pow"))
+
+    sum = staticmethod(_reduce_sum)
+    dot = staticmethod(_dot)
+    zeros = staticmethod(_zeros)
+    concatenate = staticmethod(_concatenate)
+
+    @staticmethod
+    def ones(shape, dtype=None):
+        """``jnp.ones(())`` folds to a literal under make_jaxpr (function g)."""
+        if shape == () or shape == []:
+            return 1.0
+        raise NotImplementedError("only rank-0 ones() constants are lowered")
+
+
+jnp = _JnpShim()
+
+
+def make_jaxpr(fun: Callable, arg_shapes: Sequence[Shape]) -> Jaxpr:
+    """Trace ``fun`` on per-sample avals of the given shapes (f32)."""
+    trace = _Trace()
+    invars = [Var(tuple(s), input_index=i) for i, s in enumerate(arg_shapes)]
+    _ACTIVE.append(trace)
+    try:
+        outs = fun(*[Tracer(trace, v) for v in invars])
+    finally:
+        _ACTIVE.pop()
+    out_is_sequence = isinstance(outs, (tuple, list))
+    if not out_is_sequence:
+        outs = (outs,)
+    outvars: List[Atom] = []
+    for o in outs:
+        if not isinstance(o, Tracer):
+            raise TypeError("function outputs must be traced arrays")
+        outvars.append(o.var)
+    return Jaxpr(invars, trace.eqns, outvars, trace.vmap_pads, out_is_sequence)

@@ -1,0 +1,111 @@
+/*
+ * graphax_b200 - C ABI of the B200-native jacve engine.
+ *
+ * graphax is pure Python on JAX: its hot path (`graphax.jacve`,
+ * /root/reference/src/graphax/core.py:27-93 -> vertex_elimination_jaxpr, core.py:475-581) has no
+ * FFI of its own.  This header is the boundary a `jax.ffi` custom call (or any other host) binds
+ * to; each entry point cites the reference code it stands in for.  INTEGRATION.md shows the
+ * reference-side stub.
+ *
+ * Conventions: plain C, no exceptions across the boundary; 0 = success, negative = error
+ * (message through gx_last_error(), thread local); the caller owns every buffer; launches are
+ * stream-ordered and asynchronous; a plan is immutable after creation and may be launched from
+ * several host threads.  There is no CPU fallback: without a CUDA device every compute entry
+ * point fails with GX_ERR_CUDA.
+ */
+#ifndef GRAPHAX_B200_H
+#define GRAPHAX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GX_ABI_VERSION 1
+#define GX_MAX_ARRAYS 16
+
+enum gx_status {
+  GX_OK = 0,
+  GX_ERR_BAD_BLOB = -1,   /* malformed / inconsistent elimination plan */
+  GX_ERR_BAD_ARG = -2,    /* null pointer, negative batch, misuse */
+  GX_ERR_CUDA = -3,       /* CUDA runtime / driver error (no device, launch failure, ...) */
+  GX_ERR_JIT = -4,        /* NVRTC unavailable or compilation failed */
+  GX_ERR_UNSUPPORTED = -5
+};
+
+enum gx_kernel_kind {
+  GX_KERNEL_INTERPRETER = 0, /* generic persistent plan interpreter (always available) */
+  GX_KERNEL_AOT = 1,         /* plan-specialised kernel compiled into this library by build() */
+  GX_KERNEL_JIT = 2          /* plan-specialised kernel compiled at run time with NVRTC */
+};
+
+typedef struct gx_plan gx_plan; /* opaque */
+
+typedef struct gx_info {
+  uint32_t abi_version;
+  uint32_t n_in_arrays;   /* number of function arguments */
+  uint32_t n_out_arrays;  /* number of function outputs */
+  uint32_t n_in_scalars;  /* f32 values read per sample */
+  uint32_t n_rows;        /* output scalars per sample = rows of the Jacobian tile */
+  uint32_t n_cols;        /* scalars of the argnums inputs = columns of the Jacobian tile */
+  uint32_t n_ops;         /* plan length */
+  uint32_t n_slots;       /* live values the interpreter keeps per sample */
+  uint32_t has_primal;    /* plan also evaluates the function outputs (has_aux, core.py:578-579) */
+  uint32_t kernel_kind;   /* enum gx_kernel_kind currently attached */
+  uint32_t threads;       /* samples per CTA of that kernel */
+  uint32_t smem_bytes;    /* dynamic shared memory per CTA */
+  uint32_t ctas_per_sm;   /* occupancy the persistent grid is sized with */
+  uint32_t regs_per_thread;
+  uint32_t in_sizes[GX_MAX_ARRAYS];
+  uint32_t out_sizes[GX_MAX_ARRAYS];
+  uint64_t plan_key;      /* FNV-1a 64 of the plan blob; names AOT/JIT kernels */
+  uint64_t launches;      /* kernels launched through this plan so far */
+} gx_info;
+
+/* Replaces: the trace-time work of vertex_elimination_jaxpr (core.py:522-533) being redone on every
+ * call.  `blob` is the serialised elimination plan (graphax_b200/plan.py documents the layout): the
+ * flat program that `_build_graph` (core.py:314-412) + `_eliminate_vertex` (core.py:155-272) emit
+ * for one (function, order, argnums).  Validates the blob, uploads it to `device`, and attaches the
+ * plan-specialised kernel compiled into the library for this blob if there is one. */
+int gx_plan_create(const void* blob, size_t nbytes, int device, gx_plan** out);
+void gx_plan_destroy(gx_plan* plan);
+int gx_plan_info(const gx_plan* plan, gx_info* out);
+
+/* Attach a plan-specialised kernel compiled at run time: `cuda_source` is the CUDA translation unit
+ * graphax_b200/codegen.py emits for this plan (skeleton + straight-line body).  Needs libnvrtc.  */
+int gx_plan_specialize(gx_plan* plan, const char* cuda_source, size_t nbytes, const char* arch);
+/* Force a kernel kind for subsequent launches (GX_KERNEL_INTERPRETER is always valid). */
+int gx_plan_select_kernel(gx_plan* plan, int kernel_kind);
+
+/* Replaces: the run-time half of `jax.vmap(graphax.jacve(f, order, argnums))(*xs)`, i.e. every
+ * jnp/lax op the reference emits per call (elemental partials primitives.py:150-205, sparse_mul /
+ * sparse_add tensor.py:334-397, densification core.py:555-562), as ONE kernel launch.
+ *   in_ptrs[i]  device, f32, [batch, in_sizes[i]] row-major
+ *   jac_out     device, f32, [batch, n_rows, n_cols] row-major (the caller slices it into the
+ *               per-output / per-argnum blocks of core.py:564-568)
+ *   primal_out  device, f32, [batch, n_rows], may be NULL
+ *   stream      cudaStream_t (NULL = legacy default stream)                                         */
+int gx_jacve_launch(gx_plan* plan, int64_t batch, const void* const* in_ptrs, void* jac_out,
+                    void* primal_out, void* stream);
+
+/* Same call with HOST buffers (the reference's user passes host arrays to a jitted function):
+ * host->device copies, the launch and device->host copies are chunked and pipelined over internal
+ * streams and pinned staging buffers; returns after the results are in `jac_out`.
+ * `pinned` != 0 promises that all host buffers are page-locked (copied without staging).            */
+int gx_jacve_host(gx_plan* plan, int64_t batch, const void* const* in_ptrs, void* jac_out,
+                  void* primal_out, int pinned);
+
+const char* gx_last_error(void);
+int gx_abi_version(void);
+/* Number of plan-specialised kernels compiled into this library and the key of the i-th one. */
+int gx_aot_count(void);
+uint64_t gx_aot_key(int index);
+/* FNV-1a 64 over a byte range: the key function, exported so hosts can name kernels the same way. */
+uint64_t gx_hash_bytes(const void* data, size_t nbytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAPHAX_B200_H */
