@@ -1,0 +1,12 @@
+"""graphax_b200 - B200-native engine for graphax's ``jacve`` hot path.
+
+Same call shape as the reference (``graphax/__init__.py:2-4``)::
+
+    from graphax_b200 import jacve, jnp
+    jac = jacve(f, order="rev", argnums=(0, 1))(x, y)
+"""
+from .api import jacve, vmap, tree_allclose, JacveFunction, SparseJacobian
+from .tracer import jnp, make_jaxpr
+
+__version__ = "0.1.0"
+__all__ = ["jacve", "vmap", "tree_allclose", "jnp", "make_jaxpr", "JacveFunction", "SparseJacobian"]

@@ -1,0 +1,209 @@
+"""``jacve`` - the reference's operator API on top of the B200 engine.
+
+Mirrors ``graphax.jacve(fun, order, argnums=(0,), has_aux=False, count_ops=False,
+sparse_representation=False)`` (reference ``core.py:27-93``): same argument
+meaning, same result pytree (a tuple per output of a tuple per argnum; a single
+output with several arguments is unwrapped, ``core.py:79-80``), same exceptions
+for bad orders (``ValueError``, ``core.py:302,310``) and unknown primitives
+(``NotImplementedError``, ``core.py:398``).
+
+What changes is when the work happens.  The reference re-walks the jaxpr and
+emits hundreds of jnp ops on every trace; here the first call for a given
+(shapes, order, argnums) lowers the elimination once into a plan, uploads it,
+and every call after that is one kernel launch.  Batching follows the scalable
+form ``jax.vmap(jacve(f, ...))``: ``graphax_b200.vmap(jacfun)``
+or ``jacfun.batched`` take arguments with a leading batch axis.
+
+Arrays are ``torch`` CUDA tensors (float32); Python numbers, lists and NumPy
+arrays are uploaded.  There is no CPU execution path.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from functools import wraps
+from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from .plan import Plan, build_plan
+from .tracer import Jaxpr, make_jaxpr
+
+EliminationOrder = Union[Sequence[int], str]
+
+
+def tree_allclose(tree1, tree2, equal_nan: bool = False) -> bool:
+    """Reference ``core.py:17-20``: allclose(atol=1e-5, rtol=1e-4) over a pytree."""
+    import torch
+
+    def leaves(t):
+        if isinstance(t, (tuple, list)):
+            for x in t:
+                yield from leaves(x)
+        else:
+            yield t
+    l1, l2 = list(leaves(tree1)), list(leaves(tree2))
+    if len(l1) != len(l2):
+        return False
+    for a, b in zip(l1, l2):
+        a = torch.as_tensor(a, dtype=torch.float32).cpu()
+        b = torch.as_tensor(b, dtype=torch.float32).cpu()
+        if a.shape != b.shape or not torch.allclose(a, b, atol=1e-5, rtol=1e-4, equal_nan=equal_nan):
+            return False
+    return True
+
+
+@dataclass
+class SparseJacobian:
+    """``sparse_representation=True`` result: the structure descriptor graphax's
+    SparseTensor would carry (``sparse/tensor.py:44-85``) plus the dense block."""
+    out_dims: list
+    primal_dims: list
+    val_shape: Optional[list]
+    dense: Any
+
+
+class JacveFunction:
+    """The callable ``jacve`` returns. ``__call__`` = one sample, ``batched`` = leading batch axis."""
+
+    def __init__(self, fun: Callable, order: EliminationOrder, argnums: Sequence[int], has_aux: bool,
+                 count_ops: bool, sparse_representation: bool, order_numbering: str, device: Optional[int],
+                 jit: bool):
+        self.fun = fun
+        self.order = order if isinstance(order, str) else [int(o) for o in order]
+        self.argnums = tuple(int(a) for a in (argnums if isinstance(argnums, (tuple, list, range)) else (argnums,)))
+        self.has_aux = has_aux
+        self.count_ops = count_ops
+        self.sparse_representation = sparse_representation
+        if order_numbering not in ("per_sample", "vmap"):
+            raise ValueError("order_numbering must be 'per_sample' or 'vmap'")
+        self.order_numbering = order_numbering
+        self.device = device
+        self.jit = jit
+        self._plans: Dict[Tuple, Plan] = {}
+        self._device_plans: Dict[Tuple, Any] = {}
+        wraps(fun)(self)
+
+    # ---- host side: trace + lower once per shape signature -------------------
+    def lower(self, arg_shapes: Sequence[Tuple[int, ...]]) -> Plan:
+        """Trace ``fun`` on per-sample shapes and build the elimination plan (no GPU needed)."""
+        key = tuple(tuple(s) for s in arg_shapes)
+        plan = self._plans.get(key)
+        if plan is None:
+            jaxpr = make_jaxpr(self.fun, key)
+            order = self.order
+            if not isinstance(order, str) and self.order_numbering == "vmap":
+                order = jaxpr.translate_vmap_order(order)
+            plan = build_plan(jaxpr, order, self.argnums, with_primal=True)
+            plan.jaxpr = jaxpr
+            self._plans[key] = plan
+        return plan
+
+    def _device_plan(self, plan: Plan, device: int):
+        from .runtime import DevicePlan
+        key = (plan.key, device)
+        dp = self._device_plans.get(key)
+        if dp is None:
+            dp = DevicePlan(plan, device, jit=self.jit)
+            self._device_plans[key] = dp
+        return dp
+
+    # ---- device side ---------------------------------------------------------
+    def _prepare(self, args: Sequence[Any], batched: bool):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("graphax_b200 needs a CUDA device: there is no CPU fallback for jacve")
+        device = self.device
+        if device is None:
+            dev_args = [a.device.index for a in args if isinstance(a, torch.Tensor) and a.is_cuda]
+            device = dev_args[0] if dev_args else torch.cuda.current_device()
+        tensors = []
+        for a in args:
+            if not isinstance(a, torch.Tensor):
+                a = torch.as_tensor(np.asarray(a, dtype=np.float32))
+            tensors.append(a.to(device=f"cuda:{device}", dtype=torch.float32).contiguous())
+        if batched:
+            batch = tensors[0].shape[0]
+            if any(t.ndim < 1 or t.shape[0] != batch for t in tensors):
+                raise ValueError("batched call: every argument needs the same leading batch axis")
+            shapes = [tuple(t.shape[1:]) for t in tensors]
+        else:
+            batch = 1
+            shapes = [tuple(t.shape) for t in tensors]
+        return tensors, shapes, batch, device
+
+    def _run(self, args: Sequence[Any], batched: bool):
+        import torch
+        tensors, shapes, batch, device = self._prepare(args, batched)
+        plan = self.lower(shapes)
+        dp = self._device_plan(plan, device)
+        with torch.cuda.device(device):
+            jac = torch.empty((batch, plan.n_rows, plan.n_cols), dtype=torch.float32, device=f"cuda:{device}")
+            primal = torch.empty((batch, plan.n_rows), dtype=torch.float32, device=f"cuda:{device}") \
+                if self.has_aux else None
+            stream = torch.cuda.current_stream(device).cuda_stream
+            dp.launch(batch, [t.data_ptr() for t in tensors], jac.data_ptr(),
+                      primal.data_ptr() if primal is not None else None, stream)
+        return self._package(plan, jac, primal, shapes, batch, batched)
+
+    def _package(self, plan: Plan, jac, primal, shapes, batch: int, batched: bool):
+        """Slice the packed tile into the reference's pytree (core.py:555-568, 76-92)."""
+        jaxpr: Jaxpr = plan.jaxpr
+        lead = (batch,) if batched else ()
+        out_shapes = [v.shape for v in jaxpr.outvars]
+        rows = np.concatenate([[0], np.cumsum(plan.out_sizes)]).astype(int)
+        cols = np.concatenate([[0], np.cumsum([plan.in_sizes[a] for a in self.argnums])]).astype(int)
+        jt = jac if batched else jac[0]
+        grads = []
+        for oi, oshape in enumerate(out_shapes):
+            row = []
+            for ai, a in enumerate(self.argnums):
+                block = jt[..., rows[oi]:rows[oi + 1], cols[ai]:cols[ai + 1]]
+                block = block.reshape(lead + tuple(oshape) + tuple(shapes[a]))
+                if self.sparse_representation:
+                    d = plan.structure["blocks"][f"{oi},{ai}"]
+                    block = None if d is None else SparseJacobian(d["out_dims"], d["primal_dims"], d["val_shape"], block)
+                row.append(block)
+            grads.append(tuple(row) if len(self.argnums) > 1 else row[0])
+        single = len(out_shapes) == 1 and len(jaxpr.invars) > 1
+        if jaxpr.out_is_sequence and not single:
+            grads_tree = tuple(grads)
+        else:
+            grads_tree = grads[0]
+        if self.count_ops:
+            aux = {"num_muls": plan.stats["num_muls"], "num_adds": plan.stats["num_adds"],
+                   "order_counts": list(plan.stats["order_counts"])}
+            return grads_tree, aux
+        if self.has_aux:
+            pt = primal if batched else primal[0]
+            outs = [pt[..., rows[oi]:rows[oi + 1]].reshape(lead + tuple(s)) for oi, s in enumerate(out_shapes)]
+            primal_tree = tuple(outs) if (jaxpr.out_is_sequence and not single) else outs[0]
+            return primal_tree, grads_tree
+        return grads_tree
+
+    def __call__(self, *args):
+        return self._run(args, batched=False)
+
+    def batched(self, *args):
+        return self._run(args, batched=True)
+
+
+def jacve(fun: Callable, order: EliminationOrder, argnums: Sequence[int] = (0,), has_aux: bool = False,
+          count_ops: bool = False, sparse_representation: bool = False, *, order_numbering: str = "per_sample",
+          device: Optional[int] = None, jit: bool = True) -> JacveFunction:
+    """Jacobian of ``fun`` w.r.t. ``argnums`` by vertex elimination in the given ``order``.
+
+    ``order``: ``"fwd"``/``"forward"``, ``"rev"``/``"reverse"`` or a sequence of 1-based vertex ids
+    (positions of the equations of the traced function, as in the reference).  ``order_numbering="vmap"``
+    accepts ids written against ``jacve(jax.vmap(fun))`` (reference ``example_test.py:150-166``).
+    """
+    return JacveFunction(fun, order, argnums, has_aux, count_ops, sparse_representation, order_numbering,
+                         device, jit)
+
+
+def vmap(jacfun: JacveFunction, in_axes: int = 0) -> Callable:
+    """``jax.vmap(jacve(f, ...))`` for the engine: the batch becomes the CUDA grid."""
+    if not isinstance(jacfun, JacveFunction):
+        raise TypeError("graphax_b200.vmap only batches functions returned by graphax_b200.jacve")
+    if in_axes != 0:
+        raise NotImplementedError("only in_axes=0 (leading batch axis) is supported")
+    return jacfun.batched

@@ -28,7 +28,6 @@ output scalars in output order, columns the scalars of the ``argnums`` inputs in
 """
 from __future__ import annotations
 
-import hashlib
 import struct as _struct
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -44,6 +43,13 @@ VERSION = 1
 FLAG_HAS_PRIMAL = 1
 K_SLOT, K_CONST, K_INPUT = 0, 1, 2
 MAX_INDEX = (1 << 14) - 1
+
+
+def fnv1a64(data: bytes) -> int:
+    h = 0xCBF29CE484222325
+    for b in data:
+        h = ((h ^ b) * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+    return h
 
 
 @dataclass
@@ -72,7 +78,8 @@ class Plan:
 
     @property
     def key(self) -> str:
-        return hashlib.sha1(self.blob).hexdigest()[:16]
+        """FNV-1a 64 of the blob (same function as gx_hash_bytes): names AOT/JIT kernels."""
+        return f"{fnv1a64(self.blob):016x}"
 
     @property
     def n_in_scalars(self) -> int:

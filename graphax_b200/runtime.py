@@ -1,0 +1,144 @@
+"""ctypes binding of the C ABI (include/graphax_b200.h) + device-side plan handles.
+
+PyTorch is used for what the contract allows - device memory and streams; the
+compute is the library's CUDA kernels.  There is no CPU fallback: if the shared
+library has not been built, or no CUDA device is present, calls fail loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import threading
+import warnings
+from pathlib import Path
+from typing import Dict, List, Optional, Sequence, Tuple
+
+from .plan import Plan
+
+LIB_PATH = Path(__file__).resolve().parent / "libgraphax_b200.so"
+GX_MAX_ARRAYS = 16
+KERNEL_INTERPRETER, KERNEL_AOT, KERNEL_JIT = 0, 1, 2
+KERNEL_NAMES = {0: "interpreter", 1: "aot", 2: "jit"}
+
+
+class GxInfo(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint32) for n in (
+        "abi_version", "n_in_arrays", "n_out_arrays", "n_in_scalars", "n_rows", "n_cols", "n_ops", "n_slots",
+        "has_primal", "kernel_kind", "threads", "smem_bytes", "ctas_per_sm", "regs_per_thread")] + [
+        ("in_sizes", ctypes.c_uint32 * GX_MAX_ARRAYS), ("out_sizes", ctypes.c_uint32 * GX_MAX_ARRAYS),
+        ("plan_key", ctypes.c_uint64), ("launches", ctypes.c_uint64)]
+
+
+EXPORTS = ["gx_plan_create", "gx_plan_destroy", "gx_plan_info", "gx_plan_specialize", "gx_plan_select_kernel",
+           "gx_jacve_launch", "gx_jacve_host", "gx_last_error", "gx_abi_version", "gx_aot_count", "gx_aot_key",
+           "gx_hash_bytes"]
+
+_lib = None
+_lock = threading.Lock()
+
+
+class GraphaxB200Error(RuntimeError):
+    pass
+
+
+def load_library() -> ctypes.CDLL:
+    """dlopen the engine. Raises if it was never built - nothing else can run the hot path."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not LIB_PATH.exists():
+            raise GraphaxB200Error(
+                f"{LIB_PATH} is missing: build the CUDA extension first "
+                "(python -c 'import __graft_entry__ as g; g.build()'). graphax_b200 has no CPU fallback.")
+        lib = ctypes.CDLL(str(LIB_PATH))
+        vp, i64, sz = ctypes.c_void_p, ctypes.c_int64, ctypes.c_size_t
+        lib.gx_plan_create.argtypes = [vp, sz, ctypes.c_int, ctypes.POINTER(vp)]
+        lib.gx_plan_create.restype = ctypes.c_int
+        lib.gx_plan_destroy.argtypes = [vp]
+        lib.gx_plan_destroy.restype = None
+        lib.gx_plan_info.argtypes = [vp, ctypes.POINTER(GxInfo)]
+        lib.gx_plan_info.restype = ctypes.c_int
+        lib.gx_plan_specialize.argtypes = [vp, ctypes.c_char_p, sz, ctypes.c_char_p]
+        lib.gx_plan_specialize.restype = ctypes.c_int
+        lib.gx_plan_select_kernel.argtypes = [vp, ctypes.c_int]
+        lib.gx_plan_select_kernel.restype = ctypes.c_int
+        lib.gx_jacve_launch.argtypes = [vp, i64, ctypes.POINTER(vp), vp, vp, vp]
+        lib.gx_jacve_launch.restype = ctypes.c_int
+        lib.gx_jacve_host.argtypes = [vp, i64, ctypes.POINTER(vp), vp, vp, ctypes.c_int]
+        lib.gx_jacve_host.restype = ctypes.c_int
+        lib.gx_last_error.restype = ctypes.c_char_p
+        lib.gx_abi_version.restype = ctypes.c_int
+        lib.gx_aot_count.restype = ctypes.c_int
+        lib.gx_aot_key.argtypes = [ctypes.c_int]
+        lib.gx_aot_key.restype = ctypes.c_uint64
+        lib.gx_hash_bytes.argtypes = [vp, sz]
+        lib.gx_hash_bytes.restype = ctypes.c_uint64
+        _lib = lib
+        return lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load_library().gx_last_error().decode(errors="replace")
+        raise GraphaxB200Error(f"{what} failed ({rc}): {msg}")
+
+
+def aot_keys() -> List[int]:
+    lib = load_library()
+    return [lib.gx_aot_key(i) for i in range(lib.gx_aot_count())]
+
+
+class DevicePlan:
+    """A plan uploaded to one GPU (wraps ``gx_plan*``)."""
+
+    def __init__(self, plan: Plan, device: int = 0, jit: bool = True):
+        self.plan = plan
+        self.device = device
+        self._lib = load_library()
+        self._h = ctypes.c_void_p()
+        buf = ctypes.create_string_buffer(plan.blob, len(plan.blob))
+        _check(self._lib.gx_plan_create(buf, len(plan.blob), device, ctypes.byref(self._h)), "gx_plan_create")
+        if self.info().kernel_kind == KERNEL_INTERPRETER and jit:
+            try:
+                self.specialize()
+            except GraphaxB200Error as e:  # stay on the (GPU) interpreter kernel, but say so
+                warnings.warn(f"plan {plan.key}: run-time specialisation unavailable, using the generic "
+                              f"interpreter kernel: {e}")
+
+    def specialize(self, arch: str = "sm_100a") -> None:
+        from .codegen import emit_source
+        src = emit_source(self.plan, nvrtc=True).encode()
+        _check(self._lib.gx_plan_specialize(self._h, src, len(src), arch.encode()), "gx_plan_specialize")
+
+    def select_kernel(self, kind: int) -> None:
+        _check(self._lib.gx_plan_select_kernel(self._h, kind), "gx_plan_select_kernel")
+
+    def info(self) -> GxInfo:
+        info = GxInfo()
+        _check(self._lib.gx_plan_info(self._h, ctypes.byref(info)), "gx_plan_info")
+        return info
+
+    @property
+    def kernel(self) -> str:
+        return KERNEL_NAMES[self.info().kernel_kind]
+
+    def launch(self, batch: int, in_ptrs: Sequence[int], jac_ptr: int, primal_ptr: Optional[int], stream: int) -> None:
+        arr = (ctypes.c_void_p * len(in_ptrs))(*in_ptrs)
+        _check(self._lib.gx_jacve_launch(self._h, batch, arr, jac_ptr, primal_ptr, stream), "gx_jacve_launch")
+
+    def run_host(self, batch: int, in_ptrs: Sequence[int], jac_ptr: int, primal_ptr: Optional[int],
+                 pinned: bool) -> None:
+        arr = (ctypes.c_void_p * len(in_ptrs))(*in_ptrs)
+        _check(self._lib.gx_jacve_host(self._h, batch, arr, jac_ptr, primal_ptr, 1 if pinned else 0),
+               "gx_jacve_host")
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.gx_plan_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,91 @@
+"""GPU tests of the reference-facing operator API (jacve / vmap), modelled on tests/examples/example_test.py."""
+import numpy as np
+import pytest
+
+import graphax_b200 as gx
+from graphax_b200.configs import WORKLOADS
+from graphax_b200.examples import RobotArm_6DOF, RoeFlux_1d, RoeFlux_3d, readme_f
+from helpers import GOLDEN, pack_blocks
+
+pytestmark = pytest.mark.gpu
+
+
+def _golden(name):
+    import json
+    return json.loads((GOLDEN / "jacobians_fp64.json").read_text())[name]
+
+
+def test_readme_example(built_library):
+    """README.rst:41-42: jacve(f, order=[1,3,2,4], argnums=(0,1,2,3))(1., 1., 2., 7.)"""
+    jac = gx.jacve(readme_f, order=[1, 3, 2, 4], argnums=(0, 1, 2, 3))(1., 1., 2., 7.)
+    fwd = gx.jacve(readme_f, order="fwd", argnums=(0, 1, 2, 3))(1., 1., 2., 7.)
+    rev = gx.jacve(readme_f, order="rev", argnums=(0, 1, 2, 3))(1., 1., 2., 7.)
+    assert isinstance(jac, tuple) and len(jac) == 4 and all(j.shape == () for j in jac)
+    assert gx.tree_allclose(jac, fwd) and gx.tree_allclose(jac, rev)
+    x, y, z, w = 1., 1., 2., 7.
+    a = x * y
+    expect = [(np.cos(a) * y + z * y) * w, (np.cos(a) * x + z * x) * w, a * w, np.sin(a) + a * z]
+    assert gx.tree_allclose(jac, tuple(np.float32(e) for e in expect))
+
+
+@pytest.mark.parametrize("order", ["fwd", "rev", "alphagrad", "markowitz"])
+def test_RobotArm_6DOF(built_library, order):
+    w = WORKLOADS["robotarm"]
+    g = _golden("robotarm")
+    out, aux = gx.jacve(RobotArm_6DOF, order=w.order(order), argnums=range(6), count_ops=True)(*[.02] * 6)
+    assert len(out) == 6 and len(out[0]) == 6
+    J = np.array([[float(b) for b in row] for row in out])
+    ref = np.array(g["jacobian"])
+    assert np.allclose(J, ref, atol=1e-5 * np.abs(ref).max(), rtol=1e-4)
+    assert aux["num_muls"] == {"fwd": 397, "rev": 301, "alphagrad": 254, "markowitz": 288}[order]
+
+
+@pytest.mark.parametrize("order", ["fwd", "rev", "alphagrad", "markowitz"])
+def test_RoeFlux_1d(built_library, order):
+    w = WORKLOADS["roe1d"]
+    g = _golden("roe1d")
+    primal, jac = gx.jacve(RoeFlux_1d, order=w.order(order), argnums=(0, 1, 2, 3, 4, 5), has_aux=True)(*w.base)
+    J = np.array([[float(b) for b in row] for row in jac])
+    ref = np.array(g["jacobian"])
+    assert np.allclose(J, ref, atol=1e-5 * np.abs(ref).max(), rtol=1e-4)
+    assert np.allclose([float(p) for p in primal], g["primal"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("order", ["fwd", "rev", "mixed", "mixed2"])
+def test_RoeFlux_3d(built_library, order):
+    import torch
+    w = WORKLOADS["roe3d"]
+    g = _golden("roe3d")
+    args = [torch.tensor(v) for v in ([.1], [.1, .2, .3], [.5], [.2], [.2, .2, .4], [.6])]
+    jac = gx.jacve(RoeFlux_3d, order=w.order(order), argnums=list(range(6)))(*args)
+    assert [tuple(b.shape) for b in jac[1]] == [(3, 1), (3, 3), (3, 1), (3, 1), (3, 3), (3, 1)]
+    J = pack_blocks([[b[None] for b in row] for row in jac], 1, w.sizes)[0]
+    ref = np.array(g["jacobian"])
+    assert np.allclose(J, ref, atol=1e-5 * np.abs(ref).max(), rtol=1e-4)
+    # the reference's own order list, written against jacve(vmap(f)) numbering, is accepted as is
+    if order == "mixed":
+        from graphax_b200.examples.orders import ROEFLUX_3D_VMAP_MIXED
+        jac2 = gx.jacve(RoeFlux_3d, order=ROEFLUX_3D_VMAP_MIXED, argnums=list(range(6)),
+                        order_numbering="vmap")(*args)
+        assert all(torch.equal(a, b) for ra, rb in zip(jac, jac2) for a, b in zip(ra, rb))
+
+
+def test_vmap_batch_and_argnums_subset(built_library):
+    import torch
+    w = WORKLOADS["roe3d"]
+    xs = [torch.from_numpy(x).cuda() for x in w.inputs(777)]
+    full = gx.vmap(gx.jacve(RoeFlux_3d, order="rev", argnums=list(range(6))))(*xs)
+    sub = gx.vmap(gx.jacve(RoeFlux_3d, order="rev", argnums=(4, 1)))(*xs)
+    assert tuple(full[1][4].shape) == (777, 3, 3)
+    assert torch.equal(sub[1][0], full[1][4]) and torch.equal(sub[2][1], full[2][1])
+    single = gx.vmap(gx.jacve(RoeFlux_3d, order="rev", argnums=(1,)))(*xs)
+    assert torch.equal(single[0], full[0][1])
+
+
+def test_bad_orders_raise(built_library):
+    with pytest.raises(ValueError):
+        gx.jacve(readme_f, order="sideways", argnums=(0,))(1., 1., 2., 7.)
+    with pytest.raises(ValueError):
+        gx.jacve(readme_f, order=[1, 2, 3], argnums=(0,))(1., 1., 2., 7.)      # vertex 4 missing
+    with pytest.raises(ValueError):
+        gx.jacve(readme_f, order=[1, 2, 3, 4, 5], argnums=(0,))(1., 1., 2., 7.)  # 5 is the output

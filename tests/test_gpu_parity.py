@@ -1,0 +1,181 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+from graphax_b200.configs import WORKLOADS
+from helpers import bits, pack_blocks, parity_bound, run_engine
+
+pytestmark = pytest.mark.gpu
+
+EXACT = {"roe1d", "roe3d"}           # plans made only of correctly rounded ops: bit-exact vs the replay
+CASES = [(w.name, k) for w in WORKLOADS.values() for k in w.order_names()]
+
+
+def _tile64(w, order, xs):
+    from oracle import ve_numpy
+    jac, primal, _ = ve_numpy.jacve(w.jaxpr(), w.order(order), w.argnums, [x.astype(np.float64) for x in xs],
+                                    np.float64)
+    return pack_blocks(jac, len(xs[0]), w.sizes), np.concatenate([p.reshape(len(xs[0]), -1) for p in primal], 1)
+
+
+@pytest.mark.parametrize("name,order", CASES)
+@pytest.mark.parametrize("kernel", ["aot", "interpreter"])
+def test_kernel_matches_plan_replay(built_library, name, order, kernel):
+    from oracle import replay
+    w = WORKLOADS[name]
+    plan = w.plan(order)
+    batch = 4096 + 37                                  # full tiles + ragged tail
+    xs = w.inputs(batch)
+    jac, primal, used = run_engine(plan, xs, kernel)
+    assert used == kernel
+    ref_j, ref_p = replay.replay(plan.blob, xs, plan.n_rows, plan.n_cols)
+    assert not np.isnan(jac).any() and not np.isnan(primal).any()
+    if name in EXACT:
+        assert np.array_equal(bits(jac), bits(ref_j))
+        assert np.array_equal(bits(primal), bits(ref_p))
+    else:   # sin / cos / atan2 differ between CUDA libm and glibc by a few ulp
+        t64, _ = _tile64(w, order, xs)
+        assert (np.abs(jac - ref_j) <= parity_bound(t64)).all()
+        np.testing.assert_allclose(primal, ref_p, rtol=2e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("name,order", [("roe3d", "rev"), ("roe3d", "mixed"), ("roe1d", "rev"), ("robotarm", "markowitz")])
+def test_jit_kernel_matches_plan_replay(built_library, name, order):
+    from oracle import replay
+    w = WORKLOADS[name]
+    plan = w.plan(order)
+    xs = w.inputs(1000)
+    jac, primal, used = run_engine(plan, xs, "jit")
+    assert used == "jit"
+    ref_j, ref_p = replay.replay(plan.blob, xs, plan.n_rows, plan.n_cols)
+    if name in EXACT:
+        assert np.array_equal(bits(jac), bits(ref_j)) and np.array_equal(bits(primal), bits(ref_p))
+    else:
+        t64, _ = _tile64(w, order, xs)
+        assert (np.abs(jac - ref_j) <= parity_bound(t64)).all()
+
+
+@pytest.mark.parametrize("name,order", CASES)
+def test_engine_matches_reference_order_oracle(built_library, name, order):
+    """Engine vs the NumPy restatement of the reference algorithm (fp32, unfused, tensor-level order)
+    within |dJ| <= 1e-5 max|J| + 1e-5 |J|; both are also reported against fp64."""
+    from oracle import ve_numpy
+    w = WORKLOADS[name]
+    plan = w.plan(order)
+    batch = 2048
+    xs = w.inputs(batch)
+    jac, primal, _ = run_engine(plan, xs, "aot")
+    j32, p32, aux = ve_numpy.jacve(w.jaxpr(), w.order(order), w.argnums, xs, np.float32)
+    t32 = pack_blocks(j32, batch, w.sizes)
+    t64, p64 = _tile64(w, order, xs)
+    bound = parity_bound(t64)
+    assert (np.abs(jac - t32) <= bound).all(), float((np.abs(jac - t32) / bound).max())
+    mx = np.abs(t64).max(axis=(1, 2), keepdims=True)
+    err_engine, err_oracle = (np.abs(jac - t64) / mx).max(), (np.abs(t32 - t64) / mx).max()
+    assert err_engine < 3e-5 and err_oracle < 3e-5, (err_engine, err_oracle)
+    np.testing.assert_allclose(primal, p64, rtol=1e-5, atol=1e-6)
+    assert aux["num_muls"] == plan.stats["num_muls"] and aux["num_adds"] == plan.stats["num_adds"]
+
+
+@pytest.mark.parametrize("batch", [0, 1, 127, 128, 129, 300])
+@pytest.mark.parametrize("kernel", ["aot", "interpreter"])
+def test_ragged_batches(built_library, batch, kernel):
+    from oracle import replay
+    w = WORKLOADS["roe3d"]
+    plan = w.plan("rev")
+    xs = w.inputs(max(batch, 1))
+    xs = [x[:batch] for x in xs]
+    if batch == 0:
+        import torch
+        from graphax_b200 import runtime
+        dp = runtime.DevicePlan(plan, 0, jit=False)
+        dp.launch(0, [0] * 6, 0, None, torch.cuda.current_stream().cuda_stream)   # no-op, must not fault
+        dp.close()
+        return
+    jac, primal, _ = run_engine(plan, xs, kernel)
+    ref_j, ref_p = replay.replay(plan.blob, xs, plan.n_rows, plan.n_cols)
+    assert np.array_equal(bits(jac), bits(ref_j)) and np.array_equal(bits(primal), bits(ref_p))
+
+
+def test_misaligned_buffers_take_the_guarded_path(built_library):
+    """Caller buffers that are not 16-byte aligned cannot use bulk copies; results must not change."""
+    import torch
+    from graphax_b200 import runtime
+    from oracle import replay
+    w = WORKLOADS["roe3d"]
+    plan = w.plan("rev")
+    batch = 515
+    xs = w.inputs(batch)
+    dp = runtime.DevicePlan(plan, 0, jit=False)
+    dev = []
+    for x in xs:
+        flat = torch.zeros(x.size + 1, device="cuda")
+        flat[1:] = torch.from_numpy(x.reshape(-1)).cuda()
+        dev.append(flat[1:])                                   # data_ptr() is 4 bytes off alignment
+    jac_flat = torch.zeros(batch * 50 + 1, device="cuda")
+    dp.launch(batch, [t.data_ptr() for t in dev], jac_flat[1:].data_ptr(), None,
+              torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    ref_j, _ = replay.replay(plan.blob, xs, plan.n_rows, plan.n_cols)
+    assert np.array_equal(bits(jac_flat[1:].cpu().numpy().reshape(batch, 5, 10)), bits(ref_j))
+    dp.close()
+
+
+def test_full_size_properties(built_library):
+    """Headline size (2^20): batch independence, determinism, primal consistency, NaN-freeness."""
+    import torch
+    from graphax_b200 import runtime
+    from oracle import replay
+    w = WORKLOADS["roe3d"]
+    batch = 1 << 20
+    xs = w.inputs(batch)
+    dev = [torch.from_numpy(x).cuda() for x in xs]
+    stream = torch.cuda.current_stream().cuda_stream
+    for order in ("rev", "fwd", "mixed"):
+        plan = w.plan(order)
+        dp = runtime.DevicePlan(plan, 0, jit=False)
+        assert dp.kernel == "aot"
+        jac = torch.empty((batch, 5, 10), device="cuda")
+        jac2 = torch.empty_like(jac)
+        primal = torch.empty((batch, 5), device="cuda")
+        dp.launch(batch, [t.data_ptr() for t in dev], jac.data_ptr(), primal.data_ptr(), stream)
+        dp.launch(batch, [t.data_ptr() for t in dev], jac2.data_ptr(), None, stream)
+        torch.cuda.synchronize()
+        assert torch.equal(jac, jac2)                              # deterministic
+        assert bool(torch.isfinite(jac).all())
+        # any window of the big batch equals a small run on that window (samples are independent)
+        for lo in (0, 123_457, batch - 4099):
+            sl = slice(lo, lo + 4099)
+            ref_j, ref_p = replay.replay(plan.blob, [x[sl] for x in xs], plan.n_rows, plan.n_cols)
+            assert np.array_equal(bits(jac[sl].cpu().numpy()), bits(ref_j))
+            assert np.array_equal(bits(primal[sl].cpu().numpy()), bits(ref_p))
+        dp.close()
+    # different elimination orders accumulate the same Jacobian (within the fp32 order spread)
+    j_rev = run_engine(w.plan("rev"), [x[:8192] for x in xs], "aot")[0]
+    j_mix = run_engine(w.plan("mixed"), [x[:8192] for x in xs], "aot")[0]
+    mx = np.abs(j_rev).max(axis=(1, 2), keepdims=True)
+    assert (np.abs(j_rev - j_mix) / mx).max() < 3e-5
+
+
+def test_host_pipeline(built_library):
+    """gx_jacve_host (H2D -> kernel -> D2H, chunked) equals the device-resident launch."""
+    import torch
+    from graphax_b200 import runtime
+    from oracle import replay
+    w = WORKLOADS["roe3d"]
+    plan = w.plan("rev")
+    batch = (1 << 17) + 333                                     # > 2 chunks, ragged
+    xs = w.inputs(batch)
+    ref_j, ref_p = replay.replay(plan.blob, xs, plan.n_rows, plan.n_cols)
+    dp = runtime.DevicePlan(plan, 0, jit=False)
+    for pinned in (False, True):
+        if pinned:
+            hin = [torch.from_numpy(x).pin_memory() for x in xs]
+            hj = torch.empty((batch, 5, 10)).pin_memory()
+            hp = torch.empty((batch, 5)).pin_memory()
+        else:
+            hin = [torch.from_numpy(x.copy()) for x in xs]
+            hj, hp = torch.empty((batch, 5, 10)), torch.empty((batch, 5))
+        dp.run_host(batch, [t.data_ptr() for t in hin], hj.data_ptr(), hp.data_ptr(), pinned)
+        assert np.array_equal(bits(hj.numpy()), bits(ref_j)) and np.array_equal(bits(hp.numpy()), bits(ref_p))
+    dp.close()
