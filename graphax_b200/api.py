@@ -180,10 +180,39 @@ class JacveFunction:
             return primal_tree, grads_tree
         return grads_tree
 
+    def _run_host(self, args: Sequence[Any]):
+        """Batched call on HOST arrays: pinned staging, chunked H2D -> kernel -> D2H (gx_jacve_host).
+        Results come back as (pinned) CPU tensors, like a jitted function called with NumPy arrays."""
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("graphax_b200 needs a CUDA device: there is no CPU fallback for jacve")
+        device = self.device if self.device is not None else torch.cuda.current_device()
+        tensors = [a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+                   for a in args]
+        tensors = [t.to(torch.float32).contiguous() for t in tensors]
+        batch = tensors[0].shape[0]
+        if any(t.ndim < 1 or t.shape[0] != batch for t in tensors):
+            raise ValueError("batched call: every argument needs the same leading batch axis")
+        shapes = [tuple(t.shape[1:]) for t in tensors]
+        plan = self.lower(shapes)
+        dp = self._device_plan(plan, device)
+        pinned = all(t.is_pinned() for t in tensors)
+        jac = torch.empty((batch, plan.n_rows, plan.n_cols), dtype=torch.float32, pin_memory=pinned)
+        primal = torch.empty((batch, plan.n_rows), dtype=torch.float32, pin_memory=pinned) if self.has_aux else None
+        dp.run_host(batch, [t.data_ptr() for t in tensors], jac.data_ptr(),
+                    primal.data_ptr() if primal is not None else None, pinned)
+        return self._package(plan, jac, primal, shapes, batch, True)
+
     def __call__(self, *args):
         return self._run(args, batched=False)
 
     def batched(self, *args):
+        """Leading batch axis on every argument. CUDA tensors stay on the device (one launch on the
+        current stream); host arrays (NumPy / CPU tensors) go through the pipelined host path."""
+        import torch
+        on_host = all(isinstance(a, np.ndarray) or (isinstance(a, torch.Tensor) and not a.is_cuda) for a in args)
+        if on_host and len(args) > 0:
+            return self._run_host(args)
         return self._run(args, batched=True)
 
 

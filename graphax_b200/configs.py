@@ -63,8 +63,8 @@ class Workload:
     def order_names(self) -> List[str]:
         return list(self.orders) + list(self.vmap_orders)
 
-    def plan(self, order_key: str, with_primal: bool = True) -> Plan:
-        return _plan(self.name, order_key, with_primal)
+    def plan(self, order_key: str, with_primal: bool = True, division: str = "reciprocal") -> Plan:
+        return _plan(self.name, order_key, with_primal, division)
 
     def inputs(self, batch: int, start: int = 0, seed: int = SEED) -> List[np.ndarray]:
         """float32 arrays [batch, *shape] (rank-0 arguments -> [batch])."""
@@ -105,9 +105,9 @@ def _jaxpr(name: str) -> Jaxpr:
 
 
 @lru_cache(maxsize=None)
-def _plan(name: str, order_key: str, with_primal: bool) -> Plan:
+def _plan(name: str, order_key: str, with_primal: bool, division: str) -> Plan:
     w = WORKLOADS[name]
-    return build_plan(w.jaxpr(), w.order(order_key), w.argnums, with_primal=with_primal)
+    return build_plan(w.jaxpr(), w.order(order_key), w.argnums, with_primal=with_primal, division=division)
 
 
 def named_plans() -> List[Tuple[str, Plan]]:
@@ -115,5 +115,6 @@ def named_plans() -> List[Tuple[str, Plan]]:
     out = []
     for w in WORKLOADS.values():
         for key in w.order_names():
-            out.append((f"{w.name}:{key}", w.plan(key)))
+            for division in ("reciprocal", "ieee"):
+                out.append((f"{w.name}:{key}:{division}", w.plan(key, division=division)))
     return out

@@ -47,7 +47,7 @@ int fail(int code, const std::string& msg) {
 // ------------------------------------------------------------------------------------------------
 struct GxAotKernel {
   unsigned long long key;
-  int threads, smem_bytes, n_in, n_rows, n_cols, has_primal;
+  int threads, smem_bytes, n_in, n_rows, n_cols, has_primal, samples_per_thread;
   const void* func;
 };
 std::vector<GxAotKernel>& aot_registry() {
@@ -303,8 +303,8 @@ Nvrtc& nvrtc() {
 }
 
 constexpr int kSpecThreads = 128;
-constexpr int kSpecMinBlocks = 2;
-constexpr int kSpecOutStages = 2;
+constexpr int kSpecMinBlocks = 4;
+constexpr int kSpecOutStages = 1;
 constexpr int64_t kHostChunk = 1 << 16;  // samples per pipeline stage of gx_jacve_host
 
 }  // namespace
@@ -335,6 +335,8 @@ struct gx_plan {
   CUmodule jit_module = nullptr;
   CUfunction jit_func = nullptr;
   int jit_smem = 0;
+  int jit_threads = 0;
+  int jit_spt = 1;
   int jit_ctas_per_sm = 0;
   int jit_regs = 0;
 
@@ -466,7 +468,7 @@ int config_interp(gx_plan* p, int max_smem_optin) {
 }
 
 void fill_args(const gx_plan* p, GxLaunchArgs& a, int64_t batch, const void* const* in_ptrs, void* jac, void* primal,
-               int threads) {
+               int warp_tile) {
   memset(&a, 0, sizeof a);
   bool aligned = (reinterpret_cast<uintptr_t>(jac) & 15u) == 0 &&
                  (primal == nullptr || (reinterpret_cast<uintptr_t>(primal) & 15u) == 0);
@@ -477,7 +479,7 @@ void fill_args(const gx_plan* p, GxLaunchArgs& a, int64_t batch, const void* con
   a.jac = static_cast<float*>(jac);
   a.primal = static_cast<float*>(primal);
   a.batch = batch;
-  a.n_bulk_tiles = aligned ? batch / threads : 0;
+  a.n_bulk_tiles = aligned ? batch / warp_tile : 0;  // a warp tile is 32 x samples_per_thread samples
 }
 
 int launch_on(gx_plan* p, int64_t batch, const void* const* in_ptrs, void* jac, void* primal, cudaStream_t stream) {
@@ -485,18 +487,22 @@ int launch_on(gx_plan* p, int64_t batch, const void* const* in_ptrs, void* jac, 
   const int kind = p->kernel_kind;
   if (kind == GX_KERNEL_AOT && p->aot) {
     GxLaunchArgs a;
-    fill_args(p, a, batch, in_ptrs, jac, primal, p->aot->threads);
-    const long long tiles = (batch + p->aot->threads - 1) / p->aot->threads;
-    const int grid = (int)std::min<long long>(tiles, (long long)p->sm_count * p->aot_ctas_per_sm);
+    const int wt = 32 * p->aot->samples_per_thread;
+    fill_args(p, a, batch, in_ptrs, jac, primal, wt);
+    const int wpc = p->aot->threads / 32;  // every warp is an independent pipeline over its own tiles
+    const long long ctas = ((batch + wt - 1) / wt + wpc - 1) / wpc;
+    const int grid = (int)std::min<long long>(ctas, (long long)p->sm_count * p->aot_ctas_per_sm);
     void* params[] = {&a};
     GX_CUDA(cudaLaunchKernel(p->aot->func, dim3(grid), dim3(p->aot->threads), params, p->aot->smem_bytes, stream));
   } else if (kind == GX_KERNEL_JIT && p->jit_func) {
     GxLaunchArgs a;
-    fill_args(p, a, batch, in_ptrs, jac, primal, kSpecThreads);
-    const long long tiles = (batch + kSpecThreads - 1) / kSpecThreads;
-    const int grid = (int)std::min<long long>(tiles, (long long)p->sm_count * p->jit_ctas_per_sm);
+    const int wt = 32 * p->jit_spt;
+    fill_args(p, a, batch, in_ptrs, jac, primal, wt);
+    const int wpc = p->jit_threads / 32;
+    const long long ctas = ((batch + wt - 1) / wt + wpc - 1) / wpc;
+    const int grid = (int)std::min<long long>(ctas, (long long)p->sm_count * p->jit_ctas_per_sm);
     void* params[] = {&a};
-    CUresult r = driver().LaunchKernel(p->jit_func, grid, 1, 1, kSpecThreads, 1, 1, p->jit_smem, (CUstream)stream,
+    CUresult r = driver().LaunchKernel(p->jit_func, grid, 1, 1, p->jit_threads, 1, 1, p->jit_smem, (CUstream)stream,
                                        params, nullptr);
     if (r != CUDA_SUCCESS) return fail(GX_ERR_CUDA, "cuLaunchKernel(jit): " + cu_err(r));
   } else {
@@ -655,7 +661,7 @@ int gx_plan_info(const gx_plan* p, gx_info* out) {
     out->ctas_per_sm = p->aot_ctas_per_sm;
     out->regs_per_thread = p->aot_regs;
   } else if (p->kernel_kind == GX_KERNEL_JIT && p->jit_func) {
-    out->threads = kSpecThreads;
+    out->threads = p->jit_threads;
     out->smem_bytes = p->jit_smem;
     out->ctas_per_sm = p->jit_ctas_per_sm;
     out->regs_per_thread = p->jit_regs;
@@ -681,7 +687,16 @@ int gx_plan_select_kernel(gx_plan* p, int kind) {
 }
 
 int gx_plan_specialize(gx_plan* p, const char* src, size_t nbytes, const char* arch) {
+  return gx_plan_specialize_opts(p, src, nbytes, arch, kSpecThreads, kSpecMinBlocks, kSpecOutStages, 1);
+}
+
+int gx_plan_specialize_opts(gx_plan* p, const char* src, size_t nbytes, const char* arch, int threads,
+                            int min_blocks, int out_stages, int spt) {
   if (!p || !src) return fail(GX_ERR_BAD_ARG, "gx_plan_specialize: NULL argument");
+  if (threads < 32 || threads > 1024 || threads % 32 || min_blocks < 1 || min_blocks > 32 || out_stages < 1 ||
+      out_stages > 2 || spt < 1 || spt > 2)
+    return fail(GX_ERR_BAD_ARG,
+                "gx_plan_specialize: threads must be a multiple of 32, out_stages and samples_per_thread 1 or 2");
   (void)nbytes;
   Nvrtc& rt = nvrtc();
   if (!rt.ok) return fail(GX_ERR_JIT, "NVRTC unavailable: " + rt.why);
@@ -693,12 +708,13 @@ int gx_plan_specialize(gx_plan* p, const char* src, size_t nbytes, const char* a
   if (rt.CreateProgram(&prog, src, "gx_plan.cu", 0, nullptr, nullptr) != 0)
     return fail(GX_ERR_JIT, "nvrtcCreateProgram failed");
   std::string archopt = std::string("--gpu-architecture=") + (arch && *arch ? arch : "sm_100a");
-  char d_threads[48], d_blocks[48], d_stages[48];
-  snprintf(d_threads, sizeof d_threads, "-DGX_THREADS=%d", kSpecThreads);
-  snprintf(d_blocks, sizeof d_blocks, "-DGX_MIN_BLOCKS=%d", kSpecMinBlocks);
-  snprintf(d_stages, sizeof d_stages, "-DGX_OUT_STAGES=%d", kSpecOutStages);
-  const char* opts[] = {archopt.c_str(), "-std=c++17", "-lineinfo", d_threads, d_blocks, d_stages};
-  const int rc = rt.CompileProgram(prog, 6, opts);
+  char d_threads[48], d_blocks[48], d_stages[48], d_spt[48];
+  snprintf(d_spt, sizeof d_spt, "-DGX_SPT=%d", spt);
+  snprintf(d_threads, sizeof d_threads, "-DGX_THREADS=%d", threads);
+  snprintf(d_blocks, sizeof d_blocks, "-DGX_MIN_BLOCKS=%d", min_blocks);
+  snprintf(d_stages, sizeof d_stages, "-DGX_OUT_STAGES=%d", out_stages);
+  const char* opts[] = {archopt.c_str(), "-std=c++17", "-lineinfo", d_threads, d_blocks, d_stages, d_spt};
+  const int rc = rt.CompileProgram(prog, 7, opts);
   if (rc != 0) {
     size_t n = 0;
     rt.GetProgramLogSize(prog, &n);
@@ -723,10 +739,10 @@ int gx_plan_specialize(gx_plan* p, const char* src, size_t nbytes, const char* a
     return fail(GX_ERR_JIT, "cuModuleGetFunction(gx_jacve_kernel): " + cu_err(r));
   }
   const int tile = (int)(p->h.n_rows * p->h.n_cols + ((p->h.flags & GX_FLAG_HAS_PRIMAL) ? p->h.n_rows : 0));
-  const int smem = (2 * (int)p->h.n_in_scalars * kSpecThreads + kSpecOutStages * tile * kSpecThreads) * 4 + 64;
+  const int smem = (threads / 32) * (2 * (int)p->h.n_in_scalars * 32 * spt + out_stages * tile * 32 * spt + 4) * 4;
   r = driver().FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, smem);
   int occ = 0, regs = 0;
-  if (r == CUDA_SUCCESS) r = driver().OccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kSpecThreads, smem);
+  if (r == CUDA_SUCCESS) r = driver().OccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, smem);
   if (r == CUDA_SUCCESS) r = driver().FuncGetAttribute(&regs, CU_FUNC_ATTRIBUTE_NUM_REGS, fn);
   if (r != CUDA_SUCCESS || occ < 1) {
     driver().ModuleUnload(mod);
@@ -736,6 +752,8 @@ int gx_plan_specialize(gx_plan* p, const char* src, size_t nbytes, const char* a
   p->jit_module = mod;
   p->jit_func = fn;
   p->jit_smem = smem;
+  p->jit_threads = threads;
+  p->jit_spt = spt;
   p->jit_ctas_per_sm = occ;
   p->jit_regs = regs;
   p->kernel_kind = GX_KERNEL_JIT;

@@ -8,12 +8,16 @@
 //   * global traffic is fully coalesced although every thread owns a strided [tile] row,
 //   * the loads of tile i+1 and the stores of tile i-1 overlap the arithmetic of tile i, and
 //   * no issue slots are spent on address arithmetic / LDG / STG for the 60 words per sample.
-// CTAs are persistent (grid = SMs x resident CTAs) and stride over the batch in tiles of GX_THREADS
-// samples.  A partial last tile, or misaligned caller buffers, take a guarded non-bulk path through
-// the same body.
+// CTAs are persistent (grid = SMs x resident CTAs).  Every WARP is an independent pipeline over tiles
+// of 32 samples with its own stages and mbarriers: the steady state has no CTA-wide barrier, so a
+// warp that finishes its tile early never waits for a slower sibling.  A partial last tile, or
+// misaligned caller buffers, take a guarded non-bulk path through the same body.
 //
 // The including translation unit (emitted by graphax_b200/codegen.py) defines:
 //   GX_N_ARR, GX_N_IN, GX_N_ROWS, GX_N_COLS, GX_HAS_PRIMAL, GX_THREADS, GX_MIN_BLOCKS, GX_OUT_STAGES
+//   GX_SPT                        samples per thread: 1 (scalar FFMA/FMUL/FADD) or 2 (both samples packed in
+//                                 64-bit register pairs and driven through FFMA2/FMUL2/FADD2, sm_100's
+//                                 f32x2 pipe: half the issue slots for the same arithmetic)
 //   GX_KERNEL_NAME                unique symbol of this kernel (gx_jacve_kernel for NVRTC)
 //   GX_FOREACH_ARRAY(F)           F(index, scalars_per_sample, prefix_offset) for every input array
 //   gx_body(x, jrow, prow)        __device__ __forceinline__ function: the straight-line plan; reads the
@@ -29,6 +33,10 @@ typedef unsigned long long uint64_t;
 #endif
 
 #define GX_TILE (GX_N_ROWS * GX_N_COLS)
+#ifndef GX_SPT
+#define GX_SPT 1
+#endif
+#define GX_WT (32 * GX_SPT) /* samples per warp tile */
 #define GX_MAX_ARRAYS_K 16
 
 struct GxLaunchArgs {
@@ -87,62 +95,71 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
-constexpr int kInStageFloats = GX_N_IN * GX_THREADS;
-constexpr int kOutStageFloats = (GX_TILE + (GX_HAS_PRIMAL ? GX_N_ROWS : 0)) * GX_THREADS;
-constexpr int kSmemBytes = (2 * kInStageFloats + GX_OUT_STAGES * kOutStageFloats) * 4 + 64;
+// One warp = one pipeline. A warp tile is GX_WT consecutive samples; every warp owns its stages and
+// mbarriers, so the only synchronisation in the steady state is __syncwarp().
+constexpr int kWarps = GX_THREADS / 32;
+constexpr int kInStageFloats = GX_N_IN * GX_WT;
+constexpr int kOutStageFloats = (GX_TILE + (GX_HAS_PRIMAL ? GX_N_ROWS : 0)) * GX_WT;
+constexpr int kWarpFloats = 2 * kInStageFloats + GX_OUT_STAGES * kOutStageFloats + 4;  // + 2 mbarriers
+constexpr int kSmemBytes = kWarps * kWarpFloats * 4;
 
 }  // namespace gxk
 }  // namespace
 
-// shared memory: [ in stage 0 | in stage 1 | out stage 0 (jac tile rows, then primal rows) | out stage 1 | mbarriers ]
+// shared memory, per warp: [ in stage 0 | in stage 1 | out stage 0 (tile rows, then primal rows) | out stage 1 | 2 mbarriers ]
 extern "C" __global__ void __launch_bounds__(GX_THREADS, GX_MIN_BLOCKS)
 GX_KERNEL_NAME(const __grid_constant__ GxLaunchArgs args) {
   using namespace gxk;
   extern __shared__ __align__(128) float gx_smem[];
-  float* in_stage = gx_smem;
-  float* out_stage = gx_smem + 2 * kInStageFloats;
+  const int lane = threadIdx.x & 31;
+  // broadcast from lane 0 so that the compiler knows the warp index (and everything derived from it:
+  // tile index, stage pointers, bulk-copy addresses) is warp-uniform and keeps it on the uniform datapath
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  float* in_stage = gx_smem + warp * kWarpFloats;
+  float* out_stage = in_stage + 2 * kInStageFloats;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_stage + GX_OUT_STAGES * kOutStageFloats);
 
-  const int tid = threadIdx.x;
-  const long long n_tiles = (args.batch + GX_THREADS - 1) / GX_THREADS;
+  const long long n_tiles = (args.batch + GX_WT - 1) / GX_WT;
   const long long n_bulk = args.n_bulk_tiles;
+  const long long stride = (long long)gridDim.x * kWarps;
 
-  if (tid == 0) {
+  if (lane == 0) {
     mbar_init(&full_bar[0], 1);
     mbar_init(&full_bar[1], 1);
     fence_mbar_init();
   }
-  __syncthreads();
+  __syncwarp();
 
   auto issue_loads = [&](long long tile, int stage) {
-    // one elected thread programs the TMA engine: GX_N_ARR contiguous chunks of this tile
-    mbar_expect_tx(&full_bar[stage], (uint32_t)(GX_N_IN * GX_THREADS * 4));
-#define GX_ISSUE(a, size, off)                                                                    \
-  bulk_g2s(in_stage + stage * kInStageFloats + (off) * GX_THREADS,                                \
-           args.in[a] + tile * (long long)(GX_THREADS * (size)), (uint32_t)((size) * GX_THREADS * 4), \
-           &full_bar[stage]);
+    // the warp's elected lane programs the TMA engine: one contiguous chunk per input array
+    mbar_expect_tx(&full_bar[stage], (uint32_t)(GX_N_IN * GX_WT * 4));
+#define GX_ISSUE(a, size, off)                                                                                  \
+  bulk_g2s(in_stage + stage * kInStageFloats + (off) * GX_WT, args.in[a] + tile * (long long)(GX_WT * (size)), \
+           (uint32_t)((size) * GX_WT * 4), &full_bar[stage]);
     GX_FOREACH_ARRAY(GX_ISSUE)
 #undef GX_ISSUE
   };
 
-  long long tile = blockIdx.x;
-  if (tid == 0 && tile < n_bulk) issue_loads(tile, 0);
+  long long tile = (long long)blockIdx.x * kWarps + warp;
+  if (lane == 0 && tile < n_bulk) issue_loads(tile, 0);
 
-  for (int it = 0; tile < n_tiles; ++it, tile += gridDim.x) {
+  for (int it = 0; tile < n_tiles; ++it, tile += stride) {
     const int stage = it & 1;
     const int ostage = it % GX_OUT_STAGES;
     const bool bulk = tile < n_bulk;
-    const long long next = tile + gridDim.x;
-    // prefetch the next tile: its stage was last read one iteration ago, before the barrier below
-    if (tid == 0 && next < n_bulk) issue_loads(next, stage ^ 1);
+    const long long next = tile + stride;
+    // prefetch the next tile: its stage was last read one iteration ago, before the __syncwarp below
+    if (lane == 0 && next < n_bulk) issue_loads(next, stage ^ 1);
 
+    float* tile_s = out_stage + ostage * kOutStageFloats;
+#if GX_SPT == 1
     float x[GX_N_IN];
-    const long long sample = tile * GX_THREADS + tid;
+    const long long sample = tile * GX_WT + lane;
     if (bulk) {
       mbar_wait(&full_bar[stage], (uint32_t)((it >> 1) & 1));
       const float* s = in_stage + stage * kInStageFloats;
 #define GX_RD_BULK(a, size, off) \
-  _Pragma("unroll") for (int c = 0; c < (size); ++c) x[(off) + c] = s[(off) * GX_THREADS + tid * (size) + c];
+  _Pragma("unroll") for (int c = 0; c < (size); ++c) x[(off) + c] = s[(off) * GX_WT + lane * (size) + c];
       GX_FOREACH_ARRAY(GX_RD_BULK)
 #undef GX_RD_BULK
     } else {
@@ -153,49 +170,69 @@ GX_KERNEL_NAME(const __grid_constant__ GxLaunchArgs args) {
 #undef GX_RD_DIRECT
     }
     // the out stage about to be written was handed to the TMA engine GX_OUT_STAGES iterations ago
-    if (tid == 0) bulk_wait_read<GX_OUT_STAGES - 1>();
-    __syncthreads();
-
-    float* jrow = out_stage + ostage * kOutStageFloats + tid * GX_TILE;
-    float* prow = out_stage + ostage * kOutStageFloats + GX_THREADS * GX_TILE + tid * GX_N_ROWS;
-    gx_body(x, jrow, prow);
+    if (lane == 0) bulk_wait_read<GX_OUT_STAGES - 1>();
+    __syncwarp();
+    gx_body(x, tile_s + lane * GX_TILE, tile_s + GX_WT * GX_TILE + lane * GX_N_ROWS);
+#else
+    // two samples per thread: lane and lane + 32 of the warp tile, packed as (.x, .y)
+    float2 x[GX_N_IN];
+    const long long sample = tile * GX_WT + lane;
+    if (bulk) {
+      mbar_wait(&full_bar[stage], (uint32_t)((it >> 1) & 1));
+      const float* s = in_stage + stage * kInStageFloats;
+#define GX_RD_BULK(a, size, off)                                                  \
+  _Pragma("unroll") for (int c = 0; c < (size); ++c)                              \
+      x[(off) + c] = make_float2(s[(off) * GX_WT + lane * (size) + c],           \
+                                 s[(off) * GX_WT + (lane + 32) * (size) + c]);
+      GX_FOREACH_ARRAY(GX_RD_BULK)
+#undef GX_RD_BULK
+    } else {
+#define GX_RD_DIRECT(a, size, off)                                                                          \
+  _Pragma("unroll") for (int c = 0; c < (size); ++c)                                                        \
+      x[(off) + c] = make_float2(sample < args.batch ? __ldg(args.in[a] + sample * (size) + c) : 1.0f,      \
+                                 sample + 32 < args.batch ? __ldg(args.in[a] + (sample + 32) * (size) + c) : 1.0f);
+      GX_FOREACH_ARRAY(GX_RD_DIRECT)
+#undef GX_RD_DIRECT
+    }
+    if (lane == 0) bulk_wait_read<GX_OUT_STAGES - 1>();
+    __syncwarp();
+    gx_body(x, tile_s + lane * GX_TILE, tile_s + (lane + 32) * GX_TILE,
+            tile_s + GX_WT * GX_TILE + lane * GX_N_ROWS, tile_s + GX_WT * GX_TILE + (lane + 32) * GX_N_ROWS);
+#endif
 
     if (bulk) {
       fence_async_smem();  // generic-proxy writes -> visible to the async proxy
-      __syncthreads();
-      if (tid == 0) {
-        bulk_s2g(args.jac + tile * (long long)(GX_THREADS * GX_TILE), out_stage + ostage * kOutStageFloats,
-                 (uint32_t)(GX_THREADS * GX_TILE * 4));
+      __syncwarp();
+      if (lane == 0) {
+        bulk_s2g(args.jac + tile * (long long)(GX_WT * GX_TILE), tile_s, (uint32_t)(GX_WT * GX_TILE * 4));
 #if GX_HAS_PRIMAL
         if (args.primal != nullptr)
-          bulk_s2g(args.primal + tile * (long long)(GX_THREADS * GX_N_ROWS),
-                   out_stage + ostage * kOutStageFloats + GX_THREADS * GX_TILE,
-                   (uint32_t)(GX_THREADS * GX_N_ROWS * 4));
+          bulk_s2g(args.primal + tile * (long long)(GX_WT * GX_N_ROWS), tile_s + GX_WT * GX_TILE,
+                   (uint32_t)(GX_WT * GX_N_ROWS * 4));
 #endif
         bulk_commit();
       }
     } else {
-      __syncthreads();
-      const long long base = tile * (long long)GX_THREADS;
-      const long long valid = args.batch - base < GX_THREADS ? args.batch - base : GX_THREADS;
-      const float* src = out_stage + ostage * kOutStageFloats;
-      for (long long i = tid; i < valid * GX_TILE; i += GX_THREADS) args.jac[base * GX_TILE + i] = src[i];
+      __syncwarp();
+      const long long base = tile * GX_WT;
+      const int valid = (int)(args.batch - base < GX_WT ? args.batch - base : GX_WT);
+      for (int i = lane; i < valid * GX_TILE; i += 32) args.jac[base * GX_TILE + i] = tile_s[i];
 #if GX_HAS_PRIMAL
       if (args.primal != nullptr)
-        for (long long i = tid; i < valid * GX_N_ROWS; i += GX_THREADS)
-          args.primal[base * GX_N_ROWS + i] = src[GX_THREADS * GX_TILE + i];
+        for (int i = lane; i < valid * GX_N_ROWS; i += 32)
+          args.primal[base * GX_N_ROWS + i] = tile_s[GX_WT * GX_TILE + i];
 #endif
-      __syncthreads();  // the stage may be rewritten by the next iteration
+      __syncwarp();  // the stage may be rewritten by the next iteration
     }
   }
-  if (tid == 0) bulk_wait_all();  // shared memory must outlive the stores that read it
+  if (lane == 0) bulk_wait_all();  // shared memory must outlive the stores that read it
 }
 
 #ifndef GX_NVRTC
 // ---- ahead-of-time registration: build() compiles one such TU per named plan into the library ----
 struct GxAotKernel {
   unsigned long long key;
-  int threads, smem_bytes, n_in, n_rows, n_cols, has_primal;
+  int threads, smem_bytes, n_in, n_rows, n_cols, has_primal, samples_per_thread;
   const void* func;
 };
 extern "C" void gx_register_aot(const GxAotKernel* k);
@@ -203,7 +240,7 @@ namespace {
 struct GxRegistrar {
   GxRegistrar() {
     static GxAotKernel k = {GX_KEY, GX_THREADS, gxk::kSmemBytes, GX_N_IN, GX_N_ROWS, GX_N_COLS, GX_HAS_PRIMAL,
-                            (const void*)GX_KERNEL_NAME};
+                            GX_SPT, (const void*)GX_KERNEL_NAME};
     gx_register_aot(&k);
   }
 } gx_registrar_instance;

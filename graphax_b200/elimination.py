@@ -57,7 +57,7 @@ class Graph:
         return -(var.input_index + 1) if var.input_index is not None else var.eqn_index + 1
 
 
-def build_graph(jaxpr: Jaxpr) -> Graph:
+def build_graph(jaxpr: Jaxpr, division: str = "ieee") -> Graph:
     dag = Dag()
     env: Dict[int, Vec] = {}
     k = 0
@@ -82,7 +82,7 @@ def build_graph(jaxpr: Jaxpr) -> Graph:
         for a in eqn.invars:
             if isinstance(a, Var) and Graph.key(a) in out_keys and a.eqn_index is not None:
                 g.vo_vertices.add(Graph.key(a))
-        out, edges = lower_eqn(dag, eqn, read)
+        out, edges = lower_eqn(dag, eqn, read, division)
         if out.shape != eqn.outvar.shape:
             raise AssertionError(f"shape mismatch lowering {eqn!r}: {out.shape}")
         env[v] = out
@@ -245,9 +245,9 @@ class Accumulated:
         return sum(s.num_adds for s in self.steps)
 
 
-def accumulate(jaxpr: Jaxpr, order: Order, argnums: Sequence[int]) -> Accumulated:
+def accumulate(jaxpr: Jaxpr, order: Order, argnums: Sequence[int], division: str = "ieee") -> Accumulated:
     """``vertex_elimination_jaxpr`` minus densification (core.py:522-562)."""
-    g = build_graph(jaxpr)
+    g = build_graph(jaxpr, division)
     for o in jaxpr.outvars:
         if not isinstance(o, Var) or o.eqn_index is None:
             raise NotImplementedError("outputs that are inputs or constants are not supported")

