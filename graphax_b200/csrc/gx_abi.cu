@@ -13,6 +13,7 @@
 #include <dlfcn.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -305,7 +306,15 @@ Nvrtc& nvrtc() {
 constexpr int kSpecThreads = 128;
 constexpr int kSpecMinBlocks = 4;
 constexpr int kSpecOutStages = 1;
-constexpr int64_t kHostChunk = 1 << 16;  // samples per pipeline stage of gx_jacve_host
+// samples per pipeline stage of gx_jacve_host (GX_HOST_CHUNK overrides, for tuning)
+int64_t host_chunk() {
+  static const int64_t v = [] {
+    const char* e = getenv("GX_HOST_CHUNK");
+    long long n = e ? atoll(e) : 0;
+    return (int64_t)(n >= 1024 ? n : (1 << 17));
+  }();
+  return v;
+}
 
 }  // namespace
 
@@ -785,6 +794,7 @@ int gx_jacve_host(gx_plan* p, int64_t batch, const void* const* in_ptrs, void* j
   std::lock_guard<std::mutex> lock(p->host_mu);
   GX_CUDA(cudaSetDevice(p->device));
   const size_t n_in = p->h.n_in_scalars, tile = (size_t)p->h.n_rows * p->h.n_cols, rows = p->h.n_rows;
+  const int64_t kHostChunk = host_chunk();
   const bool staging = !pinned;
   if (!p->host_ready || (staging && !p->host_staging)) {
     for (auto& s : p->slots) {
