@@ -31,7 +31,8 @@ from graphax_b200.configs import WORKLOADS  # noqa: E402
 
 METRIC = "Jacobians/s, RoeFlux_3d vmap batch"
 UNIT = "Jacobians/s"
-WORKLOAD = "roe3d"
+WORKLOAD = "roe3d"       # headline config; --workload selects the other named configs (not bench lines of record)
+TITLES = {"roe3d": "RoeFlux_3d", "roe1d": "RoeFlux_1d", "robotarm": "RobotArm_6DOF", "readme": "README f"}
 N_BUFFER_SETS = 4        # 4 x (40 MB in + 200 MB out) = 960 MB >> 126 MB L2: every step touches cold memory
 
 
@@ -108,7 +109,7 @@ def run_reference_arm(args) -> None:
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * float(np.median(times)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"RoeFlux_3d order={args.order}, NumPy port of the reference algorithm, "
+        "config": {"workload": f"{TITLES[WORKLOAD]} order={args.order}, NumPy port of the reference algorithm, "
                                f"{sample} samples per step (bounded sample of the 2^20 batch)",
                    "note": reference_note},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
@@ -286,7 +287,7 @@ def run_gpu_arm(args) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = world * batch * e2e_steps / e2e_s
-    checksum = float(out[1][1][:4096].double().abs().sum())                        # touch the result on the host
+    checksum = float(host_out[:4096].double().abs().sum())                         # touch the result on the host
 
     if rank == 0:
         ms_per_step = elapsed_ms / args.steps
@@ -297,8 +298,9 @@ def run_gpu_arm(args) -> None:
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"RoeFlux_3d (138 vertices) jacve order={args.order}, vmap batch {batch} per GPU, "
-                                   f"fp32, argnums all 6 inputs -> [5x10] Jacobian",
+            "config": {"workload": f"{TITLES[WORKLOAD]} ({plan.stats['n_vertices']} vertices) jacve order={args.order}, "
+                                   f"vmap batch {batch} per GPU, fp32, argnums all {len(w.argnums)} inputs -> "
+                                   f"[{plan.n_rows}x{plan.n_cols}] Jacobian",
                        "batch_per_gpu": batch, "order": args.order, "kernel": runtime.KERNEL_NAMES[info.kernel_kind],
                        "plan_ops": plan.stats["n_ops"], "threads_per_cta": info.threads,
                        "ctas_per_sm": info.ctas_per_sm, "regs_per_thread": info.regs_per_thread,
@@ -307,7 +309,7 @@ def run_gpu_arm(args) -> None:
                        "parallelism": f"batch sharded over {world} GPU(s), no collective"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * plan.n_in_scalars * batch,
                     "d2h_bytes_per_step": 4 * plan.n_rows * plan.n_cols * batch, "steps": e2e_steps,
-                    "api": "graphax_b200.vmap(jacve(RoeFlux_3d, order, argnums))(*pinned_host_arrays, out=pinned_result)",
+                    "api": f"graphax_b200.vmap(jacve({TITLES[WORKLOAD]}, order, argnums))(*pinned_host_arrays, out=pinned_result)",
                     "checksum": checksum},
             "gpu_launches": int(launches) * world,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -336,13 +338,21 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="graphax_b200", choices=["graphax_b200", "reference"])
-    ap.add_argument("--order", default="mixed", choices=WORKLOADS[WORKLOAD].order_names())
-    ap.add_argument("--batch", type=int, default=WORKLOADS[WORKLOAD].batch)
+    ap.add_argument("--order", default="mixed")
+    ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--kernel", default="auto", choices=["auto", "aot", "jit", "interpreter"])
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--clock-probe-s", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="roe3d", choices=list(WORKLOADS))
     args = ap.parse_args()
+    global WORKLOAD, METRIC
+    WORKLOAD = args.workload
+    METRIC = f"Jacobians/s, {TITLES[WORKLOAD]} vmap batch"
+    if args.order not in WORKLOADS[WORKLOAD].order_names():
+        args.order = "rev"
+    if args.batch == 0:
+        args.batch = WORKLOADS[WORKLOAD].batch
     if args.impl == "reference":
         run_reference_arm(args)
     else:

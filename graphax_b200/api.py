@@ -164,11 +164,10 @@ class JacveFunction:
                     block = None if d is None else SparseJacobian(d["out_dims"], d["primal_dims"], d["val_shape"], block)
                 row.append(block)
             grads.append(tuple(row) if len(self.argnums) > 1 else row[0])
+        # core.py:76-92: always a tuple over the outputs, except that a single output of a function of
+        # several arguments is unwrapped (so 1 output / 1 argument gives a 1-tuple, like the reference)
         single = len(out_shapes) == 1 and len(jaxpr.invars) > 1
-        if jaxpr.out_is_sequence and not single:
-            grads_tree = tuple(grads)
-        else:
-            grads_tree = grads[0]
+        grads_tree = grads[0] if single else tuple(grads)
         if self.count_ops:
             aux = {"num_muls": plan.stats["num_muls"], "num_adds": plan.stats["num_adds"],
                    "order_counts": list(plan.stats["order_counts"])}
@@ -176,7 +175,7 @@ class JacveFunction:
         if self.has_aux:
             pt = primal if batched else primal[0]
             outs = [pt[..., rows[oi]:rows[oi + 1]].reshape(lead + tuple(s)) for oi, s in enumerate(out_shapes)]
-            primal_tree = tuple(outs) if (jaxpr.out_is_sequence and not single) else outs[0]
+            primal_tree = outs[0] if single else tuple(outs)
             return primal_tree, grads_tree
         return grads_tree
 

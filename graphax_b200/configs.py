@@ -13,7 +13,7 @@ from typing import Callable, Dict, List, Sequence, Tuple, Union
 
 import numpy as np
 
-from .examples import RobotArm_6DOF, RoeFlux_1d, RoeFlux_3d, readme_f
+from .examples import Helmholtz, Hole, Lighthouse, RobotArm_6DOF, RoeFlux_1d, RoeFlux_3d, Simple, readme_f
 from .examples import orders as ref_orders
 from .plan import Plan, build_plan
 from .tracer import Jaxpr, make_jaxpr
@@ -98,15 +98,31 @@ WORKLOADS: Dict[str, Workload] = {
 }
 
 
+# Further functions of the reference's tests (tests/examples/example_test.py:43-75); no ahead-of-time
+# kernels: they exercise the run-time (NVRTC) specialisation path.
+EXTRA_WORKLOADS: Dict[str, Workload] = {
+    "simple": Workload("simple", Simple, [()] * 2, [5., 7.], 0.01, 1 << 10, {"fwd": "fwd", "rev": "rev"}),
+    "lighthouse": Workload("lighthouse", Lighthouse, [()] * 4, [.02] * 4, 0.01, 1 << 10,
+                           {"fwd": "fwd", "rev": "rev"}),
+    "hole": Workload("hole", Hole, [()] * 4, [.3, .5, .7, .2], 0.01, 1 << 10, {"fwd": "fwd", "rev": "rev"}),
+    "helmholtz": Workload("helmholtz", Helmholtz, [(4,)], [0.05, 0.15, 0.25, 0.35], 0.01, 1 << 10,
+                          {"fwd": "fwd", "rev": "rev", "custom": [2, 5, 4, 3, 1]}),
+}
+
+
+def get_workload(name: str) -> Workload:
+    return WORKLOADS[name] if name in WORKLOADS else EXTRA_WORKLOADS[name]
+
+
 @lru_cache(maxsize=None)
 def _jaxpr(name: str) -> Jaxpr:
-    w = WORKLOADS[name]
+    w = get_workload(name)
     return make_jaxpr(w.fun, w.arg_shapes)
 
 
 @lru_cache(maxsize=None)
 def _plan(name: str, order_key: str, with_primal: bool, division: str) -> Plan:
-    w = WORKLOADS[name]
+    w = get_workload(name)
     return build_plan(w.jaxpr(), w.order(order_key), w.argnums, with_primal=with_primal, division=division)
 
 

@@ -28,3 +28,18 @@ def Lighthouse(nu, gamma, omega, t):
     y1 = nu * jnp.tan(omega * t) / (gamma - jnp.tan(omega * t))
     y2 = gamma * y1
     return y1, y2
+
+
+def Hole(x, y, z, w):
+    a = y * z
+    b = a + x
+    c = a + w
+    d = jnp.cos(b)
+    e = jnp.exp(c)
+    return d - e, d / e, d * e
+
+
+def Helmholtz(x):
+    """Helmholtz free energy density of a mixture, x of shape (n,): a rank-0 intermediate broadcast
+    back into a vector (reference ``examples/easy.py``, tested with order [2, 5, 4, 3, 1])."""
+    return x * jnp.log(x / (1. + -jnp.sum(x)))

@@ -34,7 +34,11 @@ def init_process_group(backend: str = "nccl"):
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+        kwargs = {}
+        if backend == "nccl":
+            import torch
+            kwargs["device_id"] = torch.device(f"cuda:{local_rank}")   # no "guessing device ID" at the first barrier
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kwargs)
     return rank, local_rank, world
 
 

@@ -15,7 +15,7 @@ import torch
 
 ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
-from graphax_b200.configs import WORKLOADS  # noqa: E402
+from graphax_b200.configs import get_workload  # noqa: E402
 from graphax_b200.tracer import Literal  # noqa: E402
 
 
@@ -29,6 +29,7 @@ def evaluate(jaxpr, args):
         env[id(v)] = a
     un = {"neg": torch.neg, "abs": torch.abs, "sqrt": torch.sqrt, "sin": torch.sin, "cos": torch.cos,
           "tan": torch.tan, "exp": torch.exp, "log": torch.log, "tanh": torch.tanh}
+    # mixed rank-0 / rank-1 operands broadcast like lax does
     for e in jaxpr.eqns:
         x = [read(a) for a in e.invars]
         p = e.primitive
@@ -51,8 +52,8 @@ def evaluate(jaxpr, args):
 
 def main():
     out = {}
-    for name in ("roe3d", "roe1d", "robotarm", "readme"):
-        w = WORKLOADS[name]
+    for name in ("roe3d", "roe1d", "robotarm", "readme", "simple", "lighthouse", "hole", "helmholtz"):
+        w = get_workload(name)
         jaxpr = w.jaxpr()
         flat = torch.tensor(w.base, dtype=torch.float64)
 

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 import graphax_b200 as gx
-from graphax_b200.configs import WORKLOADS
+from graphax_b200.configs import EXTRA_WORKLOADS, WORKLOADS
 from graphax_b200.examples import RobotArm_6DOF, RoeFlux_1d, RoeFlux_3d, readme_f
 from helpers import GOLDEN, pack_blocks
 
@@ -89,3 +89,35 @@ def test_bad_orders_raise(built_library):
         gx.jacve(readme_f, order=[1, 2, 3], argnums=(0,))(1., 1., 2., 7.)      # vertex 4 missing
     with pytest.raises(ValueError):
         gx.jacve(readme_f, order=[1, 2, 3, 4, 5], argnums=(0,))(1., 1., 2., 7.)  # 5 is the output
+
+
+@pytest.mark.parametrize("name", list(EXTRA_WORKLOADS))
+def test_further_reference_examples_via_runtime_specialisation(built_library, name):
+    """Simple / Lighthouse / Hole / Helmholtz (tests/examples/example_test.py:43-75): no ahead-of-time kernel
+    exists for them, so the first call compiles the plan with NVRTC; fwd, rev and custom orders must agree
+    with each other and with the independent fp64 autodiff."""
+    import torch
+    w = EXTRA_WORKLOADS[name]
+    g = _golden(name)
+    args, off = [], 0
+    for shape, size in zip(w.arg_shapes, w.sizes):
+        args.append(torch.tensor(w.base[off:off + size], dtype=torch.float32).reshape(shape))
+        off += size
+    ref = np.array(g["jacobian"])
+    results = []
+    for key in w.order_names():
+        jf = gx.jacve(w.fun, order=w.order(key), argnums=w.argnums, count_ops=True)
+        out, aux = jf(*args)
+        dp = next(iter(jf._device_plans.values()))
+        assert dp.kernel == "jit"
+        rows = out if len(w.jaxpr().outvars) > 1 or len(w.argnums) == 1 else (out,)
+        rows = [r if isinstance(r, tuple) else (r,) for r in rows]
+        J = pack_blocks([[b[None] for b in r] for r in rows], 1, w.sizes)[0]
+        assert np.allclose(J, ref, atol=1e-5 * np.abs(ref).max(), rtol=1e-4), (name, key)
+        assert aux["num_muls"] == w.plan(key).stats["num_muls"]
+        results.append(J)
+    for J in results[1:]:
+        assert np.allclose(J, results[0], atol=1e-5 * np.abs(ref).max(), rtol=1e-4)
+    if name == "helmholtz":      # one input, one output: a 1-tuple holding the [4, 4] block (core.py:76-92)
+        out, _ = gx.jacve(w.fun, order=[2, 5, 4, 3, 1], argnums=(0,), count_ops=True)(*args)
+        assert isinstance(out, tuple) and len(out) == 1 and tuple(out[0].shape) == (4, 4)

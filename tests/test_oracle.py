@@ -4,7 +4,7 @@ import json
 import numpy as np
 import pytest
 
-from graphax_b200.configs import WORKLOADS
+from graphax_b200.configs import WORKLOADS, get_workload
 from graphax_b200.lowering import OPCODES
 from graphax_b200.tracer import make_jaxpr
 from helpers import GOLDEN, load_random_g, pack_blocks, parity_bound
@@ -29,9 +29,9 @@ def test_count_ops_known_answers_of_g():
 GOLD = json.loads((GOLDEN / "jacobians_fp64.json").read_text())
 
 
-@pytest.mark.parametrize("name", ["roe3d", "roe1d", "robotarm", "readme"])
+@pytest.mark.parametrize("name", ["roe3d", "roe1d", "robotarm", "readme", "simple", "lighthouse", "hole", "helmholtz"])
 def test_oracle_fp64_equals_independent_autodiff(name):
-    w = WORKLOADS[name]
+    w = get_workload(name)
     xs, off = [], 0
     for shape, size in zip(w.arg_shapes, w.sizes):
         xs.append(np.asarray(w.base[off:off + size], dtype=np.float64).reshape((1,) + tuple(shape)))

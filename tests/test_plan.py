@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from graphax_b200 import structure as st
-from graphax_b200.configs import WORKLOADS, named_plans
+from graphax_b200.configs import EXTRA_WORKLOADS, WORKLOADS, get_workload, named_plans
 from graphax_b200.lowering import OPCODES, Dag, _f32_from_fraction
 from graphax_b200.plan import MAGIC, build_plan, fnv1a64
 from graphax_b200.tracer import make_jaxpr
@@ -15,7 +15,7 @@ from helpers import load_random_g, pack_blocks
 from oracle import replay, ve_numpy as vo
 
 ROOT = Path(__file__).resolve().parent.parent
-CASES = [(w.name, k) for w in WORKLOADS.values() for k in w.order_names()]
+CASES = [(w.name, k) for w in list(WORKLOADS.values()) + list(EXTRA_WORKLOADS.values()) for k in w.order_names()]
 
 
 @pytest.mark.parametrize("name,order", CASES)
@@ -23,7 +23,7 @@ def test_edge_structure_and_counts_match_oracle_exactly(name, order):
     """The SparseTensor structure of every elemental edge and every final Jacobian block, and the
     reference's count_ops numbers, must be identical between the engine's symbolic elimination and
     the oracle's value-carrying restatement ("plan and edge structure bit-exact")."""
-    w = WORKLOADS[name]
+    w = get_workload(name)
     plan = w.plan(order)
     _, _, aux = vo.jacve(w.jaxpr(), w.order(order), w.argnums, w.inputs(2), np.float32)
     assert plan.structure["order"] == aux["structure"]["order"]
