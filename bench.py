@@ -289,6 +289,35 @@ def run_gpu_arm(args) -> None:
     e2e_value = world * batch * e2e_steps / e2e_s
     checksum = float(host_out[:4096].double().abs().sum())                         # touch the result on the host
 
+    # the other elimination orders of the config ("mixed ... vs fwd/rev"), same batch, fewer steps
+    other = {}
+    if args.other_orders and WORKLOAD == "roe3d":
+        for key in w.order_names():
+            if key == args.order:
+                continue
+            jf2 = gx.jacve(w.fun, order=w.order(key), argnums=w.argnums)
+            dp2 = jf2._device_plan(jf2.lower(w.arg_shapes), local_rank)
+            k2 = max(20, args.steps // 4)
+            for i in range(5):
+                ins, out_t = sets[i % N_BUFFER_SETS]
+                dp2.launch(batch, [t.data_ptr() for t in ins], out_t.data_ptr(), None, stream.cuda_stream)
+            sync_all()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for i in range(k2):
+                ins, out_t = sets[i % N_BUFFER_SETS]
+                dp2.launch(batch, [t.data_ptr() for t in ins], out_t.data_ptr(), None, stream.cuda_stream)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms2 = e0.elapsed_time(e1) / k2
+            if world > 1:
+                t = torch.tensor([ms2], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms2 = float(t.item())
+            other[key] = {"value": world * batch / (ms2 * 1e-3), "ms_per_step": ms2, "steps": k2,
+                          "roofline_frac": plan.bytes_per_jacobian * batch / (ms2 * 1e-3) / 1e9 / measured_peak_gbs()[0]}
+            sync_all()
+
     if rank == 0:
         ms_per_step = elapsed_ms / args.steps
         value = world * batch / (ms_per_step * 1e-3)
@@ -318,6 +347,8 @@ def run_gpu_arm(args) -> None:
                          "kernel_ms": ms_per_step},
             "clocks": sampler.summary(),
         }
+        if other:
+            line["other_orders"] = other
         if world == 1 and not args.no_cpu_baseline:
             cores = len(os.sched_getaffinity(0))
             sample = 1 << 19
@@ -344,6 +375,7 @@ def main() -> None:
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--clock-probe-s", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-orders", dest="other_orders", action="store_false")
     ap.add_argument("--workload", default="roe3d", choices=list(WORKLOADS))
     args = ap.parse_args()
     global WORKLOAD, METRIC

@@ -184,3 +184,33 @@ def test_host_pipeline(built_library):
         dp.run_host(batch, [t.data_ptr() for t in hin], hj.data_ptr(), hp.data_ptr(), pinned)
         assert np.array_equal(bits(hj.numpy()), bits(ref_j)) and np.array_equal(bits(hp.numpy()), bits(ref_p))
     dp.close()
+
+
+@pytest.mark.parametrize("kernel", ["aot", "jit", "interpreter"])
+@pytest.mark.parametrize("batch", [1, 95, 4096 + 33])
+def test_no_out_of_bounds_writes(built_library, kernel, batch):
+    """compute-sanitizer is closed on this pool, so bounds are checked the manual way: canary regions on
+    both sides of every output buffer must survive launches that end in a ragged tile."""
+    import torch
+    from graphax_b200 import runtime
+    from oracle import replay
+    w = WORKLOADS["roe3d"]
+    plan = w.plan("mixed")
+    xs = w.inputs(batch)
+    dp = runtime.DevicePlan(plan, 0, jit=False)
+    if kernel == "jit":
+        dp.specialize()
+    dp.select_kernel({"interpreter": 0, "aot": 1, "jit": 2}[kernel])
+    pad = 4096                                             # floats of canary on each side (16 KiB, keeps alignment)
+    dev = [torch.from_numpy(x).cuda() for x in xs]
+    jbuf = torch.full((2 * pad + batch * 50,), 12345.0, device="cuda")
+    pbuf = torch.full((2 * pad + batch * 5,), 12345.0, device="cuda")
+    dp.launch(batch, [t.data_ptr() for t in dev], jbuf[pad:].data_ptr(), pbuf[pad:].data_ptr(),
+              torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    for buf, n in ((jbuf, batch * 50), (pbuf, batch * 5)):
+        assert bool((buf[:pad] == 12345.0).all()) and bool((buf[pad + n:] == 12345.0).all())
+    ref_j, ref_p = replay.replay(plan.blob, xs, plan.n_rows, plan.n_cols)
+    assert np.array_equal(bits(jbuf[pad:pad + batch * 50].cpu().numpy().reshape(batch, 5, 10)), bits(ref_j))
+    assert np.array_equal(bits(pbuf[pad:pad + batch * 5].cpu().numpy().reshape(batch, 5)), bits(ref_p))
+    dp.close()
