@@ -226,8 +226,7 @@ struct DriverApi {
   CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
   CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
   CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
-  CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
-                           CUstream, void**, void**) = nullptr;
+  CUresult (*LaunchKernelEx)(const CUlaunchConfig*, CUfunction, void**, void**) = nullptr;
   CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
   bool ok = false;
 };
@@ -250,7 +249,7 @@ DriverApi& driver() {
            load_entry("cuFuncSetAttribute", d.FuncSetAttribute) &&
            load_entry("cuFuncGetAttribute", d.FuncGetAttribute) &&
            load_entry("cuOccupancyMaxActiveBlocksPerMultiprocessor", d.OccupancyMaxActiveBlocksPerMultiprocessor) &&
-           load_entry("cuLaunchKernel", d.LaunchKernel) && load_entry("cuGetErrorString", d.GetErrorString);
+           load_entry("cuLaunchKernelEx", d.LaunchKernelEx) && load_entry("cuGetErrorString", d.GetErrorString);
   });
   return d;
 }
@@ -306,6 +305,15 @@ Nvrtc& nvrtc() {
 constexpr int kSpecThreads = 128;
 constexpr int kSpecMinBlocks = 4;
 constexpr int kSpecOutStages = 1;
+// GX_PDL=0 switches programmatic dependent launch off (A/B measurements)
+bool use_pdl() {
+  static const bool v = [] {
+    const char* e = getenv("GX_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return v;
+}
+
 // samples per pipeline stage of gx_jacve_host (GX_HOST_CHUNK overrides, for tuning)
 int64_t host_chunk() {
   static const int64_t v = [] {
@@ -502,7 +510,20 @@ int launch_on(gx_plan* p, int64_t batch, const void* const* in_ptrs, void* jac, 
     const long long ctas = ((batch + wt - 1) / wt + wpc - 1) / wpc;
     const int grid = (int)std::min<long long>(ctas, (long long)p->sm_count * p->aot_ctas_per_sm);
     void* params[] = {&a};
-    GX_CUDA(cudaLaunchKernel(p->aot->func, dim3(grid), dim3(p->aot->threads), params, p->aot->smem_bytes, stream));
+    // programmatic dependent launch: the kernel's prologue may overlap the tail of its predecessor on the
+    // stream; the kernel itself waits (griddepcontrol.wait) before it touches global memory
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(p->aot->threads);
+    cfg.dynamicSmemBytes = p->aot->smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = use_pdl() ? 1 : 0;
+    GX_CUDA(cudaLaunchKernelExC(&cfg, p->aot->func, params));
   } else if (kind == GX_KERNEL_JIT && p->jit_func) {
     GxLaunchArgs a;
     const int wt = 32 * p->jit_spt;
@@ -511,9 +532,21 @@ int launch_on(gx_plan* p, int64_t batch, const void* const* in_ptrs, void* jac, 
     const long long ctas = ((batch + wt - 1) / wt + wpc - 1) / wpc;
     const int grid = (int)std::min<long long>(ctas, (long long)p->sm_count * p->jit_ctas_per_sm);
     void* params[] = {&a};
-    CUresult r = driver().LaunchKernel(p->jit_func, grid, 1, 1, p->jit_threads, 1, 1, p->jit_smem, (CUstream)stream,
-                                       params, nullptr);
-    if (r != CUDA_SUCCESS) return fail(GX_ERR_CUDA, "cuLaunchKernel(jit): " + cu_err(r));
+    CUlaunchConfig cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDimX = grid;
+    cfg.gridDimY = cfg.gridDimZ = 1;
+    cfg.blockDimX = p->jit_threads;
+    cfg.blockDimY = cfg.blockDimZ = 1;
+    cfg.sharedMemBytes = p->jit_smem;
+    cfg.hStream = (CUstream)stream;
+    CUlaunchAttribute attr[1];
+    attr[0].id = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;
+    attr[0].value.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = use_pdl() ? 1 : 0;
+    CUresult r = driver().LaunchKernelEx(&cfg, p->jit_func, params, nullptr);
+    if (r != CUDA_SUCCESS) return fail(GX_ERR_CUDA, "cuLaunchKernelEx(jit): " + cu_err(r));
   } else {
     GxInterpArgs a;
     memset(&a, 0, sizeof a);

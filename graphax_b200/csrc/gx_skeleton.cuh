@@ -94,6 +94,23 @@ __device__ __forceinline__ void bulk_wait_read() {
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// One lane of the (converged) warp. Unlike `lane == 0`, elect.sync tells the compiler that exactly one
+// thread runs the guarded region, so uniform-datapath instructions (UBLKCP) need no election loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// Programmatic dependent launch: let the next grid on the stream start its prologue while this one
+// drains, and make this grid wait for its predecessor before it touches global memory.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // One warp = one pipeline. A warp tile is GX_WT consecutive samples; every warp owns its stages and
 // mbarriers, so the only synchronisation in the steady state is __syncwarp().
@@ -123,12 +140,14 @@ GX_KERNEL_NAME(const __grid_constant__ GxLaunchArgs args) {
   const long long n_bulk = args.n_bulk_tiles;
   const long long stride = (long long)gridDim.x * kWarps;
 
+  pdl_launch_dependents();
   if (lane == 0) {
     mbar_init(&full_bar[0], 1);
     mbar_init(&full_bar[1], 1);
     fence_mbar_init();
   }
   __syncwarp();
+  pdl_wait();  // everything above overlaps the tail of the previous kernel on the stream
 
   auto issue_loads = [&](long long tile, int stage) {
     // the warp's elected lane programs the TMA engine: one contiguous chunk per input array
@@ -141,7 +160,7 @@ GX_KERNEL_NAME(const __grid_constant__ GxLaunchArgs args) {
   };
 
   long long tile = (long long)blockIdx.x * kWarps + warp;
-  if (lane == 0 && tile < n_bulk) issue_loads(tile, 0);
+  if (tile < n_bulk && elect_one()) issue_loads(tile, 0);
 
   for (int it = 0; tile < n_tiles; ++it, tile += stride) {
     const int stage = it & 1;
@@ -149,7 +168,7 @@ GX_KERNEL_NAME(const __grid_constant__ GxLaunchArgs args) {
     const bool bulk = tile < n_bulk;
     const long long next = tile + stride;
     // prefetch the next tile: its stage was last read one iteration ago, before the __syncwarp below
-    if (lane == 0 && next < n_bulk) issue_loads(next, stage ^ 1);
+    if (next < n_bulk && elect_one()) issue_loads(next, stage ^ 1);
 
     float* tile_s = out_stage + ostage * kOutStageFloats;
 #if GX_SPT == 1
@@ -203,7 +222,7 @@ GX_KERNEL_NAME(const __grid_constant__ GxLaunchArgs args) {
     if (bulk) {
       fence_async_smem();  // generic-proxy writes -> visible to the async proxy
       __syncwarp();
-      if (lane == 0) {
+      if (elect_one()) {
         bulk_s2g(args.jac + tile * (long long)(GX_WT * GX_TILE), tile_s, (uint32_t)(GX_WT * GX_TILE * 4));
 #if GX_HAS_PRIMAL
         if (args.primal != nullptr)
