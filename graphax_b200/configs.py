@@ -13,7 +13,7 @@ from typing import Callable, Dict, List, Sequence, Tuple, Union
 
 import numpy as np
 
-from .examples import Helmholtz, Hole, Lighthouse, RobotArm_6DOF, RoeFlux_1d, RoeFlux_3d, Simple, readme_f
+from .examples import ElementalZoo, Helmholtz, Hole, Lighthouse, RobotArm_6DOF, RoeFlux_1d, RoeFlux_3d, Simple, readme_f
 from .examples import orders as ref_orders
 from .plan import Plan, build_plan
 from .tracer import Jaxpr, make_jaxpr
@@ -107,6 +107,8 @@ EXTRA_WORKLOADS: Dict[str, Workload] = {
     "hole": Workload("hole", Hole, [()] * 4, [.3, .5, .7, .2], 0.01, 1 << 10, {"fwd": "fwd", "rev": "rev"}),
     "helmholtz": Workload("helmholtz", Helmholtz, [(4,)], [0.05, 0.15, 0.25, 0.35], 0.01, 1 << 10,
                           {"fwd": "fwd", "rev": "rev", "custom": [2, 5, 4, 3, 1]}),
+    "zoo": Workload("zoo", ElementalZoo, [(), (), (3,)], [0.4, 1.7, 0.3, 1.1, 2.2], 0.01, 1 << 10,
+                    {"fwd": "fwd", "rev": "rev"}),
 }
 
 

@@ -85,6 +85,12 @@ struct GxInterpArgs {
 
 namespace {
 
+__host__ __device__ __forceinline__ bool gx_is_binary(unsigned op) {
+  return op == GX_OP_ADD || op == GX_OP_SUB || op == GX_OP_MUL || op == GX_OP_DIV || op == GX_OP_FMA ||
+         op == GX_OP_ATAN2 || op == GX_OP_POW || op == GX_OP_MAX || op == GX_OP_MIN || op == GX_OP_GT ||
+         op == GX_OP_LT;
+}
+
 __device__ __forceinline__ float gx_apply(unsigned op, float a, float b, float c) {
   switch (op) {
     case GX_OP_ADD: return __fadd_rn(a, b);
@@ -114,6 +120,10 @@ __device__ __forceinline__ float gx_apply(unsigned op, float a, float b, float c
     case GX_OP_ERF: return erff(a);
     case GX_OP_POW: return powf(a, b);
     case GX_OP_LOGISTIC: return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-a)));
+    case GX_OP_MAX: return fmaxf(a, b);
+    case GX_OP_MIN: return fminf(a, b);
+    case GX_OP_GT: return a > b ? 1.0f : 0.0f;
+    case GX_OP_LT: return a < b ? 1.0f : 0.0f;
     default: return 0.0f;
   }
 }
@@ -180,10 +190,7 @@ __global__ void __launch_bounds__(T) gx_interp_kernel(const __grid_constant__ Gx
         my_out[tile_words + dst] = fetch(oa);
       } else {
         const float va = fetch(oa);
-        const float vb = (op == GX_OP_ADD || op == GX_OP_SUB || op == GX_OP_MUL || op == GX_OP_DIV ||
-                          op == GX_OP_FMA || op == GX_OP_ATAN2 || op == GX_OP_POW)
-                             ? fetch(ob)
-                             : 0.0f;
+        const float vb = gx_is_binary(op) ? fetch(ob) : 0.0f;
         const float vc = op == GX_OP_FMA ? fetch(oc) : 0.0f;
         s_slots[dst * T + tid] = gx_apply(op, va, vb, vc);
       }
@@ -445,8 +452,7 @@ int validate_blob(const void* blob, size_t nbytes, gx_plan* p) {
       return fail(GX_ERR_BAD_BLOB, "plan blob: invalid opcode in op stream");
     int rc = check_operand(o.a, i);
     if (rc) return rc;
-    const bool binary = o.op == GX_OP_ADD || o.op == GX_OP_SUB || o.op == GX_OP_MUL || o.op == GX_OP_DIV ||
-                        o.op == GX_OP_FMA || o.op == GX_OP_ATAN2 || o.op == GX_OP_POW;
+    const bool binary = gx_is_binary(o.op);
     if (binary && (rc = check_operand(o.b, i))) return rc;
     if (o.op == GX_OP_FMA && (rc = check_operand(o.c, i))) return rc;
     if (o.op == GX_OP_STORE_JAC) {

@@ -9,7 +9,8 @@
   X(SIN, sin) X(COS, cos) X(TAN, tan) X(ATAN2, atan2) X(EXP, exp) X(LOG, log) X(LOG1P, log1p) \
   X(TANH, tanh) X(SINH, sinh) X(COSH, cosh) X(ASIN, asin) X(ACOS, acos) X(ATAN, atan) \
   X(ASINH, asinh) X(ACOSH, acosh) X(ATANH, atanh) X(ERF, erf) X(POW, pow) X(LOGISTIC, logistic) \
-  X(STORE_JAC, store_jac) X(STORE_PRIMAL, store_primal)
+  X(STORE_JAC, store_jac) X(STORE_PRIMAL, store_primal) \
+  X(MAX, max) X(MIN, min) X(GT, gt) X(LT, lt)
 
 enum gx_opcode {
 #define GX_ENUM(NAME, name) GX_OP_##NAME,

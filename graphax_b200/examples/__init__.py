@@ -1,5 +1,6 @@
 from .roe_flux import RoeFlux_1d, RoeFlux_3d
 from .robot_arm import RobotArm_6DOF
 from .simple import readme_f, Simple, Lighthouse, Hole, Helmholtz
+from .zoo import ElementalZoo
 
-__all__ = ["RoeFlux_1d", "RoeFlux_3d", "RobotArm_6DOF", "readme_f", "Simple", "Lighthouse", "Hole", "Helmholtz"]
+__all__ = ["RoeFlux_1d", "RoeFlux_3d", "RobotArm_6DOF", "readme_f", "Simple", "Lighthouse", "Hole", "Helmholtz", "ElementalZoo"]

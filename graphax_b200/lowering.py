@@ -32,6 +32,7 @@ OPCODES = [
     "sin", "cos", "tan", "atan2", "exp", "log", "log1p", "tanh", "sinh", "cosh",
     "asin", "acos", "atan", "asinh", "acosh", "atanh", "erf", "pow", "logistic",
     "store_jac", "store_primal",
+    "max", "min", "gt", "lt",
 ]
 OP = {name: i for i, name in enumerate(OPCODES)}
 _UNARY = {"neg", "abs", "sqrt", "sin", "cos", "tan", "exp", "log", "log1p", "tanh", "sinh", "cosh",
@@ -279,6 +280,12 @@ def lower_eqn(dag: Dag, eqn: Eqn, read, division: str = "ieee") -> Tuple[Vec, Li
         return out, [(eqn.invars[i],) + _parallel_jacobian(ops[i], out, partials[i], len(ops)) for i in traced]
 
     # ---- elementwise binary (primitives.py:180-205, 237-239) ----------------
+    if prim in ("max", "min"):     # primitives.py:208-215: ties send the derivative to the second operand
+        x, y = ops
+        out = ew.binary(prim, x, y)
+        first = ew.binary("gt" if prim == "max" else "lt", x, y)          # 1.0 where x wins, else 0.0
+        second = ew.sub(ew.lit(1.0), first)
+        return edges(out, (first, second))
     if prim in ("add", "sub", "mul", "div", "atan2", "pow"):
         x, y = ops
         if prim == "div" and recip:

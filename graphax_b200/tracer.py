@@ -350,6 +350,10 @@ class _JnpShim:
     divide = staticmethod(_binary_fn("div"))
     arctan2 = staticmethod(_binary_fn("atan2"))
     power = staticmethod(_binary_fn("pow"))
+    maximum = staticmethod(_binary_fn("max"))
+    minimum = staticmethod(_binary_fn("min"))
+    erf = staticmethod(_unary("erf"))
+    sigmoid = staticmethod(_unary("logistic"))
 
     sum = staticmethod(_reduce_sum)
     dot = staticmethod(_dot)

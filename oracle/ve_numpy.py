@@ -455,6 +455,7 @@ _UNARY_RULES: Dict[str, Tuple[Callable, Callable]] = {
     "acosh": (np.arccosh, lambda out, x: 1. / np.sqrt(x * x - 1.)),
     "tanh": (np.tanh, lambda out, x: 1. - out * out),
     "atanh": (np.arctanh, lambda out, x: 1. / (1. - x * x)),
+    "erf": (None, lambda out, x: 2. * np.exp(-(x * x)) / np.sqrt(np.pi)),
 }
 
 
@@ -477,7 +478,7 @@ def _elemental(eqn, invals, dtype, batch: int):
 
     prim = eqn.primitive
     traced = [i for i, a in enumerate(eqn.invars) if isinstance(a, Var)]
-    if prim in ("add", "sub", "mul", "div", "atan2", "pow"):
+    if prim in ("add", "sub", "mul", "div", "atan2", "pow", "max", "min"):
         X, Y = invals
         nd = max(len(shp(X)), len(shp(Y)))
         x, y = bc(X, nd), bc(Y, nd)
@@ -494,6 +495,10 @@ def _elemental(eqn, invals, dtype, batch: int):
             out = np.arctan2(x, y)
             abs2 = x * x + y * y
             parts = (y / abs2, -x / abs2)
+        elif prim in ("max", "min"):       # primitives.py:208-215
+            first = (x > y) if prim == "max" else (x < y)
+            out = np.where(first, x, y) + 0 * (x + y)
+            parts = (np.where(first, 1., 0.) + 0 * (x + y), np.where(first, 0., 1.) + 0 * (x + y))
         else:
             out = np.power(x, y)
             parts = (y * np.power(x, y - 1.), np.log(x) * out)
@@ -530,6 +535,9 @@ def _elemental(eqn, invals, dtype, batch: int):
     if prim in _UNARY_RULES:
         (x,) = invals
         f, df = _UNARY_RULES[prim]
+        if f is None:
+            import math
+            f = np.vectorize(math.erf, otypes=[np.float64])
         out = f(x).astype(dtype)
         return out, [_make_parallel_jacobian(x, out, df(out, x).astype(dtype), 1, shp)]
     if prim == "reduce_sum":            # primitives.py:243-272

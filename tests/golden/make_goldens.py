@@ -28,7 +28,10 @@ def evaluate(jaxpr, args):
     for v, a in zip(jaxpr.invars, args):
         env[id(v)] = a
     un = {"neg": torch.neg, "abs": torch.abs, "sqrt": torch.sqrt, "sin": torch.sin, "cos": torch.cos,
-          "tan": torch.tan, "exp": torch.exp, "log": torch.log, "tanh": torch.tanh}
+          "tan": torch.tan, "exp": torch.exp, "log": torch.log, "tanh": torch.tanh, "log1p": torch.log1p,
+          "sinh": torch.sinh, "cosh": torch.cosh, "asin": torch.asin, "acos": torch.acos, "atan": torch.atan,
+          "asinh": torch.asinh, "acosh": torch.acosh, "atanh": torch.atanh, "erf": torch.erf,
+          "logistic": torch.sigmoid, "square": torch.square}
     # mixed rank-0 / rank-1 operands broadcast like lax does
     for e in jaxpr.eqns:
         x = [read(a) for a in e.invars]
@@ -38,6 +41,9 @@ def evaluate(jaxpr, args):
         elif p == "mul": r = x[0] * x[1]
         elif p == "div": r = x[0] / x[1]
         elif p == "atan2": r = torch.atan2(x[0], x[1])
+        elif p == "pow": r = torch.pow(x[0], x[1])
+        elif p == "max": r = torch.maximum(x[0], x[1])
+        elif p == "min": r = torch.minimum(x[0], x[1])
         elif p == "integer_pow": r = x[0] ** e.params["y"]
         elif p in un: r = un[p](x[0])
         elif p == "reduce_sum": r = x[0].sum()
@@ -52,7 +58,7 @@ def evaluate(jaxpr, args):
 
 def main():
     out = {}
-    for name in ("roe3d", "roe1d", "robotarm", "readme", "simple", "lighthouse", "hole", "helmholtz"):
+    for name in ("roe3d", "roe1d", "robotarm", "readme", "simple", "lighthouse", "hole", "helmholtz", "zoo"):
         w = get_workload(name)
         jaxpr = w.jaxpr()
         flat = torch.tensor(w.base, dtype=torch.float64)

@@ -29,7 +29,7 @@ def test_count_ops_known_answers_of_g():
 GOLD = json.loads((GOLDEN / "jacobians_fp64.json").read_text())
 
 
-@pytest.mark.parametrize("name", ["roe3d", "roe1d", "robotarm", "readme", "simple", "lighthouse", "hole", "helmholtz"])
+@pytest.mark.parametrize("name", ["roe3d", "roe1d", "robotarm", "readme", "simple", "lighthouse", "hole", "helmholtz", "zoo"])
 def test_oracle_fp64_equals_independent_autodiff(name):
     w = get_workload(name)
     xs, off = [], 0
