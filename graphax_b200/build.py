@@ -59,7 +59,7 @@ def build_library(verbose: bool = False, with_aot: bool = True) -> Path:
     OBJ.mkdir(parents=True, exist_ok=True)
     for old in OBJ.glob("*.o"):
         old.unlink()
-    sources = [CSRC / "gx_abi.cu"] + (generate_aot_sources() if with_aot else [])
+    sources = [CSRC / "gx_abi.cu", CSRC / "gx_gemm.cu"] + (generate_aot_sources() if with_aot else [])
     objs = [OBJ / (s.stem + ".o") for s in sources]
     extra = ["-Xptxas", "-v"] if verbose else []
     workers = max(1, min(len(sources), len(os.sched_getaffinity(0))))

@@ -902,3 +902,109 @@ int gx_jacve_host(gx_plan* p, int64_t batch, const void* const* in_ptrs, void* j
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// generic run-time compiled kernels (fused elementwise kernels of the dense / tensor-valued path)
+// ------------------------------------------------------------------------------------------------
+struct gx_jit_kernel {
+  CUmodule module = nullptr;
+  CUfunction func = nullptr;
+  int device = 0;
+};
+
+namespace {
+// out[c] (+)= sum_r in[r, c]; one CTA owns a 32-column strip of up to rows_per_cta rows
+__global__ void gx_colsum_f32_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols,
+                                     int rows_per_cta) {
+  __shared__ float part[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int r0 = blockIdx.y * rows_per_cta;
+  const int r1 = min(rows, r0 + rows_per_cta);
+  float acc = 0.0f;
+  if (c < cols)
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) acc += in[(size_t)r * cols + c];
+  part[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += part[i][threadIdx.x];
+    atomicAdd(out + c, s);
+  }
+}
+}  // namespace
+
+extern "C" {
+
+int gx_jit_compile(const char* src, const char* kernel_name, int device, gx_jit_kernel** out) {
+  if (!src || !kernel_name || !out) return fail(GX_ERR_BAD_ARG, "gx_jit_compile: NULL argument");
+  *out = nullptr;
+  Nvrtc& rt = nvrtc();
+  if (!rt.ok) return fail(GX_ERR_JIT, "NVRTC unavailable: " + rt.why);
+  GX_CUDA(cudaSetDevice(device));
+  GX_CUDA(cudaFree(0));
+  if (!driver().ok) return fail(GX_ERR_JIT, "CUDA driver entry points unavailable");
+  Nvrtc::Program prog = nullptr;
+  if (rt.CreateProgram(&prog, src, "gx_jit.cu", 0, nullptr, nullptr) != 0)
+    return fail(GX_ERR_JIT, "nvrtcCreateProgram failed");
+  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
+  if (rt.CompileProgram(prog, 3, opts) != 0) {
+    size_t n = 0;
+    rt.GetProgramLogSize(prog, &n);
+    std::string log(n, '\0');
+    if (n) rt.GetProgramLog(prog, &log[0]);
+    rt.DestroyProgram(&prog);
+    return fail(GX_ERR_JIT, "nvrtcCompileProgram failed:\n" + log);
+  }
+  size_t n = 0;
+  rt.GetCUBINSize(prog, &n);
+  std::vector<char> cubin(n);
+  rt.GetCUBIN(prog, cubin.data());
+  rt.DestroyProgram(&prog);
+  gx_jit_kernel* k = new gx_jit_kernel();
+  k->device = device;
+  CUresult r = driver().ModuleLoadData(&k->module, cubin.data());
+  if (r == CUDA_SUCCESS) r = driver().ModuleGetFunction(&k->func, k->module, kernel_name);
+  if (r != CUDA_SUCCESS) {
+    if (k->module) driver().ModuleUnload(k->module);
+    delete k;
+    return fail(GX_ERR_JIT, "loading the compiled kernel failed: " + cu_err(r));
+  }
+  *out = k;
+  return GX_OK;
+}
+
+void gx_jit_destroy(gx_jit_kernel* k) {
+  if (!k) return;
+  if (k->module && driver().ok) driver().ModuleUnload(k->module);
+  delete k;
+}
+
+// args[i] points at the value of the i-th kernel parameter (the cuLaunchKernel convention)
+int gx_jit_launch(gx_jit_kernel* k, unsigned grid_x, unsigned grid_y, unsigned block_x, void** args, void* stream) {
+  if (!k || !args) return fail(GX_ERR_BAD_ARG, "gx_jit_launch: NULL argument");
+  CUlaunchConfig cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDimX = grid_x;
+  cfg.gridDimY = grid_y ? grid_y : 1;
+  cfg.gridDimZ = 1;
+  cfg.blockDimX = block_x;
+  cfg.blockDimY = cfg.blockDimZ = 1;
+  cfg.hStream = (CUstream)stream;
+  CUresult r = driver().LaunchKernelEx(&cfg, k->func, args, nullptr);
+  if (r != CUDA_SUCCESS) return fail(GX_ERR_CUDA, "cuLaunchKernelEx(jit kernel): " + cu_err(r));
+  return GX_OK;
+}
+
+// out[cols] += column sums of in[rows, cols] (fp32). The caller zeroes `out` first.
+int gx_colsum_f32(const void* in, void* out, int rows, int cols, void* stream) {
+  if (!in || !out || rows <= 0 || cols <= 0) return fail(GX_ERR_BAD_ARG, "gx_colsum_f32: bad argument");
+  const int rows_per_cta = 256;
+  dim3 grid((cols + 31) / 32, (rows + rows_per_cta - 1) / rows_per_cta), block(32, 8);
+  gx_colsum_f32_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const float*>(in), static_cast<float*>(out), rows, cols, rows_per_cta);
+  GX_CUDA(cudaGetLastError());
+  return GX_OK;
+}
+
+}  // extern "C"

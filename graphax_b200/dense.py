@@ -1,0 +1,503 @@
+"""Tensor-valued vertices: reverse-order elimination with dense contractions on tcgen05 (scope row (f)1).
+
+For graphs whose vertices are matrices (config 5: an MLP over a batch, ``argnums`` = the weights) the
+per-sample engine does not apply: the Jacobian blocks are [H, I] weight gradients and the products
+``J[s,p] += J[s,v] . J[v,p]`` are real tensor contractions.  This module implements the part of that
+space the named config needs - a scalar output eliminated in reverse order - at tensor level:
+
+* every product has the dense cotangent edge ``() | vertex-shape`` on its left (reference: ``out_dims = ()``,
+  all primal dims dense);
+* times an elementwise (diagonal / Kronecker) edge it is a broadcast multiply
+  (``_pure_broadcast_mul``, ``sparse/tensor.py:826-866``) -> fused elementwise kernels, compiled per plan;
+* times a ``dot_general`` edge (Kronecker x operand, ``primitives.py:349-441``) it is the mixed product
+  (``_mixed_mul``, ``tensor.py:1062-1231``: contract the dense pair, carry the Kronecker pair) -> one GEMM
+  on the tensor cores (``csrc/gx_gemm.cu``), e.g. ``dW[H,I] = g[B,H]^T x[B,I]``;
+* times a broadcast (bias) edge it is a contraction over the broadcast axis -> column sum;
+* fill-in on an existing edge is ``_sparse_add`` of two dense edges -> fused into the elementwise kernels.
+
+Precision: matrix operands of the contractions are bf16, accumulation and all elementwise arithmetic fp32
+("bf16-in / fp32-accumulate" of BASELINE.json); results (weight Jacobians) are fp32.
+
+Anything else (other orders, vector outputs, rank > 2, batch dimensions) raises ``NotImplementedError``.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .codegen import _FMT
+from .tracer import Jaxpr, Literal, Var, make_jaxpr
+
+Shape2 = Tuple[int, int]
+
+
+def _norm(shape: Tuple[int, ...]) -> Shape2:
+    if len(shape) == 0:
+        return (1, 1)
+    if len(shape) == 1:
+        return (1, shape[0])
+    if len(shape) == 2:
+        return (shape[0], shape[1])
+    raise NotImplementedError("tensor-valued path handles vertices of rank <= 2")
+
+
+@dataclass
+class TNode:
+    kind: str                       # input | const | ew | gemm | colsum | sumall
+    shape: Shape2
+    op: str = ""                    # ew: scalar op name (lowering.OPCODES) or "copy"
+    args: Tuple[int, ...] = ()
+    value: float = 0.0              # const
+    input_index: int = -1
+    tx: bool = False                # gemm: out = op(X) . op(Y)^T with op(Z) = Z^T when the flag is set
+    ty: bool = False
+
+
+class TensorDag:
+    def __init__(self) -> None:
+        self.nodes: List[TNode] = []
+        self._memo: Dict[tuple, int] = {}
+
+    def _add(self, key: tuple, node: TNode) -> int:
+        if key in self._memo:
+            return self._memo[key]
+        self.nodes.append(node)
+        self._memo[key] = len(self.nodes) - 1
+        return len(self.nodes) - 1
+
+    def input(self, idx: int, shape: Shape2) -> int:
+        return self._add(("input", idx), TNode("input", shape, input_index=idx))
+
+    def const(self, v: float) -> int:
+        return self._add(("const", float(np.float32(v))), TNode("const", (1, 1), value=float(np.float32(v))))
+
+    def ew(self, op: str, *args: int, shape: Optional[Shape2] = None) -> int:
+        shapes = [self.nodes[a].shape for a in args]
+        if shape is None:
+            shape = (max(s[0] for s in shapes), max(s[1] for s in shapes))
+        for s in shapes:
+            if (s[0] not in (1, shape[0])) or (s[1] not in (1, shape[1])):
+                raise TypeError(f"incompatible shapes for elementwise {op}: {shapes}")
+        if op == "mul":      # exact identities, as in the per-sample engine
+            for i, j in ((0, 1), (1, 0)):
+                n = self.nodes[args[i]]
+                if n.kind == "const" and n.value == 1.0 and self.nodes[args[j]].shape == shape:
+                    return args[j]
+        return self._add(("ew", op, args, shape), TNode("ew", shape, op=op, args=tuple(args)))
+
+    def gemm(self, x: int, tx: bool, y: int, ty: bool) -> int:
+        xs, ys = self.nodes[x].shape, self.nodes[y].shape
+        m, k = (xs[1], xs[0]) if tx else xs
+        n, k2 = (ys[1], ys[0]) if ty else ys
+        if k != k2:
+            raise TypeError(f"gemm: contraction sizes differ: {xs} (t={tx}) vs {ys} (t={ty})")
+        return self._add(("gemm", x, tx, y, ty), TNode("gemm", (m, n), args=(x, y), tx=tx, ty=ty))
+
+    def colsum(self, x: int) -> int:
+        return self._add(("colsum", x), TNode("colsum", (1, self.nodes[x].shape[1]), args=(x,)))
+
+    def sumall(self, x: int) -> int:
+        return self._add(("sumall", x), TNode("sumall", (1, 1), args=(x,)))
+
+    def reduce_to(self, x: int, shape: Shape2) -> int:
+        """Contract a cotangent over the axes along which its operand was broadcast."""
+        s = self.nodes[x].shape
+        if s == shape:
+            return x
+        if shape == (1, s[1]):
+            return self.colsum(x)
+        if shape == (1, 1):
+            return self.sumall(x)
+        raise NotImplementedError(f"reduction of a {s} cotangent to operand shape {shape}")
+
+
+_UNARY_PARTIALS = {
+    # out, x -> partial   (reference primitives.py:150-175)
+    "neg": lambda d, out, x: d.const(-1.0),
+    "exp": lambda d, out, x: out,
+    "log": lambda d, out, x: d.ew("div", d.const(1.0), x),
+    "sqrt": lambda d, out, x: d.ew("div", d.const(0.5), out),
+    "tanh": lambda d, out, x: d.ew("sub", d.const(1.0), d.ew("mul", out, out)),
+    "logistic": lambda d, out, x: d.ew("mul", out, d.ew("sub", d.const(1.0), out)),
+    "sin": lambda d, out, x: d.ew("cos", x),
+    "cos": lambda d, out, x: d.ew("neg", d.ew("sin", x)),
+}
+
+
+@dataclass
+class DensePlan:
+    jaxpr: Jaxpr
+    dag: TensorDag
+    argnums: List[int]
+    grads: List[Optional[int]]            # per argnum: node holding the weight Jacobian (None = structurally zero)
+    primal: int
+    in_shapes: List[Shape2]
+    steps: List[dict] = field(default_factory=list)
+    stats: Dict[str, object] = field(default_factory=dict)
+
+
+def build_dense_plan(jaxpr: Jaxpr, order, argnums: Sequence[int]) -> DensePlan:
+    if order not in ("rev", "reverse"):
+        n = len(jaxpr.eqns)
+        if list(order) != list(range(n - 1, 0, -1)):
+            raise NotImplementedError("the tensor-valued path implements reverse-order elimination only")
+    if len(jaxpr.outvars) != 1 or _norm(jaxpr.outvars[0].shape) != (1, 1):
+        raise NotImplementedError("the tensor-valued path needs a single scalar output")
+    dag = TensorDag()
+    env: Dict[int, int] = {}
+    key = lambda v: -(v.input_index + 1) if v.input_index is not None else v.eqn_index + 1
+    in_shapes = [_norm(v.shape) for v in jaxpr.invars]
+    for i, v in enumerate(jaxpr.invars):
+        env[key(v)] = dag.input(i, in_shapes[i])
+
+    def read(a) -> int:
+        return dag.const(a.val) if isinstance(a, Literal) else env[key(a)]
+
+    # ---- forward: primal values (core.py:380-403) ------------------------------------------------
+    for eqn in jaxpr.eqns:
+        p, ins = eqn.primitive, [read(a) for a in eqn.invars]
+        shape = _norm(eqn.outvar.shape)
+        if p == "dot_general":
+            (ca, cb), _ = eqn.params["dimension_numbers"]
+            if len(ca) != 1 or eqn.invars[0].ndim != 2 or eqn.invars[1].ndim != 2:
+                raise NotImplementedError("dot_general: exactly one contracting dimension of two matrices")
+            out = dag.gemm(ins[0], ca[0] == 0, ins[1], cb[0] == 0)
+        elif p == "broadcast_in_dim":
+            if _norm(eqn.invars[0].shape) != shape:
+                raise NotImplementedError("broadcast_in_dim other than rank promotion (n,) -> (1, n)")
+            out = ins[0]
+        elif p == "reduce_sum":
+            axes = tuple(eqn.params["axes"])
+            nd = eqn.invars[0].ndim
+            if axes == tuple(range(nd)):
+                out = dag.sumall(ins[0])
+            elif nd == 2 and axes == (0,):
+                out = dag.colsum(ins[0])
+            else:
+                raise NotImplementedError(f"reduce_sum over axes {axes}")
+        elif p == "integer_pow":
+            y = int(eqn.params["y"])
+            if y != 2:
+                raise NotImplementedError("integer_pow with y != 2 on the tensor-valued path")
+            out = dag.ew("mul", ins[0], ins[0])
+        elif p in ("add", "sub", "mul", "div"):
+            out = dag.ew(p, ins[0], ins[1], shape=shape)
+        elif p in _UNARY_PARTIALS:
+            out = dag.ew(p, ins[0])
+        else:
+            raise NotImplementedError(f"{p} does not have registered elemental partial (tensor-valued path).")
+        if dag.nodes[out].shape != shape:
+            raise AssertionError(f"shape mismatch lowering {eqn!r}")
+        env[key(eqn.outvar)] = out
+
+    # ---- reverse elimination (core.py:155-272 with a dense cotangent as the post edge) -----------
+    cot: Dict[int, int] = {key(jaxpr.outvars[0]): dag.const(1.0)}
+    n_products = 0
+
+    def accumulate(v: Var, contrib: int) -> None:
+        k = key(v)
+        contrib = dag.reduce_to(contrib, _norm(v.shape))
+        cot[k] = dag.ew("add", contrib, cot[k]) if k in cot else contrib      # product + existing edge
+
+    for eqn in reversed(jaxpr.eqns):
+        g = cot.pop(key(eqn.outvar), None)
+        if g is None:
+            continue                                  # no path from this vertex to the output
+        p = eqn.primitive
+        ins = [read(a) for a in eqn.invars]
+        out = env[key(eqn.outvar)]
+        traced = [i for i, a in enumerate(eqn.invars) if isinstance(a, Var)]
+        oshape = _norm(eqn.outvar.shape)
+        gfull = g if dag.nodes[g].shape == oshape else dag.ew("copy", g, shape=oshape)
+        for i in traced:
+            a = eqn.invars[i]
+            n_products += 1
+            if p == "dot_general":
+                # out[M,N] = A[M,K] . B[N,K]^T with A = op_ta(a), B = op_tb(b); gemm(X,tx,Y,ty) = op(X) . op(Y)^T
+                (ca, cb), _ = eqn.params["dimension_numbers"]
+                ta, tb = ca[0] == 0, cb[0] == 0
+                if i == 0:      # dA = g . B, stored transposed when the operand was
+                    eff = dag.gemm(gfull, False, ins[1], not tb) if not ta else dag.gemm(ins[1], not tb, gfull, False)
+                else:           # dB = g^T . A  (the batch axis is the contraction: [B,H]^T [B,H'])
+                    eff = dag.gemm(gfull, True, ins[0], not ta) if not tb else dag.gemm(ins[0], not ta, gfull, True)
+                accumulate(a, eff)
+            elif p == "broadcast_in_dim":
+                accumulate(a, gfull)
+            elif p == "reduce_sum":
+                accumulate(a, dag.ew("copy", g, shape=_norm(a.shape)))
+            elif p == "integer_pow":
+                accumulate(a, dag.ew("mul", gfull, dag.ew("mul", dag.const(2.0), ins[0])))
+            elif p == "add":
+                accumulate(a, gfull)
+            elif p == "sub":
+                accumulate(a, gfull if i == 0 else dag.ew("neg", gfull))
+            elif p == "mul":
+                accumulate(a, dag.ew("mul", gfull, ins[1 - i]))
+            elif p == "div":
+                x, y = ins
+                part = dag.ew("div", dag.const(1.0), y) if i == 0 else \
+                    dag.ew("div", dag.ew("neg", x), dag.ew("mul", y, y))
+                accumulate(a, dag.ew("mul", gfull, part))
+            else:
+                accumulate(a, dag.ew("mul", gfull, _UNARY_PARTIALS[p](dag, out, ins[0])))
+
+    grads = [cot.get(key(jaxpr.invars[a])) for a in argnums]
+    plan = DensePlan(jaxpr, dag, list(argnums), grads, env[key(jaxpr.outvars[0])], in_shapes)
+    plan.stats = {"n_vertices": len(jaxpr.eqns), "n_products": n_products}
+    return plan
+
+
+# ------------------------------------------------------------------------------------------------
+# kernel partition + execution
+# ------------------------------------------------------------------------------------------------
+_EW_FMT = dict(_FMT)
+_EW_FMT["copy"] = "({0})"
+
+
+class DenseExecutor:
+    """Materialises the tensor DAG with the library's kernels: tcgen05 GEMMs, fused elementwise kernels
+    (NVRTC), column sums.  torch supplies device memory and the stream only."""
+
+    def __init__(self, plan: DensePlan, device: int = 0):
+        import torch
+        from . import runtime
+        self.plan, self.device, self.rt, self.torch = plan, device, runtime, torch
+        self.lib = runtime.load_library()
+        dag = plan.dag
+        roots = [g for g in plan.grads if g is not None] + [plan.primal]
+        self.consumers: Dict[int, List[int]] = {}
+        reach, stack = set(), list(roots)
+        while stack:
+            n = stack.pop()
+            if n in reach:
+                continue
+            reach.add(n)
+            for a in dag.nodes[n].args:
+                self.consumers.setdefault(a, []).append(n)
+                stack.append(a)
+        self.reach = reach
+        heavy = lambda n: dag.nodes[n].kind in ("gemm", "colsum", "sumall")
+        self.materialised = set()
+        for n in sorted(reach):
+            node = dag.nodes[n]
+            if node.kind in ("input", "gemm", "colsum", "sumall"):
+                self.materialised.add(n)
+            elif node.kind == "ew":
+                cons = self.consumers.get(n, [])
+                if n in roots or any(heavy(c) for c in cons) or len(cons) > 1:
+                    self.materialised.add(n)
+        self.needs_bf16 = {a for n in reach if dag.nodes[n].kind == "gemm" for a in dag.nodes[n].args}
+        self.kernels: Dict[int, object] = {}
+        self.order = [n for n in sorted(reach) if n in self.materialised and dag.nodes[n].kind != "input"]
+        self.buffers: Dict[Tuple[int, str], object] = {}
+        self.launches = 0
+        self._ew_meta: Dict[int, tuple] = {}
+        self.input_dtypes: Optional[List[str]] = None     # elementwise kernels are compiled once these are known
+
+    # ---- fused elementwise kernels -------------------------------------------------------------
+    def _leaves_and_expr(self, root: int):
+        dag = self.plan.dag
+        leaves: List[int] = []
+        lines: List[str] = []
+        names: Dict[int, str] = {}
+
+        def visit(n: int) -> str:
+            if n in names:
+                return names[n]
+            node = dag.nodes[n]
+            if node.kind == "const":
+                bits = int(np.array(node.value, dtype=np.float32).view(np.uint32))
+                names[n] = f"__int_as_float(0x{bits:08x})"
+                return names[n]
+            if n != root and n in self.materialised:
+                if n not in leaves:
+                    leaves.append(n)
+                names[n] = f"l{leaves.index(n)}"
+                return names[n]
+            args = [visit(a) for a in node.args]
+            names[n] = f"t{n}"
+            lines.append(f"    const float t{n} = {_EW_FMT[node.op].format(*args)};")
+            return names[n]
+        result = visit(root)
+        return leaves, lines, result
+
+    def _compile_ew(self, n: int) -> None:
+        dag = self.plan.dag
+        leaves, lines, result = self._leaves_and_expr(n)
+        rows, cols = dag.nodes[n].shape
+        params, loads = [], []
+        for i, leaf in enumerate(leaves):
+            lr, lc = dag.nodes[leaf].shape
+            dt = self._leaf_dtype(leaf)
+            params.append(f"const {'unsigned short' if dt == 'bf16' else 'float'}* __restrict__ p{i}")
+            idx = "0" if (lr, lc) == (1, 1) else ("c" if lr == 1 else ("r" if lc == 1 else "i"))
+            conv = f"gx_bf16_to_f32(p{i}[{idx}])" if dt == "bf16" else f"p{i}[{idx}]"
+            loads.append(f"    const float l{i} = {conv};")
+        want_bf16 = n in self.needs_bf16
+        src = "\n".join([
+            f"// fused elementwise kernel for tensor node {n}: [{rows} x {cols}] from {len(leaves)} operand(s)",
+            "__device__ __forceinline__ float gx_bf16_to_f32(unsigned short h) { return __uint_as_float((unsigned)h << 16); }",
+            "__device__ __forceinline__ unsigned short gx_f32_to_bf16(float f) {   // round to nearest even",
+            "  unsigned u = __float_as_uint(f);",
+            "  if ((u & 0x7fffffffu) > 0x7f800000u) return (unsigned short)((u >> 16) | 0x40u);",
+            "  return (unsigned short)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);",
+            "}",
+            "extern \"C\" __global__ void gx_ew(" + ", ".join(params + ["float* __restrict__ o32",
+                                                                     "unsigned short* __restrict__ o16",
+                                                                     "int rows", "int cols"]) + ") {",
+            "  const long long total = (long long)rows * cols;",
+            "  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {",
+            "    const int r = (int)(i / cols), c = (int)(i - (long long)r * cols); (void)r; (void)c;",
+            *loads, *lines,
+            f"    o32[i] = {result};",
+            f"    if (o16) o16[i] = gx_f32_to_bf16({result});",
+            "  }", "}"]) + "\n"
+        h = ctypes.c_void_p()
+        rc = self.lib.gx_jit_compile(src.encode(), b"gx_ew", self.device, ctypes.byref(h))
+        if rc != 0:
+            raise self.rt.GraphaxB200Error(f"gx_jit_compile failed ({rc}): {self.lib.gx_last_error().decode()}")
+        self.kernels[n] = h
+        self._ew_meta[n] = (leaves, want_bf16)
+
+    def _leaf_dtype(self, leaf: int) -> str:
+        node = self.plan.dag.nodes[leaf]
+        if node.kind == "input":
+            return self.input_dtypes[node.input_index]
+        return "f32"
+
+    # ---- execution -------------------------------------------------------------------------------
+    def _buf(self, n: int, kind: str):
+        key = (n, kind)
+        if key not in self.buffers:
+            r, c = self.plan.dag.nodes[n].shape
+            shape = (c, r) if kind == "bf16_t" else (r, c)
+            dt = self.torch.float32 if kind == "f32" else self.torch.bfloat16
+            self.buffers[key] = self.torch.empty(shape, dtype=dt, device=f"cuda:{self.device}")
+        return self.buffers[key]
+
+    def _bf16(self, n: int, transposed: bool):
+        """bf16 copy of node n with the requested axis contiguous (contraction axis last for the GEMM)."""
+        node = self.plan.dag.nodes[n]
+        if node.kind == "input":
+            base = self.inputs_bf16[node.input_index]
+        else:
+            base = self._buf(n, "bf16")
+        if not transposed:
+            return base
+        key = (n, "bf16_t")
+        if key not in self._fresh:
+            out = self._buf(n, "bf16_t")
+            self.rt.transpose_bf16(base, out=out)
+            self.launches += 1
+            self._fresh.add(key)
+        return self.buffers[key]
+
+    def run(self, inputs: Sequence) -> Tuple[List, object]:
+        torch, dag = self.torch, self.plan.dag
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._fresh = set()
+        self.inputs_f32, self.inputs_bf16 = {}, {}
+        dts = []
+        for i, t in enumerate(inputs):
+            t = t.reshape(self.plan.in_shapes[i]).contiguous()
+            dts.append("bf16" if t.dtype == torch.bfloat16 else "f32")
+            if t.dtype == torch.bfloat16:
+                self.inputs_bf16[i] = t
+            else:
+                self.inputs_f32[i] = t.float()
+        if self.input_dtypes != dts:
+            self.input_dtypes = dts                 # elementwise kernels read inputs in their own dtype
+            for n in list(self.kernels):
+                self.lib.gx_jit_destroy(self.kernels[n])
+            self.kernels.clear()
+            for n in self.order:
+                if dag.nodes[n].kind == "ew":
+                    self._compile_ew(n)
+        for i in range(len(inputs)):                # GEMM operands must be bf16
+            if i not in self.inputs_bf16 and any(dag.nodes[n].kind == "input" and dag.nodes[n].input_index == i
+                                                 for n in self.needs_bf16):
+                self.inputs_bf16[i] = self.inputs_f32[i].bfloat16()
+
+        def data(n: int):
+            node = dag.nodes[n]
+            if node.kind == "input":
+                return self.inputs_bf16[node.input_index] if self.input_dtypes[node.input_index] == "bf16" \
+                    else self.inputs_f32[node.input_index]
+            return self._buf(n, "f32")
+
+        for n in self.order:
+            node = dag.nodes[n]
+            if node.kind == "gemm":
+                x, y = node.args
+                a = self._bf16(x, node.tx)          # [M, K] with K contiguous
+                b = self._bf16(y, node.ty)          # [N, K] with K contiguous
+                m, k = a.shape
+                nn = b.shape[0]
+                tiles = (m // 128) * (nn // 128)
+                splits = 1
+                if tiles < 96:
+                    for s in (16, 8, 4, 2):
+                        if (k // 64) % s == 0 and tiles * s <= 160:
+                            splits = s
+                            break
+                out = self._buf(n, "f32")
+                self.rt.gemm_bf16_tn(a, b, out=out, k_splits=splits)
+                self.launches += 1 + (1 if splits > 1 else 0)
+                if n in self.needs_bf16:
+                    self._buf(n, "bf16").copy_(out)
+                    self.launches += 1
+            elif node.kind in ("colsum", "sumall"):
+                src = data(node.args[0])
+                out = self._buf(n, "f32")
+                out.zero_()
+                r, c = dag.nodes[node.args[0]].shape
+                if node.kind == "colsum":
+                    rcs = [self.lib.gx_colsum_f32(src.data_ptr(), out.data_ptr(), r, c, stream)]
+                elif (r * c) % 32 == 0:             # all elements: [r*c/32, 32] column sums, then fold the 32 partials
+                    part = self.buffers.setdefault((n, "part"), torch.empty(32, device=out.device))
+                    part.zero_()
+                    rcs = [self.lib.gx_colsum_f32(src.data_ptr(), part.data_ptr(), r * c // 32, 32, stream),
+                           self.lib.gx_colsum_f32(part.data_ptr(), out.data_ptr(), 32, 1, stream)]
+                else:
+                    rcs = [self.lib.gx_colsum_f32(src.data_ptr(), out.data_ptr(), r * c, 1, stream)]
+                self.launches += len(rcs)
+                if any(rcs):
+                    raise self.rt.GraphaxB200Error(self.lib.gx_last_error().decode())
+            else:
+                leaves, want_bf16 = self._ew_meta[n]
+                r, c = node.shape
+                out32 = self._buf(n, "f32")
+                out16 = self._buf(n, "bf16") if want_bf16 else None
+                vals = [ctypes.c_void_p(data(l).data_ptr()) for l in leaves]
+                vals += [ctypes.c_void_p(out32.data_ptr()), ctypes.c_void_p(out16.data_ptr() if out16 is not None else 0),
+                         ctypes.c_int(r), ctypes.c_int(c)]
+                argv = (ctypes.c_void_p * len(vals))(*[ctypes.cast(ctypes.pointer(v), ctypes.c_void_p) for v in vals])
+                grid = min((r * c + 255) // 256, 148 * 8)
+                rc = self.lib.gx_jit_launch(self.kernels[n], max(grid, 1), 1, 256, argv, stream)
+                if rc != 0:
+                    raise self.rt.GraphaxB200Error(self.lib.gx_last_error().decode())
+                self.launches += 1
+        grads = []
+        for a, g in zip(self.plan.argnums, self.plan.grads):
+            shape = self.plan.jaxpr.invars[a].shape
+            if g is None:
+                grads.append(torch.zeros(shape, device=f"cuda:{self.device}"))
+            else:
+                grads.append(data(g).float().reshape(shape))
+        return grads, data(self.plan.primal).reshape(())
+
+
+def dense_jacve(fun, order, argnums, *args, has_aux: bool = False, device: int = 0, _cache={}):
+    """``jacve`` for a scalar function of matrices (reverse order): returns the weight Jacobians as fp32
+    tensors of the arguments' shapes (tuple over ``argnums``; with ``has_aux`` also the function value)."""
+    shapes = tuple(tuple(a.shape) for a in args)
+    key = (fun, str(order), tuple(argnums), shapes, device)
+    if key not in _cache:
+        plan = build_dense_plan(make_jaxpr(fun, shapes), order, argnums)
+        _cache[key] = DenseExecutor(plan, device)
+    ex = _cache[key]
+    grads, primal = ex.run(args)
+    return (primal, tuple(grads)) if has_aux else tuple(grads)

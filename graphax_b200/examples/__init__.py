@@ -2,5 +2,6 @@ from .roe_flux import RoeFlux_1d, RoeFlux_3d
 from .robot_arm import RobotArm_6DOF
 from .simple import readme_f, Simple, Lighthouse, Hole, Helmholtz
 from .zoo import ElementalZoo
+from .mlp import MLP_loss
 
-__all__ = ["RoeFlux_1d", "RoeFlux_3d", "RobotArm_6DOF", "readme_f", "Simple", "Lighthouse", "Hole", "Helmholtz", "ElementalZoo"]
+__all__ = ["RoeFlux_1d", "RoeFlux_3d", "RobotArm_6DOF", "readme_f", "Simple", "Lighthouse", "Hole", "Helmholtz", "ElementalZoo", "MLP_loss"]

@@ -31,7 +31,8 @@ class GxInfo(ctypes.Structure):
 EXPORTS = ["gx_plan_create", "gx_plan_destroy", "gx_plan_info", "gx_plan_specialize", "gx_plan_specialize_opts",
            "gx_plan_select_kernel",
            "gx_jacve_launch", "gx_jacve_host", "gx_last_error", "gx_abi_version", "gx_aot_count", "gx_aot_key",
-           "gx_hash_bytes"]
+           "gx_hash_bytes", "gx_gemm_bf16_tn", "gx_transpose_bf16", "gx_gemm_last_error",
+           "gx_jit_compile", "gx_jit_destroy", "gx_jit_launch", "gx_colsum_f32"]
 
 _lib = None
 _lock = threading.Lock()
@@ -77,6 +78,19 @@ def load_library() -> ctypes.CDLL:
         lib.gx_aot_key.restype = ctypes.c_uint64
         lib.gx_hash_bytes.argtypes = [vp, sz]
         lib.gx_hash_bytes.restype = ctypes.c_uint64
+        lib.gx_gemm_bf16_tn.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.c_int, ctypes.c_int, vp]
+        lib.gx_gemm_bf16_tn.restype = ctypes.c_int
+        lib.gx_transpose_bf16.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp, vp]
+        lib.gx_transpose_bf16.restype = ctypes.c_int
+        lib.gx_gemm_last_error.restype = ctypes.c_char_p
+        lib.gx_jit_compile.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(vp)]
+        lib.gx_jit_compile.restype = ctypes.c_int
+        lib.gx_jit_destroy.argtypes = [vp]
+        lib.gx_jit_destroy.restype = None
+        lib.gx_jit_launch.argtypes = [vp, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint, ctypes.POINTER(vp), vp]
+        lib.gx_jit_launch.restype = ctypes.c_int
+        lib.gx_colsum_f32.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, vp]
+        lib.gx_colsum_f32.restype = ctypes.c_int
         _lib = lib
         return lib
 
@@ -151,3 +165,36 @@ class DevicePlan:
             self.close()
         except Exception:
             pass
+
+
+def gemm_bf16_tn(a, b, out=None, out_dtype=None, k_splits: int = 1):
+    """``a[M,K] @ b[N,K].T`` on the tcgen05 tensor cores (bf16 operands, fp32 accumulate); torch tensors in,
+    torch tensor out.  ``k_splits > 1`` splits the contraction axis over CTAs (fp32 output, atomics)."""
+    import torch
+    lib = load_library()
+    assert a.is_cuda and b.is_cuda and a.dtype == b.dtype == torch.bfloat16 and a.is_contiguous() and b.is_contiguous()
+    (m, k), (n, k2) = a.shape, b.shape
+    assert k == k2
+    out_dtype = out_dtype or (out.dtype if out is not None else torch.float32)
+    if out is None:
+        out = (torch.zeros if k_splits > 1 else torch.empty)((m, n), dtype=out_dtype, device=a.device)
+    elif k_splits > 1:
+        out.zero_()
+    rc = lib.gx_gemm_bf16_tn(m, n, k, a.data_ptr(), b.data_ptr(), out.data_ptr(), 1 if out.dtype == torch.bfloat16 else 0,
+                             k_splits, torch.cuda.current_stream().cuda_stream)
+    if rc != 0:
+        raise GraphaxB200Error(f"gx_gemm_bf16_tn failed ({rc}): {lib.gx_gemm_last_error().decode()}")
+    return out
+
+
+def transpose_bf16(x, out=None):
+    import torch
+    lib = load_library()
+    assert x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous() and x.ndim == 2
+    rows, cols = x.shape
+    if out is None:
+        out = torch.empty((cols, rows), dtype=torch.bfloat16, device=x.device)
+    rc = lib.gx_transpose_bf16(rows, cols, x.data_ptr(), out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    if rc != 0:
+        raise GraphaxB200Error(f"gx_transpose_bf16 failed ({rc}): {lib.gx_gemm_last_error().decode()}")
+    return out

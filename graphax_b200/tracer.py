@@ -205,6 +205,15 @@ class Tracer:
         a, b = _atom(self), _atom(other)
         if reflected:
             a, b = b, a
+        if a.shape and b.shape and len(a.shape) != len(b.shape):
+            # jnp rank promotion: the lower-rank operand gets leading size-1 axes through one
+            # broadcast_in_dim equation (lax.broadcast_to_rank), e.g. [B,H] + [H] -> [B,H] + [1,H]
+            lo, hi = (a, b) if len(a.shape) < len(b.shape) else (b, a)
+            diff = len(hi.shape) - len(lo.shape)
+            new_shape = (1,) * diff + tuple(lo.shape)
+            promoted = self.trace.emit("broadcast_in_dim", (lo,), new_shape, shape=new_shape,
+                                       broadcast_dimensions=tuple(range(diff, diff + len(lo.shape)))).var
+            a, b = (promoted, b) if lo is a else (a, promoted)
         shape = _bcast_shape(a.shape, b.shape)
         # jax.vmap pads the lower-rank traced operand of a mixed-rank binary op
         pads = 1 if (isinstance(a, Var) and isinstance(b, Var) and len(a.shape) != len(b.shape)) else 0
@@ -242,6 +251,17 @@ class Tracer:
             raise NotImplementedError("strided slices are not lowered")
         return self.trace.emit("slice", (self.var,), (max(stop - start, 0),),
                                start_indices=(start,), limit_indices=(stop,), strides=None)
+
+    @property
+    def T(self) -> "Tracer":
+        if self.ndim != 2:
+            raise NotImplementedError("only 2-D transposes are lowered")
+        return self.trace.emit("transpose", (self.var,), self.shape[::-1], permutation=(1, 0))
+
+    def __matmul__(self, other) -> "Tracer":
+        if not isinstance(other, Tracer) or self.ndim != 2 or other.ndim != 2:
+            raise NotImplementedError("only 2-D @ 2-D products are lowered")
+        return _dot_general(self, other, (((1,), (0,)), ((), ())))
 
     def sum(self, axis=None) -> "Tracer":
         return _reduce_sum(self, axis)
@@ -291,6 +311,26 @@ def _dot(a: Tracer, b: Tracer) -> Tracer:
         return a.trace.emit("dot_general", (a.var, b.var), (), dimension_numbers=dn,
                             pads=0)
     raise NotImplementedError("only 1-D . 1-D dot products are lowered")
+
+
+def _dot_general(a: Tracer, b: Tracer, dimension_numbers, precision=None, preferred_element_type=None) -> Tracer:
+    """``lax.dot_general`` without batch dimensions: out = free dims of a, then free dims of b."""
+    (ca, cb), (ba, bb) = dimension_numbers
+    if tuple(ba) or tuple(bb):
+        raise NotImplementedError("dot_general batch dimensions are not lowered")
+    ca, cb = tuple(int(c) for c in ca), tuple(int(c) for c in cb)
+    if [a.shape[i] for i in ca] != [b.shape[i] for i in cb]:
+        raise TypeError(f"dot_general: contracting dimensions differ: {a.shape} {ca} vs {b.shape} {cb}")
+    shape = tuple(s for i, s in enumerate(a.shape) if i not in ca) + tuple(s for i, s in enumerate(b.shape) if i not in cb)
+    return a.trace.emit("dot_general", (a.var, b.var), shape, dimension_numbers=((ca, cb), ((), ())))
+
+
+class _LaxShim:
+    """The slice of ``jax.lax`` the workloads touch."""
+    dot_general = staticmethod(_dot_general)
+
+
+lax = _LaxShim()
 
 
 def _square(x: Tracer) -> Tracer:

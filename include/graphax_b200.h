@@ -102,6 +102,28 @@ int gx_jacve_launch(gx_plan* plan, int64_t batch, const void* const* in_ptrs, vo
 int gx_jacve_host(gx_plan* plan, int64_t batch, const void* const* in_ptrs, void* jac_out,
                   void* primal_out, int pinned);
 
+/* ---- dense x dense contraction (scope row (f)1: tensor-valued vertices, config 5) -----------------
+ * Replaces: `lax.dot_general` inside `_pure_dot_product_mul` (sparse/tensor.py:1052-1057) when both edge
+ * Jacobians are genuinely dense matrices, e.g. the weight Jacobians of an MLP over a batch.
+ *   C[M,N] (+)= A[M,K] * B[N,K]^T,  A and B bf16 row-major (contraction axis contiguous), fp32 accumulate
+ * on the tcgen05 tensor cores.  C is fp32 (c_is_bf16 = 0) or bf16, row-major.  M, N multiples of 128,
+ * K a multiple of 64 * k_splits.  k_splits > 1 accumulates into a caller-zeroed fp32 C with atomics.
+ * gx_transpose_bf16 provides [rows, cols] -> [cols, rows] for operands stored the other way round.       */
+int gx_gemm_bf16_tn(int M, int N, int K, const void* A, const void* B, void* C, int c_is_bf16, int k_splits,
+                    void* stream);
+int gx_transpose_bf16(int rows, int cols, const void* in, void* out, void* stream);
+const char* gx_gemm_last_error(void);
+
+/* Fused elementwise kernels of the tensor-valued path are emitted per plan (graphax_b200/dense.py) and
+ * compiled at run time: the elementwise half of `_pure_broadcast_mul` / `_sparse_add` (sparse/tensor.py:
+ * 826-866, 1267-1411) and of the elemental partials (primitives.py:150-205) on [B, H] tensors.
+ * gx_colsum_f32 is the contraction of a dense cotangent with a broadcast (bias) edge: out[c] += sum_r in[r,c]. */
+typedef struct gx_jit_kernel gx_jit_kernel;
+int gx_jit_compile(const char* cuda_source, const char* kernel_name, int device, gx_jit_kernel** out);
+void gx_jit_destroy(gx_jit_kernel* kernel);
+int gx_jit_launch(gx_jit_kernel* kernel, unsigned grid_x, unsigned grid_y, unsigned block_x, void** args, void* stream);
+int gx_colsum_f32(const void* in, void* out, int rows, int cols, void* stream);
+
 const char* gx_last_error(void);
 int gx_abi_version(void);
 /* Number of plan-specialised kernels compiled into this library and the key of the i-th one. */

@@ -1,0 +1,90 @@
+"""Tensor-valued path (scope row (f)1): tcgen05 contraction kernel and reverse-order elimination of an MLP."""
+import numpy as np
+import pytest
+
+from graphax_b200.examples import MLP_loss
+from graphax_b200.tracer import make_jaxpr
+
+
+def _mlp_args(B, I, H, O, seed=0):
+    rng = np.random.default_rng(seed)
+    return [(rng.standard_normal(s) * sc).astype(np.float32) for s, sc in
+            [((B, I), 1.0), ((H, I), I ** -0.5), ((H,), 0.1), ((O, H), H ** -0.5), ((O,), 0.1), ((B, O), 1.0)]]
+
+
+def test_dense_oracle_matches_independent_autodiff():
+    """Pin the tensor-level oracle with torch.autograd in fp64 (the role jax.jacrev plays in the reference's
+    tests/examples/example_test.py:168-238)."""
+    import torch
+    from oracle import dense_numpy as dn
+    args = [a.astype(np.float64) for a in _mlp_args(64, 16, 32, 8)]
+    jaxpr = make_jaxpr(MLP_loss, [a.shape for a in args])
+    grads, loss = dn.jacve_rev(jaxpr, (1, 2, 3, 4), args)
+    t = [torch.tensor(a, requires_grad=True) for a in args]
+    d = torch.tanh(torch.tanh(t[0] @ t[1].T + t[2]) @ t[3].T + t[4]) - t[5]
+    L = .5 * (d ** 2).sum()
+    L.backward()
+    assert abs(float(loss) - float(L.detach())) < 1e-10
+    for g, ti in zip(grads, (t[1], t[2], t[3], t[4])):
+        assert np.abs(g - ti.grad.numpy()).max() < 1e-12
+
+
+def test_dense_plan_structure():
+    from graphax_b200.dense import build_dense_plan
+    jaxpr = make_jaxpr(MLP_loss, [(256, 128), (256, 128), (256,), (128, 256), (128,), (256, 128)])
+    assert [e.primitive for e in jaxpr.eqns] == ["dot_general", "broadcast_in_dim", "add", "tanh", "dot_general",
+                                                 "broadcast_in_dim", "add", "tanh", "sub", "integer_pow",
+                                                 "reduce_sum", "mul"]
+    plan = build_dense_plan(jaxpr, "rev", (1, 2, 3, 4))
+    kinds = [n.kind for n in plan.dag.nodes]
+    assert kinds.count("gemm") == 6 and kinds.count("colsum") == 2 and kinds.count("sumall") == 1
+    assert [plan.dag.nodes[g].shape for g in plan.grads] == [(256, 128), (1, 256), (128, 256), (1, 128)]
+    with pytest.raises(NotImplementedError):
+        build_dense_plan(jaxpr, "fwd", (1,))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("m,n,k,splits", [(128, 128, 64, 1), (256, 384, 1024, 1), (512, 256, 2048, 4),
+                                          (1024, 512, 4096, 8)])
+def test_tcgen05_gemm(built_library, m, n, k, splits):
+    """C = A B^T on the tensor cores vs an fp64 product of the same bf16-rounded operands."""
+    import torch
+    from graphax_b200 import runtime
+    torch.manual_seed(1)
+    a = (torch.randn(m, k) * 0.5).bfloat16()
+    b = (torch.randn(n, k) * 0.5).bfloat16()
+    ref = (a.double() @ b.double().T).numpy()
+    c = runtime.gemm_bf16_tn(a.cuda(), b.cuda(), k_splits=splits).cpu().numpy()
+    assert np.abs(c - ref).max() <= 2e-6 * k * 0.25 + 1e-5          # fp32 accumulation of k products of size ~0.25
+    if splits == 1:
+        cb = runtime.gemm_bf16_tn(a.cuda(), b.cuda(), out_dtype=torch.bfloat16).float().cpu().numpy()
+        assert np.abs(cb - ref).max() <= 2 ** -8 * np.abs(ref).max()
+    x = torch.randn(384, 640).bfloat16().cuda()
+    assert torch.equal(runtime.transpose_bf16(x), x.T.contiguous())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["bf16", "f32"])
+def test_mlp_weight_jacobians(built_library, dtype):
+    """jacve(MLP_loss, 'rev', argnums=(W1, b1, W2, b2)) on the GPU vs the oracle."""
+    import torch
+    from graphax_b200.dense import dense_jacve
+    from oracle import dense_numpy as dn
+    B, I, H, O = 512, 128, 256, 128
+    args = _mlp_args(B, I, H, O)
+    tens = [torch.from_numpy(a).cuda() for a in args]
+    if dtype == "bf16":
+        tens = [t.bfloat16() if t.ndim == 2 else t for t in tens]
+        args = [t.float().cpu().numpy() for t in tens]              # the oracle sees the same rounded inputs
+    jaxpr = make_jaxpr(MLP_loss, [a.shape for a in args])
+    loss, grads = dense_jacve(MLP_loss, "rev", (1, 2, 3, 4), *tens, has_aux=True)
+    torch.cuda.synchronize()
+    ref64, loss64 = dn.jacve_rev(jaxpr, (1, 2, 3, 4), [a.astype(np.float64) for a in args], np.float64)
+    emu, loss_emu = dn.jacve_rev(jaxpr, (1, 2, 3, 4), args, np.float32, bf16_operands=True)
+    assert abs(float(loss) - float(loss_emu)) <= 2e-3 * abs(float(loss_emu))
+    for g, e, r in zip(grads, emu, ref64):
+        g = g.cpu().numpy()
+        assert g.shape == r.shape
+        scale = np.abs(r).max()
+        assert np.abs(g - e).max() <= 2e-3 * scale       # same rounding points as the engine: tight
+        assert np.abs(g - r).max() <= 3e-2 * scale       # vs exact arithmetic: bf16 operand rounding
