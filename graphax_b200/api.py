@@ -131,8 +131,27 @@ class JacveFunction:
             shapes = [tuple(t.shape) for t in tensors]
         return tensors, shapes, batch, device
 
+    def _run_dense(self, args: Sequence[Any]):
+        """Matrix-valued arguments: tensor-level reverse elimination with tcgen05 contractions (dense.py)."""
+        import torch
+        from .dense import dense_jacve
+        if not torch.cuda.is_available():
+            raise RuntimeError("graphax_b200 needs a CUDA device: there is no CPU fallback for jacve")
+        if self.count_ops or self.sparse_representation:
+            raise NotImplementedError("count_ops / sparse_representation for tensor-valued vertices")
+        device = self.device if self.device is not None else torch.cuda.current_device()
+        tensors = [a if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a, dtype=np.float32)) for a in args]
+        tensors = [t.to(f"cuda:{device}") for t in tensors]
+        out = dense_jacve(self.fun, self.order, self.argnums, *tensors, has_aux=self.has_aux, device=device)
+        if self.has_aux:
+            primal, grads = out
+            return primal, (grads if len(self.argnums) > 1 else grads[0])
+        return out if len(self.argnums) > 1 else out[0]
+
     def _run(self, args: Sequence[Any], batched: bool):
         import torch
+        if not batched and any(getattr(a, "ndim", 0) >= 2 for a in args):
+            return self._run_dense(args)
         tensors, shapes, batch, device = self._prepare(args, batched)
         plan = self.lower(shapes)
         dp = self._device_plan(plan, device)

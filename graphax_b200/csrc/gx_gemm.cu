@@ -29,7 +29,7 @@
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 64, UMMA_K = 16;
-constexpr int kStages = 6;
+constexpr int kStages = 3;   // 96 KB of operand ring: two CTAs per SM, one's epilogue overlaps the other's main loop
 constexpr int kThreads = 192;
 constexpr int kTmemCols = 128;
 constexpr uint32_t kStageBytesA = BM * BK * 2, kStageBytesB = BN * BK * 2;
@@ -79,16 +79,23 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-// kind::f16: D fp32, A/B bf16, both K-major, M = 128, N = 128
-constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | ((BN >> 3) << 17) | ((BM >> 4) << 24);
+// MN-major operand (stored [K, MN] with the M/N axis contiguous), 128-byte swizzle: the tile is two boxes of
+// [64 K-rows x 64 MN-elements] (8 KB each); LBO = distance between the two 64-element MN atoms, SBO = distance
+// between groups of 8 K-rows (8 x 128 B)
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(8192 >> 4) << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16: D fp32, A/B bf16, M = 128, N = 128; bit 15 / 16 select MN-major A / B
+constexpr uint32_t kInstrDescBase = (1u << 4) | (1u << 7) | (1u << 10) | ((BN >> 3) << 17) | ((BM >> 4) << 24);
 
 struct GemmArgs {
   float* c_f32;
   __nv_bfloat16* c_bf16;
   int M, N, K, ldc, epilogue, k_per_split;
+  int a_mn, b_mn;   // operand stored [K, M] / [K, N] (MN-major) instead of [M, K] / [N, K]
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 gx_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const GemmArgs args) {
   extern __shared__ uint8_t gg_smem_raw[];
@@ -134,8 +141,19 @@ gx_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const int s = kb % kStages;
         mbar_wait(&empty_bar[s], ((kb / kStages) & 1) ^ 1);  // slot free (passes immediately the first round)
         mbar_expect_tx(&full_bar[s], kStageBytesA + kStageBytesB);
-        tma_load_2d(smem_a + s * kStageBytesA, &map_a, k_begin + kb * BK, m0, &full_bar[s]);
-        tma_load_2d(smem_b + s * kStageBytesB, &map_b, k_begin + kb * BK, n0, &full_bar[s]);
+        const int k0 = k_begin + kb * BK;
+        if (!args.a_mn) {
+          tma_load_2d(smem_a + s * kStageBytesA, &map_a, k0, m0, &full_bar[s]);
+        } else {   // two [64 k x 64 m] boxes
+          tma_load_2d(smem_a + s * kStageBytesA, &map_a, m0, k0, &full_bar[s]);
+          tma_load_2d(smem_a + s * kStageBytesA + 8192, &map_a, m0 + 64, k0, &full_bar[s]);
+        }
+        if (!args.b_mn) {
+          tma_load_2d(smem_b + s * kStageBytesB, &map_b, k0, n0, &full_bar[s]);
+        } else {
+          tma_load_2d(smem_b + s * kStageBytesB, &map_b, n0, k0, &full_bar[s]);
+          tma_load_2d(smem_b + s * kStageBytesB + 8192, &map_b, n0 + 64, k0, &full_bar[s]);
+        }
       }
     }
   } else if (warp == 1) {
@@ -145,13 +163,16 @@ gx_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       mbar_wait(&full_bar[s], (kb / kStages) & 1);
       tc_fence_after();
       if (elect_one()) {
-        const uint64_t da = make_smem_desc(smem_u32(smem_a + s * kStageBytesA));
-        const uint64_t db = make_smem_desc(smem_u32(smem_b + s * kStageBytesB));
+        const uint32_t sa = smem_u32(smem_a + s * kStageBytesA), sb = smem_u32(smem_b + s * kStageBytesB);
+        const uint64_t da = args.a_mn ? make_smem_desc_mn(sa) : make_smem_desc(sa);
+        const uint64_t db = args.b_mn ? make_smem_desc_mn(sb) : make_smem_desc(sb);
+        // one MMA consumes 16 K: K-major = 32 B inside the swizzle atom (+2 in the 16-byte address field),
+        // MN-major = 16 rows of 128 B (+128)
+        const uint32_t step_a = args.a_mn ? 128u : 2u, step_b = args.b_mn ? 128u : 2u;
+        const uint32_t idesc = kInstrDescBase | (args.a_mn ? (1u << 15) : 0u) | (args.b_mn ? (1u << 16) : 0u);
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the 16-byte address field
-          umma_f16(tmem_base, da + 2 * k, db + 2 * k, kInstrDesc, (kb | k) != 0 ? 1u : 0u);
-        }
+        for (int k = 0; k < BK / UMMA_K; ++k)
+          umma_f16(tmem_base, da + step_a * k, db + step_b * k, idesc, (kb | k) != 0 ? 1u : 0u);
         umma_commit(&empty_bar[s]);                       // smem slot reusable once these MMAs have read it
         if (kb == num_k_blocks - 1) umma_commit(tmem_full_bar);  // accumulator complete
       }
@@ -246,12 +267,13 @@ EncodeTiledFn encode_tiled() {
   return fn;
 }
 
+// row-major [rows, cols] bf16 matrix, box of box_rows x 64 elements (64 elements = one 128-byte swizzle row)
 int make_map(CUtensorMap* map, const void* ptr, int rows, int k, int box_rows) {
   EncodeTiledFn enc = encode_tiled();
   if (!enc) return -1;
   cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)k * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)64, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -269,6 +291,12 @@ const char* gx_gemm_last_error(void) { return g_gemm_error.c_str(); }
 // k_splits > 1 accumulates with fp32 atomics into C, which the caller must have zeroed (fp32 only).
 int gx_gemm_bf16_tn(int M, int N, int K, const void* A, const void* B, void* C, int c_is_bf16, int k_splits,
                     void* stream) {
+  return gx_gemm_bf16(M, N, K, A, 0, B, 0, C, c_is_bf16, k_splits, stream);
+}
+
+// General form: a_mn != 0 means A is stored [K, M] row-major (M contiguous), likewise b_mn for B = [K, N].
+int gx_gemm_bf16(int M, int N, int K, const void* A, int a_mn, const void* B, int b_mn, void* C, int c_is_bf16,
+                 int k_splits, void* stream) {
   if (M <= 0 || N <= 0 || K <= 0 || !A || !B || !C) {
     g_gemm_error = "gx_gemm_bf16_tn: bad argument";
     return GX_ERR_BAD_ARG;
@@ -278,7 +306,9 @@ int gx_gemm_bf16_tn(int M, int N, int K, const void* A, const void* B, void* C, 
     return GX_ERR_UNSUPPORTED;
   }
   CUtensorMap map_a, map_b;
-  if (make_map(&map_a, A, M, K, BM) || make_map(&map_b, B, N, K, BN)) {
+  const int ra = a_mn ? make_map(&map_a, A, K, M, BK) : make_map(&map_a, A, M, K, BM);
+  const int rb = b_mn ? make_map(&map_b, B, K, N, BK) : make_map(&map_b, B, N, K, BN);
+  if (ra || rb) {
     g_gemm_error = "gx_gemm_bf16_tn: cuTensorMapEncodeTiled failed (pointers must be 16-byte aligned)";
     return GX_ERR_CUDA;
   }
@@ -300,6 +330,8 @@ int gx_gemm_bf16_tn(int M, int N, int K, const void* A, const void* B, void* C, 
   args.ldc = N;
   args.epilogue = k_splits > 1 ? EPI_ATOMIC_F32 : (c_is_bf16 ? EPI_STORE_BF16 : EPI_STORE_F32);
   args.k_per_split = K / k_splits;
+  args.a_mn = a_mn ? 1 : 0;
+  args.b_mn = b_mn ? 1 : 0;
   dim3 grid(N / BN, M / BM, k_splits);
   gx_gemm_tn_kernel<<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(map_a, map_b, args);
   cudaError_t e = cudaGetLastError();

@@ -258,18 +258,25 @@ _EW_FMT["copy"] = "({0})"
 
 
 class DenseExecutor:
-    """Materialises the tensor DAG with the library's kernels: tcgen05 GEMMs, fused elementwise kernels
-    (NVRTC), column sums.  torch supplies device memory and the stream only."""
+    """Materialises the tensor DAG with the library's kernels: tcgen05 GEMMs and fused elementwise kernels
+    compiled per plan (NVRTC).  torch supplies device memory and the stream only.
 
-    def __init__(self, plan: DensePlan, device: int = 0):
+    Partition: contractions (GEMM) and full reductions are kernels of their own.  An elementwise value goes to
+    HBM only if a contraction reads it (bf16 copy), another kernel must read it (fp32 copy) or it is a result;
+    otherwise every consumer recomputes it from its materialised ancestors - a tanh is cheaper than a 16 MB
+    round trip.  The contraction of a cotangent with a broadcast (bias) edge, a column sum, is folded into the
+    kernel that produces the cotangent (per-thread partial sums + one atomicAdd per column)."""
+
+    def __init__(self, plan: DensePlan, device: int = 0, with_primal: bool = False):
         import torch
         from . import runtime
         self.plan, self.device, self.rt, self.torch = plan, device, runtime, torch
         self.lib = runtime.load_library()
+        self.with_primal = with_primal
         dag = plan.dag
-        roots = [g for g in plan.grads if g is not None] + [plan.primal]
+        self.roots = [g for g in plan.grads if g is not None] + ([plan.primal] if with_primal else [])
         self.consumers: Dict[int, List[int]] = {}
-        reach, stack = set(), list(roots)
+        reach, stack = set(), list(self.roots)
         while stack:
             n = stack.pop()
             if n in reach:
@@ -285,17 +292,31 @@ class DenseExecutor:
             node = dag.nodes[n]
             if node.kind in ("input", "gemm", "colsum", "sumall"):
                 self.materialised.add(n)
-            elif node.kind == "ew":
-                cons = self.consumers.get(n, [])
-                if n in roots or any(heavy(c) for c in cons) or len(cons) > 1:
-                    self.materialised.add(n)
+            elif node.kind == "ew" and (n in self.roots or any(heavy(c) for c in self.consumers.get(n, []))):
+                self.materialised.add(n)
+        # column sums of an elementwise value ride along in the kernel that computes it
+        self.fused_colsums: Dict[int, List[int]] = {}
+        for n in sorted(reach):
+            node = dag.nodes[n]
+            if node.kind == "colsum" and dag.nodes[node.args[0]].kind == "ew" and dag.nodes[node.args[0]].shape[1] % 4 == 0:
+                self.fused_colsums.setdefault(node.args[0], []).append(n)
+        fused = {c for cs in self.fused_colsums.values() for c in cs}
         self.needs_bf16 = {a for n in reach if dag.nodes[n].kind == "gemm" for a in dag.nodes[n].args}
+        self.order = [n for n in sorted(reach)
+                      if n in self.materialised and dag.nodes[n].kind != "input" and n not in fused]
         self.kernels: Dict[int, object] = {}
-        self.order = [n for n in sorted(reach) if n in self.materialised and dag.nodes[n].kind != "input"]
         self.buffers: Dict[Tuple[int, str], object] = {}
         self.launches = 0
         self._ew_meta: Dict[int, tuple] = {}
         self.input_dtypes: Optional[List[str]] = None     # elementwise kernels are compiled once these are known
+        # which fp32 copies does anybody read?
+        self.f32_read = set(self.roots)
+        for n in self.order:
+            node = dag.nodes[n]
+            if node.kind == "ew":
+                self.f32_read.update(self._leaves_and_expr(n)[0])
+            elif node.kind in ("colsum", "sumall"):
+                self.f32_read.add(node.args[0])
 
     # ---- fused elementwise kernels -------------------------------------------------------------
     def _leaves_and_expr(self, root: int):
@@ -315,28 +336,56 @@ class DenseExecutor:
             if n != root and n in self.materialised:
                 if n not in leaves:
                     leaves.append(n)
-                names[n] = f"l{leaves.index(n)}"
+                names[n] = f"l{leaves.index(n)}_@"
                 return names[n]
             args = [visit(a) for a in node.args]
-            names[n] = f"t{n}"
-            lines.append(f"    const float t{n} = {_EW_FMT[node.op].format(*args)};")
+            names[n] = f"t{n}_@"
+            lines.append(f"      const float t{n}_@ = {_EW_FMT[node.op].format(*args)};")
             return names[n]
         result = visit(root)
         return leaves, lines, result
 
+    def _leaf_dtype(self, leaf: int) -> str:
+        node = self.plan.dag.nodes[leaf]
+        return self.input_dtypes[node.input_index] if node.kind == "input" else "f32"
+
     def _compile_ew(self, n: int) -> None:
+        """One kernel per materialised elementwise node: every thread owns 4 consecutive columns (128-bit
+        loads/stores) and strides over rows; optional outputs: fp32 copy, bf16 copy, column sums."""
         dag = self.plan.dag
         leaves, lines, result = self._leaves_and_expr(n)
         rows, cols = dag.nodes[n].shape
+        vec = 4 if cols % 4 == 0 else 1
         params, loads = [], []
         for i, leaf in enumerate(leaves):
             lr, lc = dag.nodes[leaf].shape
-            dt = self._leaf_dtype(leaf)
-            params.append(f"const {'unsigned short' if dt == 'bf16' else 'float'}* __restrict__ p{i}")
-            idx = "0" if (lr, lc) == (1, 1) else ("c" if lr == 1 else ("r" if lc == 1 else "i"))
-            conv = f"gx_bf16_to_f32(p{i}[{idx}])" if dt == "bf16" else f"p{i}[{idx}]"
-            loads.append(f"    const float l{i} = {conv};")
-        want_bf16 = n in self.needs_bf16
+            bf = self._leaf_dtype(leaf) == "bf16"
+            params.append(f"const {'unsigned short' if bf else 'float'}* __restrict__ p{i}")
+            for j in range(vec):
+                idx = "0" if (lr, lc) == (1, 1) else (f"c + {j}" if lr == 1 else ("r" if lc == 1 else f"i + {j}"))
+                src = f"p{i}[{idx}]"
+                loads.append(f"      const float l{i}_{j} = {'gx_bf16_to_f32(' + src + ')' if bf else src};")
+        body: List[str] = []
+        for j in range(vec):
+            body += [ln.replace("_@", f"_{j}") for ln in lines]
+            body.append(f"      const float y{j} = {result.replace('_@', f'_{j}')};")
+        stores = []
+        if vec == 4:
+            stores.append("      if (o32) *reinterpret_cast<float4*>(o32 + i) = make_float4(y0, y1, y2, y3);")
+            stores.append("      if (o16) *reinterpret_cast<uint2*>(o16 + i) = make_uint2(gx_f32_to_bf16(y0) | ((unsigned)gx_f32_to_bf16(y1) << 16), "
+                          "gx_f32_to_bf16(y2) | ((unsigned)gx_f32_to_bf16(y3) << 16));")
+            stores.append("      s0 += y0; s1 += y1; s2 += y2; s3 += y3;")
+            tail = ["  if (csum) {   // fold the 8 row lanes of the CTA in shared memory: one atomic per column and CTA",
+                    "    part[ty][tx] = make_float4(s0, s1, s2, s3);",
+                    "    __syncthreads();",
+                    "    if (ty == 0 && c < cols) {",
+                    "      for (int k = 1; k < 8; ++k) { const float4 q = part[k][tx]; s0 += q.x; s1 += q.y; s2 += q.z; s3 += q.w; }",
+                    "      atomicAdd(csum + c, s0); atomicAdd(csum + c + 1, s1); atomicAdd(csum + c + 2, s2); atomicAdd(csum + c + 3, s3);",
+                    "    }",
+                    "  }"]
+        else:
+            stores += ["      if (o32) o32[i] = y0;", "      if (o16) o16[i] = gx_f32_to_bf16(y0);", "      s0 += y0;"]
+            tail = ["  if (csum && c < cols) atomicAdd(csum + c, s0);"]
         src = "\n".join([
             f"// fused elementwise kernel for tensor node {n}: [{rows} x {cols}] from {len(leaves)} operand(s)",
             "__device__ __forceinline__ float gx_bf16_to_f32(unsigned short h) { return __uint_as_float((unsigned)h << 16); }",
@@ -345,60 +394,42 @@ class DenseExecutor:
             "  if ((u & 0x7fffffffu) > 0x7f800000u) return (unsigned short)((u >> 16) | 0x40u);",
             "  return (unsigned short)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);",
             "}",
-            "extern \"C\" __global__ void gx_ew(" + ", ".join(params + ["float* __restrict__ o32",
-                                                                     "unsigned short* __restrict__ o16",
-                                                                     "int rows", "int cols"]) + ") {",
-            "  const long long total = (long long)rows * cols;",
-            "  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {",
-            "    const int r = (int)(i / cols), c = (int)(i - (long long)r * cols); (void)r; (void)c;",
-            *loads, *lines,
-            f"    o32[i] = {result};",
-            f"    if (o16) o16[i] = gx_f32_to_bf16({result});",
-            "  }", "}"]) + "\n"
+            "extern \"C\" __global__ void gx_ew(" + ", ".join(params + [
+                "float* __restrict__ o32", "unsigned short* __restrict__ o16", "float* __restrict__ csum",
+                "int rows", "int cols"]) + ") {",
+            "  __shared__ float4 part[8][32];",
+            "  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 column groups x 8 row lanes",
+            f"  const int c = (blockIdx.x * 32 + tx) * {vec};",
+            "  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f; (void)s1; (void)s2; (void)s3; (void)part;",
+            "  if (c < cols)",
+            "  for (int r = blockIdx.y * 8 + ty; r < rows; r += gridDim.y * 8) {",
+            "      const long long i = (long long)r * cols + c;",
+            *loads, *body, *stores,
+            "  }", *tail, "}"]) + "\n"
         h = ctypes.c_void_p()
         rc = self.lib.gx_jit_compile(src.encode(), b"gx_ew", self.device, ctypes.byref(h))
         if rc != 0:
             raise self.rt.GraphaxB200Error(f"gx_jit_compile failed ({rc}): {self.lib.gx_last_error().decode()}")
         self.kernels[n] = h
-        self._ew_meta[n] = (leaves, want_bf16)
-
-    def _leaf_dtype(self, leaf: int) -> str:
-        node = self.plan.dag.nodes[leaf]
-        if node.kind == "input":
-            return self.input_dtypes[node.input_index]
-        return "f32"
+        self._ew_meta[n] = (leaves, vec)
 
     # ---- execution -------------------------------------------------------------------------------
     def _buf(self, n: int, kind: str):
         key = (n, kind)
         if key not in self.buffers:
             r, c = self.plan.dag.nodes[n].shape
-            shape = (c, r) if kind == "bf16_t" else (r, c)
             dt = self.torch.float32 if kind == "f32" else self.torch.bfloat16
-            self.buffers[key] = self.torch.empty(shape, dtype=dt, device=f"cuda:{self.device}")
+            self.buffers[key] = self.torch.empty((r, c), dtype=dt, device=f"cuda:{self.device}")
         return self.buffers[key]
 
-    def _bf16(self, n: int, transposed: bool):
-        """bf16 copy of node n with the requested axis contiguous (contraction axis last for the GEMM)."""
+    def _bf16(self, n: int):
+        """bf16 copy of node n as stored ([rows, cols] row-major); the GEMM reads it K-major or MN-major."""
         node = self.plan.dag.nodes[n]
-        if node.kind == "input":
-            base = self.inputs_bf16[node.input_index]
-        else:
-            base = self._buf(n, "bf16")
-        if not transposed:
-            return base
-        key = (n, "bf16_t")
-        if key not in self._fresh:
-            out = self._buf(n, "bf16_t")
-            self.rt.transpose_bf16(base, out=out)
-            self.launches += 1
-            self._fresh.add(key)
-        return self.buffers[key]
+        return self.inputs_bf16[node.input_index] if node.kind == "input" else self._buf(n, "bf16")
 
     def run(self, inputs: Sequence) -> Tuple[List, object]:
         torch, dag = self.torch, self.plan.dag
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        self._fresh = set()
         self.inputs_f32, self.inputs_bf16 = {}, {}
         dts = []
         for i, t in enumerate(inputs):
@@ -432,10 +463,9 @@ class DenseExecutor:
             node = dag.nodes[n]
             if node.kind == "gemm":
                 x, y = node.args
-                a = self._bf16(x, node.tx)          # [M, K] with K contiguous
-                b = self._bf16(y, node.ty)          # [N, K] with K contiguous
-                m, k = a.shape
-                nn = b.shape[0]
+                a, b = self._bf16(x), self._bf16(y)  # op(X) = X^T is read in place as an MN-major operand
+                m, k = a.shape[::-1] if node.tx else a.shape
+                nn = b.shape[1] if node.ty else b.shape[0]
                 tiles = (m // 128) * (nn // 128)
                 splits = 1
                 if tiles < 96:
@@ -444,7 +474,7 @@ class DenseExecutor:
                             splits = s
                             break
                 out = self._buf(n, "f32")
-                self.rt.gemm_bf16_tn(a, b, out=out, k_splits=splits)
+                self.rt.gemm_bf16_tn(a, b, out=out, k_splits=splits, a_mn=node.tx, b_mn=node.ty)
                 self.launches += 1 + (1 if splits > 1 else 0)
                 if n in self.needs_bf16:
                     self._buf(n, "bf16").copy_(out)
@@ -463,23 +493,31 @@ class DenseExecutor:
                            self.lib.gx_colsum_f32(part.data_ptr(), out.data_ptr(), 32, 1, stream)]
                 else:
                     rcs = [self.lib.gx_colsum_f32(src.data_ptr(), out.data_ptr(), r * c, 1, stream)]
-                self.launches += len(rcs)
+                self.launches += len(rcs) + 1
                 if any(rcs):
                     raise self.rt.GraphaxB200Error(self.lib.gx_last_error().decode())
             else:
-                leaves, want_bf16 = self._ew_meta[n]
+                leaves, vec = self._ew_meta[n]
                 r, c = node.shape
-                out32 = self._buf(n, "f32")
-                out16 = self._buf(n, "bf16") if want_bf16 else None
+                o32 = self._buf(n, "f32").data_ptr() if n in self.f32_read else 0
+                o16 = self._buf(n, "bf16").data_ptr() if n in self.needs_bf16 else 0
+                csum = 0
+                if n in self.fused_colsums:
+                    cbuf = self._buf(self.fused_colsums[n][0], "f32")
+                    cbuf.zero_()
+                    self.launches += 1
+                    csum = cbuf.data_ptr()
                 vals = [ctypes.c_void_p(data(l).data_ptr()) for l in leaves]
-                vals += [ctypes.c_void_p(out32.data_ptr()), ctypes.c_void_p(out16.data_ptr() if out16 is not None else 0),
-                         ctypes.c_int(r), ctypes.c_int(c)]
+                vals += [ctypes.c_void_p(o32), ctypes.c_void_p(o16), ctypes.c_void_p(csum), ctypes.c_int(r), ctypes.c_int(c)]
                 argv = (ctypes.c_void_p * len(vals))(*[ctypes.cast(ctypes.pointer(v), ctypes.c_void_p) for v in vals])
-                grid = min((r * c + 255) // 256, 148 * 8)
-                rc = self.lib.gx_jit_launch(self.kernels[n], max(grid, 1), 1, 256, argv, stream)
+                gx = (c // vec + 31) // 32
+                gy = max(1, min((r + 7) // 8, (148 * 6) // gx))
+                rc = self.lib.gx_jit_launch(self.kernels[n], gx, gy, 256, argv, stream)
                 if rc != 0:
                     raise self.rt.GraphaxB200Error(self.lib.gx_last_error().decode())
                 self.launches += 1
+                for extra in self.fused_colsums.get(n, [])[1:]:       # same sums requested twice: copy
+                    self._buf(extra, "f32").copy_(self._buf(self.fused_colsums[n][0], "f32"))
         grads = []
         for a, g in zip(self.plan.argnums, self.plan.grads):
             shape = self.plan.jaxpr.invars[a].shape
@@ -487,17 +525,17 @@ class DenseExecutor:
                 grads.append(torch.zeros(shape, device=f"cuda:{self.device}"))
             else:
                 grads.append(data(g).float().reshape(shape))
-        return grads, data(self.plan.primal).reshape(())
+        return grads, (data(self.plan.primal).reshape(()) if self.with_primal else None)
 
 
 def dense_jacve(fun, order, argnums, *args, has_aux: bool = False, device: int = 0, _cache={}):
     """``jacve`` for a scalar function of matrices (reverse order): returns the weight Jacobians as fp32
     tensors of the arguments' shapes (tuple over ``argnums``; with ``has_aux`` also the function value)."""
     shapes = tuple(tuple(a.shape) for a in args)
-    key = (fun, str(order), tuple(argnums), shapes, device)
+    key = (fun, str(order), tuple(argnums), shapes, device, has_aux)
     if key not in _cache:
         plan = build_dense_plan(make_jaxpr(fun, shapes), order, argnums)
-        _cache[key] = DenseExecutor(plan, device)
+        _cache[key] = DenseExecutor(plan, device, with_primal=has_aux)
     ex = _cache[key]
     grads, primal = ex.run(args)
     return (primal, tuple(grads)) if has_aux else tuple(grads)

@@ -31,7 +31,7 @@ class GxInfo(ctypes.Structure):
 EXPORTS = ["gx_plan_create", "gx_plan_destroy", "gx_plan_info", "gx_plan_specialize", "gx_plan_specialize_opts",
            "gx_plan_select_kernel",
            "gx_jacve_launch", "gx_jacve_host", "gx_last_error", "gx_abi_version", "gx_aot_count", "gx_aot_key",
-           "gx_hash_bytes", "gx_gemm_bf16_tn", "gx_transpose_bf16", "gx_gemm_last_error",
+           "gx_hash_bytes", "gx_gemm_bf16_tn", "gx_gemm_bf16", "gx_transpose_bf16", "gx_gemm_last_error",
            "gx_jit_compile", "gx_jit_destroy", "gx_jit_launch", "gx_colsum_f32"]
 
 _lib = None
@@ -80,6 +80,9 @@ def load_library() -> ctypes.CDLL:
         lib.gx_hash_bytes.restype = ctypes.c_uint64
         lib.gx_gemm_bf16_tn.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, ctypes.c_int, ctypes.c_int, vp]
         lib.gx_gemm_bf16_tn.restype = ctypes.c_int
+        lib.gx_gemm_bf16.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, vp, ctypes.c_int, vp,
+                                     ctypes.c_int, ctypes.c_int, vp]
+        lib.gx_gemm_bf16.restype = ctypes.c_int
         lib.gx_transpose_bf16.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp, vp]
         lib.gx_transpose_bf16.restype = ctypes.c_int
         lib.gx_gemm_last_error.restype = ctypes.c_char_p
@@ -167,21 +170,22 @@ class DevicePlan:
             pass
 
 
-def gemm_bf16_tn(a, b, out=None, out_dtype=None, k_splits: int = 1):
-    """``a[M,K] @ b[N,K].T`` on the tcgen05 tensor cores (bf16 operands, fp32 accumulate); torch tensors in,
-    torch tensor out.  ``k_splits > 1`` splits the contraction axis over CTAs (fp32 output, atomics)."""
+def gemm_bf16_tn(a, b, out=None, out_dtype=None, k_splits: int = 1, a_mn: bool = False, b_mn: bool = False):
+    """``A @ B.T`` on the tcgen05 tensor cores (bf16 operands, fp32 accumulate); torch tensors in, torch tensor
+    out.  ``a`` is A[M,K] (or, with ``a_mn``, A stored as [K,M]); ``b`` is B[N,K] (with ``b_mn`` stored [K,N]).
+    ``k_splits > 1`` splits the contraction axis over CTAs (fp32 output, atomics)."""
     import torch
     lib = load_library()
     assert a.is_cuda and b.is_cuda and a.dtype == b.dtype == torch.bfloat16 and a.is_contiguous() and b.is_contiguous()
-    (m, k), (n, k2) = a.shape, b.shape
+    (m, k), (n, k2) = (a.shape[::-1] if a_mn else a.shape), (b.shape[::-1] if b_mn else b.shape)
     assert k == k2
     out_dtype = out_dtype or (out.dtype if out is not None else torch.float32)
     if out is None:
         out = (torch.zeros if k_splits > 1 else torch.empty)((m, n), dtype=out_dtype, device=a.device)
     elif k_splits > 1:
         out.zero_()
-    rc = lib.gx_gemm_bf16_tn(m, n, k, a.data_ptr(), b.data_ptr(), out.data_ptr(), 1 if out.dtype == torch.bfloat16 else 0,
-                             k_splits, torch.cuda.current_stream().cuda_stream)
+    rc = lib.gx_gemm_bf16(m, n, k, a.data_ptr(), 1 if a_mn else 0, b.data_ptr(), 1 if b_mn else 0, out.data_ptr(),
+                          1 if out.dtype == torch.bfloat16 else 0, k_splits, torch.cuda.current_stream().cuda_stream)
     if rc != 0:
         raise GraphaxB200Error(f"gx_gemm_bf16_tn failed ({rc}): {lib.gx_gemm_last_error().decode()}")
     return out

@@ -111,6 +111,10 @@ int gx_jacve_host(gx_plan* plan, int64_t batch, const void* const* in_ptrs, void
  * gx_transpose_bf16 provides [rows, cols] -> [cols, rows] for operands stored the other way round.       */
 int gx_gemm_bf16_tn(int M, int N, int K, const void* A, const void* B, void* C, int c_is_bf16, int k_splits,
                     void* stream);
+/* General operand layouts: a_mn != 0 means A is stored [K, M] row-major (the M axis contiguous, "MN-major"),
+ * likewise b_mn for B stored [K, N]; no transposed copies are needed for g^T x style contractions. */
+int gx_gemm_bf16(int M, int N, int K, const void* A, int a_mn, const void* B, int b_mn, void* C, int c_is_bf16,
+                 int k_splits, void* stream);
 int gx_transpose_bf16(int rows, int cols, const void* in, void* out, void* stream);
 const char* gx_gemm_last_error(void);
 

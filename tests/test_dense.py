@@ -88,3 +88,23 @@ def test_mlp_weight_jacobians(built_library, dtype):
         scale = np.abs(r).max()
         assert np.abs(g - e).max() <= 2e-3 * scale       # same rounding points as the engine: tight
         assert np.abs(g - r).max() <= 3e-2 * scale       # vs exact arithmetic: bf16 operand rounding
+
+
+@pytest.mark.gpu
+def test_jacve_api_dispatches_matrix_arguments(built_library):
+    """graphax_b200.jacve(f, 'rev', argnums)(x, W1, b1, W2, b2, y): matrix arguments take the tensor-valued path
+    and come back like jax.jacrev would return them - one array per argnum, shaped like the argument."""
+    import torch
+    import graphax_b200 as gx
+    args = _mlp_args(256, 128, 128, 128, seed=3)
+    tens = [torch.from_numpy(a).cuda() for a in args]
+    loss, grads = gx.jacve(MLP_loss, order="rev", argnums=(1, 2, 3, 4), has_aux=True)(*tens)
+    t = [torch.tensor(a, dtype=torch.float64, requires_grad=True) for a in args]
+    L = .5 * ((torch.tanh(torch.tanh(t[0] @ t[1].T + t[2]) @ t[3].T + t[4]) - t[5]) ** 2).sum()
+    L.backward()
+    assert [tuple(g.shape) for g in grads] == [(128, 128), (128,), (128, 128), (128,)]
+    assert abs(float(loss) - float(L)) <= 5e-3 * abs(float(L))
+    for g, ti in zip(grads, (t[1], t[2], t[3], t[4])):
+        assert float((g.double().cpu() - ti.grad).abs().max()) <= 3e-2 * float(ti.grad.abs().max())
+    with pytest.raises(NotImplementedError):
+        gx.jacve(MLP_loss, order="fwd", argnums=(1,))(*tens)

@@ -34,6 +34,16 @@ for (m, n, k, splits) in shapes:
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) / 50 * 1e3
         print(f"    {name}: {us:.1f} us  {2 * m * n * k / us / 1e6:.1f} TFLOP/s")
+for (m, n, k) in [(128, 128, 64), (256, 128, 256), (512, 1024, 4096), (4096, 1024, 512)]:
+    at = (torch.randn(k, m, device="cuda") * 0.5).bfloat16()      # A stored [K, M]
+    bt = (torch.randn(k, n, device="cuda") * 0.5).bfloat16()      # B stored [K, N]
+    a, b = at.t().contiguous(), bt.t().contiguous()
+    ref = a.float() @ b.float().t()
+    for amn, bmn in ((True, False), (False, True), (True, True)):
+        c = rt.gemm_bf16_tn(at if amn else a, bt if bmn else b, a_mn=amn, b_mn=bmn)
+        torch.cuda.synchronize()
+        err = (c - ref).abs().max().item()
+        print(f"MN-major A={amn} B={bmn} M{m} N{n} K{k}: max err {err:.3e}", "ok" if err < 1e-3 * k ** 0.5 else "FAIL", flush=True)
 x = torch.randn(4096, 1024, device="cuda").bfloat16()
 assert torch.equal(rt.transpose_bf16(x), x.t().contiguous())
 print("gemm_check done")
