@@ -150,8 +150,8 @@ class JacveFunction:
 
     def _run(self, args: Sequence[Any], batched: bool):
         import torch
-        if not batched and any(getattr(a, "ndim", 0) >= 2 for a in args):
-            return self._run_dense(args)
+        if not batched and any(getattr(a, "ndim", 0) >= 2 and int(np.prod(a.shape)) >= 4096 for a in args):
+            return self._run_dense(args)        # big matrices: tensor-level path; small ones are scalarised per sample
         tensors, shapes, batch, device = self._prepare(args, batched)
         plan = self.lower(shapes)
         dp = self._device_plan(plan, device)
@@ -188,6 +188,9 @@ class JacveFunction:
         single = len(out_shapes) == 1 and len(jaxpr.invars) > 1
         grads_tree = grads[0] if single else tuple(grads)
         if self.count_ops:
+            if plan.stats["num_muls"] is None:
+                raise NotImplementedError("count_ops needs tensor-level edge structure, which is only tracked for "
+                                          "vertices of rank <= 1 and slice / concatenate shape ops")
             aux = {"num_muls": plan.stats["num_muls"], "num_adds": plan.stats["num_adds"],
                    "order_counts": list(plan.stats["order_counts"])}
             return grads_tree, aux

@@ -88,7 +88,7 @@ namespace {
 __host__ __device__ __forceinline__ bool gx_is_binary(unsigned op) {
   return op == GX_OP_ADD || op == GX_OP_SUB || op == GX_OP_MUL || op == GX_OP_DIV || op == GX_OP_FMA ||
          op == GX_OP_ATAN2 || op == GX_OP_POW || op == GX_OP_MAX || op == GX_OP_MIN || op == GX_OP_GT ||
-         op == GX_OP_LT;
+         op == GX_OP_LT || op == GX_OP_EQ;
 }
 
 __device__ __forceinline__ float gx_apply(unsigned op, float a, float b, float c) {
@@ -124,6 +124,7 @@ __device__ __forceinline__ float gx_apply(unsigned op, float a, float b, float c
     case GX_OP_MIN: return fminf(a, b);
     case GX_OP_GT: return a > b ? 1.0f : 0.0f;
     case GX_OP_LT: return a < b ? 1.0f : 0.0f;
+    case GX_OP_EQ: return a == b ? 1.0f : 0.0f;
     default: return 0.0f;
   }
 }

@@ -10,7 +10,7 @@
   X(TANH, tanh) X(SINH, sinh) X(COSH, cosh) X(ASIN, asin) X(ACOS, acos) X(ATAN, atan) \
   X(ASINH, asinh) X(ACOSH, acosh) X(ATANH, atanh) X(ERF, erf) X(POW, pow) X(LOGISTIC, logistic) \
   X(STORE_JAC, store_jac) X(STORE_PRIMAL, store_primal) \
-  X(MAX, max) X(MIN, min) X(GT, gt) X(LT, lt)
+  X(MAX, max) X(MIN, min) X(GT, gt) X(LT, lt) X(EQ, eq)
 
 enum gx_opcode {
 #define GX_ENUM(NAME, name) GX_OP_##NAME,

@@ -161,8 +161,8 @@ def build_dense_plan(jaxpr: Jaxpr, order, argnums: Sequence[int]) -> DensePlan:
         p, ins = eqn.primitive, [read(a) for a in eqn.invars]
         shape = _norm(eqn.outvar.shape)
         if p == "dot_general":
-            (ca, cb), _ = eqn.params["dimension_numbers"]
-            if len(ca) != 1 or eqn.invars[0].ndim != 2 or eqn.invars[1].ndim != 2:
+            (ca, cb), (ba, _bb) = eqn.params["dimension_numbers"]
+            if len(ca) != 1 or ba or eqn.invars[0].ndim != 2 or eqn.invars[1].ndim != 2:
                 raise NotImplementedError("dot_general: exactly one contracting dimension of two matrices")
             out = dag.gemm(ins[0], ca[0] == 0, ins[1], cb[0] == 0)
         elif p == "broadcast_in_dim":

@@ -36,8 +36,9 @@ Order = Union[str, Sequence[int]]
 
 @dataclass
 class Edge:
-    struct: st.Struct
-    entries: Entries          # (i, j) -> DAG node; i over dst components, j over src components
+    struct: Optional[st.Struct]   # tensor-level descriptor; None when a vertex of rank > 1 or a shape op other than
+                                  # slice / concatenate is involved (values stay exact, count_ops is unavailable)
+    entries: Entries              # (i, j) -> DAG node; i over dst components, j over src components
 
 
 @dataclass
@@ -48,7 +49,7 @@ class Graph:
     fwd: Dict[int, Dict[int, Edge]]                      # graph[src][dst]
     bwd: Dict[int, Dict[int, Edge]]                      # transpose_graph[dst][src]
     vo_vertices: Set[int]                                # outputs that are consumed later (core.py:387-390)
-    elemental: List[Tuple[int, int, st.Struct]] = field(default_factory=list)
+    elemental: List[Tuple[int, int, Optional[st.Struct]]] = field(default_factory=list)
     first_elim_node: int = 0
 
     @staticmethod
@@ -98,7 +99,8 @@ def build_graph(jaxpr: Jaxpr, division: str = "ieee") -> Graph:
                 merged = dict(old.entries)
                 for ij, n in entries.items():
                     merged[ij] = dag.add(n, merged[ij]) if ij in merged else n
-                edge = Edge(st.add(struct, old.struct), merged)
+                both = struct is not None and old.struct is not None
+                edge = Edge(st.add(struct, old.struct) if both else None, merged)
             else:
                 edge = Edge(struct, entries)
             g.fwd[src][v] = edge
@@ -172,6 +174,7 @@ class StepStats:
     num_adds: int = 0
     pairs: int = 0
     classes: Dict[str, int] = field(default_factory=dict)
+    structure_complete: bool = True
 
 
 def eliminate(g: Graph, vertex: int) -> StepStats:
@@ -184,6 +187,14 @@ def eliminate(g: Graph, vertex: int) -> StepStats:
         for p in list(g.bwd[v].keys()):
             pre = g.bwd[v][p]
             stats.pairs += 1
+            old = g.fwd[p].get(s)
+            if post.struct is None or pre.struct is None or (old is not None and old.struct is None):
+                stats.structure_complete = False
+                entries = _product_entries(dag, post.entries, pre.entries, None if old is None else old.entries)
+                edge = Edge(None, entries)
+                g.fwd[p][s] = edge
+                g.bwd[s][p] = edge
+                continue
             pre_s = pre.struct
             if post.struct.pre and pre.struct.has_val:
                 # unload_pre_transforms: shape-op Jacobians pending on the outgoing edge act on the incoming one
@@ -204,7 +215,6 @@ def eliminate(g: Graph, vertex: int) -> StepStats:
                 out_s, pending = _strip(post.struct), pre.struct.pre + post.struct.pre
             out_s = replace(out_s, pre=pending)
 
-            old = g.fwd[p].get(s)
             if old is not None:
                 # fill-in onto an existing edge: flush deferred transforms on both, then add
                 new_m, old_m = st.materialise(out_s), st.materialise(old.struct)
@@ -237,6 +247,10 @@ class Accumulated:
     blocks: Dict[Tuple[int, int], Tuple[Optional[st.Struct], Entries]]
 
     @property
+    def structure_complete(self) -> bool:
+        return all(s.structure_complete for s in self.steps) and all(s is not None for _, _, s in self.graph.elemental)
+
+    @property
     def num_muls(self) -> int:
         return sum(s.num_muls for s in self.steps)
 
@@ -261,5 +275,5 @@ def accumulate(jaxpr: Jaxpr, order: Order, argnums: Sequence[int], division: str
             if edge is None:
                 blocks[(oi, ai)] = (None, {})
             else:
-                blocks[(oi, ai)] = (st.materialise(edge.struct), edge.entries)
+                blocks[(oi, ai)] = (st.materialise(edge.struct) if edge.struct is not None else None, edge.entries)
     return Accumulated(g, vertices, steps, blocks)

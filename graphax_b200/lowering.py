@@ -32,7 +32,7 @@ OPCODES = [
     "sin", "cos", "tan", "atan2", "exp", "log", "log1p", "tanh", "sinh", "cosh",
     "asin", "acos", "atan", "asinh", "acosh", "atanh", "erf", "pow", "logistic",
     "store_jac", "store_primal",
-    "max", "min", "gt", "lt",
+    "max", "min", "gt", "lt", "eq",
 ]
 OP = {name: i for i, name in enumerate(OPCODES)}
 _UNARY = {"neg", "abs", "sqrt", "sin", "cos", "tan", "exp", "log", "log1p", "tanh", "sinh", "cosh",
@@ -158,24 +158,26 @@ class Dag:
 
 
 class Vec:
-    """A traced value lowered to scalar nodes: shape () or (n,)."""
+    """A traced value lowered to scalar nodes: any shape, components in row-major order."""
     __slots__ = ("shape", "nodes", "is_literal")
 
     def __init__(self, shape: Tuple[int, ...], nodes: Sequence[int], is_literal: bool = False):
-        if len(shape) > 1:
-            raise NotImplementedError("vertices of rank > 1 are not lowered yet (scope row (f)1)")
-        self.shape = tuple(shape)
+        self.shape = tuple(int(s) for s in shape)
         self.nodes = list(nodes)
         self.is_literal = is_literal
         assert len(self.nodes) == self.size
 
     @property
     def size(self) -> int:
-        return self.shape[0] if self.shape else 1
+        return int(np.prod(self.shape, dtype=np.int64)) if self.shape else 1
 
     @property
     def ndim(self) -> int:
         return len(self.shape)
+
+    def index_array(self) -> np.ndarray:
+        """Flat component indices arranged in the value's shape (the currency of every shape op)."""
+        return np.arange(self.size, dtype=np.int64).reshape(self.shape)
 
 
 def _bshape(a: Tuple[int, ...], b: Tuple[int, ...]) -> Tuple[int, ...]:
@@ -183,7 +185,17 @@ def _bshape(a: Tuple[int, ...], b: Tuple[int, ...]) -> Tuple[int, ...]:
         return b
     if b == ():
         return a
-    return (max(a[0], b[0]),)
+    return tuple(max(x, y) for x, y in zip(a, b))
+
+
+def _bcast_index(v: "Vec", shape: Tuple[int, ...]) -> np.ndarray:
+    """For every component of a result of ``shape`` (flat order): the component of ``v`` it reads
+    (lax broadcasting: equal rank with size-1 axes stretched, or a rank-0 operand)."""
+    if v.shape == tuple(shape):
+        return np.arange(v.size, dtype=np.int64)
+    if v.ndim == 0:
+        return np.zeros(int(np.prod(shape, dtype=np.int64)) if shape else 1, dtype=np.int64)
+    return np.broadcast_to(v.index_array(), shape).reshape(-1)
 
 
 class _Ew:
@@ -197,10 +209,8 @@ class _Ew:
 
     def binary(self, op: str, a: Vec, b: Vec) -> Vec:
         shape = _bshape(a.shape, b.shape)
-        n = shape[0] if shape else 1
-        out = [self.dag.emit(op, a.nodes[i if a.size == n else 0], b.nodes[i if b.size == n else 0])
-               for i in range(n)]
-        return Vec(shape, out)
+        ia, ib = _bcast_index(a, shape), _bcast_index(b, shape)
+        return Vec(shape, [self.dag.emit(op, a.nodes[i], b.nodes[j]) for i, j in zip(ia, ib)])
 
     def unary(self, op: str, a: Vec) -> Vec:
         return Vec(a.shape, [self.dag.emit(op, x) for x in a.nodes])
@@ -233,8 +243,12 @@ class _Ew:
 Entries = Dict[Tuple[int, int], int]
 
 
-def _parallel_jacobian(primal: Vec, out: Vec, partial: Vec, n_operands: int) -> Tuple[st.Struct, Entries]:
-    """``make_parallel_jacobian`` (reference primitives.py:42-107) for rank <= 1."""
+def _parallel_jacobian(primal: Vec, out: Vec, partial: Vec, n_operands: int) -> Tuple[Optional[st.Struct], Entries]:
+    """``make_parallel_jacobian`` (reference primitives.py:42-107).  Entries are exact for any rank; the
+    structure descriptor is produced for rank <= 1 (``None`` above: no ``count_ops`` for such graphs)."""
+    if out.ndim > 1 or primal.ndim > 1:
+        ip, iq = _bcast_index(primal, out.shape), _bcast_index(partial, out.shape)
+        return None, {(i, int(ip[i])): partial.nodes[int(iq[i])] for i in range(out.size)}
     n = out.size
     if primal.ndim == 0 and out.ndim == 0:
         return st.SCALAR, {(0, 0): partial.nodes[0]}
@@ -387,6 +401,10 @@ def lower_eqn(dag: Dag, eqn: Eqn, read, division: str = "ieee") -> Tuple[Vec, Li
         return edges(out, (part,))
 
     # ---- structural rules ----------------------------------------------------
+    if prim in ("reduce_sum", "dot_general", "slice", "concatenate", "broadcast_in_dim") and \
+            (eqn.outvar.ndim > 1 or any(o.ndim > 1 for o in ops) or (prim == "broadcast_in_dim" and traced)
+             or (prim == "dot_general" and eqn.params["dimension_numbers"][1] != ((), ()))):
+        return lower_eqn(dag, Eqn(prim + "_nd", eqn.invars, eqn.outvar, eqn.params), read, division)
     if prim == "reduce_sum":          # primitives.py:243-272: row of ones over the reduced axis
         (x,) = ops
         if x.ndim == 0:
@@ -436,4 +454,111 @@ def lower_eqn(dag: Dag, eqn: Eqn, read, division: str = "ieee") -> Tuple[Vec, Li
         shape = tuple(eqn.params["shape"])
         n = shape[0] if shape else 1
         return Vec(shape, [x.nodes[0]] * n), []
+    # ---- shape ops and contractions of any rank: exact index maps, no tensor-level descriptor --------
+    def gather_edge(x: Vec, index_map: np.ndarray, fill: Optional[int] = None):
+        """out = x[index_map] (entries -1 read ``fill``): a selection Jacobian with structural ones."""
+        flat = index_map.reshape(-1)
+        nodes = [x.nodes[int(j)] if j >= 0 else fill for j in flat]
+        entries = {(i, int(j)): dag.const(1.0) for i, j in enumerate(flat) if j >= 0}
+        return Vec(tuple(index_map.shape), nodes), entries
+
+    if prim in ("transpose", "reshape", "squeeze", "expand_dims"):
+        (x,) = ops
+        idx = x.index_array()
+        if prim == "transpose":
+            idx = np.transpose(idx, eqn.params["permutation"])
+        else:
+            idx = idx.reshape(eqn.outvar.shape)
+        out, entries = gather_edge(x, idx)
+        return out, ([(eqn.invars[0], None, entries)] if traced else [])
+    if prim == "slice_nd":
+        (x,) = ops
+        idx = x.index_array()[tuple(slice(a, b) for a, b in zip(eqn.params["start_indices"], eqn.params["limit_indices"]))]
+        out, entries = gather_edge(x, idx)
+        return out, ([(eqn.invars[0], None, entries)] if traced else [])
+    if prim == "concatenate_nd":
+        axis, off, pieces, es = int(eqn.params["dimension"]), 0, [], []
+        for o in ops:
+            pieces.append(np.full(o.shape, -1, dtype=np.int64))
+        full = np.concatenate(pieces, axis=axis)
+        nodes: List[Optional[int]] = [None] * full.size
+        out_idx = np.arange(full.size, dtype=np.int64).reshape(full.shape)
+        for a, o in zip(eqn.invars, ops):
+            sel = [slice(None)] * full.ndim
+            sel[axis] = slice(off, off + o.shape[axis])
+            dst = out_idx[tuple(sel)].reshape(-1)
+            for i, j in zip(dst, range(o.size)):
+                nodes[int(i)] = o.nodes[j]
+            if isinstance(a, Var):
+                es.append((a, None, {(int(i), j): dag.const(1.0) for i, j in zip(dst, range(o.size))}))
+            off += o.shape[axis]
+        return Vec(full.shape, nodes), es
+    if prim == "broadcast_in_dim_nd":
+        (x,) = ops
+        shape, bdims = tuple(eqn.params["shape"]), tuple(eqn.params["broadcast_dimensions"])
+        view = [1] * len(shape)
+        for d, ax in zip(x.shape, bdims):
+            view[ax] = d
+        idx = np.broadcast_to(x.index_array().reshape(view) if x.ndim else np.zeros(view, dtype=np.int64), shape)
+        out, entries = gather_edge(x, np.ascontiguousarray(idx))
+        return out, ([(eqn.invars[0], None, entries)] if traced else [])
+    if prim == "reduce_sum_nd":
+        (x,) = ops
+        axes = tuple(eqn.params["axes"])
+        moved = np.moveaxis(x.index_array(), axes, range(-len(axes), 0)) if axes else x.index_array()
+        groups = moved.reshape(int(np.prod(eqn.outvar.shape, dtype=np.int64)) if eqn.outvar.shape else 1, -1)
+        nodes, entries = [], {}
+        for i, grp in enumerate(groups):
+            acc = x.nodes[int(grp[0])]
+            for j in grp[1:]:
+                acc = dag.add(acc, x.nodes[int(j)])
+            nodes.append(acc)
+            for j in grp:
+                entries[(i, int(j))] = dag.const(1.0)
+        return Vec(eqn.outvar.shape, nodes), ([(eqn.invars[0], None, entries)] if traced else [])
+    if prim in ("reduce_max", "reduce_min"):      # primitives.py:275-346: where(x == out) / count
+        (x,) = ops
+        axes = tuple(eqn.params["axes"])
+        moved = np.moveaxis(x.index_array(), axes, range(-len(axes), 0))
+        groups = moved.reshape(int(np.prod(eqn.outvar.shape, dtype=np.int64)) if eqn.outvar.shape else 1, -1)
+        nodes, entries = [], {}
+        for i, grp in enumerate(groups):
+            acc = x.nodes[int(grp[0])]
+            for j in grp[1:]:
+                acc = dag.emit("max" if prim == "reduce_max" else "min", acc, x.nodes[int(j)])
+            nodes.append(acc)
+            hits = [dag.emit("eq", x.nodes[int(j)], acc) for j in grp]
+            count = hits[0]
+            for h in hits[1:]:
+                count = dag.add(count, h)
+            for j, h in zip(grp, hits):
+                entries[(i, int(j))] = dag.div(h, count)
+        return Vec(eqn.outvar.shape, nodes), ([(eqn.invars[0], None, entries)] if traced else [])
+    if prim == "dot_general_nd":                  # primitives.py:349-441, any rank, batch dimensions allowed
+        x, y = ops
+        (cx, cy), (bx, by) = eqn.params["dimension_numbers"]
+        fx = [d for d in range(x.ndim) if d not in cx and d not in bx]
+        fy = [d for d in range(y.ndim) if d not in cy and d not in by]
+        ix = np.transpose(x.index_array(), list(bx) + fx + list(cx)) if x.ndim else x.index_array()
+        iy = np.transpose(y.index_array(), list(by) + fy + list(cy)) if y.ndim else y.index_array()
+        nb = int(np.prod([x.shape[d] for d in bx], dtype=np.int64)) if bx else 1
+        nk = int(np.prod([x.shape[d] for d in cx], dtype=np.int64)) if cx else 1
+        ix, iy = ix.reshape(nb, -1, nk), iy.reshape(nb, -1, nk)
+        nodes, ex, ey = [], {}, {}
+        o = 0
+        for b in range(nb):
+            for i in range(ix.shape[1]):
+                for j in range(iy.shape[1]):
+                    acc = dag.mul(x.nodes[int(ix[b, i, 0])], y.nodes[int(iy[b, j, 0])])
+                    for k in range(1, nk):
+                        acc = dag.fma(x.nodes[int(ix[b, i, k])], y.nodes[int(iy[b, j, k])], acc)
+                    nodes.append(acc)
+                    for k in range(nk):
+                        ex[(o, int(ix[b, i, k]))] = y.nodes[int(iy[b, j, k])]
+                        ey[(o, int(iy[b, j, k]))] = x.nodes[int(ix[b, i, k])]
+                    o += 1
+        es = []
+        for i in traced:
+            es.append((eqn.invars[i], None, ex if i == 0 else ey))
+        return Vec(eqn.outvar.shape, nodes), es
     raise NotImplementedError(f"{prim} does not have registered elemental partial.")   # core.py:398

@@ -194,6 +194,9 @@ def build_plan(jaxpr: Jaxpr, order, argnums: Sequence[int], with_primal: bool = 
 
     in_sizes = [v.size for v in jaxpr.invars]
     out_sizes = [v.size for v in jaxpr.outvars]
+    if sum(in_sizes) > 4096 or sum(out_sizes) * sum(in_sizes[a] for a in argnums) > 16384:
+        raise NotImplementedError("per-sample plans are scalarised: use the tensor-valued path (dense.py) for "
+                                  "arguments with thousands of elements")
     n_rows, n_cols = sum(out_sizes), sum(in_sizes[a] for a in argnums)
     row0 = np.concatenate([[0], np.cumsum(out_sizes)]).astype(int)
     col0 = np.concatenate([[0], np.cumsum([in_sizes[a] for a in argnums])]).astype(int)
@@ -318,16 +321,17 @@ def _collect_stats(plan: Plan, acc: Accumulated) -> None:
         "n_ops": len(plan.ssa),
         "n_slots": plan.n_slots,
         "op_histogram": hist,
-        "num_muls": acc.num_muls,                       # reference count_ops semantics
-        "num_adds": acc.num_adds,
-        "order_counts": [(s.vertex, s.num_muls) for s in acc.steps],
+        # reference count_ops semantics; None when a tensor-level descriptor is unavailable (rank > 1 vertices)
+        "num_muls": acc.num_muls if acc.structure_complete else None,
+        "num_adds": acc.num_adds if acc.structure_complete else None,
+        "order_counts": [(s.vertex, s.num_muls) for s in acc.steps] if acc.structure_complete else None,
         "pairs": sum(s.pairs for s in acc.steps),
         "max_pairs_per_step": max((s.pairs for s in acc.steps), default=0),
         "product_classes": classes,
         "bytes_per_jacobian": plan.bytes_per_jacobian,
     }
     plan.structure = {
-        "elemental": [[src, dst, s.descriptor()] for src, dst, s in acc.graph.elemental],
+        "elemental": [[src, dst, None if s is None else s.descriptor()] for src, dst, s in acc.graph.elemental],
         "blocks": {f"{oi},{ai}": (None if s is None else s.descriptor())
                    for (oi, ai), (s, _) in sorted(acc.blocks.items())},
         "order": list(acc.order),

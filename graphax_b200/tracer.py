@@ -244,24 +244,55 @@ class Tracer:
 
     # ---- static indexing ---------------------------------------------------
     def __getitem__(self, idx: Any) -> "Tracer":
-        if self.ndim != 1 or not isinstance(idx, slice):
-            raise NotImplementedError("only static 1-D slices x[a:b] are lowered")
-        start, stop, step = idx.indices(self.shape[0])
-        if step != 1:
-            raise NotImplementedError("strided slices are not lowered")
-        return self.trace.emit("slice", (self.var,), (max(stop - start, 0),),
-                               start_indices=(start,), limit_indices=(stop,), strides=None)
+        """Static basic indexing: slices become one ``slice`` equation, integer indices a ``slice`` followed
+        by a ``squeeze`` (how jnp lowers static indexing without gathers)."""
+        idx = idx if isinstance(idx, tuple) else (idx,)
+        if len(idx) > self.ndim or any(not isinstance(i, (slice, int, np.integer)) for i in idx):
+            raise NotImplementedError("only static basic indexing (slices and integers) is lowered")
+        idx = idx + (slice(None),) * (self.ndim - len(idx))
+        starts, limits, squeeze = [], [], []
+        for ax, (i, n) in enumerate(zip(idx, self.shape)):
+            if isinstance(i, slice):
+                a, b, step = i.indices(n)
+                if step != 1:
+                    raise NotImplementedError("strided slices are not lowered")
+                starts.append(a)
+                limits.append(max(b, a))
+            else:
+                i = int(i) + (n if int(i) < 0 else 0)
+                if not 0 <= i < n:
+                    raise IndexError(f"index {i} out of bounds for axis {ax} of size {n}")
+                starts.append(i)
+                limits.append(i + 1)
+                squeeze.append(ax)
+        out = self
+        if any(a != 0 or b != n for a, b, n in zip(starts, limits, self.shape)):
+            out = self.trace.emit("slice", (self.var,), tuple(b - a for a, b in zip(starts, limits)),
+                                  start_indices=tuple(starts), limit_indices=tuple(limits), strides=None)
+        if squeeze:
+            shape = tuple(s for ax, s in enumerate(out.shape) if ax not in squeeze)
+            out = out.trace.emit("squeeze", (out.var,), shape, dimensions=tuple(squeeze))
+        return out
+
+    def reshape(self, *shape) -> "Tracer":
+        shape = tuple(shape[0]) if len(shape) == 1 and isinstance(shape[0], (tuple, list)) else tuple(shape)
+        shape = tuple(int(s) for s in shape)
+        if -1 in shape:
+            known = int(np.prod([s for s in shape if s != -1], dtype=np.int64))
+            shape = tuple(self.size // known if s == -1 else s for s in shape)
+        if int(np.prod(shape, dtype=np.int64)) != self.size:
+            raise TypeError(f"cannot reshape {self.shape} into {shape}")
+        return self.trace.emit("reshape", (self.var,), shape, new_sizes=shape, dimensions=None)
 
     @property
     def T(self) -> "Tracer":
-        if self.ndim != 2:
-            raise NotImplementedError("only 2-D transposes are lowered")
-        return self.trace.emit("transpose", (self.var,), self.shape[::-1], permutation=(1, 0))
+        return _transpose(self)
 
     def __matmul__(self, other) -> "Tracer":
-        if not isinstance(other, Tracer) or self.ndim != 2 or other.ndim != 2:
-            raise NotImplementedError("only 2-D @ 2-D products are lowered")
-        return _dot_general(self, other, (((1,), (0,)), ((), ())))
+        return _matmul(self, other)
+
+    def __rmatmul__(self, other) -> "Tracer":
+        return _matmul(other, self)
 
     def sum(self, axis=None) -> "Tracer":
         return _reduce_sum(self, axis)
@@ -304,6 +335,8 @@ def _reduce_sum(x: Tracer, axis=None) -> Tracer:
 def _dot(a: Tracer, b: Tracer) -> Tracer:
     if not (isinstance(a, Tracer) and isinstance(b, Tracer)):
         raise TypeError("dot expects two traced values")
+    if a.ndim > 1 or b.ndim > 1:
+        return _matmul(a, b)
     if a.ndim == 1 and b.ndim == 1:
         if a.shape != b.shape:
             raise TypeError(f"dot: incompatible shapes {a.shape} and {b.shape}")
@@ -314,15 +347,57 @@ def _dot(a: Tracer, b: Tracer) -> Tracer:
 
 
 def _dot_general(a: Tracer, b: Tracer, dimension_numbers, precision=None, preferred_element_type=None) -> Tracer:
-    """``lax.dot_general`` without batch dimensions: out = free dims of a, then free dims of b."""
+    """``lax.dot_general``: out = batch dims, then free dims of a, then free dims of b."""
     (ca, cb), (ba, bb) = dimension_numbers
-    if tuple(ba) or tuple(bb):
-        raise NotImplementedError("dot_general batch dimensions are not lowered")
     ca, cb = tuple(int(c) for c in ca), tuple(int(c) for c in cb)
-    if [a.shape[i] for i in ca] != [b.shape[i] for i in cb]:
-        raise TypeError(f"dot_general: contracting dimensions differ: {a.shape} {ca} vs {b.shape} {cb}")
-    shape = tuple(s for i, s in enumerate(a.shape) if i not in ca) + tuple(s for i, s in enumerate(b.shape) if i not in cb)
-    return a.trace.emit("dot_general", (a.var, b.var), shape, dimension_numbers=((ca, cb), ((), ())))
+    ba, bb = tuple(int(c) for c in ba), tuple(int(c) for c in bb)
+    if [a.shape[i] for i in ca] != [b.shape[i] for i in cb] or [a.shape[i] for i in ba] != [b.shape[i] for i in bb]:
+        raise TypeError(f"dot_general: dimension sizes differ: {a.shape} {ca} {ba} vs {b.shape} {cb} {bb}")
+    shape = tuple(a.shape[i] for i in ba) + \
+        tuple(s for i, s in enumerate(a.shape) if i not in ca and i not in ba) + \
+        tuple(s for i, s in enumerate(b.shape) if i not in cb and i not in bb)
+    return a.trace.emit("dot_general", (a.var, b.var), shape, dimension_numbers=((ca, cb), (ba, bb)))
+
+
+def _matmul(a: Tracer, b: Tracer) -> Tracer:
+    """``a @ b`` / ``jnp.dot`` for ranks 1 and 2: one dot_general contracting the last axis of a with the
+    first (for a 1-D b: only) axis of b."""
+    if not (isinstance(a, Tracer) and isinstance(b, Tracer)) or not (1 <= a.ndim <= 2 and 1 <= b.ndim <= 2):
+        raise NotImplementedError("matmul of ranks 1 and 2 only")
+    return _dot_general(a, b, (((a.ndim - 1,), (0,)), ((), ())))
+
+
+def _transpose(x: Tracer, axes=None) -> Tracer:
+    perm = tuple(range(x.ndim))[::-1] if axes is None else tuple(int(a) for a in axes)
+    if x.ndim < 2:
+        return x
+    return x.trace.emit("transpose", (x.var,), tuple(x.shape[p] for p in perm), permutation=perm)
+
+
+def _outer(a: Tracer, b: Tracer) -> Tracer:
+    """jnp.outer: ravel both, then multiply [n,1] * [1,m] (two broadcast_in_dim-free reshapes in jnp)."""
+    return a.reshape(a.size, 1) * b.reshape(1, b.size)
+
+
+def _squeeze(x: Tracer, axis=None) -> Tracer:
+    axes = tuple(i for i, s in enumerate(x.shape) if s == 1) if axis is None else \
+        tuple(sorted(a % x.ndim for a in ((axis,) if isinstance(axis, int) else axis)))
+    return x.trace.emit("squeeze", (x.var,), tuple(s for i, s in enumerate(x.shape) if i not in axes), dimensions=axes)
+
+
+def _expand_dims(x: Tracer, axis: int) -> Tracer:
+    axis = axis % (x.ndim + 1)
+    shape = x.shape[:axis] + (1,) + x.shape[axis:]
+    bdims = tuple(i for i in range(len(shape)) if i != axis)
+    return x.trace.emit("broadcast_in_dim", (x.var,), shape, shape=shape, broadcast_dimensions=bdims)
+
+
+def _reduce_extreme(prim: str):
+    def fn(x: Tracer, axis=None) -> Tracer:
+        axes = tuple(range(x.ndim)) if axis is None else tuple(sorted(a % x.ndim for a in ((axis,) if isinstance(axis, int) else axis)))
+        shape = tuple(s for i, s in enumerate(x.shape) if i not in axes)
+        return x.trace.emit(prim, (x.var,), shape, axes=axes)
+    return fn
 
 
 class _LaxShim:
@@ -347,8 +422,15 @@ def _concatenate(parts: Sequence[Tracer], axis: int = 0) -> Tracer:
     parts = list(parts)
     if not parts or not all(isinstance(p, Tracer) for p in parts):
         raise TypeError("concatenate expects a sequence of traced values")
-    if any(p.ndim != 1 for p in parts) or axis not in (0, -1):
-        raise NotImplementedError("only 1-D concatenation is lowered")
+    if any(p.ndim != parts[0].ndim for p in parts):
+        raise TypeError("concatenate: operands must have the same rank")
+    if parts[0].ndim > 1:
+        axis = axis % parts[0].ndim
+        shape = list(parts[0].shape)
+        shape[axis] = sum(p.shape[axis] for p in parts)
+        return parts[0].trace.emit("concatenate", tuple(p.var for p in parts), tuple(shape), dimension=axis)
+    if axis not in (0, -1):
+        raise TypeError("axis out of range for 1-D concatenation")
     n = sum(p.shape[0] for p in parts)
     # vmap broadcasts an un-batched operand (the literal zeros) before concatenating
     pads = sum(1 for p in parts
@@ -396,7 +478,18 @@ class _JnpShim:
     sigmoid = staticmethod(_unary("logistic"))
 
     sum = staticmethod(_reduce_sum)
+    max = staticmethod(_reduce_extreme("reduce_max"))
+    min = staticmethod(_reduce_extreme("reduce_min"))
     dot = staticmethod(_dot)
+    matmul = staticmethod(_matmul)
+    outer = staticmethod(_outer)
+    transpose = staticmethod(_transpose)
+    squeeze = staticmethod(_squeeze)
+    expand_dims = staticmethod(_expand_dims)
+
+    @staticmethod
+    def reshape(x, shape):
+        return x.reshape(shape)
     zeros = staticmethod(_zeros)
     concatenate = staticmethod(_concatenate)
 

@@ -69,3 +69,57 @@ def run_engine(plan, inputs: List[np.ndarray], kernel: str = "auto", device: int
     out = jac.cpu().numpy(), (primal.cpu().numpy() if primal is not None else None), name
     dp.close()
     return out
+
+
+def torch_eval_jaxpr(jaxpr, args):
+    """Primal evaluation of a traced function with torch ops (float64): the independent autodiff the tests
+    differentiate, in the role jax.jacrev / jax.jacfwd play in the reference's tests."""
+    import torch
+    from graphax_b200.tracer import Literal
+    env = {}
+    read = lambda a: torch.tensor(a.val, dtype=torch.float64) if isinstance(a, Literal) else env[id(a)]
+    for v, a in zip(jaxpr.invars, args):
+        env[id(v)] = a
+    un = {"neg": torch.neg, "abs": torch.abs, "sqrt": torch.sqrt, "sin": torch.sin, "cos": torch.cos,
+          "tan": torch.tan, "exp": torch.exp, "log": torch.log, "tanh": torch.tanh, "log1p": torch.log1p,
+          "sinh": torch.sinh, "cosh": torch.cosh, "asin": torch.asin, "acos": torch.acos, "atan": torch.atan,
+          "asinh": torch.asinh, "acosh": torch.acosh, "atanh": torch.atanh, "erf": torch.erf,
+          "logistic": torch.sigmoid, "square": torch.square}
+    for e in jaxpr.eqns:
+        x = [read(a) for a in e.invars]
+        p, prm = e.primitive, e.params
+        if p in ("add", "sub", "mul", "div"):
+            r = {"add": torch.add, "sub": torch.sub, "mul": torch.mul, "div": torch.div}[p](x[0], x[1])
+        elif p == "atan2": r = torch.atan2(x[0], x[1])
+        elif p == "pow": r = torch.pow(x[0], x[1])
+        elif p == "max": r = torch.maximum(x[0], x[1])
+        elif p == "min": r = torch.minimum(x[0], x[1])
+        elif p == "integer_pow": r = x[0] ** prm["y"]
+        elif p in un: r = un[p](x[0])
+        elif p == "reduce_sum": r = x[0].sum(dim=tuple(prm["axes"])) if x[0].ndim else x[0]
+        elif p == "reduce_max": r = torch.amax(x[0], dim=tuple(prm["axes"]))
+        elif p == "reduce_min": r = torch.amin(x[0], dim=tuple(prm["axes"]))
+        elif p == "dot_general":
+            (ca, cb), (ba, bb) = prm["dimension_numbers"]
+            letters = iter("abcdefghijklmnopqrstuvw")
+            la, lb = [None] * x[0].ndim, [None] * x[1].ndim
+            for i, j in list(zip(ba, bb)) + list(zip(ca, cb)):
+                la[i] = lb[j] = next(letters)
+            la = [c or next(letters) for c in la]
+            lb = [c or next(letters) for c in lb]
+            out = [la[i] for i in ba] + [c for i, c in enumerate(la) if i not in ba and i not in ca] + \
+                  [c for i, c in enumerate(lb) if i not in bb and i not in cb]
+            r = torch.einsum(f"{''.join(la)},{''.join(lb)}->{''.join(out)}", x[0], x[1])
+        elif p == "transpose": r = x[0].permute(*prm["permutation"])
+        elif p in ("reshape", "squeeze"): r = x[0].reshape(e.outvar.shape)
+        elif p == "slice": r = x[0][tuple(slice(a, b) for a, b in zip(prm["start_indices"], prm["limit_indices"]))]
+        elif p == "concatenate": r = torch.cat([t.expand(v.shape) if hasattr(v, "shape") else t for t, v in zip(x, e.invars)], dim=prm["dimension"])
+        elif p == "broadcast_in_dim":
+            view = [1] * len(prm["shape"])
+            for d, ax in zip(x[0].shape, prm["broadcast_dimensions"]):
+                view[ax] = d
+            r = x[0].reshape(view).expand(prm["shape"]).clone()
+        else:
+            raise NotImplementedError(p)
+        env[id(e.outvar)] = r
+    return tuple(env[id(o)] for o in jaxpr.outvars)
