@@ -292,10 +292,12 @@ def run_gpu_arm(args) -> None:
     # the other elimination orders of the config ("mixed ... vs fwd/rev"), same batch, fewer steps
     other = {}
     if args.other_orders and WORKLOAD == "roe3d":
-        for key in w.order_names():
-            if key == args.order:
+        # "+contract_sums": the opt-in plan variant that folds edge sums into FMA chains (plan._contract_sums);
+        # compiled at run time with NVRTC, reported for information, never the headline
+        for key, contract in [(k, c) for c in (False, True) for k in w.order_names()]:
+            if key == args.order and not contract:
                 continue
-            jf2 = gx.jacve(w.fun, order=w.order(key), argnums=w.argnums)
+            jf2 = gx.jacve(w.fun, order=w.order(key), argnums=w.argnums, contract_sums=contract)
             dp2 = jf2._device_plan(jf2.lower(w.arg_shapes), local_rank)
             k2 = max(20, args.steps // 4)
             for i in range(5):
@@ -314,7 +316,7 @@ def run_gpu_arm(args) -> None:
                 t = torch.tensor([ms2], device=dev, dtype=torch.float64)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 ms2 = float(t.item())
-            other[key] = {"value": world * batch / (ms2 * 1e-3), "ms_per_step": ms2, "steps": k2,
+            other[key + ("+contract_sums" if contract else "")] = {"value": world * batch / (ms2 * 1e-3), "ms_per_step": ms2, "steps": k2,
                           "roofline_frac": plan.bytes_per_jacobian * batch / (ms2 * 1e-3) / 1e9 / measured_peak_gbs()[0]}
             sync_all()
 

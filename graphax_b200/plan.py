@@ -140,6 +140,76 @@ def _linearise(dag: Dag, first_elim: int, roots: Sequence[int]) -> List[int]:
     return out
 
 
+def _contract_sums(dag: Dag, roots: Sequence[int], max_terms: int = 1 << 30) -> Dict[int, int]:
+    """Fold additions into the multiply chains that feed them: ``c + (a0*b0 + a1*b1 + ..)`` becomes
+    ``fma(ak, bk, .. fma(a0, b0, c))`` and ``c - (..)`` the same with negated ``a``s, whenever the chain's
+    intermediate values have no other reader.  One instruction less per accumulation into an existing edge
+    (core.py:262-272 adds the product to the old edge value); the sum is still one rounded operation per
+    node, only its association changes (old edge first instead of last), which stays inside the stated
+    fp32 tolerance and is what the plan, its replay and every kernel then agree on bit for bit.
+    Returns old node -> new node for every reachable node."""
+    reach, stack = set(), list(roots)
+    while stack:
+        n = stack.pop()
+        if n not in reach:
+            reach.add(n)
+            if dag.op[n] not in ("const", "input"):
+                stack.extend(dag.args[n])
+    uses: Dict[int, int] = {}
+    for n in reach:
+        if dag.op[n] not in ("const", "input"):
+            for a in dag.args[n]:
+                uses[a] = uses.get(a, 0) + 1
+    for r in roots:
+        uses[r] = uses.get(r, 0) + 1
+
+    def chain(t: int) -> Optional[List[Tuple[int, int]]]:
+        """[(a0,b0), (a1,b1), ..] if t is a privately owned mul/fma chain."""
+        terms = []
+        while True:
+            if uses.get(t, 0) != 1:
+                return None
+            if dag.op[t] == "mul":
+                terms.append(dag.args[t])
+                return terms[::-1]
+            if dag.op[t] != "fma":
+                return None
+            a, b, c = dag.args[t]
+            terms.append((a, b))
+            t = c
+
+    new: Dict[int, int] = {}
+    for n in sorted(reach):                       # node ids are topological (operands are created first)
+        op = dag.op[n]
+        if op in ("const", "input"):
+            new[n] = n
+            continue
+        args = dag.args[n]
+        done = False
+        if op in ("add", "sub"):
+            x, y = args
+            for t, other, negate_terms, negate_other in ((y, x, op == "sub", False), (x, y, False, op == "sub")):
+                terms = chain(t)
+                if terms is None or len(terms) > max_terms:
+                    continue
+                acc = new[other]
+                if negate_other:
+                    acc = dag.neg(acc)
+                for a, b in terms:
+                    a, b = new[a], new[b]
+                    if negate_terms:
+                        if dag.op[b] in ("neg", "const") and dag.op[a] not in ("neg", "const"):
+                            a, b = b, a
+                        a = dag.neg(a)
+                    acc = dag.fma(a, b, acc)
+                new[n] = acc
+                done = True
+                break
+        if not done:
+            new[n] = dag.emit(op, *[new[a] for a in args])
+    return new
+
+
 def _reschedule_for_pressure(dag: Dag, sched: List[int], roots: Sequence[int]) -> List[int]:
     """Greedy list scheduling of the straight-line program for few live values.
 
@@ -181,10 +251,12 @@ def _reschedule_for_pressure(dag: Dag, sched: List[int], roots: Sequence[int]) -
 
 
 def build_plan(jaxpr: Jaxpr, order, argnums: Sequence[int], with_primal: bool = True,
-               division: str = "reciprocal", schedule: str = "pressure") -> Plan:
+               division: str = "reciprocal", schedule: str = "pressure", contract: bool = False) -> Plan:
     """Lower (jaxpr, order, argnums) to a plan. ``division`` selects how x/y and its partials are
     evaluated (``lowering.lower_eqn``): "reciprocal" (default, one IEEE reciprocal + multiplies) or
-    "ieee" (the reference's formulas verbatim, three IEEE divisions)."""
+    "ieee" (the reference's formulas verbatim, three IEEE divisions).  ``contract=True`` additionally folds
+    additions into the multiply chains feeding them (``_contract_sums``): 6-12 % fewer instructions, but a
+    different association of the sums than the reference's, so it is opt-in."""
     argnums = [int(a) for a in argnums]
     for a in argnums:
         if not 0 <= a < len(jaxpr.invars):
@@ -209,6 +281,10 @@ def build_plan(jaxpr: Jaxpr, order, argnums: Sequence[int], with_primal: bool = 
             tile[(row0[oi] + i) * n_cols + col0[ai] + j] = node
     primal_nodes = [n for o in jaxpr.outvars for n in g.env[Graph.key(o)].nodes] if with_primal else []
 
+    if contract:
+        new = _contract_sums(dag, [n for n in tile if n is not None] + primal_nodes)
+        tile = [None if n is None else new[n] for n in tile]
+        primal_nodes = [new[n] for n in primal_nodes]
     roots = [n for n in tile if n is not None] + primal_nodes
     sched = _linearise(dag, g.first_elim_node, roots)
     if schedule == "pressure":

@@ -214,3 +214,18 @@ def test_no_out_of_bounds_writes(built_library, kernel, batch):
     assert np.array_equal(bits(jbuf[pad:pad + batch * 50].cpu().numpy().reshape(batch, 5, 10)), bits(ref_j))
     assert np.array_equal(bits(pbuf[pad:pad + batch * 5].cpu().numpy().reshape(batch, 5)), bits(ref_p))
     dp.close()
+
+
+@pytest.mark.parametrize("order", ["fwd", "rev", "mixed", "mixed2"])
+def test_contracted_plans_run_bit_exact(built_library, order):
+    """Opt-in sum contraction (plan._contract_sums): the kernel compiled at run time must reproduce the C
+    replay of the contracted plan bit for bit, like every other Roe plan."""
+    from graphax_b200.plan import build_plan
+    from oracle import replay
+    w = WORKLOADS["roe3d"]
+    plan = build_plan(w.jaxpr(), w.order(order), w.argnums, contract=True)
+    xs = w.inputs(1000)
+    jac, primal, used = run_engine(plan, xs, "jit")
+    ref_j, ref_p = replay.replay(plan.blob, xs, plan.n_rows, plan.n_cols)
+    assert used == "jit"
+    assert np.array_equal(bits(jac), bits(ref_j)) and np.array_equal(bits(primal), bits(ref_p))

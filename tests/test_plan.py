@@ -148,3 +148,29 @@ def test_constant_folding_is_exactly_rounded():
     assert dag.mul(x, dag.const(1.0)) == x and dag.op[dag.mul(x, dag.const(-1.0))] == "neg"
     assert dag.fma(x, dag.const(1.0), a) == dag.add(x, a)
     assert dag.mul(x, a) == dag.mul(a, x)                       # hash-consing of commutative ops
+
+
+def test_sum_contraction_is_opt_in_and_stays_close():
+    """plan._contract_sums: fewer operations, same values up to the association of the edge sums.  Against
+    fp64 the contracted plan must be at least as accurate (rms) as the reference-order plan; against the
+    reference-order plan it may differ by up to 1.5x the parity bound on the ill-conditioned mixed order
+    (two independent fp32 roundings), which is why it is not the default."""
+    from helpers import pack_blocks, parity_bound
+    from oracle import ve_numpy
+    w = WORKLOADS["roe3d"]
+    xs = w.inputs(2000)
+    for order in w.order_names():
+        strict = build_plan(w.jaxpr(), w.order(order), w.argnums)
+        fused = build_plan(w.jaxpr(), w.order(order), w.argnums, contract=True)
+        assert strict.key == w.plan(order).key                                   # default = reference association
+        n = lambda p: sum(1 for o in p.ssa if o.op not in ("neg", "store_jac", "store_primal"))
+        assert n(fused) < 0.95 * n(strict)
+        assert sum(o.op in ("add", "sub") for o in fused.ssa) < 0.6 * sum(o.op in ("add", "sub") for o in strict.ssa)
+        a = replay.replay(strict.blob, xs, 5, 10)[0]
+        b = replay.replay(fused.blob, xs, 5, 10)[0]
+        j64, _, _ = ve_numpy.jacve(w.jaxpr(), w.order(order), w.argnums, [x.astype(np.float64) for x in xs], np.float64)
+        t64 = pack_blocks(j64, 2000, w.sizes)
+        assert (np.abs(a - b) <= 1.5 * parity_bound(t64)).all()
+        mx = np.abs(t64).max(axis=(1, 2), keepdims=True)
+        rms = lambda e: float(np.sqrt(np.mean((e / mx) ** 2)))
+        assert rms(b - t64) <= 1.02 * rms(a - t64)
