@@ -6,7 +6,7 @@ Same call shape as the reference (``graphax/__init__.py:2-4``)::
     jac = jacve(f, order="rev", argnums=(0, 1))(x, y)
 """
 from .api import jacve, vmap, tree_allclose, JacveFunction, SparseJacobian
-from .tracer import jnp, lax, make_jaxpr
+from .tracer import jnn, jnp, lax, make_jaxpr
 
 __version__ = "0.1.0"
-__all__ = ["jacve", "vmap", "tree_allclose", "jnp", "lax", "make_jaxpr", "JacveFunction", "SparseJacobian"]
+__all__ = ["jacve", "vmap", "tree_allclose", "jnn", "jnp", "lax", "make_jaxpr", "JacveFunction", "SparseJacobian"]

@@ -81,6 +81,8 @@ struct GxInterpArgs {
   int n_ops, n_consts, n_slots, n_in, n_rows, n_cols, n_arr, has_primal;
   int in_size[GX_MAX_ARRAYS];
   int in_off[GX_MAX_ARRAYS];
+  float* scratch;        // large-plan interpreter: live values, [grid][n_slots][T]
+  const int* in_map;     // large-plan interpreter: input scalar -> (array, component)
 };
 
 namespace {
@@ -210,6 +212,49 @@ __global__ void __launch_bounds__(T) gx_interp_kernel(const __grid_constant__ Gx
     __syncthreads();
   }
 }
+
+// Plans whose program or live values do not fit in shared memory (forward mode over matrix-valued vertices:
+// 10^5 operations, thousands of live values).  The program and the constants stay in global memory - every
+// thread of the CTA reads the same word, one broadcast transaction served from L1 - the live values of the
+// CTA's T samples sit in a private [n_slots][T] scratch area (slot-major: coalesced), and inputs and outputs
+// are accessed in place.  Slow (it is the fallback of the fallback) but it runs every valid plan.
+template <int T>
+__global__ void __launch_bounds__(T) gx_interp_large_kernel(const __grid_constant__ GxInterpArgs a) {
+  const int tid = threadIdx.x;
+  const int tile_words = a.n_rows * a.n_cols;
+  float* slots = a.scratch + (size_t)blockIdx.x * a.n_slots * T;
+  const unsigned* ops = reinterpret_cast<const unsigned*>(a.ops);
+  const long long n_tiles = (a.batch + T - 1) / T;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long smp = tile * T + tid;
+    const bool valid = smp < a.batch;
+    auto fetch = [&](unsigned o) -> float {
+      const unsigned kind = GX_OPERAND_KIND(o), idx = GX_OPERAND_INDEX(o);
+      if (kind == GX_K_SLOT) return slots[(size_t)idx * T + tid];
+      if (kind == GX_K_CONST) return __ldg(a.consts + idx);
+      const int arr = __ldg(a.in_map + 2 * idx), comp = __ldg(a.in_map + 2 * idx + 1);
+      return valid ? __ldg(a.in[arr] + smp * a.in_size[arr] + comp) : 1.0f;
+    };
+    for (int i = 0; i < a.n_ops; ++i) {
+      const unsigned w0 = __ldg(ops + 3 * i), w1 = __ldg(ops + 3 * i + 1), w2 = __ldg(ops + 3 * i + 2);
+      const unsigned op = w0 & 0xffffu, dst = w0 >> 16, oa = w1 & 0xffffu, ob = w1 >> 16, oc = w2 & 0xffffu;
+      if (op == GX_OP_STORE_JAC) {
+        const float v = fetch(oa);
+        if (valid) a.jac[smp * tile_words + dst] = v;
+      } else if (op == GX_OP_STORE_PRIMAL) {
+        const float v = fetch(oa);
+        if (valid && a.has_primal && a.primal != nullptr) a.primal[smp * a.n_rows + dst] = v;
+      } else {
+        const float va = fetch(oa);
+        const float vb = gx_is_binary(op) ? fetch(ob) : 0.0f;
+        const float vc = op == GX_OP_FMA ? fetch(oc) : 0.0f;
+        slots[(size_t)dst * T + tid] = gx_apply(op, va, vb, vc);
+      }
+    }
+  }
+}
+constexpr int GX_LARGE_T = 64;           // samples per CTA of the large-plan interpreter
+constexpr int GX_LARGE_CTAS_PER_SM = 2;
 
 size_t interp_smem_bytes(const gx_blob_header& h, int T) {
   const size_t tile = (size_t)h.n_rows * h.n_cols + ((h.flags & GX_FLAG_HAS_PRIMAL) ? h.n_rows : 0);
@@ -352,6 +397,9 @@ struct gx_plan {
   int interp_threads = 0;
   size_t interp_smem = 0;
   int interp_ctas_per_sm = 1;
+  bool interp_large = false;   // program / live values exceed shared memory: gx_interp_large_kernel
+  float* d_scratch = nullptr;
+  int* d_in_map = nullptr;
   // AOT kernel
   const GxAotKernel* aot = nullptr;
   int aot_ctas_per_sm = 0;
@@ -580,7 +628,11 @@ int launch_on(gx_plan* p, int64_t batch, const void* const* in_ptrs, void* jac, 
     const int T = p->interp_threads;
     const long long tiles = (batch + T - 1) / T;
     const int grid = (int)std::min<long long>(tiles, (long long)p->sm_count * p->interp_ctas_per_sm);
-    if (T == 128)
+    a.scratch = p->d_scratch;
+    a.in_map = p->d_in_map;
+    if (p->interp_large)
+      gx_interp_large_kernel<GX_LARGE_T><<<grid, GX_LARGE_T, 0, stream>>>(a);
+    else if (T == 128)
       gx_interp_kernel<128><<<grid, 128, p->interp_smem, stream>>>(a);
     else if (T == 64)
       gx_interp_kernel<64><<<grid, 64, p->interp_smem, stream>>>(a);
@@ -646,7 +698,25 @@ int gx_plan_create(const void* blob, size_t nbytes, int device, gx_plan** out) {
   if (rc == 1) rc = config_interp<128>(p, max_optin);
   if (rc == 1) rc = config_interp<64>(p, max_optin);
   if (rc == 1) rc = config_interp<32>(p, max_optin);
-  if (rc == 1) return cleanup(fail(GX_ERR_UNSUPPORTED, "plan keeps too many live values for shared memory"));
+  if (rc == 1) {
+    // too long or too many live values for shared memory: global-memory interpreter with a private scratch area
+    p->interp_large = true;
+    p->interp_threads = GX_LARGE_T;
+    p->interp_smem = 0;
+    p->interp_ctas_per_sm = GX_LARGE_CTAS_PER_SM;
+    const size_t ctas = (size_t)p->sm_count * GX_LARGE_CTAS_PER_SM;
+    GX_CUDA_P(cudaMalloc(&p->d_scratch, std::max<size_t>(4 * ctas * p->h.n_slots * GX_LARGE_T, 16)));
+    std::vector<int> in_map(2 * (size_t)p->h.n_in_scalars);
+    size_t k = 0;
+    for (unsigned arr = 0; arr < p->h.n_in_arrays; ++arr)
+      for (unsigned c = 0; c < p->in_sizes[arr]; ++c, ++k) {
+        in_map[2 * k] = (int)arr;
+        in_map[2 * k + 1] = (int)c;
+      }
+    GX_CUDA_P(cudaMalloc(&p->d_in_map, std::max<size_t>(4 * in_map.size(), 16)));
+    GX_CUDA_P(cudaMemcpy(p->d_in_map, in_map.data(), 4 * in_map.size(), cudaMemcpyHostToDevice));
+    rc = GX_OK;
+  }
   if (rc != GX_OK) return cleanup(rc);
 
   // plan-specialised kernel compiled into the library for exactly this blob?
@@ -688,6 +758,8 @@ void gx_plan_destroy(gx_plan* p) {
   if (p->jit_module && driver().ok) driver().ModuleUnload(p->jit_module);
   if (p->d_ops) cudaFree(p->d_ops);
   if (p->d_consts) cudaFree(p->d_consts);
+  if (p->d_scratch) cudaFree(p->d_scratch);
+  if (p->d_in_map) cudaFree(p->d_in_map);
   delete p;
 }
 

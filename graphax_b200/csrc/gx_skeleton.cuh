@@ -37,7 +37,7 @@ typedef unsigned long long uint64_t;
 #define GX_SPT 1
 #endif
 #define GX_WT (32 * GX_SPT) /* samples per warp tile */
-#define GX_MAX_ARRAYS_K 16
+#define GX_MAX_ARRAYS_K 32
 
 struct GxLaunchArgs {
   const float* in[GX_MAX_ARRAYS_K];

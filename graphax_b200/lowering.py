@@ -293,6 +293,9 @@ def lower_eqn(dag: Dag, eqn: Eqn, read, division: str = "ieee") -> Tuple[Vec, Li
     def edges(out: Vec, partials: Sequence[Vec]):
         return out, [(eqn.invars[i],) + _parallel_jacobian(ops[i], out, partials[i], len(ops)) for i in traced]
 
+    if prim == "stop_gradient":    # primitives.py:458-462: value passes through, no edge
+        return ops[0], []
+
     # ---- elementwise binary (primitives.py:180-205, 237-239) ----------------
     if prim in ("max", "min"):     # primitives.py:208-215: ties send the derivative to the second operand
         x, y = ops
@@ -309,10 +312,10 @@ def lower_eqn(dag: Dag, eqn: Eqn, read, division: str = "ieee") -> Tuple[Vec, Li
             r = ew.div(ew.lit(1.0), y)
             q0 = ew.mul(x, r)
             n = q0.size
-            rem = Vec(q0.shape, [dag.fma(dag.neg(y.nodes[i if y.size == n else 0]), q0.nodes[i],
-                                         x.nodes[i if x.size == n else 0]) for i in range(n)])
-            out = Vec(q0.shape, [dag.fma(rem.nodes[i], r.nodes[i if r.size == n else 0], q0.nodes[i])
+            ix, iy, ir = _bcast_index(x, q0.shape), _bcast_index(y, q0.shape), _bcast_index(r, q0.shape)
+            rem = Vec(q0.shape, [dag.fma(dag.neg(y.nodes[int(iy[i])]), q0.nodes[i], x.nodes[int(ix[i])])
                                  for i in range(n)])
+            out = Vec(q0.shape, [dag.fma(rem.nodes[i], r.nodes[int(ir[i])], q0.nodes[i]) for i in range(n)])
         else:
             out = ew.binary(prim, x, y)
         if prim == "add":

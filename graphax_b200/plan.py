@@ -250,6 +250,61 @@ def _reschedule_for_pressure(dag: Dag, sched: List[int], roots: Sequence[int]) -
     return out
 
 
+def _reschedule_for_ilp(dag: Dag, sched: List[int], limit: int, window: int) -> List[int]:
+    """List scheduling for instruction-level parallelism under a cap on live values.
+
+    A warp issues a dependent FFMA only every ~4 cycles, and with 168 registers per thread there are
+    just 3 warps per scheduler to hide that, so the straight-line body must interleave independent
+    chains itself.  Among the ready operations prefer one whose operands were all produced at least
+    ``window`` operations ago, then the one with the longest path to the end of the program; once
+    ``limit`` values are live, fall back to the pressure rule (end as many live ranges as possible)."""
+    nodeset = set(sched)
+    pos = {n: i for i, n in enumerate(sched)}
+    args = {n: [a for a in dict.fromkeys(dag.args[n]) if a in nodeset] for n in sched}
+    users: Dict[int, List[int]] = {n: [] for n in sched}
+    for n in sched:
+        for a in args[n]:
+            users[a].append(n)
+    height: Dict[int, int] = {}
+    for n in reversed(sched):
+        lat = 8 if dag.op[n] in ("div", "sqrt") or dag.op[n] not in ("add", "sub", "mul", "fma", "neg") else 1
+        height[n] = lat + max((height[u] for u in users[n]), default=0)
+    remaining = {n: len(users[n]) for n in sched}
+    indeg = {n: len(args[n]) for n in sched}
+    ready = [n for n in sched if indeg[n] == 0]
+    issued: Dict[int, int] = {}
+    out: List[int] = []
+    live = 0
+    while ready:
+        now = len(out)
+        best, best_score = None, None
+        for n in ready:
+            freed = sum(1 for a in args[n] if remaining[a] == 1)
+            creates = 1 if users[n] else 0
+            rested = all(now - issued[a] >= window for a in args[n])
+            if live < limit:
+                score = (rested, height[n], freed - creates, -pos[n])
+            else:
+                score = (freed - creates, rested, height[n], -pos[n])
+            if best_score is None or score > best_score:
+                best, best_score = n, score
+        ready.remove(best)
+        issued[best] = now
+        out.append(best)
+        live += 1 if users[best] else 0
+        for a in args[best]:
+            remaining[a] -= 1
+            if remaining[a] == 0:
+                live -= 1
+        for u in users[best]:
+            indeg[u] -= 1
+            if indeg[u] == 0:
+                ready.append(u)
+    if len(out) != len(sched):
+        raise AssertionError("scheduler lost operations")
+    return out
+
+
 def build_plan(jaxpr: Jaxpr, order, argnums: Sequence[int], with_primal: bool = True,
                division: str = "reciprocal", schedule: str = "pressure", contract: bool = False) -> Plan:
     """Lower (jaxpr, order, argnums) to a plan. ``division`` selects how x/y and its partials are
@@ -289,8 +344,13 @@ def build_plan(jaxpr: Jaxpr, order, argnums: Sequence[int], with_primal: bool = 
     sched = _linearise(dag, g.first_elim_node, roots)
     if schedule == "pressure":
         sched = _reschedule_for_pressure(dag, sched, roots)
+    elif schedule.startswith("ilp"):
+        # "ilp:<live limit>:<window>"
+        parts = schedule.split(":")
+        sched = _reschedule_for_ilp(dag, sched, int(parts[1]) if len(parts) > 1 else 120,
+                                    int(parts[2]) if len(parts) > 2 else 4)
     elif schedule != "elimination":
-        raise ValueError("schedule must be 'pressure' or 'elimination'")
+        raise ValueError("schedule must be 'pressure', 'ilp[:limit[:window]]' or 'elimination'")
 
     # stores directly after the value they read; constant / input / zero stores at the end
     stores_after: Dict[int, List[SsaOp]] = {}

@@ -7,6 +7,7 @@ library has not been built, or no CUDA device is present, calls fail loudly.
 from __future__ import annotations
 
 import ctypes
+import os
 import threading
 import warnings
 from pathlib import Path
@@ -15,7 +16,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 from .plan import Plan
 
 LIB_PATH = Path(__file__).resolve().parent / "libgraphax_b200.so"
-GX_MAX_ARRAYS = 16
+GX_MAX_ARRAYS = 32
 KERNEL_INTERPRETER, KERNEL_AOT, KERNEL_JIT = 0, 1, 2
 KERNEL_NAMES = {0: "interpreter", 1: "aot", 2: "jit"}
 
@@ -109,6 +110,12 @@ def aot_keys() -> List[int]:
     return [lib.gx_aot_key(i) for i in range(lib.gx_aot_count())]
 
 
+def jit_max_ops() -> int:
+    """Longest plan that is compiled at run time (straight-line code: NVRTC time grows faster than linearly
+    with the body); longer plans run on the generic interpreter kernel.  ``GX_JIT_MAX_OPS`` overrides."""
+    return int(os.environ.get("GX_JIT_MAX_OPS", "12000"))
+
+
 class DevicePlan:
     """A plan uploaded to one GPU (wraps ``gx_plan*``)."""
 
@@ -119,9 +126,11 @@ class DevicePlan:
         self._h = ctypes.c_void_p()
         buf = ctypes.create_string_buffer(plan.blob, len(plan.blob))
         _check(self._lib.gx_plan_create(buf, len(plan.blob), device, ctypes.byref(self._h)), "gx_plan_create")
-        if self.info().kernel_kind == KERNEL_INTERPRETER and jit:
+        if self.info().kernel_kind == KERNEL_INTERPRETER and jit and plan.stats.get("n_ops", 0) <= jit_max_ops():
             try:
                 self.specialize()
+            except ValueError:             # staging does not fit in shared memory: interpreter kernel by design
+                pass
             except GraphaxB200Error as e:  # stay on the (GPU) interpreter kernel, but say so
                 warnings.warn(f"plan {plan.key}: run-time specialisation unavailable, using the generic "
                               f"interpreter kernel: {e}")

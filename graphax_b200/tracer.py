@@ -294,8 +294,11 @@ class Tracer:
     def __rmatmul__(self, other) -> "Tracer":
         return _matmul(other, self)
 
-    def sum(self, axis=None) -> "Tracer":
-        return _reduce_sum(self, axis)
+    def sum(self, axis=None, keepdims: bool = False) -> "Tracer":
+        return _reduce_sum(self, axis, keepdims)
+
+    def mean(self, axis=None) -> "Tracer":
+        return _mean(self, axis)
 
     def dot(self, other) -> "Tracer":
         return _dot(self, other)
@@ -321,7 +324,18 @@ def _binary_fn(prim: str):
     return fn
 
 
-def _reduce_sum(x: Tracer, axis=None) -> Tracer:
+def _keepdims(x: Tracer, reduced: Tracer, axes) -> Tracer:
+    """``keepdims=True``: jnp re-inserts the reduced axes with a broadcast_in_dim of the result."""
+    shape = tuple(1 if i in axes else s for i, s in enumerate(x.shape))
+    bdims = tuple(i for i in range(x.ndim) if i not in axes)
+    return x.trace.emit("broadcast_in_dim", (reduced.var,), shape, shape=shape, broadcast_dimensions=bdims)
+
+
+def _reduce_sum(x: Tracer, axis=None, keepdims: bool = False) -> Tracer:
+    if keepdims:
+        r = _reduce_sum(x, axis)
+        axes = tuple(range(x.ndim)) if axis is None else tuple(sorted(a % x.ndim for a in ((axis,) if isinstance(axis, int) else axis)))
+        return _keepdims(x, r, axes)
     if axis is None:
         axes = tuple(range(x.ndim))
     elif isinstance(axis, int):
@@ -393,19 +407,52 @@ def _expand_dims(x: Tracer, axis: int) -> Tracer:
 
 
 def _reduce_extreme(prim: str):
-    def fn(x: Tracer, axis=None) -> Tracer:
+    def fn(x: Tracer, axis=None, keepdims: bool = False) -> Tracer:
         axes = tuple(range(x.ndim)) if axis is None else tuple(sorted(a % x.ndim for a in ((axis,) if isinstance(axis, int) else axis)))
         shape = tuple(s for i, s in enumerate(x.shape) if i not in axes)
-        return x.trace.emit(prim, (x.var,), shape, axes=axes)
+        r = x.trace.emit(prim, (x.var,), shape, axes=axes)
+        return _keepdims(x, r, axes) if keepdims else r
     return fn
+
+
+def _mean(x: Tracer, axis=None) -> Tracer:
+    """jnp.mean: reduce_sum, then a division by the literal element count."""
+    axes = tuple(range(x.ndim)) if axis is None else tuple(a % x.ndim for a in ((axis,) if isinstance(axis, int) else axis))
+    n = 1
+    for a in axes:
+        n *= x.shape[a]
+    return _reduce_sum(x, axis) / float(n)
+
+
+def _stop_gradient(x: Tracer) -> Tracer:
+    return x.trace.emit("stop_gradient", (x.var,), x.shape)
+
+
+def _softmax(x: Tracer, axis=-1) -> Tracer:
+    """jax.nn.softmax without its custom_jvp wrapper (the reference has no rule for custom_jvp_call):
+    exp(x - stop_gradient(max(x))) / sum(...), both reductions with keepdims."""
+    x_max = _reduce_extreme("reduce_max")(x, axis, keepdims=True)
+    unnormalized = _unary("exp")(x - _stop_gradient(x_max))
+    return unnormalized / _reduce_sum(unnormalized, axis, keepdims=True)
 
 
 class _LaxShim:
     """The slice of ``jax.lax`` the workloads touch."""
     dot_general = staticmethod(_dot_general)
+    stop_gradient = staticmethod(_stop_gradient)
 
 
 lax = _LaxShim()
+
+
+class _NnShim:
+    """The slice of ``jax.nn`` the reference's deep-learning examples touch."""
+    softmax = staticmethod(lambda x, axis=-1: _softmax(x, axis))
+    sigmoid = staticmethod(lambda x: _unary("logistic")(x))
+    tanh = staticmethod(lambda x: _unary("tanh")(x))
+
+
+jnn = _NnShim()
 
 
 def _square(x: Tracer) -> Tracer:
@@ -478,6 +525,7 @@ class _JnpShim:
     sigmoid = staticmethod(_unary("logistic"))
 
     sum = staticmethod(_reduce_sum)
+    mean = staticmethod(_mean)
     max = staticmethod(_reduce_extreme("reduce_max"))
     min = staticmethod(_reduce_extreme("reduce_min"))
     dot = staticmethod(_dot)

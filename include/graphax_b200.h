@@ -23,8 +23,8 @@
 extern "C" {
 #endif
 
-#define GX_ABI_VERSION 1
-#define GX_MAX_ARRAYS 16
+#define GX_ABI_VERSION 2
+#define GX_MAX_ARRAYS 32
 
 enum gx_status {
   GX_OK = 0,
@@ -36,7 +36,9 @@ enum gx_status {
 };
 
 enum gx_kernel_kind {
-  GX_KERNEL_INTERPRETER = 0, /* generic persistent plan interpreter (always available) */
+  GX_KERNEL_INTERPRETER = 0, /* generic persistent plan interpreter (always available; plans too large for
+                                shared memory run from global memory with a per-plan scratch area, so two
+                                launches of such a plan must be ordered on one stream) */
   GX_KERNEL_AOT = 1,         /* plan-specialised kernel compiled into this library by build() */
   GX_KERNEL_JIT = 2          /* plan-specialised kernel compiled at run time with NVRTC */
 };

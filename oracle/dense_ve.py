@@ -26,6 +26,8 @@ def _apply(eqn, vals: List[np.ndarray], batched: List[bool]):
     p, params = eqn.primitive, eqn.params
     lead = 1 if any(batched) else 0
     x = [v if b or not lead else v[None] for v, b in zip(vals, batched)]
+    if p == "stop_gradient":
+        return x[0]
     if p in ("add", "sub", "mul", "div", "atan2", "pow", "max", "min"):
         nd = max(a.ndim for a in x)
         a, b = [v.reshape(v.shape[:1] + (1,) * (nd - v.ndim) + v.shape[1:]) if v.ndim > 1 or lead else v for v in x]
@@ -183,7 +185,7 @@ def jacve(jaxpr, order, argnums: Sequence[int], args: Sequence[np.ndarray], dtyp
             vals = [env[key(a)] if isinstance(a, Var) else np.full((B,), a.val, dtype=dtype) for a in eqn.invars]
             out = np.asarray(_apply(eqn, vals, [True] * len(vals)), dtype=dtype).reshape((B,) + tuple(eqn.outvar.shape))
             env[v] = out
-            if not any(is_var):
+            if not any(is_var) or eqn.primitive == "stop_gradient":       # primitives.py:458-462: no edge
                 continue
             for a, J in zip([a for a in eqn.invars if isinstance(a, Var)], _elemental_jacobians(eqn, vals, out, is_var, dtype)):
                 src = key(a)

@@ -160,7 +160,7 @@ int gxo_replay(const void* blob, size_t nbytes, int64_t batch, const float* cons
   if (!blob || nbytes < sizeof(header_t)) return -1;
   const header_t* h = (const header_t*)blob;
   if (h->magic != 0x4C505847u || h->version != 1u || h->total_bytes != nbytes) return -1;
-  if (h->n_in_arrays > 16 || h->n_in_scalars > 0x3fff) return -1;
+  if (h->n_in_arrays > 32 || h->n_in_scalars > 0x3fff) return -1;
   const unsigned char* cur = (const unsigned char*)blob + sizeof(header_t);
   const uint32_t* in_sizes = (const uint32_t*)cur;
   cur += 4 * (size_t)(2 * h->n_in_arrays + h->n_out_arrays);

@@ -96,6 +96,7 @@ def torch_eval_jaxpr(jaxpr, args):
         elif p == "min": r = torch.minimum(x[0], x[1])
         elif p == "integer_pow": r = x[0] ** prm["y"]
         elif p in un: r = un[p](x[0])
+        elif p == "stop_gradient": r = x[0].detach()
         elif p == "reduce_sum": r = x[0].sum(dim=tuple(prm["axes"])) if x[0].ndim else x[0]
         elif p == "reduce_max": r = torch.amax(x[0], dim=tuple(prm["axes"]))
         elif p == "reduce_min": r = torch.amin(x[0], dim=tuple(prm["axes"]))

@@ -19,7 +19,7 @@ def test_exports_every_declared_symbol(built_library):
     assert declared == set(runtime.EXPORTS)
     for name in declared:
         assert hasattr(built_library, name), name
-    assert built_library.gx_abi_version() == 1
+    assert built_library.gx_abi_version() == 2
 
 
 def test_aot_kernels_cover_every_named_plan(built_library):

@@ -16,6 +16,7 @@ from helpers import bits, torch_eval_jaxpr
 def broadcast_add(x, y): return jnp.tanh(x + y)
 def broadcast_sub(x, y): return jnp.tanh(x - y)
 def broadcast_mul(x, y): return jnp.sin(x * jnp.exp(y))
+def broadcast_div(x, y): return jnp.exp(x) / jnp.sum(jnp.exp(y), axis=1, keepdims=True) + y / x[0]
 def outer_product(x, y): return jnp.sin(x * y)
 def transpose(x, y): return jnp.cos(x).T * y
 def matmul(x, y): return jnp.sin(x @ y)
@@ -40,7 +41,7 @@ def NeuralNetwork(x, W1, b1, W2, b2, y):
 
 CASES = {
     "broadcast_add": (broadcast_add, [(2, 3), (1, 3)]), "broadcast_sub": (broadcast_sub, [(2, 3), (1, 3)]),
-    "broadcast_mul": (broadcast_mul, [(2, 3), (3,)]), "outer_product": (outer_product, [(4, 1), (1, 3)]),
+    "broadcast_mul": (broadcast_mul, [(2, 3), (3,)]), "broadcast_div": (broadcast_div, [(2, 3), (2, 3)]), "outer_product": (outer_product, [(4, 1), (1, 3)]),
     "transpose": (transpose, [(2, 3), (3, 2)]), "matmul": (matmul, [(2, 3), (3,)]),
     "reduce_sum": (sums, [(2, 3), (3, 4)]), "reduce_max": (maxs, [(2, 3), (3, 4)]),
     "slicing": (slicing, [(2, 3), (3, 4)]), "squeezing": (squeezing, [(2, 3), (3, 1)]),

@@ -49,6 +49,8 @@ def main():
     ap.add_argument("--min-blocks", default="2,3,4,5,6")
     ap.add_argument("--out-stages", default="2,1")
     ap.add_argument("--spt", default="1,2")
+    ap.add_argument("--schedules", default="", help="comma list of plan schedules to compare (default: the plan default)")
+    ap.add_argument("--contract", type=int, default=0)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--out", default="gpurun_out/tune.json")
@@ -60,13 +62,18 @@ def main():
         batch = args.batch or min(w.batch, 1 << 20)
         host = w.inputs(batch)
         for order in (args.orders.split(",") if args.orders else w.order_names()):
-            for division in args.divisions.split(","):
-                plan = w.plan(order, division=division)
+            for division, sched in [(d, sc) for d in args.divisions.split(",") for sc in (args.schedules.split(",") if args.schedules else [""])]:
+                if sched or args.contract:
+                    from graphax_b200.plan import build_plan
+                    plan = build_plan(w.jaxpr(), w.order(order), w.argnums, division=division,
+                                      schedule=sched or "pressure", contract=bool(args.contract))
+                else:
+                    plan = w.plan(order, division=division)
                 nsets = 4
                 sets = [([torch.from_numpy(x).cuda() for x in host],
                          torch.empty((batch, plan.n_rows, plan.n_cols), device="cuda")) for _ in range(nsets)]
                 dp = runtime.DevicePlan(plan, 0, jit=False)
-                name = f"{wname}:{order}:{division}"
+                name = f"{wname}:{order}:{division}" + (f":{sched}" if sched else "") + (":contract" if args.contract else "")
                 rows = []
                 if dp.info().kernel_kind == runtime.KERNEL_AOT:
                     i = dp.info()
