@@ -26,7 +26,7 @@ from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple, Union
 import numpy as np
 
 from .plan import Plan, build_plan
-from .tracer import Jaxpr, make_jaxpr
+from .tracer import Jaxpr, Literal, make_jaxpr
 
 EliminationOrder = Union[Sequence[int], str]
 
@@ -149,8 +149,82 @@ class JacveFunction:
             return primal, (grads if len(self.argnums) > 1 else grads[0])
         return out if len(self.argnums) > 1 else out[0]
 
+    _ELEMENTWISE = {"add", "sub", "mul", "div", "atan2", "pow", "max", "min", "integer_pow", "square", "neg", "abs",
+                    "sqrt", "sin", "cos", "tan", "exp", "log", "log1p", "tanh", "sinh", "cosh", "asin", "acos", "atan",
+                    "asinh", "acosh", "atanh", "erf", "logistic"}
+
+    def _elementwise_scalar_jaxpr(self, shapes):
+        """If ``fun`` is elementwise over arguments of one common shape (every equation maps that shape to
+        itself; other operands are literals), its Jacobian blocks are diagonal - in the reference every edge
+        is a pair of SparseDimensions sharing one val (primitives.py:42-107) - and their values are the
+        Jacobians of the scalar function, one per element.  Returns the scalar function's jaxpr, else None."""
+        common = shapes[0]
+        if not common or any(tuple(s) != tuple(common) for s in shapes):
+            return None
+        try:
+            full = make_jaxpr(self.fun, shapes)
+            scalar = make_jaxpr(self.fun, [()] * len(shapes))
+        except Exception:
+            return None
+        if len(full.eqns) != len(scalar.eqns) or len(full.outvars) != len(scalar.outvars):
+            return None
+        for e, f in zip(full.eqns, scalar.eqns):
+            if e.primitive != f.primitive or e.primitive not in self._ELEMENTWISE or e.outvar.shape != tuple(common):
+                return None
+            if any(hasattr(a, "shape") and not isinstance(a, Literal) and a.shape != tuple(common) for a in e.invars):
+                return None
+        if any(o.shape != tuple(common) for o in full.outvars):
+            return None
+        return scalar
+
+    def _run_elementwise(self, args: Sequence[Any]):
+        """Elementwise functions of large tensors (reference test_Simple, 50x50 arguments): the elements are
+        the batch of the per-sample engine; the diagonal values are scattered into ``out.shape + in.shape``
+        blocks (or returned as the SparseTensor-like descriptor with ``sparse_representation=True``)."""
+        import torch
+        tensors, shapes, _, device = self._prepare(args, batched=False)
+        common = tuple(shapes[0])
+        n = int(np.prod(common, dtype=np.int64))
+        plan = self.lower([()] * len(shapes))
+        dp = self._device_plan(plan, device)
+        with torch.cuda.device(device):
+            jac = torch.empty((n, plan.n_rows, plan.n_cols), dtype=torch.float32, device=f"cuda:{device}")
+            primal = torch.empty((n, plan.n_rows), dtype=torch.float32, device=f"cuda:{device}") if self.has_aux else None
+            dp.launch(n, [t.reshape(n).data_ptr() for t in tensors], jac.data_ptr(),
+                      primal.data_ptr() if primal is not None else None, torch.cuda.current_stream(device).cuda_stream)
+            nd = len(common)
+            blocks = []
+            for oi in range(plan.n_rows):
+                row = []
+                for ai in range(len(self.argnums)):
+                    vals = jac[:, oi, ai]
+                    if self.sparse_representation:
+                        dims_o = [["sparse", d, common[d], d, nd + d] for d in range(nd)]
+                        dims_p = [["sparse", nd + d, common[d], d, d] for d in range(nd)]
+                        row.append(SparseJacobian(dims_o, dims_p, list(common), vals.reshape(common)))
+                    else:
+                        dense = torch.zeros((n, n), dtype=torch.float32, device=f"cuda:{device}")
+                        dense.diagonal().copy_(vals)
+                        row.append(dense.reshape(common + common))
+                blocks.append(row)
+        grads_tree, single = self._tree(blocks, len(shapes))
+        if self.count_ops:
+            # every scalar multiplication / addition of the per-element plan happens once per element
+            # (get_num_muls / get_num_adds of diagonal edges count the val size, tensor.py:1414-1493)
+            return grads_tree, {"num_muls": plan.stats["num_muls"] * n, "num_adds": plan.stats["num_adds"] * n,
+                                "order_counts": [tuple(int(c) * n if i else c for i, c in enumerate(t))
+                                                 for t in plan.stats["order_counts"]]}
+        if self.has_aux:
+            outs = [primal[:, oi].reshape(common) for oi in range(plan.n_rows)]
+            return (outs[0] if single else tuple(outs)), grads_tree
+        return grads_tree
+
     def _run(self, args: Sequence[Any], batched: bool):
         import torch
+        if not batched and any(getattr(a, "ndim", 0) >= 1 and int(np.prod(a.shape)) >= 1024 for a in args):
+            shapes = [tuple(getattr(a, "shape", ())) for a in args]
+            if self._elementwise_scalar_jaxpr(shapes) is not None:
+                return self._run_elementwise(args)
         if not batched and any(getattr(a, "ndim", 0) >= 2 and int(np.prod(a.shape)) >= 4096 for a in args):
             return self._run_dense(args)        # big matrices: tensor-level path; small ones are scalarised per sample
         tensors, shapes, batch, device = self._prepare(args, batched)
@@ -234,7 +308,104 @@ class JacveFunction:
                     primal.data_ptr() if primal is not None else None, pinned)
         return self._package(plan, jac, primal, shapes, batch, True)
 
+    def _tree(self, blocks, n_invars: int):
+        """core.py:76-92: tuple over outputs of tuple over argnums; a single output of a function of several
+        arguments is unwrapped, a single argnum gives the bare block."""
+        grads = [tuple(row) if len(self.argnums) > 1 else row[0] for row in blocks]
+        single = len(blocks) == 1 and n_invars > 1
+        return (grads[0] if single else tuple(grads)), single
+
+    def _run_traced(self, args: Sequence[Any]):
+        """Nested use (reference economics.py:21-22, BlackScholes_Jacobian): called on traced values while an
+        outer function is being lowered.  The inner elimination plan is replayed operation by operation on the
+        outer trace - every plan operation becomes one outer equation on rank-0 values - so the outer jacve
+        differentiates through the inner Jacobian accumulation (second-order derivatives).  The inner plan uses
+        the reference's division formulas (``division="ieee"``): one equation per division to differentiate."""
+        from .tracer import Tracer, jnp as tjnp
+        if self.sparse_representation:
+            raise NotImplementedError("sparse_representation inside a traced function")
+        shapes = [tuple(a.shape) if isinstance(a, Tracer) else tuple(np.shape(a)) for a in args]
+        jaxpr = make_jaxpr(self.fun, shapes)
+        order = self.order
+        if not isinstance(order, str) and self.order_numbering == "vmap":
+            order = jaxpr.translate_vmap_order(order)
+        plan = build_plan(jaxpr, order, self.argnums, with_primal=True, division="ieee")
+        comps: List[Any] = []
+        for a, shape in zip(args, shapes):
+            size = int(np.prod(shape, dtype=np.int64)) if shape else 1
+            if not shape:
+                comps.append(a if isinstance(a, Tracer) else float(a))
+            elif isinstance(a, Tracer):
+                flat = a.reshape(size)
+                comps.extend(flat[i] for i in range(size))
+            else:
+                comps.extend(float(v) for v in np.asarray(a, dtype=np.float32).reshape(-1))
+        dag = plan.dag
+        unary = {"neg": lambda x: -x, "abs": tjnp.abs, "sqrt": tjnp.sqrt, "sin": tjnp.sin, "cos": tjnp.cos,
+                 "tan": tjnp.tan, "exp": tjnp.exp, "log": tjnp.log, "log1p": tjnp.log1p, "tanh": tjnp.tanh,
+                 "sinh": tjnp.sinh, "cosh": tjnp.cosh, "asin": tjnp.arcsin, "acos": tjnp.arccos,
+                 "atan": tjnp.arctan, "asinh": tjnp.arcsinh, "acosh": tjnp.arccosh, "atanh": tjnp.arctanh,
+                 "erf": tjnp.erf, "logistic": tjnp.sigmoid}
+        binary = {"add": lambda x, y: x + y, "sub": lambda x, y: x - y, "mul": lambda x, y: x * y,
+                  "div": lambda x, y: x / y, "atan2": tjnp.arctan2, "pow": tjnp.power, "max": tjnp.maximum,
+                  "min": tjnp.minimum, "gt": tjnp.greater, "lt": tjnp.less, "eq": tjnp.equal}
+        vals: Dict[int, Any] = {}
+
+        def value(node: int):
+            kind = dag.op[node]
+            if kind == "const":
+                return float(dag.cval[node])
+            if kind == "input":
+                return comps[dag.args[node][0]]
+            return vals[node]
+
+        tile: List[Any] = [0.0] * (plan.n_rows * plan.n_cols)
+        primal: List[Any] = [0.0] * plan.n_rows
+        for op in plan.ssa:
+            xs = [value(a) for a in op.args]
+            if op.op == "store_jac":
+                tile[op.dst] = xs[0]
+            elif op.op == "store_primal":
+                primal[op.dst] = xs[0]
+            elif not any(isinstance(x, Tracer) for x in xs):
+                raise NotImplementedError(f"nested jacve: constant sub-expression ({op.op}) left to the device")
+            elif op.op == "fma":
+                vals[op.dst] = xs[0] * xs[1] + xs[2]
+            elif op.op in unary:
+                vals[op.dst] = unary[op.op](xs[0])
+            else:
+                vals[op.dst] = binary[op.op](xs[0], xs[1])
+
+        def assemble(entries: List[Any], shape: Tuple[int, ...]):
+            if not shape:
+                return entries[0]
+            parts = [e.reshape(1) if isinstance(e, Tracer) else tjnp.zeros((1,)) + e for e in entries]
+            return tjnp.concatenate(parts).reshape(shape) if len(parts) > 1 else parts[0].reshape(shape)
+
+        rows = np.concatenate([[0], np.cumsum(plan.out_sizes)]).astype(int)
+        cols = np.concatenate([[0], np.cumsum([plan.in_sizes[a] for a in self.argnums])]).astype(int)
+        blocks = []
+        for oi, o in enumerate(jaxpr.outvars):
+            row = []
+            for ai, a in enumerate(self.argnums):
+                entries = [tile[r * plan.n_cols + c] for r in range(rows[oi], rows[oi + 1])
+                           for c in range(cols[ai], cols[ai + 1])]
+                row.append(assemble(entries, tuple(o.shape) + tuple(shapes[a])))
+            blocks.append(row)
+        grads_tree, single = self._tree(blocks, len(jaxpr.invars))
+        if self.count_ops:
+            if plan.stats["num_muls"] is None:
+                raise NotImplementedError("count_ops needs tensor-level edge structure (rank <= 1 vertices)")
+            return grads_tree, {"num_muls": plan.stats["num_muls"], "num_adds": plan.stats["num_adds"]}
+        if self.has_aux:
+            outs = [assemble(primal[rows[oi]:rows[oi + 1]], tuple(o.shape)) for oi, o in enumerate(jaxpr.outvars)]
+            return (outs[0] if single else tuple(outs)), grads_tree
+        return grads_tree
+
     def __call__(self, *args):
+        from .tracer import Tracer
+        if any(isinstance(a, Tracer) for a in args):
+            return self._run_traced(args)
         return self._run(args, batched=False)
 
     def batched(self, *args, out=None):
@@ -269,6 +440,32 @@ def vmap(jacfun: JacveFunction, in_axes: int = 0) -> Callable:
     """``jax.vmap(jacve(f, ...))`` for the engine: the batch becomes the CUDA grid."""
     if not isinstance(jacfun, JacveFunction):
         raise TypeError("graphax_b200.vmap only batches functions returned by graphax_b200.jacve")
-    if in_axes != 0:
-        raise NotImplementedError("only in_axes=0 (leading batch axis) is supported")
-    return jacfun.batched
+    if in_axes == 0:
+        return jacfun.batched
+    if not isinstance(in_axes, (tuple, list)) or any(a not in (0, None) for a in in_axes):
+        raise NotImplementedError("in_axes must be 0 or a tuple of 0 / None (leading batch axis or shared argument)")
+    axes = tuple(in_axes)
+
+    def batched(*args, out=None):
+        """Shared (in_axes None) arguments - e.g. the weights in ``vmap(f, in_axes=(0, None, ...))`` of the
+        reference's vmap_NeuralNetwork test - are broadcast along the batch: every sample's Jacobian block
+        with respect to them has shape ``[batch, *out, *arg.shape]``."""
+        import torch
+        if len(args) != len(axes):
+            raise ValueError(f"in_axes has {len(axes)} entries for {len(args)} arguments")
+        lead = [a for a, ax in zip(args, axes) if ax == 0]
+        if not lead:
+            raise ValueError("at least one argument must carry the batch axis")
+        batch = lead[0].shape[0]
+        full = []
+        for a, ax in zip(args, axes):
+            if ax is None:
+                t = a if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a, dtype=np.float32))
+                if isinstance(lead[0], torch.Tensor):
+                    t = t.to(lead[0].device)
+                a = t.expand((batch,) + tuple(t.shape)).contiguous()
+                if not isinstance(lead[0], torch.Tensor):
+                    a = a.numpy()
+            full.append(a)
+        return jacfun.batched(*full, out=out)
+    return batched

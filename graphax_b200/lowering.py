@@ -303,6 +303,11 @@ def lower_eqn(dag: Dag, eqn: Eqn, read, division: str = "ieee") -> Tuple[Vec, Li
         first = ew.binary("gt" if prim == "max" else "lt", x, y)          # 1.0 where x wins, else 0.0
         second = ew.sub(ew.lit(1.0), first)
         return edges(out, (first, second))
+    if prim in ("gt", "lt", "eq"):   # primitives.py:218-223: comparisons carry zero partials
+        x, y = ops
+        out = ew.binary(prim, x, y)
+        zero = Vec(out.shape, [dag.const(0.0)] * out.size)
+        return edges(out, (zero, zero))
     if prim in ("add", "sub", "mul", "div", "atan2", "pow"):
         x, y = ops
         if prim == "div" and recip:

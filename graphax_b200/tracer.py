@@ -304,9 +304,15 @@ class Tracer:
         return _dot(self, other)
 
 
+_CONST_UNARY = {"sqrt": np.sqrt, "abs": np.abs, "neg": np.negative, "exp": np.exp, "log": np.log, "sin": np.sin,
+                "cos": np.cos, "tan": np.tan, "tanh": np.tanh}
+
+
 def _unary(prim: str):
     def fn(x: Any) -> Tracer:
         if not isinstance(x, Tracer):
+            if isinstance(x, (int, float, np.floating, np.integer)) and prim in _CONST_UNARY:
+                return float(np.float32(_CONST_UNARY[prim](np.float32(x))))   # constants fold at trace time
             raise TypeError(f"{prim} expects a traced value")
         return x.trace.emit(prim, (x.var,), x.shape)
     fn.__name__ = prim
@@ -519,6 +525,9 @@ class _JnpShim:
     divide = staticmethod(_binary_fn("div"))
     arctan2 = staticmethod(_binary_fn("atan2"))
     power = staticmethod(_binary_fn("pow"))
+    greater = staticmethod(_binary_fn("gt"))      # 1.0 / 0.0 (the tracer has one dtype); zero partials
+    less = staticmethod(_binary_fn("lt"))
+    equal = staticmethod(_binary_fn("eq"))
     maximum = staticmethod(_binary_fn("max"))
     minimum = staticmethod(_binary_fn("min"))
     erf = staticmethod(_unary("erf"))

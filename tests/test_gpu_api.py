@@ -121,3 +121,30 @@ def test_further_reference_examples_via_runtime_specialisation(built_library, na
     if name == "helmholtz":      # one input, one output: a 1-tuple holding the [4, 4] block (core.py:76-92)
         out, _ = gx.jacve(w.fun, order=[2, 5, 4, 3, 1], argnums=(0,), count_ops=True)(*args)
         assert isinstance(out, tuple) and len(out) == 1 and tuple(out[0].shape) == (4, 4)
+
+
+@pytest.mark.parametrize("order", ["fwd", "rev"])
+def test_elementwise_function_of_matrices(built_library, order):
+    """Reference test_Simple with 50x50 arguments (example_test.py:49-54): every edge is diagonal, the blocks
+    come back dense as out.shape + in.shape = [50,50,50,50] (or as their diagonal values with
+    sparse_representation=True)."""
+    import torch
+    from graphax_b200.examples import Simple
+    rng = np.random.default_rng(4)
+    x, y = rng.uniform(0.5, 1.5, (50, 50)).astype(np.float32), rng.uniform(0.5, 1.5, (50, 50)).astype(np.float32)
+    jac = gx.jacve(Simple, order=order, argnums=(0, 1))(x, y)
+    assert len(jac) == 2 and len(jac[0]) == 2 and tuple(jac[0][0].shape) == (50, 50, 50, 50)
+    xt, yt = torch.tensor(x, dtype=torch.float64), torch.tensor(y, dtype=torch.float64)
+    z = xt * yt
+    want = {(0, 0): (torch.cos(z) + 1) * yt, (0, 1): (torch.cos(z) + 1) * xt,
+            (1, 0): torch.cos(z) / torch.sin(z) * yt, (1, 1): torch.cos(z) / torch.sin(z) * xt}
+    for (o, a), d in want.items():
+        blk = jac[o][a].cpu().double().reshape(2500, 2500)
+        assert torch.allclose(blk.diagonal(), d.reshape(-1), rtol=1e-5, atol=1e-6)
+        assert float((blk - torch.diag(blk.diagonal())).abs().max()) == 0.0
+    sp = gx.jacve(Simple, order=order, argnums=(0, 1), sparse_representation=True)(x, y)
+    assert sp[1][0].val_shape == [50, 50] and sp[1][0].out_dims[0][0] == "sparse"
+    assert torch.allclose(sp[1][0].dense.cpu().double(), want[(1, 0)], rtol=1e-5, atol=1e-6)
+    _, aux = gx.jacve(Simple, order=order, argnums=(0, 1), count_ops=True)(x, y)
+    _, aux1 = gx.jacve(Simple, order=order, argnums=(0, 1), count_ops=True)(5., 7.)
+    assert aux["num_muls"] == 2500 * aux1["num_muls"] and aux["num_adds"] == 2500 * aux1["num_adds"]

@@ -150,3 +150,30 @@ def test_gpu_kernels_match_plan_replay(built_library, name):
         for o, row in zip(jaxpr.outvars, outs):
             for a, blk in zip(argnums, row):
                 assert tuple(blk.shape) == (300,) + tuple(o.shape) + tuple(shapes[a])
+
+
+@pytest.mark.gpu
+def test_vmap_with_shared_weights(built_library):
+    """Reference test_vmap_NeuralNetwork (example_test.py:200-238): x and y batched, weights shared
+    (in_axes=(0, None, None, None, None, 0)); the per-sample weight Jacobians summed over the batch are the
+    gradient of the summed loss, checked against torch.autograd."""
+    import torch
+    fn, shapes = CASES["NeuralNetwork"]
+    rng = np.random.default_rng(8)
+    B = 16
+    x, y = rng.normal(size=(B, 4)).astype(np.float32), rng.normal(size=(B, 4)).astype(np.float32)
+    W1, b1 = rng.normal(size=(8, 4)).astype(np.float32), rng.normal(size=(8,)).astype(np.float32)
+    W2, b2 = rng.normal(size=(4, 8)).astype(np.float32), rng.normal(size=(4,)).astype(np.float32)
+    for order in ("fwd", "rev"):
+        jf = gx.jacve(fn, order=order, argnums=(1, 2, 3, 4))
+        cuda = lambda a: torch.from_numpy(a).cuda()
+        jac = gx.vmap(jf, in_axes=(0, None, None, None, None, 0))(cuda(x), cuda(W1), cuda(b1), cuda(W2), cuda(b2), cuda(y))
+        assert [tuple(j.shape) for j in jac] == [(B, 8, 4), (B, 8), (B, 4, 8), (B, 4)]
+        t = [torch.tensor(a, dtype=torch.float64, requires_grad=True) for a in (W1, b1, W2, b2)]
+        xt, yt = torch.tensor(x, dtype=torch.float64), torch.tensor(y, dtype=torch.float64)
+        a1 = torch.tanh(xt @ t[0].T + t[1])
+        a2 = torch.tanh(a1 @ t[2].T + t[3])
+        loss = (0.5 * (a2 - yt) ** 2).sum()
+        grads = torch.autograd.grad(loss, t)
+        for j, g in zip(jac, grads):
+            assert torch.allclose(j.sum(0).cpu().double(), g, rtol=1e-4, atol=1e-5)
