@@ -369,12 +369,9 @@ bool use_pdl() {
 
 // samples per pipeline stage of gx_jacve_host (GX_HOST_CHUNK overrides, for tuning)
 int64_t host_chunk() {
-  static const int64_t v = [] {
-    const char* e = getenv("GX_HOST_CHUNK");
-    long long n = e ? atoll(e) : 0;
-    return (int64_t)(n >= 1024 ? n : (1 << 17));
-  }();
-  return v;
+  const char* e = getenv("GX_HOST_CHUNK");
+  long long n = e ? atoll(e) : 0;
+  return (int64_t)(n >= 1024 ? n : (1 << 17));
 }
 
 }  // namespace
@@ -418,6 +415,7 @@ struct gx_plan {
 
   // host pipeline resources (lazily created, guarded by host_mu)
   std::mutex host_mu;
+  int64_t host_chunk = 0;
   struct HostSlot {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
@@ -906,7 +904,8 @@ int gx_jacve_host(gx_plan* p, int64_t batch, const void* const* in_ptrs, void* j
   std::lock_guard<std::mutex> lock(p->host_mu);
   GX_CUDA(cudaSetDevice(p->device));
   const size_t n_in = p->h.n_in_scalars, tile = (size_t)p->h.n_rows * p->h.n_cols, rows = p->h.n_rows;
-  const int64_t kHostChunk = host_chunk();
+  if (p->host_chunk == 0) p->host_chunk = host_chunk();   // fixed at the plan's first host call (sizes the staging buffers)
+  const int64_t kHostChunk = p->host_chunk;
   const bool staging = !pinned;
   if (!p->host_ready || (staging && !p->host_staging)) {
     for (auto& s : p->slots) {

@@ -79,8 +79,13 @@ class Plan:
 
     @property
     def key(self) -> str:
-        """FNV-1a 64 of the blob (same function as gx_hash_bytes): names AOT/JIT kernels."""
-        return f"{fnv1a64(self.blob):016x}"
+        """FNV-1a 64 of the blob (same function as gx_hash_bytes): names AOT/JIT kernels.  Cached per blob
+        object: the pure-Python hash of a 16 KB blob costs ~1 ms, which the host call path must not pay."""
+        cached = self.__dict__.get("_key_cache")
+        if cached is None or cached[0] is not self.blob:
+            cached = (self.blob, f"{fnv1a64(self.blob):016x}")
+            self.__dict__["_key_cache"] = cached
+        return cached[1]
 
     @property
     def n_in_scalars(self) -> int:

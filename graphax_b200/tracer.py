@@ -551,6 +551,24 @@ class _JnpShim:
     concatenate = staticmethod(_concatenate)
 
     @staticmethod
+    def split(x, indices_or_sections, axis: int = 0):
+        """jnp.split: a chain of slices (reference tests/core/multi_output_primitives_test.py:14-21)."""
+        axis = axis % x.ndim
+        n = x.shape[axis]
+        if isinstance(indices_or_sections, (int, np.integer)):
+            if n % int(indices_or_sections):
+                raise ValueError("array split does not result in an equal division")
+            step = n // int(indices_or_sections)
+            cuts = list(range(step, n, step))
+        else:
+            cuts = [int(i) for i in indices_or_sections]
+        parts, lo = [], 0
+        for hi in cuts + [n]:
+            parts.append(x[tuple(slice(None) if d != axis else slice(lo, hi) for d in range(x.ndim))])
+            lo = hi
+        return parts
+
+    @staticmethod
     def ones(shape, dtype=None):
         """``jnp.ones(())`` folds to a literal under make_jaxpr (function g)."""
         if shape == () or shape == []:

@@ -32,6 +32,11 @@ def outer(x, y): return jnp.outer(x, y) + x.reshape(3, 1)
 def indexing(x, y): return x[1] * y[:, 2] + x[0, 1:3].sum()
 
 
+def array_split(x, y):
+    z, u, v = jnp.split(x, [2, 4], axis=0)
+    return jnp.sin(z) @ y, u + jnp.log(v)
+
+
 def NeuralNetwork(x, W1, b1, W2, b2, y):
     a1 = jnp.tanh(W1 @ x + b1)
     a2 = jnp.tanh(W2 @ a1 + b2)
@@ -47,7 +52,7 @@ CASES = {
     "slicing": (slicing, [(2, 3), (3, 4)]), "squeezing": (squeezing, [(2, 3), (3, 1)]),
     "concatenate_1": (concatenate_1, [(2, 3), (2, 4), (1, 4)]), "concatenate_2": (concatenate_2, [(4,), (2,), (3,)]),
     "reshape": (reshape, [(6,), (3,)]), "large_matmul": (large_matmul, [(3, 1, 4), (4, 3, 2)]),
-    "outer": (outer, [(3,), (4,)]), "indexing": (indexing, [(3, 4), (4, 3)]),
+    "outer": (outer, [(3,), (4,)]), "array_split": (array_split, [(6, 3), (3, 2)]), "indexing": (indexing, [(3, 4), (4, 3)]),
     "NeuralNetwork": (NeuralNetwork, [(4,), (8, 4), (8,), (4, 8), (4,), (4,)]),
 }
 
