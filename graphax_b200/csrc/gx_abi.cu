@@ -982,7 +982,10 @@ struct gx_jit_kernel {
   CUmodule module = nullptr;
   CUfunction func = nullptr;
   int device = 0;
+  bool smem_set = false;
 };
+
+#include "gx_gemm_kernel_decl.h"
 
 namespace {
 // out[c] (+)= sum_r in[r, c]; one CTA owns a 32-column strip of up to rows_per_cta rows
@@ -1065,6 +1068,51 @@ int gx_jit_launch(gx_jit_kernel* k, unsigned grid_x, unsigned grid_y, unsigned b
   cfg.hStream = (CUstream)stream;
   CUresult r = driver().LaunchKernelEx(&cfg, k->func, args, nullptr);
   if (r != CUDA_SUCCESS) return fail(GX_ERR_CUDA, "cuLaunchKernelEx(jit kernel): " + cu_err(r));
+  return GX_OK;
+}
+
+// A run-time compiled instance of gx_gemm_kernel.cuh with a generated epilogue (GX_GEMM_FUSED): same tiling and
+// tensor maps as gx_gemm_bf16; `epi` is the kernel's GxEpi parameter block (pointers of the fused operands and
+// outputs), copied by the launch.
+int gx_gemm_fused_launch(gx_jit_kernel* k, int M, int N, int K, const void* A, int a_mn, const void* B, int b_mn,
+                         const void* epi, void* stream) {
+  if (!k || !A || !B || !epi) return fail(GX_ERR_BAD_ARG, "gx_gemm_fused_launch: NULL argument");
+  if (M <= 0 || N <= 0 || K <= 0 || M % 128 || N % 128 || K % 64)
+    return fail(GX_ERR_UNSUPPORTED, "gx_gemm_fused_launch: M, N must be multiples of 128, K of 64");
+  CUtensorMap map_a, map_b;
+  if (gxg_make_maps(&map_a, &map_b, M, N, K, A, a_mn, B, b_mn))
+    return fail(GX_ERR_CUDA, "gx_gemm_fused_launch: cuTensorMapEncodeTiled failed (pointers must be 16-byte aligned)");
+  if (!k->smem_set) {
+    CUresult r = driver().FuncSetAttribute(k->func, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)gxg::kSmemBytes);
+    if (r != CUDA_SUCCESS) return fail(GX_ERR_CUDA, "cuFuncSetAttribute(fused gemm): " + cu_err(r));
+    k->smem_set = true;
+  }
+  gxg::GemmArgs args;
+  memset(&args, 0, sizeof args);
+  args.M = M;
+  args.N = N;
+  args.K = K;
+  args.ldc = N;
+  args.k_per_split = K;
+  args.a_mn = a_mn ? 1 : 0;
+  args.b_mn = b_mn ? 1 : 0;
+  CUlaunchConfig cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDimX = N / 128;
+  cfg.gridDimY = M / 128;
+  cfg.gridDimZ = 1;
+  cfg.blockDimX = gxg::kThreads;
+  cfg.blockDimY = cfg.blockDimZ = 1;
+  cfg.sharedMemBytes = gxg::kSmemBytes;
+  cfg.hStream = (CUstream)stream;
+  CUlaunchAttribute attr[1];
+  attr[0].id = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;
+  attr[0].value.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl() ? 1 : 0;
+  void* params[] = {&map_a, &map_b, &args, const_cast<void*>(epi)};
+  CUresult r = driver().LaunchKernelEx(&cfg, k->func, params, nullptr);
+  if (r != CUDA_SUCCESS) return fail(GX_ERR_CUDA, "cuLaunchKernelEx(fused gemm): " + cu_err(r));
   return GX_OK;
 }
 

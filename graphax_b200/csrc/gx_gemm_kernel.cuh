@@ -1,0 +1,395 @@
+// gx_gemm_kernel.cuh - device side of the dense x dense contraction on the 5th-generation tensor cores
+// (tcgen05 + TMEM + TMA).  Included by gx_gemm.cu (compiled into the library with the plain store / bf16 /
+// split-K epilogues) and compiled at run time with NVRTC in front of a generated epilogue (GX_GEMM_FUSED:
+// graphax_b200/dense.py emits `struct GxEpi`, `gx_epi_chunk` and `gx_epi_finish`), so that the elementwise
+// half of the reference's products (`_pure_broadcast_mul`, sparse/tensor.py:826-866, and the elemental
+// partials, primitives.py:150-205) runs on the accumulator while it is still in registers.
+//
+//     C[M,N] (+)= op(A) * op(B)^T     A, B bf16; K-major ([M,K] / [N,K] row-major) or MN-major ([K,M] / [K,N])
+//
+// One CTA computes one 128 x 128 tile (optionally one K-split of it):
+//   warp 0   TMA producer  - cp.async.bulk.tensor.2d of 128x64 A and B boxes (SWIZZLE_128B) into a
+//                            kStages-deep shared-memory ring, completion on per-stage mbarriers
+//   warp 1   MMA issuer    - allocates 128 TMEM columns; one elected lane issues tcgen05.mma
+//                            (kind::f16, M128 N128 K16) four times per stage and tcgen05.commit's the
+//                            stage back to the producer, finally signals the epilogue
+//   warps 2-9 epilogue     - tcgen05.ld the fp32 accumulator (32 lanes x 32 columns at a time; two warps per
+//                            TMEM lane quadrant, each owning 64 of the 128 columns), then the epilogue: store
+//                            fp32 / bf16 rows, red.global.add.v4.f32 (split-K), or the fused one
+// The prologue (barrier init, TMEM allocation, descriptor prefetch) may overlap the tail of the previous
+// kernel on the stream (programmatic dependent launch); nothing touches global memory before
+// griddepcontrol.wait.
+#pragma once
+
+#ifdef GX_NVRTC
+typedef unsigned char uint8_t;
+typedef unsigned short uint16_t;
+typedef unsigned int uint32_t;
+typedef unsigned long long uint64_t;
+typedef unsigned long long uintptr_t;
+struct alignas(64) CUtensorMap {
+  uint64_t opaque[16];
+};
+#else
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#endif
+
+namespace gxg {
+
+constexpr int BM = 128, BN = 128, BK = 64, UMMA_K = 16;
+constexpr int kStages = 3;   // 96 KB of operand ring: two CTAs per SM, one's epilogue overlaps the other's main loop
+constexpr int kThreads = 320;   // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quadrant)
+constexpr int kTmemCols = 128;
+constexpr uint32_t kStageBytesA = BM * BK * 2, kStageBytesB = BN * BK * 2;
+constexpr uint32_t kSmemBytes = kStages * (kStageBytesA + kStageBytesB) + 1024 /*align*/ + 256 /*barriers*/;
+
+enum { EPI_STORE_F32 = 0, EPI_STORE_BF16 = 1, EPI_ATOMIC_F32 = 2 };
+
+struct GemmArgs {
+  float* c_f32;
+  uint16_t* c_bf16;
+  int M, N, K, ldc, epilogue, k_per_split;
+  int a_mn, b_mn;   // operand stored [K, M] / [K, N] (MN-major) instead of [M, K] / [N, K]
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nGG_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra GG_DONE;\nbra GG_WAIT;\nGG_DONE:\n}\n" ::"r"(
+          smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// fp32 -> bf16 bits, round to nearest even (NaN stays NaN)
+__device__ __forceinline__ uint32_t f32_to_bf16_bits(float f) {
+  const uint32_t u = __float_as_uint(f);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (u >> 16) | 0x40u;
+  return (u + 0x7fffu + ((u >> 16) & 1u)) >> 16;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {   // one F2FP instruction, round to nearest even
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float bf16_bits_to_f32(uint32_t h) { return __uint_as_float(h << 16); }
+
+// Sum v[j] over the 32 lanes of the warp for every j at once: recursive halving, 31 shuffles in total.
+// Afterwards v[0] of lane l holds the sum over all lanes of the original v[l].
+__device__ __forceinline__ void warp_transpose_reduce(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+}
+
+// Epilogue staging.  tcgen05.ld hands every lane one ROW of the chunk (32 consecutive columns), so direct stores
+// touch 32 different lines per instruction with 8-16 bytes each, and the LSU -> L2 transaction rate, not bandwidth,
+// bounds the epilogue (measured: ~8 us per million partial-line stores).  Each warp therefore passes its 32 x 32
+// chunk through a private 4 KB shared-memory tile (the operand ring is free once the accumulator is complete;
+// 16-byte groups XOR-swizzled by the row so that both directions are conflict-free) and writes global memory
+// with row-contiguous 128-bit accesses: four full 128-byte lines per instruction.
+__device__ __forceinline__ void stage_rows(float* tile, const float (&y)[32], int lane) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    *reinterpret_cast<float4*>(tile + lane * 32 + ((q ^ (lane & 7)) << 2)) =
+        make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+  __syncwarp();
+}
+// i-th read-back step (i = 0..7): this lane's 4 consecutive columns (lane & 7) * 4 .. of tile row 4 * i + (lane >> 3)
+__device__ __forceinline__ float4 staged_quad(const float* tile, int i, int lane) {
+  const int r = 4 * i + (lane >> 3);
+  return *reinterpret_cast<const float4*>(tile + r * 32 + (((lane & 7) ^ (r & 7)) << 2));
+}
+// The reverse direction for [M, N] operands of a fused epilogue: row-contiguous 128-bit loads into the tile, then
+// every lane picks up its own row.  (Per-lane row loads would hit 32 lines per instruction, and with two CTAs'
+// operand rings resident there is too little L1 left to keep those lines until their other 7 quads are read.)
+__device__ __forceinline__ void unstage_rows(const float* tile, float (&y)[32], int lane) {
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 t = *reinterpret_cast<const float4*>(tile + lane * 32 + ((q ^ (lane & 7)) << 2));
+    y[4 * q] = t.x, y[4 * q + 1] = t.y, y[4 * q + 2] = t.z, y[4 * q + 3] = t.w;
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void load_rows_f32(float* tile, float (&y)[32], const float* base, int ld, int m_base, int M,
+                                              int col0, int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = 4 * i + (lane >> 3), row = m_base + r;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < M) t = __ldg(reinterpret_cast<const float4*>(base + (size_t)row * ld + col0 + (lane & 7) * 4));
+    *reinterpret_cast<float4*>(tile + r * 32 + (((lane & 7) ^ (r & 7)) << 2)) = t;
+  }
+  unstage_rows(tile, y, lane);
+}
+__device__ __forceinline__ void load_rows_bf16(float* tile, float (&y)[32], const uint16_t* base, int ld, int m_base, int M,
+                                               int col0, int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = 4 * i + (lane >> 3), row = m_base + r;
+    uint2 u = make_uint2(0u, 0u);
+    if (row < M) u = __ldg(reinterpret_cast<const uint2*>(base + (size_t)row * ld + col0 + (lane & 7) * 4));
+    *reinterpret_cast<float4*>(tile + r * 32 + (((lane & 7) ^ (r & 7)) << 2)) =
+        make_float4(bf16_bits_to_f32(u.x & 0xffffu), bf16_bits_to_f32(u.x >> 16), bf16_bits_to_f32(u.y & 0xffffu),
+                    bf16_bits_to_f32(u.y >> 16));
+  }
+  unstage_rows(tile, y, lane);
+}
+__device__ __forceinline__ void store_rows_f32(float* tile, const float (&y)[32], float* base, int ld, int m_base, int M,
+                                               int col0, int lane) {
+  stage_rows(tile, y, lane);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = m_base + 4 * i + (lane >> 3);
+    if (row < M) *reinterpret_cast<float4*>(base + (size_t)row * ld + col0 + (lane & 7) * 4) = staged_quad(tile, i, lane);
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void store_rows_bf16(float* tile, const float (&y)[32], uint16_t* base, int ld, int m_base, int M,
+                                                int col0, int lane) {
+  stage_rows(tile, y, lane);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = m_base + 4 * i + (lane >> 3);
+    const float4 t = staged_quad(tile, i, lane);
+    if (row < M)
+      *reinterpret_cast<uint2*>(base + (size_t)row * ld + col0 + (lane & 7) * 4) =
+          make_uint2(pack_bf16x2(t.x, t.y), pack_bf16x2(t.z, t.w));
+  }
+  __syncwarp();
+}
+// both copies from one staging pass (either pointer may be null)
+__device__ __forceinline__ void store_rows(float* tile, const float (&y)[32], float* o32, uint16_t* o16, int ld, int m_base,
+                                           int M, int col0, int lane) {
+  if (!o32 && !o16) return;
+  stage_rows(tile, y, lane);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = m_base + 4 * i + (lane >> 3);
+    const float4 t = staged_quad(tile, i, lane);
+    if (row < M) {
+      const size_t off = (size_t)row * ld + col0 + (lane & 7) * 4;
+      if (o32) *reinterpret_cast<float4*>(o32 + off) = t;
+      if (o16) *reinterpret_cast<uint2*>(o16 + off) = make_uint2(pack_bf16x2(t.x, t.y), pack_bf16x2(t.z, t.w));
+    }
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void red_rows_f32(float* tile, const float (&y)[32], float* base, int ld, int m_base, int M,
+                                             int col0, int lane) {
+  stage_rows(tile, y, lane);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = m_base + 4 * i + (lane >> 3);
+    const float4 t = staged_quad(tile, i, lane);
+    if (row < M)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(base + (size_t)row * ld + col0 + (lane & 7) * 4),
+                   "f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w)
+                   : "memory");
+  }
+  __syncwarp();
+}
+
+// K-major, 128-byte swizzled operand tile: 8-row groups of 1024 B (SBO), LBO unused (=1), version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// MN-major operand (stored [K, MN] with the M/N axis contiguous), 128-byte swizzle: the tile is two boxes of
+// [64 K-rows x 64 MN-elements] (8 KB each); LBO = distance between the two 64-element MN atoms, SBO = distance
+// between groups of 8 K-rows (8 x 128 B)
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(8192 >> 4) << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16: D fp32, A/B bf16, M = 128, N = 128; bit 15 / 16 select MN-major A / B
+constexpr uint32_t kInstrDescBase = (1u << 4) | (1u << 7) | (1u << 10) | ((BN >> 3) << 17) | ((BM >> 4) << 24);
+
+}  // namespace gxg
+
+#ifndef GX_GEMM_KERNEL_NAME
+#define GX_GEMM_KERNEL_NAME gx_gemm_tn_kernel
+#endif
+
+#ifdef GX_GEMM_FUSED
+#define GX_GEMM_EPI_PARAM , const __grid_constant__ GxEpi epi
+#else
+#define GX_GEMM_EPI_PARAM
+#endif
+
+extern "C" __global__ void __launch_bounds__(gxg::kThreads, 2)
+GX_GEMM_KERNEL_NAME(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const gxg::GemmArgs args GX_GEMM_EPI_PARAM) {
+  using namespace gxg;
+  extern __shared__ uint8_t gg_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gg_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * kStageBytesA;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * (kStageBytesA + kStageBytesB));
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int k_begin = blockIdx.z * args.k_per_split;
+  const int num_k_blocks = (args.k_per_split + BK - 1) / BK;
+
+  if (warp == 0 && elect_one()) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // the allocating warp also owns the deallocation
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
+                 "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+  // everything above overlapped the previous kernel's tail; from here on its results are needed
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        const int s = kb % kStages;
+        mbar_wait(&empty_bar[s], ((kb / kStages) & 1) ^ 1);  // slot free (passes immediately the first round)
+        mbar_expect_tx(&full_bar[s], kStageBytesA + kStageBytesB);
+        const int k0 = k_begin + kb * BK;
+        if (!args.a_mn) {
+          tma_load_2d(smem_a + s * kStageBytesA, &map_a, k0, m0, &full_bar[s]);
+        } else {   // two [64 k x 64 m] boxes
+          tma_load_2d(smem_a + s * kStageBytesA, &map_a, m0, k0, &full_bar[s]);
+          tma_load_2d(smem_a + s * kStageBytesA + 8192, &map_a, m0 + 64, k0, &full_bar[s]);
+        }
+        if (!args.b_mn) {
+          tma_load_2d(smem_b + s * kStageBytesB, &map_b, k0, n0, &full_bar[s]);
+        } else {
+          tma_load_2d(smem_b + s * kStageBytesB, &map_b, n0, k0, &full_bar[s]);
+          tma_load_2d(smem_b + s * kStageBytesB + 8192, &map_b, n0 + 64, k0, &full_bar[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    for (int kb = 0; kb < num_k_blocks; ++kb) {
+      const int s = kb % kStages;
+      mbar_wait(&full_bar[s], (kb / kStages) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = smem_u32(smem_a + s * kStageBytesA), sb = smem_u32(smem_b + s * kStageBytesB);
+        const uint64_t da = args.a_mn ? make_smem_desc_mn(sa) : make_smem_desc(sa);
+        const uint64_t db = args.b_mn ? make_smem_desc_mn(sb) : make_smem_desc(sb);
+        // one MMA consumes 16 K: K-major = 32 B inside the swizzle atom (+2 in the 16-byte address field),
+        // MN-major = 16 rows of 128 B (+128)
+        const uint32_t step_a = args.a_mn ? 128u : 2u, step_b = args.b_mn ? 128u : 2u;
+        const uint32_t idesc = kInstrDescBase | (args.a_mn ? (1u << 15) : 0u) | (args.b_mn ? (1u << 16) : 0u);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k)
+          umma_f16(tmem_base, da + step_a * k, db + step_b * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        umma_commit(&empty_bar[s]);                       // smem slot reusable once these MMAs have read it
+        if (kb == num_k_blocks - 1) umma_commit(tmem_full_bar);  // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue: warp w may only touch TMEM lanes 32*(w%4) .. 32*(w%4)+31 =====
+    const int quad = warp & 3;
+    const int c_begin = ((warp - 2) >> 2) * (BN / 2);
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int m_base = m0 + quad * 32;
+    float* tile = reinterpret_cast<float*>(smem) + (warp - 2) * 1024;   // 4 KB of the (now idle) operand ring per warp
+#ifdef GX_GEMM_FUSED
+    GxEpiState epi_state;
+    gx_epi_begin(epi_state);
+#endif
+#pragma unroll 1
+    for (int c = c_begin; c < c_begin + BN / 2; c += 32) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float acc[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
+#ifdef GX_GEMM_FUSED
+      gx_epi_chunk(epi, epi_state, tile, m_base, n0 + c, args.M, args.N, acc, lane);
+#else
+      if (args.epilogue == EPI_STORE_F32)
+        store_rows_f32(tile, acc, args.c_f32, args.ldc, m_base, args.M, n0 + c, lane);
+      else if (args.epilogue == EPI_STORE_BF16)
+        store_rows_bf16(tile, acc, args.c_bf16, args.ldc, m_base, args.M, n0 + c, lane);
+      else
+        red_rows_f32(tile, acc, args.c_f32, args.ldc, m_base, args.M, n0 + c, lane);
+#endif
+    }
+#ifdef GX_GEMM_FUSED
+    gx_epi_finish(epi, epi_state, lane);
+#endif
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+  }
+}

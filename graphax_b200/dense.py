@@ -23,6 +23,8 @@ Anything else (other orders, vector outputs, rank > 2, batch dimensions) raises 
 from __future__ import annotations
 
 import ctypes
+from pathlib import Path
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -255,6 +257,15 @@ def build_dense_plan(jaxpr: Jaxpr, order, argnums: Sequence[int]) -> DensePlan:
 # ------------------------------------------------------------------------------------------------
 _EW_FMT = dict(_FMT)
 _EW_FMT["copy"] = "({0})"
+# tanh on [B, H] tensors is the dominant elementwise cost of an MLP step: libm's tanhf is ~30 instructions, this
+# form is 7 (ex2.approx + rcp.approx, absolute error ~2e-7, far below the bf16 rounding of the GEMM operands)
+_EW_FMT["tanh"] = "gx_tanh({0})"
+_GX_TANH = """__device__ __forceinline__ float gx_tanh(float x) {
+  const float e = __expf(2.0f * fabsf(x));                 // ex2.approx; overflows to +inf -> result 1
+  const float r = 1.0f - __fdividef(2.0f, e + 1.0f);
+  return copysignf(r, x);
+}
+"""
 
 
 class DenseExecutor:
@@ -309,14 +320,56 @@ class DenseExecutor:
         self.launches = 0
         self._ew_meta: Dict[int, tuple] = {}
         self.input_dtypes: Optional[List[str]] = None     # elementwise kernels are compiled once these are known
-        # which fp32 copies does anybody read?
+        self.fuse = os.environ.get("GX_DENSE_FUSE", "1") != "0"
+        self.gemm_fused: Dict[int, List[int]] = {}      # gemm node -> elementwise nodes evaluated in its epilogue
+        self.fused_into: Dict[int, int] = {}
+        if self.fuse:
+            self._plan_fusion()
+        # which fp32 copies does anybody read?  (an epilogue reads its own accumulator from registers)
         self.f32_read = set(self.roots)
-        for n in self.order:
+        for n in sorted(reach):
             node = dag.nodes[n]
+            if n not in self.materialised or n in fused:
+                continue
             if node.kind == "ew":
-                self.f32_read.update(self._leaves_and_expr(n)[0])
+                self.f32_read.update(l for l in self._leaves_and_expr(n)[0] if l != self.fused_into.get(n))
             elif node.kind in ("colsum", "sumall"):
                 self.f32_read.add(node.args[0])
+        self.order = [n for n in self.order if n not in self.fused_into]
+        self.fused_kernels: Dict[int, object] = {}
+        self._fused_meta: Dict[int, tuple] = {}
+        # accumulators that kernels add into (column sums, split-K outputs, full reductions) live in one arena
+        # that a single memset clears at the start of a step
+        self.arena_keys: Dict[Tuple[int, str], Tuple[int, Shape2]] = {}
+        off = 0
+        def reserve(key, shape):
+            nonlocal off
+            if key not in self.arena_keys:
+                self.arena_keys[key] = (off, shape)
+                off += (shape[0] * shape[1] + 3) // 4 * 4
+        for n in sorted(reach):
+            node = dag.nodes[n]
+            if n not in self.materialised:
+                continue
+            if node.kind == "gemm" and n in self.order and self._gemm_geometry(n)[3] > 1:
+                reserve((n, "f32"), node.shape)
+            elif node.kind in ("colsum", "sumall"):
+                reserve((n, "f32"), node.shape)
+                if node.kind == "sumall":
+                    reserve((n, "part"), (1, 32))
+        self.arena_size = off
+        self.arena = None
+        self.concurrent = os.environ.get("GX_DENSE_STREAMS", "2") != "1"
+        # kernels that add into the arena, and results that nothing downstream reads (side-stream candidates)
+        self.arena_users = set()
+        for n in self.order:
+            if (n, "f32") in self.arena_keys:
+                self.arena_users.add(n)
+            for o in [n] + self.gemm_fused.get(n, []):
+                if o in self.fused_colsums:
+                    self.arena_users.add(n)
+        self.side_nodes = {n for n in self.order if dag.nodes[n].kind == "gemm" and n in self.roots
+                           and not self.consumers.get(n) and n not in self.gemm_fused}
 
     # ---- fused elementwise kernels -------------------------------------------------------------
     def _leaves_and_expr(self, root: int):
@@ -394,6 +447,7 @@ class DenseExecutor:
             "  if ((u & 0x7fffffffu) > 0x7f800000u) return (unsigned short)((u >> 16) | 0x40u);",
             "  return (unsigned short)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);",
             "}",
+            _GX_TANH,
             "extern \"C\" __global__ void gx_ew(" + ", ".join(params + [
                 "float* __restrict__ o32", "unsigned short* __restrict__ o16", "float* __restrict__ csum",
                 "int rows", "int cols"]) + ") {",
@@ -413,9 +467,153 @@ class DenseExecutor:
         self.kernels[n] = h
         self._ew_meta[n] = (leaves, vec)
 
+    # ---- elementwise consumers fused into the contraction's epilogue ------------------------------------
+    def _gemm_geometry(self, n: int):
+        """(M, N, K, k_splits) of gemm node n: op(X)[M,K] . op(Y)[N,K]^T."""
+        dag = self.plan.dag
+        node = dag.nodes[n]
+        xs, ys = dag.nodes[node.args[0]].shape, dag.nodes[node.args[1]].shape
+        m, k = xs[::-1] if node.tx else xs
+        nn = ys[1] if node.ty else ys[0]
+        tiles = (m // 128) * (nn // 128)
+        splits = 1
+        if tiles < 96:
+            for sp in (16, 8, 4, 2):
+                if (k // 64) % sp == 0 and tiles * sp <= 160:
+                    splits = sp
+                    break
+        return m, nn, k, splits
+
+    def _plan_fusion(self) -> None:
+        """An elementwise node moves into a contraction's epilogue when the contraction result is one of its
+        operands, has its shape and is not split along K, and every other operand is already in memory when
+        the contraction runs (an input, or something materialised earlier)."""
+        dag = self.plan.dag
+        pos = {n: i for i, n in enumerate(self.order)}
+        for n in list(self.order):
+            node = dag.nodes[n]
+            if node.kind != "ew" or node.shape[1] % 128 or node.shape[0] % 128:
+                continue
+            leaves = self._leaves_and_expr(n)[0]
+            gemms = [l for l in leaves if dag.nodes[l].kind == "gemm" and dag.nodes[l].shape == node.shape]
+            if not gemms:
+                continue
+            g = max(gemms, key=lambda l: pos[l])              # the last one to be computed hosts the epilogue
+            if self._gemm_geometry(g)[3] != 1:
+                continue
+            ok = True
+            for l in leaves:
+                if l == g:
+                    continue
+                ln = dag.nodes[l]
+                shape_ok = ln.shape in (node.shape, (1, node.shape[1]), (node.shape[0], 1), (1, 1))
+                ready = ln.kind == "input" or (l in pos and pos[l] < pos[g])
+                if not (shape_ok and ready):
+                    ok = False
+            if ok:
+                self.gemm_fused.setdefault(g, []).append(n)
+                self.fused_into[n] = g
+
+    def _compile_fused(self, g: int) -> None:
+        """gx_gemm_kernel.cuh + a generated epilogue: per 32-column chunk every lane (= tile row) evaluates the
+        fused expressions on its accumulator values four columns at a time, stores fp32 / bf16 copies with
+        128 / 64-bit stores and folds column sums across the warp's 32 rows with 31 shuffles."""
+        import re
+        dag = self.plan.dag
+        M, N = dag.nodes[g].shape
+        outs = [g] + self.gemm_fused[g]                     # output slot 0 = the contraction result itself
+        leaves: List[int] = []                              # global operand list (memory operands only)
+        bodies = []
+        for n in outs[1:]:
+            lv, lines, result = self._leaves_and_expr(n)
+            def sub(text: str) -> str:
+                def repl(mo):
+                    leaf = lv[int(mo.group(1))]
+                    if leaf == g:
+                        return "acc_@"
+                    if leaf not in leaves:
+                        leaves.append(leaf)
+                    return f"L{leaves.index(leaf)}_@"
+                return re.sub(r"\bl(\d+)_@", repl, text)
+            bodies.append(([sub(ln) for ln in lines], sub(result)))
+        nl, no = max(1, len(leaves)), len(outs)
+        src = ["#define GX_NVRTC", "#define GX_GEMM_FUSED", "#define GX_GEMM_KERNEL_NAME gx_gemm_fused"]
+        epi = [_GX_TANH,
+               f"struct GxEpi {{ const void* leaf[{nl}]; float* o32[{no}]; unsigned short* o16[{no}]; float* csum[{no}]; }};",
+               "struct GxEpiState { int unused; };",
+               "__device__ __forceinline__ void gx_epi_begin(GxEpiState&) {}",
+               "__device__ __forceinline__ void gx_epi_finish(const GxEpi&, GxEpiState&, int) {}",
+               "__device__ __forceinline__ void gx_epi_chunk(const GxEpi& e, GxEpiState&, float* tile, int m_base, int col0,",
+               "                                             int M, int N, const float (&acc)[32], int lane) {",
+               "  const int row = m_base + lane;",
+               "  const bool ok = row < M;",
+               "  const size_t off = (size_t)(ok ? row : 0) * N + col0;"]
+        csum_slots = [k for k, n in enumerate(outs) if k > 0 and n in self.fused_colsums]
+        for k in range(1, no):
+            epi.append(f"  float Y{k}[32];")
+        for i, leaf in enumerate(leaves):          # [M, N] operands: coalesced loads through the staging tile
+            if dag.nodes[leaf].shape == (M, N) and self._leaf_dtype(leaf) != "bf16":   # (bf16 rows are 64 B: direct loads win)
+                bf = False
+                epi.append(f"  float Lm{i}[32];")
+                epi.append(f"  gxg::load_rows_{'bf16' if bf else 'f32'}(tile, Lm{i}, reinterpret_cast<const "
+                           f"{'uint16_t' if bf else 'float'}*>(e.leaf[{i}]), N, m_base, M, col0, lane);")
+        epi.append("#pragma unroll")
+        epi.append("  for (int q = 0; q < 8; ++q) {")
+        for i, leaf in enumerate(leaves):
+            lr, lc = dag.nodes[leaf].shape
+            bf = self._leaf_dtype(leaf) == "bf16"
+            ptr = f"reinterpret_cast<const {'unsigned short' if bf else 'float'}*>(e.leaf[{i}])"
+            if (lr, lc) == (M, N) and not bf:
+                epi.append(f"    const float L{i}_0 = Lm{i}[4 * q], L{i}_1 = Lm{i}[4 * q + 1], L{i}_2 = Lm{i}[4 * q + 2], "
+                           f"L{i}_3 = Lm{i}[4 * q + 3];")
+            elif (lr, lc) == (1, 1) or lc == 1:
+                idx = "0" if (lr, lc) == (1, 1) else "(ok ? row : 0)"
+                val = f"gxg::bf16_bits_to_f32({ptr}[{idx}])" if bf else f"__ldg({ptr} + {idx})"
+                epi.append(f"    const float L{i}_0 = {val}, L{i}_1 = L{i}_0, L{i}_2 = L{i}_0, L{i}_3 = L{i}_0;")
+            else:
+                base = "col0 + 4 * q" if lr == 1 else "off + 4 * q"
+                if bf:
+                    epi.append(f"    const uint2 R{i} = __ldg(reinterpret_cast<const uint2*>({ptr} + {base}));")
+                    epi.append(f"    const float L{i}_0 = gxg::bf16_bits_to_f32(R{i}.x & 0xffffu), L{i}_1 = gxg::bf16_bits_to_f32(R{i}.x >> 16), "
+                               f"L{i}_2 = gxg::bf16_bits_to_f32(R{i}.y & 0xffffu), L{i}_3 = gxg::bf16_bits_to_f32(R{i}.y >> 16);")
+                else:
+                    epi.append(f"    const float4 R{i} = __ldg(reinterpret_cast<const float4*>({ptr} + {base}));")
+                    epi.append(f"    const float L{i}_0 = R{i}.x, L{i}_1 = R{i}.y, L{i}_2 = R{i}.z, L{i}_3 = R{i}.w;")
+        for j in range(4):
+            epi.append(f"    const float acc_{j} = acc[4 * q + {j}];")
+        for k, (lines, result) in enumerate(bodies, start=1):
+            for j in range(4):
+                epi += [ln.replace("_@", f"_{j}").replace("      const", "    const") for ln in lines]
+                epi.append(f"    Y{k}[4 * q + {j}] = {result.replace('_@', f'_{j}')};")
+        epi.append("  }")
+        # row-contiguous stores through the warp's staging tile (gx_gemm_kernel.cuh: store_rows)
+        epi.append("  gxg::store_rows(tile, acc, e.o32[0], e.o16[0], N, m_base, M, col0, lane);")
+        for k in range(1, no):
+            epi.append(f"  gxg::store_rows(tile, Y{k}, e.o32[{k}], e.o16[{k}], N, m_base, M, col0, lane);")
+        for k in csum_slots:
+            epi.append("#pragma unroll")
+            epi.append(f"  for (int j = 0; j < 32; ++j) Y{k}[j] = ok ? Y{k}[j] : 0.0f;")
+            epi.append(f"  gxg::warp_transpose_reduce(Y{k}, lane);")
+            epi.append(f"  atomicAdd(e.csum[{k}] + col0 + lane, Y{k}[0]);")
+        epi.append("}")
+        header = (Path(__file__).resolve().parent / "csrc" / "gx_gemm_kernel.cuh").read_text().replace("#pragma once", "")
+        marker = "#ifndef GX_GEMM_KERNEL_NAME"
+        text = "\n".join(src) + "\n" + header.replace(marker, "\n".join(epi) + "\n" + marker, 1)
+        h = ctypes.c_void_p()
+        rc = self.lib.gx_jit_compile(text.encode(), b"gx_gemm_fused", self.device, ctypes.byref(h))
+        if rc != 0:
+            raise self.rt.GraphaxB200Error(f"gx_jit_compile(fused gemm) failed ({rc}): {self.lib.gx_last_error().decode()}")
+        self.fused_kernels[g] = h
+        self._fused_meta[g] = (leaves, outs, csum_slots)
+
     # ---- execution -------------------------------------------------------------------------------
     def _buf(self, n: int, kind: str):
         key = (n, kind)
+        if key not in self.buffers and key in self.arena_keys:
+            if self.arena is None:
+                self.arena = self.torch.zeros(max(4, self.arena_size), dtype=self.torch.float32, device=f"cuda:{self.device}")
+            off, shape = self.arena_keys[key]
+            self.buffers[key] = self.arena[off:off + shape[0] * shape[1]].view(shape)
         if key not in self.buffers:
             r, c = self.plan.dag.nodes[n].shape
             dt = self.torch.float32 if kind == "f32" else self.torch.bfloat16
@@ -426,6 +624,86 @@ class DenseExecutor:
         """bf16 copy of node n as stored ([rows, cols] row-major); the GEMM reads it K-major or MN-major."""
         node = self.plan.dag.nodes[n]
         return self.inputs_bf16[node.input_index] if node.kind == "input" else self._buf(n, "bf16")
+
+    def _launch_node(self, n: int) -> None:
+        """Enqueue the kernel(s) that materialise node n on the current stream."""
+        torch, dag = self.torch, self.plan.dag
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        data = self._data
+        node = dag.nodes[n]
+        if node.kind == "gemm" and n in self.fused_kernels:
+            x, y = node.args
+            a, b = self._bf16(x), self._bf16(y)
+            m, nn, k, _ = self._gemm_geometry(n)
+            leaves, outs, csum_slots = self._fused_meta[n]
+            ptrs = [data(l).data_ptr() for l in leaves] or [0]
+            o32, o16, cs = [], [], []
+            for slot, o in enumerate(outs):
+                o32.append(self._buf(o, "f32").data_ptr() if o in self.f32_read else 0)
+                o16.append(self._buf(o, "bf16").data_ptr() if o in self.needs_bf16 else 0)
+                if slot in csum_slots:
+                    cs.append(self._buf(self.fused_colsums[o][0], "f32").data_ptr())
+                else:
+                    cs.append(0)
+            block = (ctypes.c_void_p * (len(ptrs) + 3 * len(outs)))(*(ptrs + o32 + o16 + cs))
+            rc = self.lib.gx_gemm_fused_launch(self.fused_kernels[n], m, nn, k, a.data_ptr(), int(node.tx), b.data_ptr(),
+                                               int(node.ty), ctypes.cast(block, ctypes.c_void_p), stream)
+            if rc != 0:
+                raise self.rt.GraphaxB200Error(self.lib.gx_last_error().decode())
+            self.launches += 1
+            for o in outs[1:]:
+                for extra in self.fused_colsums.get(o, [])[1:]:
+                    self._buf(extra, "f32").copy_(self._buf(self.fused_colsums[o][0], "f32"))
+        elif node.kind == "gemm":
+            x, y = node.args
+            a, b = self._bf16(x), self._bf16(y)  # op(X) = X^T is read in place as an MN-major operand
+            m, k = a.shape[::-1] if node.tx else a.shape
+            nn = b.shape[1] if node.ty else b.shape[0]
+            tiles = (m // 128) * (nn // 128)
+            splits = 1
+            if tiles < 96:
+                for s in (16, 8, 4, 2):
+                    if (k // 64) % s == 0 and tiles * s <= 160:
+                        splits = s
+                        break
+            out = self._buf(n, "f32")
+            self.rt.gemm_bf16_tn(a, b, out=out, k_splits=splits, a_mn=node.tx, b_mn=node.ty, zero=False)
+            self.launches += 1
+            if n in self.needs_bf16:
+                self._buf(n, "bf16").copy_(out)
+                self.launches += 1
+        elif node.kind in ("colsum", "sumall"):
+            src = data(node.args[0])
+            out = self._buf(n, "f32")
+            r, c = dag.nodes[node.args[0]].shape
+            if node.kind == "colsum":
+                rcs = [self.lib.gx_colsum_f32(src.data_ptr(), out.data_ptr(), r, c, stream)]
+            elif (r * c) % 32 == 0:             # all elements: [r*c/32, 32] column sums, then fold the 32 partials
+                part = self._buf(n, "part")
+                rcs = [self.lib.gx_colsum_f32(src.data_ptr(), part.data_ptr(), r * c // 32, 32, stream),
+                       self.lib.gx_colsum_f32(part.data_ptr(), out.data_ptr(), 32, 1, stream)]
+            else:
+                rcs = [self.lib.gx_colsum_f32(src.data_ptr(), out.data_ptr(), r * c, 1, stream)]
+            self.launches += len(rcs)
+            if any(rcs):
+                raise self.rt.GraphaxB200Error(self.lib.gx_last_error().decode())
+        else:
+            leaves, vec = self._ew_meta[n]
+            r, c = node.shape
+            o32 = self._buf(n, "f32").data_ptr() if n in self.f32_read else 0
+            o16 = self._buf(n, "bf16").data_ptr() if n in self.needs_bf16 else 0
+            csum = self._buf(self.fused_colsums[n][0], "f32").data_ptr() if n in self.fused_colsums else 0
+            vals = [ctypes.c_void_p(data(l).data_ptr()) for l in leaves]
+            vals += [ctypes.c_void_p(o32), ctypes.c_void_p(o16), ctypes.c_void_p(csum), ctypes.c_int(r), ctypes.c_int(c)]
+            argv = (ctypes.c_void_p * len(vals))(*[ctypes.cast(ctypes.pointer(v), ctypes.c_void_p) for v in vals])
+            gx = (c // vec + 31) // 32
+            gy = max(1, min((r + 7) // 8, (148 * 6) // gx))
+            rc = self.lib.gx_jit_launch(self.kernels[n], gx, gy, 256, argv, stream)
+            if rc != 0:
+                raise self.rt.GraphaxB200Error(self.lib.gx_last_error().decode())
+            self.launches += 1
+            for extra in self.fused_colsums.get(n, [])[1:]:       # same sums requested twice: copy
+                self._buf(extra, "f32").copy_(self._buf(self.fused_colsums[n][0], "f32"))
 
     def run(self, inputs: Sequence) -> Tuple[List, object]:
         torch, dag = self.torch, self.plan.dag
@@ -447,6 +725,11 @@ class DenseExecutor:
             for n in self.order:
                 if dag.nodes[n].kind == "ew":
                     self._compile_ew(n)
+            for h in self.fused_kernels.values():
+                self.lib.gx_jit_destroy(h)
+            self.fused_kernels.clear()
+            for g in self.gemm_fused:
+                self._compile_fused(g)
         for i in range(len(inputs)):                # GEMM operands must be bf16
             if i not in self.inputs_bf16 and any(dag.nodes[n].kind == "input" and dag.nodes[n].input_index == i
                                                  for n in self.needs_bf16):
@@ -459,65 +742,41 @@ class DenseExecutor:
                     else self.inputs_f32[node.input_index]
             return self._buf(n, "f32")
 
+        self._data = data
+        # Two streams: the accumulator memset and the contractions nobody downstream waits for (the weight
+        # Jacobians themselves) run beside the critical chain forward -> cotangents; under CUDA-graph capture the
+        # events become parallel branches.
+        main = torch.cuda.current_stream(self.device)
+        if getattr(self, "side", None) is None:
+            self.side = torch.cuda.Stream(device=self.device)
+        side = self.side
+        fork = torch.cuda.Event()
+        fork.record(main)
+        side.wait_event(fork)
+        zeroed = None
+        if self.arena_size:
+            for key in self.arena_keys:
+                self._buf(*key)
+            with torch.cuda.stream(side):
+                self.arena.zero_()
+                zeroed = torch.cuda.Event()
+                zeroed.record(side)
+            self.launches += 1
         for n in self.order:
-            node = dag.nodes[n]
-            if node.kind == "gemm":
-                x, y = node.args
-                a, b = self._bf16(x), self._bf16(y)  # op(X) = X^T is read in place as an MN-major operand
-                m, k = a.shape[::-1] if node.tx else a.shape
-                nn = b.shape[1] if node.ty else b.shape[0]
-                tiles = (m // 128) * (nn // 128)
-                splits = 1
-                if tiles < 96:
-                    for s in (16, 8, 4, 2):
-                        if (k // 64) % s == 0 and tiles * s <= 160:
-                            splits = s
-                            break
-                out = self._buf(n, "f32")
-                self.rt.gemm_bf16_tn(a, b, out=out, k_splits=splits, a_mn=node.tx, b_mn=node.ty)
-                self.launches += 1 + (1 if splits > 1 else 0)
-                if n in self.needs_bf16:
-                    self._buf(n, "bf16").copy_(out)
-                    self.launches += 1
-            elif node.kind in ("colsum", "sumall"):
-                src = data(node.args[0])
-                out = self._buf(n, "f32")
-                out.zero_()
-                r, c = dag.nodes[node.args[0]].shape
-                if node.kind == "colsum":
-                    rcs = [self.lib.gx_colsum_f32(src.data_ptr(), out.data_ptr(), r, c, stream)]
-                elif (r * c) % 32 == 0:             # all elements: [r*c/32, 32] column sums, then fold the 32 partials
-                    part = self.buffers.setdefault((n, "part"), torch.empty(32, device=out.device))
-                    part.zero_()
-                    rcs = [self.lib.gx_colsum_f32(src.data_ptr(), part.data_ptr(), r * c // 32, 32, stream),
-                           self.lib.gx_colsum_f32(part.data_ptr(), out.data_ptr(), 32, 1, stream)]
-                else:
-                    rcs = [self.lib.gx_colsum_f32(src.data_ptr(), out.data_ptr(), r * c, 1, stream)]
-                self.launches += len(rcs) + 1
-                if any(rcs):
-                    raise self.rt.GraphaxB200Error(self.lib.gx_last_error().decode())
-            else:
-                leaves, vec = self._ew_meta[n]
-                r, c = node.shape
-                o32 = self._buf(n, "f32").data_ptr() if n in self.f32_read else 0
-                o16 = self._buf(n, "bf16").data_ptr() if n in self.needs_bf16 else 0
-                csum = 0
-                if n in self.fused_colsums:
-                    cbuf = self._buf(self.fused_colsums[n][0], "f32")
-                    cbuf.zero_()
-                    self.launches += 1
-                    csum = cbuf.data_ptr()
-                vals = [ctypes.c_void_p(data(l).data_ptr()) for l in leaves]
-                vals += [ctypes.c_void_p(o32), ctypes.c_void_p(o16), ctypes.c_void_p(csum), ctypes.c_int(r), ctypes.c_int(c)]
-                argv = (ctypes.c_void_p * len(vals))(*[ctypes.cast(ctypes.pointer(v), ctypes.c_void_p) for v in vals])
-                gx = (c // vec + 31) // 32
-                gy = max(1, min((r + 7) // 8, (148 * 6) // gx))
-                rc = self.lib.gx_jit_launch(self.kernels[n], gx, gy, 256, argv, stream)
-                if rc != 0:
-                    raise self.rt.GraphaxB200Error(self.lib.gx_last_error().decode())
-                self.launches += 1
-                for extra in self.fused_colsums.get(n, [])[1:]:       # same sums requested twice: copy
-                    self._buf(extra, "f32").copy_(self._buf(self.fused_colsums[n][0], "f32"))
+            if n in self.side_nodes and self.concurrent:
+                ready = torch.cuda.Event()
+                ready.record(main)
+                side.wait_event(ready)
+                with torch.cuda.stream(side):
+                    self._launch_node(n)
+                continue
+            if zeroed is not None and n in self.arena_users:
+                main.wait_event(zeroed)
+                zeroed = None
+            self._launch_node(n)
+        join = torch.cuda.Event()
+        join.record(side)
+        main.wait_event(join)
         grads = []
         for a, g in zip(self.plan.argnums, self.plan.grads):
             shape = self.plan.jaxpr.invars[a].shape

@@ -33,7 +33,7 @@ EXPORTS = ["gx_plan_create", "gx_plan_destroy", "gx_plan_info", "gx_plan_special
            "gx_plan_select_kernel",
            "gx_jacve_launch", "gx_jacve_host", "gx_last_error", "gx_abi_version", "gx_aot_count", "gx_aot_key",
            "gx_hash_bytes", "gx_gemm_bf16_tn", "gx_gemm_bf16", "gx_transpose_bf16", "gx_gemm_last_error",
-           "gx_jit_compile", "gx_jit_destroy", "gx_jit_launch", "gx_colsum_f32"]
+           "gx_jit_compile", "gx_jit_destroy", "gx_jit_launch", "gx_colsum_f32", "gx_gemm_fused_launch"]
 
 _lib = None
 _lock = threading.Lock()
@@ -93,6 +93,9 @@ def load_library() -> ctypes.CDLL:
         lib.gx_jit_destroy.restype = None
         lib.gx_jit_launch.argtypes = [vp, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint, ctypes.POINTER(vp), vp]
         lib.gx_jit_launch.restype = ctypes.c_int
+        lib.gx_gemm_fused_launch.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, vp,
+                                             ctypes.c_int, vp, vp]
+        lib.gx_gemm_fused_launch.restype = ctypes.c_int
         lib.gx_colsum_f32.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, vp]
         lib.gx_colsum_f32.restype = ctypes.c_int
         _lib = lib
@@ -179,7 +182,8 @@ class DevicePlan:
             pass
 
 
-def gemm_bf16_tn(a, b, out=None, out_dtype=None, k_splits: int = 1, a_mn: bool = False, b_mn: bool = False):
+def gemm_bf16_tn(a, b, out=None, out_dtype=None, k_splits: int = 1, a_mn: bool = False, b_mn: bool = False,
+                 zero: bool = True):
     """``A @ B.T`` on the tcgen05 tensor cores (bf16 operands, fp32 accumulate); torch tensors in, torch tensor
     out.  ``a`` is A[M,K] (or, with ``a_mn``, A stored as [K,M]); ``b`` is B[N,K] (with ``b_mn`` stored [K,N]).
     ``k_splits > 1`` splits the contraction axis over CTAs (fp32 output, atomics)."""
@@ -191,7 +195,7 @@ def gemm_bf16_tn(a, b, out=None, out_dtype=None, k_splits: int = 1, a_mn: bool =
     out_dtype = out_dtype or (out.dtype if out is not None else torch.float32)
     if out is None:
         out = (torch.zeros if k_splits > 1 else torch.empty)((m, n), dtype=out_dtype, device=a.device)
-    elif k_splits > 1:
+    elif k_splits > 1 and zero:      # zero=False: the caller has already cleared the split-K accumulator
         out.zero_()
     rc = lib.gx_gemm_bf16(m, n, k, a.data_ptr(), 1 if a_mn else 0, b.data_ptr(), 1 if b_mn else 0, out.data_ptr(),
                           1 if out.dtype == torch.bfloat16 else 0, k_splits, torch.cuda.current_stream().cuda_stream)

@@ -16,6 +16,7 @@ ap.add_argument("--batch", type=int, default=4096)
 ap.add_argument("--widths", default="512,1024,512")
 ap.add_argument("--steps", type=int, default=200)
 ap.add_argument("--graph", action="store_true")
+ap.add_argument("--profile", action="store_true", help="per-kernel times (serialised, warm) to stderr")
 a = ap.parse_args()
 I, H, O = map(int, a.widths.split(","))
 B = a.batch
@@ -36,6 +37,31 @@ torch.cuda.synchronize()
 l0 = ex.launches
 ex.run(args)
 per_step_launches = ex.launches - l0
+if a.profile:
+    # warm GPU-side time of every kernel group: a CUDA graph with 10 back-to-back copies of the node's launches
+    side = torch.cuda.Stream()
+    tot = 0.0
+    for n in ex.order:
+        node = plan.dag.nodes[n]
+        with torch.cuda.stream(side):
+            ex._launch_node(n)
+            torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=side):
+                for _ in range(10):
+                    ex._launch_node(n)
+            gr.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                gr.replay()
+            e1.record()
+            torch.cuda.synchronize()
+        us_n = e0.elapsed_time(e1) * 1e3 / 100
+        tot += us_n
+        print(f"  {n}:{node.kind}:{'x'.join(map(str, node.shape))} tx={getattr(node, 'tx', None)} ty={getattr(node, 'ty', None)}  {us_n:7.2f} us", file=sys.stderr)
+    print(f"  sum {tot:.1f} us", file=sys.stderr)
 runner = lambda: ex.run(args)
 if a.graph:
     s = torch.cuda.Stream()
