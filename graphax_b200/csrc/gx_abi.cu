@@ -1075,15 +1075,16 @@ int gx_jit_launch(gx_jit_kernel* k, unsigned grid_x, unsigned grid_y, unsigned b
 // tensor maps as gx_gemm_bf16; `epi` is the kernel's GxEpi parameter block (pointers of the fused operands and
 // outputs), copied by the launch.
 int gx_gemm_fused_launch(gx_jit_kernel* k, int M, int N, int K, const void* A, int a_mn, const void* B, int b_mn,
-                         const void* epi, void* stream) {
+                         const void* epi, int stages, void* stream) {
   if (!k || !A || !B || !epi) return fail(GX_ERR_BAD_ARG, "gx_gemm_fused_launch: NULL argument");
   if (M <= 0 || N <= 0 || K <= 0 || M % 128 || N % 128 || K % 64)
     return fail(GX_ERR_UNSUPPORTED, "gx_gemm_fused_launch: M, N must be multiples of 128, K of 64");
+  if (stages != 3 && stages != 6) return fail(GX_ERR_BAD_ARG, "gx_gemm_fused_launch: stages must be 3 or 6 (GX_GEMM_STAGES)");
   CUtensorMap map_a, map_b;
   if (gxg_make_maps(&map_a, &map_b, M, N, K, A, a_mn, B, b_mn))
     return fail(GX_ERR_CUDA, "gx_gemm_fused_launch: cuTensorMapEncodeTiled failed (pointers must be 16-byte aligned)");
   if (!k->smem_set) {
-    CUresult r = driver().FuncSetAttribute(k->func, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)gxg::kSmemBytes);
+    CUresult r = driver().FuncSetAttribute(k->func, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)gxg::smem_bytes(stages));
     if (r != CUDA_SUCCESS) return fail(GX_ERR_CUDA, "cuFuncSetAttribute(fused gemm): " + cu_err(r));
     k->smem_set = true;
   }
@@ -1103,7 +1104,7 @@ int gx_gemm_fused_launch(gx_jit_kernel* k, int M, int N, int K, const void* A, i
   cfg.gridDimZ = 1;
   cfg.blockDimX = gxg::kThreads;
   cfg.blockDimY = cfg.blockDimZ = 1;
-  cfg.sharedMemBytes = gxg::kSmemBytes;
+  cfg.sharedMemBytes = gxg::smem_bytes(stages);
   cfg.hStream = (CUstream)stream;
   CUlaunchAttribute attr[1];
   attr[0].id = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;

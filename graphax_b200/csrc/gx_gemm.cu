@@ -67,6 +67,15 @@ int make_map(CUtensorMap* map, const void* ptr, int rows, int k, int box_rows) {
   return r == CUDA_SUCCESS ? 0 : -2;
 }
 
+int sm_count() {
+  static const int v = [] {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+  }();
+  return v;
+}
+
 bool gemm_use_pdl() {
   static const bool v = [] {
     const char* e = getenv("GX_PDL");
@@ -115,7 +124,11 @@ int gx_gemm_bf16(int M, int N, int K, const void* A, int a_mn, const void* B, in
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gx_gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    attr_err = cudaFuncSetAttribute(gx_gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem_bytes(kStagesShallow));
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(gx_gemm_tn_kernel_deep, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem_bytes(kStagesDeep));
   });
   if (attr_err != cudaSuccess) {
     g_gemm_error = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(attr_err);
@@ -136,7 +149,9 @@ int gx_gemm_bf16(int M, int N, int K, const void* A, int a_mn, const void* B, in
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = dim3(N / BN, M / BM, k_splits);
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = kSmemBytes;
+  // a grid that fits the GPU once gets the deep ring (twice the bytes in flight per SM)
+  const bool deep = (long long)(N / BN) * (M / BM) * k_splits <= sm_count();
+  cfg.dynamicSmemBytes = smem_bytes(deep ? kStagesDeep : kStagesShallow);
   cfg.stream = static_cast<cudaStream_t>(stream);
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // prologue overlaps the predecessor's tail
@@ -144,7 +159,8 @@ int gx_gemm_bf16(int M, int N, int K, const void* A, int a_mn, const void* B, in
   cfg.attrs = attr;
   cfg.numAttrs = gemm_use_pdl() ? 1 : 0;
   void* params[] = {&map_a, &map_b, &args};
-  cudaError_t e = cudaLaunchKernelExC(&cfg, (const void*)gx_gemm_tn_kernel, params);
+  cudaError_t e = cudaLaunchKernelExC(&cfg, deep ? (const void*)gx_gemm_tn_kernel_deep : (const void*)gx_gemm_tn_kernel,
+                                      params);
   if (e != cudaSuccess) {
     g_gemm_error = std::string("gx_gemm_tn_kernel launch: ") + cudaGetErrorString(e);
     return GX_ERR_CUDA;

@@ -39,11 +39,15 @@ struct alignas(64) CUtensorMap {
 namespace gxg {
 
 constexpr int BM = 128, BN = 128, BK = 64, UMMA_K = 16;
-constexpr int kStages = 3;   // 96 KB of operand ring: two CTAs per SM, one's epilogue overlaps the other's main loop
+// operand ring depth: 3 stages = 96 KB, two CTAs per SM (one's epilogue overlaps the other's main loop); grids that
+// fill the GPU only once (<= one CTA per SM) use 6 stages so that twice as many bytes are in flight per SM
+constexpr int kStagesShallow = 3, kStagesDeep = 6;
 constexpr int kThreads = 320;   // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quadrant)
 constexpr int kTmemCols = 128;
 constexpr uint32_t kStageBytesA = BM * BK * 2, kStageBytesB = BN * BK * 2;
-constexpr uint32_t kSmemBytes = kStages * (kStageBytesA + kStageBytesB) + 1024 /*align*/ + 256 /*barriers*/;
+#ifndef GX_NVRTC
+constexpr uint32_t smem_bytes(int stages) { return stages * (kStageBytesA + kStageBytesB) + 1024 /*align*/ + 256 /*barriers*/; }
+#endif
 
 enum { EPI_STORE_F32 = 0, EPI_STORE_BF16 = 1, EPI_ATOMIC_F32 = 2 };
 
@@ -250,13 +254,21 @@ constexpr uint32_t kInstrDescBase = (1u << 4) | (1u << 7) | (1u << 10) | ((BN >>
 
 #ifdef GX_GEMM_FUSED
 #define GX_GEMM_EPI_PARAM , const __grid_constant__ GxEpi epi
+#define GX_GEMM_EPI_PARAM_REF , const GxEpi& epi
 #else
 #define GX_GEMM_EPI_PARAM
+#define GX_GEMM_EPI_PARAM_REF
 #endif
 
-extern "C" __global__ void __launch_bounds__(gxg::kThreads, 2)
-GX_GEMM_KERNEL_NAME(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    const gxg::GemmArgs args GX_GEMM_EPI_PARAM) {
+#ifdef GX_GEMM_FUSED
+#define GX_GEMM_EPI_ARG , epi
+#else
+#define GX_GEMM_EPI_ARG
+#endif
+
+template <int kStages>
+__device__ __forceinline__ void gx_gemm_body(const CUtensorMap& map_a, const CUtensorMap& map_b,
+                                             const gxg::GemmArgs& args GX_GEMM_EPI_PARAM_REF) {
   using namespace gxg;
   extern __shared__ uint8_t gg_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gg_smem_raw) + 1023) & ~uintptr_t(1023));
@@ -393,3 +405,20 @@ GX_GEMM_KERNEL_NAME(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
   }
 }
+
+#ifndef GX_GEMM_STAGES
+#define GX_GEMM_STAGES 3
+#endif
+extern "C" __global__ void __launch_bounds__(gxg::kThreads, GX_GEMM_STAGES > 3 ? 1 : 2)
+GX_GEMM_KERNEL_NAME(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const gxg::GemmArgs args GX_GEMM_EPI_PARAM) {
+  gx_gemm_body<GX_GEMM_STAGES>(map_a, map_b, args GX_GEMM_EPI_ARG);
+}
+#ifndef GX_NVRTC
+// the library's second instance: deep ring, one CTA per SM
+extern "C" __global__ void __launch_bounds__(gxg::kThreads, 1)
+gx_gemm_tn_kernel_deep(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                       const gxg::GemmArgs args) {
+  gx_gemm_body<gxg::kStagesDeep>(map_a, map_b, args);
+}
+#endif

@@ -5,7 +5,7 @@
 #include <stdint.h>
 namespace gxg {
 constexpr int kThreads = 320;
-constexpr uint32_t kSmemBytes = 3 * (128 * 64 * 2 + 128 * 64 * 2) + 1024 + 256;
+constexpr uint32_t smem_bytes(int stages) { return stages * (128 * 64 * 2 + 128 * 64 * 2) + 1024 + 256; }
 struct GemmArgs {
   float* c_f32;
   uint16_t* c_bf16;

@@ -478,8 +478,9 @@ class DenseExecutor:
         tiles = (m // 128) * (nn // 128)
         splits = 1
         if tiles < 96:
+            limit = int(os.environ.get("GX_SPLITK_CTAS", "160"))
             for sp in (16, 8, 4, 2):
-                if (k // 64) % sp == 0 and tiles * sp <= 160:
+                if (k // 64) % sp == 0 and tiles * sp <= limit:
                     splits = sp
                     break
         return m, nn, k, splits
@@ -537,7 +538,9 @@ class DenseExecutor:
                 return re.sub(r"\bl(\d+)_@", repl, text)
             bodies.append(([sub(ln) for ln in lines], sub(result)))
         nl, no = max(1, len(leaves)), len(outs)
-        src = ["#define GX_NVRTC", "#define GX_GEMM_FUSED", "#define GX_GEMM_KERNEL_NAME gx_gemm_fused"]
+        stages = 6 if (M // 128) * (N // 128) <= 148 else 3      # single-wave grids: deep operand ring, one CTA per SM
+        src = ["#define GX_NVRTC", "#define GX_GEMM_FUSED", "#define GX_GEMM_KERNEL_NAME gx_gemm_fused",
+               f"#define GX_GEMM_STAGES {stages}"]
         epi = [_GX_TANH,
                f"struct GxEpi {{ const void* leaf[{nl}]; float* o32[{no}]; unsigned short* o16[{no}]; float* csum[{no}]; }};",
                "struct GxEpiState { int unused; };",
@@ -581,9 +584,14 @@ class DenseExecutor:
                     epi.append(f"    const float L{i}_0 = R{i}.x, L{i}_1 = R{i}.y, L{i}_2 = R{i}.z, L{i}_3 = R{i}.w;")
         for j in range(4):
             epi.append(f"    const float acc_{j} = acc[4 * q + {j}];")
+        emitted = set()                                 # temporaries are named after their node: shared by outputs
         for k, (lines, result) in enumerate(bodies, start=1):
             for j in range(4):
-                epi += [ln.replace("_@", f"_{j}").replace("      const", "    const") for ln in lines]
+                for ln in lines:
+                    ln = ln.replace("_@", f"_{j}").replace("      const", "    const")
+                    if ln not in emitted:
+                        emitted.add(ln)
+                        epi.append(ln)
                 epi.append(f"    Y{k}[4 * q + {j}] = {result.replace('_@', f'_{j}')};")
         epi.append("  }")
         # row-contiguous stores through the warp's staging tile (gx_gemm_kernel.cuh: store_rows)
@@ -604,7 +612,7 @@ class DenseExecutor:
         if rc != 0:
             raise self.rt.GraphaxB200Error(f"gx_jit_compile(fused gemm) failed ({rc}): {self.lib.gx_last_error().decode()}")
         self.fused_kernels[g] = h
-        self._fused_meta[g] = (leaves, outs, csum_slots)
+        self._fused_meta[g] = (leaves, outs, csum_slots, stages)
 
     # ---- execution -------------------------------------------------------------------------------
     def _buf(self, n: int, kind: str):
@@ -635,7 +643,7 @@ class DenseExecutor:
             x, y = node.args
             a, b = self._bf16(x), self._bf16(y)
             m, nn, k, _ = self._gemm_geometry(n)
-            leaves, outs, csum_slots = self._fused_meta[n]
+            leaves, outs, csum_slots, stages = self._fused_meta[n]
             ptrs = [data(l).data_ptr() for l in leaves] or [0]
             o32, o16, cs = [], [], []
             for slot, o in enumerate(outs):
@@ -647,7 +655,7 @@ class DenseExecutor:
                     cs.append(0)
             block = (ctypes.c_void_p * (len(ptrs) + 3 * len(outs)))(*(ptrs + o32 + o16 + cs))
             rc = self.lib.gx_gemm_fused_launch(self.fused_kernels[n], m, nn, k, a.data_ptr(), int(node.tx), b.data_ptr(),
-                                               int(node.ty), ctypes.cast(block, ctypes.c_void_p), stream)
+                                               int(node.ty), ctypes.cast(block, ctypes.c_void_p), stages, stream)
             if rc != 0:
                 raise self.rt.GraphaxB200Error(self.lib.gx_last_error().decode())
             self.launches += 1
@@ -657,15 +665,7 @@ class DenseExecutor:
         elif node.kind == "gemm":
             x, y = node.args
             a, b = self._bf16(x), self._bf16(y)  # op(X) = X^T is read in place as an MN-major operand
-            m, k = a.shape[::-1] if node.tx else a.shape
-            nn = b.shape[1] if node.ty else b.shape[0]
-            tiles = (m // 128) * (nn // 128)
-            splits = 1
-            if tiles < 96:
-                for s in (16, 8, 4, 2):
-                    if (k // 64) % s == 0 and tiles * s <= 160:
-                        splits = s
-                        break
+            m, nn, k, splits = self._gemm_geometry(n)
             out = self._buf(n, "f32")
             self.rt.gemm_bf16_tn(a, b, out=out, k_splits=splits, a_mn=node.tx, b_mn=node.ty, zero=False)
             self.launches += 1

@@ -94,7 +94,7 @@ def load_library() -> ctypes.CDLL:
         lib.gx_jit_launch.argtypes = [vp, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint, ctypes.POINTER(vp), vp]
         lib.gx_jit_launch.restype = ctypes.c_int
         lib.gx_gemm_fused_launch.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, vp,
-                                             ctypes.c_int, vp, vp]
+                                             ctypes.c_int, vp, ctypes.c_int, vp]
         lib.gx_gemm_fused_launch.restype = ctypes.c_int
         lib.gx_colsum_f32.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, vp]
         lib.gx_colsum_f32.restype = ctypes.c_int

@@ -132,9 +132,10 @@ int gx_colsum_f32(const void* in, void* out, int rows, int cols, void* stream);
 /* The contraction with the elementwise consumers of its result fused into the epilogue: `kernel` is
  * csrc/gx_gemm_kernel.cuh compiled by gx_jit_compile behind a generated `GxEpi` / `gx_epi_chunk` (dense.py) -
  * the reference's `_mixed_mul` followed by `_pure_broadcast_mul` / elemental partials (sparse/tensor.py:1062-1231,
- * 826-866) without the intermediate edge ever reaching HBM.  `epi` points to the kernel's GxEpi block. */
+ * 826-866) without the intermediate edge ever reaching HBM.  `epi` points to the kernel's GxEpi block; `stages` is
+ * the operand-ring depth the kernel was compiled with (GX_GEMM_STAGES: 3, or 6 for grids of at most one CTA per SM). */
 int gx_gemm_fused_launch(gx_jit_kernel* kernel, int M, int N, int K, const void* A, int a_mn, const void* B, int b_mn,
-                         const void* epi, void* stream);
+                         const void* epi, int stages, void* stream);
 
 const char* gx_last_error(void);
 int gx_abi_version(void);

@@ -65,12 +65,16 @@ def test_tcgen05_gemm(built_library, m, n, k, splits):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("dtype", ["bf16", "f32"])
-def test_mlp_weight_jacobians(built_library, dtype):
-    """jacve(MLP_loss, 'rev', argnums=(W1, b1, W2, b2)) on the GPU vs the oracle."""
+@pytest.mark.parametrize("sizes", [(512, 128, 256, 128), (2048, 256, 1024, 768)])
+def test_mlp_weight_jacobians(built_library, dtype, sizes, monkeypatch):
+    """jacve(MLP_loss, 'rev', argnums=(W1, b1, W2, b2)) on the GPU vs the oracle.  The small case runs split-K
+    contractions and separate elementwise kernels, the large one (>= 96 output tiles per contraction) the
+    run-time compiled contractions with fused epilogues; both must also agree with the unfused execution."""
     import torch
+    from graphax_b200 import dense
     from graphax_b200.dense import dense_jacve
     from oracle import dense_numpy as dn
-    B, I, H, O = 512, 128, 256, 128
+    B, I, H, O = sizes
     args = _mlp_args(B, I, H, O)
     tens = [torch.from_numpy(a).cuda() for a in args]
     if dtype == "bf16":
@@ -88,6 +92,16 @@ def test_mlp_weight_jacobians(built_library, dtype):
         scale = np.abs(r).max()
         assert np.abs(g - e).max() <= 2e-3 * scale       # same rounding points as the engine: tight
         assert np.abs(g - r).max() <= 3e-2 * scale       # vs exact arithmetic: bf16 operand rounding
+    ex = [v for k, v in dense_jacve.__kwdefaults__["_cache"].items() if k[3] == tuple(a.shape for a in args)][-1]
+    assert bool(ex.gemm_fused) == (B >= 2048)            # the large case really took the fused path
+    if ex.gemm_fused:
+        monkeypatch.setenv("GX_DENSE_FUSE", "0")
+        dense_jacve.__kwdefaults__["_cache"].clear()
+        _, plain = dense_jacve(MLP_loss, "rev", (1, 2, 3, 4), *tens, has_aux=True)
+        dense_jacve.__kwdefaults__["_cache"].clear()
+        for g, p in zip(grads, plain):
+            # same rounding points; only the summation order of column sums / split-K partials differs
+            assert float((g - p).abs().max()) <= 1e-4 * float(p.abs().max())
 
 
 @pytest.mark.gpu
