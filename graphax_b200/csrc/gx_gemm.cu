@@ -76,6 +76,22 @@ int sm_count() {
   return v;
 }
 
+int gemm_tile_n() {
+  static const int v = [] {
+    const char* e = getenv("GX_GEMM_TILE_N");
+    return e ? atoi(e) : 256;
+  }();
+  return v;
+}
+
+bool gemm_use_persistent() {
+  static const bool v = [] {
+    const char* e = getenv("GX_GEMM_PERSISTENT");
+    return !(e && e[0] == '0');
+  }();
+  return v;
+}
+
 bool gemm_use_pdl() {
   static const bool v = [] {
     const char* e = getenv("GX_PDL");
@@ -129,6 +145,12 @@ int gx_gemm_bf16(int M, int N, int K, const void* A, int a_mn, const void* B, in
     if (attr_err == cudaSuccess)
       attr_err = cudaFuncSetAttribute(gx_gemm_tn_kernel_deep, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem_bytes(kStagesDeep));
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(gx_gemm_tn_kernel_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)kSmemPersistent);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(gx_gemm_tn_kernel_persistent_n256, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)kSmemPersistent);
   });
   if (attr_err != cudaSuccess) {
     g_gemm_error = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(attr_err);
@@ -159,8 +181,23 @@ int gx_gemm_bf16(int M, int N, int K, const void* A, int a_mn, const void* B, in
   cfg.attrs = attr;
   cfg.numAttrs = gemm_use_pdl() ? 1 : 0;
   void* params[] = {&map_a, &map_b, &args};
-  cudaError_t e = cudaLaunchKernelExC(&cfg, deep ? (const void*)gx_gemm_tn_kernel_deep : (const void*)gx_gemm_tn_kernel,
-                                      params);
+  // several waves of tiles: persistent CTAs (one per SM) with a double-buffered accumulator
+  const long long tiles = (long long)(N / BN) * (M / BM);
+  const bool persistent = k_splits == 1 && tiles > 2LL * sm_count() && gemm_use_persistent();
+  const void* fn = deep ? (const void*)gx_gemm_tn_kernel_deep : (const void*)gx_gemm_tn_kernel;
+  if (persistent) {
+    cfg.gridDim = dim3(sm_count());
+    cfg.dynamicSmemBytes = kSmemPersistent;
+    fn = (const void*)gx_gemm_tn_kernel_persistent;
+    if (N % 256 == 0 && tiles / 2 > 2LL * sm_count() && gemm_tile_n() == 256) {   // 128 x 256 tiles
+      fn = (const void*)gx_gemm_tn_kernel_persistent_n256;
+      if (!b_mn && make_map(&map_b, B, N, K, 256)) {      // K-major B: one 256-row box per stage
+        g_gemm_error = "gx_gemm_bf16_tn: cuTensorMapEncodeTiled failed (256-row box)";
+        return GX_ERR_CUDA;
+      }
+    }
+  }
+  cudaError_t e = cudaLaunchKernelExC(&cfg, fn, params);
   if (e != cudaSuccess) {
     g_gemm_error = std::string("gx_gemm_tn_kernel launch: ") + cudaGetErrorString(e);
     return GX_ERR_CUDA;

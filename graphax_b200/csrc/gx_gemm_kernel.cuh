@@ -406,6 +406,208 @@ __device__ __forceinline__ void gx_gemm_body(const CUtensorMap& map_a, const CUt
   }
 }
 
+#ifndef GX_NVRTC
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent variant for grids of several waves: one CTA per SM walks over output tiles; the accumulator is
+// double-buffered in TMEM (2 x 128 columns) so that the epilogue of tile i (warps 2-9, through their own 32 KB of
+// staging tiles) overlaps the main loop of tile i+1, and the 6-stage operand ring keeps loading across tile
+// boundaries.  Plain store epilogues only (fp32 / bf16).
+// ---------------------------------------------------------------------------------------------------------------
+namespace gxg {
+constexpr uint32_t kRingBytesPersistent = 6 * (kStageBytesA + kStageBytesB);     // 192 KB: 6 x 32 KB or 4 x 48 KB
+constexpr uint32_t kSmemPersistent = kRingBytesPersistent + 8 * 4096 + 1024 + 256;
+// Tile order of the persistent CTAs: groups of kGroupM tile rows, column by column inside a group, so that the
+// ~148 tiles in flight form a compact block of the output (16 x ~9 tiles) and re-use each other's A and B
+// panels in L2 instead of streaming a whole operand per wave.
+constexpr int kGroupM = 16;
+__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int& tm, int& tn) {
+  const int per_group = kGroupM * tiles_n;
+  const int g = t / per_group, r = t - g * per_group;
+  const int first = g * kGroupM;
+  const int gsize = tiles_m - first < kGroupM ? tiles_m - first : kGroupM;
+  tm = first + r % gsize;
+  tn = r / gsize;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+}  // namespace gxg
+
+template <int BNP>   // tile width: 128, or 256 (A re-read half as often: 85 instead of 64 flop per operand byte)
+__device__ __forceinline__ void gx_gemm_persistent_body(const CUtensorMap& map_a, const CUtensorMap& map_b,
+                                                        const gxg::GemmArgs& args) {
+  using namespace gxg;
+  constexpr uint32_t kStageBytesB = BNP * BK * 2;                        // shadows the 128-wide constant
+  constexpr int kStages = kRingBytesPersistent / (kStageBytesA + kStageBytesB);   // 6 or 4
+  constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | ((BNP >> 3) << 17) | ((BM >> 4) << 24);
+  extern __shared__ uint8_t gg_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gg_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * kStageBytesA;
+  float* staging = reinterpret_cast<float*>(smem + kStages * (kStageBytesA + kStageBytesB));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * (kStageBytesA + kStageBytesB) + 8 * 4096);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;    // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int tiles_m = args.M / BM, tiles_n = args.N / BNP, n_tiles = tiles_m * tiles_n;
+  const int num_k_blocks = (args.K + BK - 1) / BK;
+
+  if (warp == 0 && elect_one()) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], 8);   // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
+                 "n"(2 * BNP)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  if (warp == 0) {
+    // ===== TMA producer: the ring position runs on across tiles =====
+    if (elect_one()) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        int tm, tn;
+        tile_coords(t, tiles_m, tiles_n, tm, tn);
+        const int m0 = tm * BM, n0 = tn * BNP;
+        for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+          const int s = it % kStages;
+          mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
+          mbar_expect_tx(&full_bar[s], kStageBytesA + kStageBytesB);
+          const int k0 = kb * BK;
+          if (!args.a_mn) {
+            tma_load_2d(smem_a + s * kStageBytesA, &map_a, k0, m0, &full_bar[s]);
+          } else {
+            tma_load_2d(smem_a + s * kStageBytesA, &map_a, m0, k0, &full_bar[s]);
+            tma_load_2d(smem_a + s * kStageBytesA + 8192, &map_a, m0 + 64, k0, &full_bar[s]);
+          }
+          if (!args.b_mn) {
+            tma_load_2d(smem_b + s * kStageBytesB, &map_b, k0, n0, &full_bar[s]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < BNP / 64; ++q)
+              tma_load_2d(smem_b + s * kStageBytesB + q * 8192, &map_b, n0 + 64 * q, k0, &full_bar[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: accumulator i & 1 =====
+    uint32_t it = 0, i = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+      const uint32_t buf = i & 1;
+      mbar_wait(&tmem_empty_bar[buf], ((i >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
+      tc_fence_after();
+      for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+        const int s = it % kStages;
+        mbar_wait(&full_bar[s], (it / kStages) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem_a + s * kStageBytesA), sb = smem_u32(smem_b + s * kStageBytesB);
+          const uint64_t da = args.a_mn ? make_smem_desc_mn(sa) : make_smem_desc(sa);
+          const uint64_t db = args.b_mn ? make_smem_desc_mn(sb) : make_smem_desc(sb);
+          const uint32_t step_a = args.a_mn ? 128u : 2u, step_b = args.b_mn ? 128u : 2u;
+          const uint32_t idesc = kInstrDesc | (args.a_mn ? (1u << 15) : 0u) | (args.b_mn ? (1u << 16) : 0u);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_f16(tmem_base + buf * BNP, da + step_a * k, db + step_b * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+          if (kb == num_k_blocks - 1) umma_commit(&tmem_full_bar[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===== epilogue =====
+    const int quad = warp & 3;
+    const int c_begin = ((warp - 2) >> 2) * (BNP / 2);
+    float* tile = staging + (warp - 2) * 1024;
+    uint32_t i = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+      const uint32_t buf = i & 1;
+      int tm, tn;
+      tile_coords(t, tiles_m, tiles_n, tm, tn);
+      const int m_base = tm * BM + quad * 32, n0 = tn * BNP;
+      mbar_wait(&tmem_full_bar[buf], (i >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = c_begin; c < c_begin + BNP / 2; c += 64) {
+        float acc[2][32];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          const uint32_t taddr = tmem_base + buf * BNP + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c + 32 * h);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+              : "r"(taddr)
+              : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[h][j] = __uint_as_float(v[j]);
+        }
+        if (c + 64 >= c_begin + BNP / 2) {
+          // the last of this warp's columns is in registers: hand the TMEM buffer back before the global stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int col0 = n0 + c + 32 * h;
+          if (args.epilogue == EPI_STORE_F32)
+            store_rows_f32(tile, acc[h], args.c_f32, args.ldc, m_base, args.M, col0, lane);
+          else
+            store_rows_bf16(tile, acc[h], args.c_bf16, args.ldc, m_base, args.M, col0, lane);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BNP) : "memory");
+  }
+}
+
+extern "C" __global__ void __launch_bounds__(gxg::kThreads, 1)
+gx_gemm_tn_kernel_persistent(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                             const gxg::GemmArgs args) {
+  gx_gemm_persistent_body<128>(map_a, map_b, args);
+}
+extern "C" __global__ void __launch_bounds__(gxg::kThreads, 1)
+gx_gemm_tn_kernel_persistent_n256(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                                  const gxg::GemmArgs args) {
+  gx_gemm_persistent_body<256>(map_a, map_b, args);
+}
+#endif  // !GX_NVRTC
+
 #ifndef GX_GEMM_STAGES
 #define GX_GEMM_STAGES 3
 #endif
