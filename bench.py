@@ -359,6 +359,19 @@ def run_gpu_arm(args) -> None:
                                     "sample": f"{sample} samples x 3 reps, NumPy port of the reference algorithm, "
                                               f"fp32, {cores} processes",
                                     "c_replay_value": cpu_replay_throughput(args.order, 1 << 18, 3, cores)}
+            # generic autodiff on the same GPU (stand-in for the reference's XLA-on-one-B200 run, JAX
+            # not being installed): torch.func.vmap(jacrev(f)), eager.  Reported for context only.
+            try:
+                sys.path.insert(0, str(ROOT / "tools"))
+                from torch_baseline import measure as torch_measure
+                del sets
+                torch.cuda.empty_cache()
+                tb = min(batch, 1 << 18)
+                tv, _ = torch_measure(w, tb, reps=3, device="cuda")
+                line["gpu_autodiff_baseline"] = {"value": tv, "unit": UNIT, "kind": "torch.func.vmap(jacrev(f)), eager, fp32",
+                                                 "sample": f"{tb} samples x 3 reps on cuda:0"}
+            except Exception as e:          # a baseline must never take the bench line down
+                line["gpu_autodiff_baseline"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
