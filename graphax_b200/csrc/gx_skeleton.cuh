@@ -20,7 +20,7 @@
 //                                 f32x2 pipe: half the issue slots for the same arithmetic)
 //   GX_KERNEL_NAME                unique symbol of this kernel (gx_jacve_kernel for NVRTC)
 //   GX_FOREACH_ARRAY(F)           F(index, scalars_per_sample, prefix_offset) for every input array
-//   gx_body(x, jrow, prow)        __device__ __forceinline__ function: the straight-line plan; reads the
+//   gx_body<kPrecise>(x, jrow, prow)  __device__ __forceinline__ function: the straight-line plan; reads the
 //                                 sample's inputs x[k], writes tile entries jrow[pos] and outputs prow[row]
 #pragma once
 
@@ -33,6 +33,9 @@ typedef unsigned long long uint64_t;
 #endif
 
 #define GX_TILE (GX_N_ROWS * GX_N_COLS)
+#ifndef GX_CHECKED_FAST_MATH
+#define GX_CHECKED_FAST_MATH 1
+#endif
 #ifndef GX_SPT
 #define GX_SPT 1
 #endif
@@ -191,7 +194,14 @@ GX_KERNEL_NAME(const __grid_constant__ GxLaunchArgs args) {
     // the out stage about to be written was handed to the TMA engine GX_OUT_STAGES iterations ago
     if (lane == 0) bulk_wait_read<GX_OUT_STAGES - 1>();
     __syncwarp();
-    gx_body(x, tile_s + lane * GX_TILE, tile_s + GX_WT * GX_TILE + lane * GX_N_ROWS);
+#if GX_CHECKED_FAST_MATH
+    // branch-free reciprocals / square roots; a lane whose operand left their exact range flags the tile, which
+    // is then re-evaluated with the IEEE intrinsics (identical results wherever both are defined)
+    if (__any_sync(0xffffffffu, gx_body<false>(x, tile_s + lane * GX_TILE, tile_s + GX_WT * GX_TILE + lane * GX_N_ROWS)))
+      gx_body<true>(x, tile_s + lane * GX_TILE, tile_s + GX_WT * GX_TILE + lane * GX_N_ROWS);
+#else
+    gx_body<true>(x, tile_s + lane * GX_TILE, tile_s + GX_WT * GX_TILE + lane * GX_N_ROWS);
+#endif
 #else
     // two samples per thread: lane and lane + 32 of the warp tile, packed as (.x, .y)
     float2 x[GX_N_IN];

@@ -229,3 +229,33 @@ def test_contracted_plans_run_bit_exact(built_library, order):
     ref_j, ref_p = replay.replay(plan.blob, xs, plan.n_rows, plan.n_cols)
     assert used == "jit"
     assert np.array_equal(bits(jac), bits(ref_j)) and np.array_equal(bits(primal), bits(ref_p))
+
+
+@pytest.mark.gpu
+def test_checked_fast_math_falls_back_exactly(built_library):
+    """The kernels evaluate 1/y and sqrt(x) through the branch-free fast paths of the IEEE intrinsics and
+    re-evaluate a warp tile with the intrinsics themselves when an operand leaves the range where the two agree
+    (tools/rcp_sqrt_exhaustive.py: all 2^32 operands).  Zeros, denormals, huge values, infinities, NaNs and
+    negative radicands must therefore still reproduce the C replay (IEEE division / sqrtf) bit for bit."""
+    from graphax_b200.plan import build_plan
+    from graphax_b200.tracer import jnp, make_jaxpr
+    from oracle import replay
+
+    def f(x, y):
+        return jnp.sqrt(x) / y, x / jnp.sqrt(y)
+    plan = build_plan(make_jaxpr(f, [(), ()]), "rev", (0, 1))
+    specials = np.array([0.0, -0.0, 1e-45, 1e-40, 1.1754944e-38, 3e-38, 1e-30, 0.5, 1.0, 4.0, 1e30, 3e38,
+                         np.inf, -np.inf, np.nan, -1.0, -1e-40], dtype=np.float32)
+    xs, ys = np.meshgrid(specials, specials, indexing="ij")
+    rng = np.random.default_rng(0)
+    # several warp tiles: some all regular (fast path only), some with special lanes mixed in (fallback)
+    x = np.concatenate([rng.uniform(0.5, 2.0, 128).astype(np.float32), xs.reshape(-1), rng.uniform(0.5, 2.0, 77).astype(np.float32)])
+    y = np.concatenate([rng.uniform(0.5, 2.0, 128).astype(np.float32), ys.reshape(-1), rng.uniform(0.5, 2.0, 77).astype(np.float32)])
+    with np.errstate(all="ignore"):
+        ref_j, ref_p = replay.replay(plan.blob, [x, y], plan.n_rows, plan.n_cols)
+    for kernel in ("jit", "interpreter"):
+        jac, primal, used = run_engine(plan, [x, y], kernel)
+        assert used == kernel
+        for got, ref in ((jac, ref_j), (primal, ref_p)):
+            same = (bits(got) == bits(ref)) | (np.isnan(got) & np.isnan(ref))
+            assert same.all(), (kernel, np.argwhere(~same)[:5])

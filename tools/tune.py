@@ -51,6 +51,7 @@ def main():
     ap.add_argument("--spt", default="1,2")
     ap.add_argument("--schedules", default="", help="comma list of plan schedules to compare (default: the plan default)")
     ap.add_argument("--contract", type=int, default=0)
+    ap.add_argument("--fast", default="", help="comma list of GX_CHECKED_FAST settings to compare, e.g. 0,1")
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--out", default="gpurun_out/tune.json")
@@ -87,7 +88,11 @@ def main():
                 dp.launch(nchk, [t.data_ptr() for t in chk_in], ref.data_ptr(), None,
                           torch.cuda.current_stream().cuda_stream)
                 torch.cuda.synchronize()
-                for spt in map(int, args.spt.split(",")):
+                for fast in (args.fast.split(",") if args.fast else [""]):
+                 if fast:
+                    import os
+                    os.environ["GX_CHECKED_FAST"] = fast
+                 for spt in map(int, args.spt.split(",")):
                   for threads in map(int, args.threads.split(",")):
                     for mb in map(int, args.min_blocks.split(",")):
                         if threads * mb * spt > 2048 or threads * mb * spt < 192:
@@ -95,6 +100,8 @@ def main():
                         for st in map(int, args.out_stages.split(",")):
                             cfg = {"variant": "jit", "threads": threads, "min_blocks": mb, "out_stages": st,
                                    "samples_per_thread": spt}
+                            if fast:
+                                cfg["checked_fast"] = int(fast)
                             try:
                                 t0 = time.time()
                                 dp.specialize(threads=threads, min_blocks=mb, out_stages=st, samples_per_thread=spt)
@@ -114,6 +121,7 @@ def main():
                 best[plan.key] = {"name": name, "threads": b["threads"], "min_blocks": b["min_blocks"],
                                   "out_stages": b["out_stages"], "samples_per_thread": b["samples_per_thread"],
                                   "bit_exact": b["bit_exact"], "us": b["us"], "regs": b["regs"],
+                                  **({"checked_fast": b["checked_fast"]} if "checked_fast" in b else {}),
                                   "gjac_per_s": batch / b["us"] / 1e3}
                 results[name] = rows
                 print(name, plan.key, "best", b, flush=True)
