@@ -205,6 +205,11 @@ def run_gpu_arm(args) -> None:
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device. graphax_b200 has no CPU fallback (use --impl reference for the CPU arm).")
+    # stdout carries exactly one JSON line: libraries that print there (NCCL announces its version on the first
+    # collective) are sent to stderr, the result goes to the saved descriptor
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
     rank, local_rank, world = init_process_group("nccl")
     torch.cuda.set_device(local_rank)
     dev = f"cuda:{local_rank}"
@@ -403,7 +408,8 @@ def run_gpu_arm(args) -> None:
                                                  "sample": f"{tb} samples x 3 reps on cuda:0"}
             except Exception as e:          # a baseline must never take the bench line down
                 line["gpu_autodiff_baseline"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(result_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
