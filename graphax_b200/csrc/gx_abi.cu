@@ -1074,14 +1074,16 @@ int gx_jit_launch(gx_jit_kernel* k, unsigned grid_x, unsigned grid_y, unsigned b
 // A run-time compiled instance of gx_gemm_kernel.cuh with a generated epilogue (GX_GEMM_FUSED): same tiling and
 // tensor maps as gx_gemm_bf16; `epi` is the kernel's GxEpi parameter block (pointers of the fused operands and
 // outputs), copied by the launch.
-int gx_gemm_fused_launch(gx_jit_kernel* k, int M, int N, int K, const void* A, int a_mn, const void* B, int b_mn,
-                         const void* epi, int stages, void* stream) {
+int gx_gemm_fused_launch(gx_jit_kernel* k, int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb,
+                         int b_mn, int ldn, const void* epi, int stages, void* stream) {
   if (!k || !A || !B || !epi) return fail(GX_ERR_BAD_ARG, "gx_gemm_fused_launch: NULL argument");
-  if (M <= 0 || N <= 0 || K <= 0 || M % 128 || N % 128 || K % 64)
-    return fail(GX_ERR_UNSUPPORTED, "gx_gemm_fused_launch: M, N must be multiples of 128, K of 64");
+  if (M <= 0 || N <= 0 || K <= 0) return fail(GX_ERR_BAD_ARG, "gx_gemm_fused_launch: empty problem");
+  if (ldn == 0) ldn = N;
+  if (ldn % 4 || ldn < ((N + 127) / 128) * 128)
+    return fail(GX_ERR_UNSUPPORTED, "gx_gemm_fused_launch: epilogue operands must be tile padded (ldn >= ceil(N/128)*128)");
   if (stages != 3 && stages != 6) return fail(GX_ERR_BAD_ARG, "gx_gemm_fused_launch: stages must be 3 or 6 (GX_GEMM_STAGES)");
   CUtensorMap map_a, map_b;
-  if (gxg_make_maps(&map_a, &map_b, M, N, K, A, a_mn, B, b_mn))
+  if (gxg_make_maps(&map_a, &map_b, M, N, K, A, a_mn, B, b_mn, lda, ldb))
     return fail(GX_ERR_CUDA, "gx_gemm_fused_launch: cuTensorMapEncodeTiled failed (pointers must be 16-byte aligned)");
   if (!k->smem_set) {
     CUresult r = driver().FuncSetAttribute(k->func, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)gxg::smem_bytes(stages));
@@ -1093,14 +1095,14 @@ int gx_gemm_fused_launch(gx_jit_kernel* k, int M, int N, int K, const void* A, i
   args.M = M;
   args.N = N;
   args.K = K;
-  args.ldc = N;
-  args.k_per_split = K;
+  args.ldc = ldn;
+  args.k_per_split = ((K + 63) / 64) * 64;
   args.a_mn = a_mn ? 1 : 0;
   args.b_mn = b_mn ? 1 : 0;
   CUlaunchConfig cfg;
   memset(&cfg, 0, sizeof cfg);
-  cfg.gridDimX = N / 128;
-  cfg.gridDimY = M / 128;
+  cfg.gridDimX = (N + 127) / 128;
+  cfg.gridDimY = (M + 127) / 128;
   cfg.gridDimZ = 1;
   cfg.blockDimX = gxg::kThreads;
   cfg.blockDimY = cfg.blockDimZ = 1;

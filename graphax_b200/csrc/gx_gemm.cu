@@ -54,11 +54,13 @@ EncodeTiledFn encode_tiled() {
 }
 
 // row-major [rows, cols] bf16 matrix, box of box_rows x 64 elements (64 elements = one 128-byte swizzle row)
-int make_map(CUtensorMap* map, const void* ptr, int rows, int k, int box_rows) {
+// `rows` x `k` are the TRUE extents (the TMA engine zero-fills whatever a box reaches beyond them), `ld` the
+// row stride in elements (0 = k)
+int make_map(CUtensorMap* map, const void* ptr, int rows, int k, int box_rows, int ld = 0) {
   EncodeTiledFn enc = encode_tiled();
   if (!enc) return -1;
   cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)k * 2};
+  cuuint64_t strides[1] = {(cuuint64_t)(ld ? ld : k) * 2};
   cuuint32_t box[2] = {(cuuint32_t)64, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
@@ -104,9 +106,9 @@ bool gemm_use_pdl() {
 
 // tensor maps of both operands (shared with the run-time compiled kernels launched from gx_abi.cu)
 int gxg_make_maps(CUtensorMap* map_a, CUtensorMap* map_b, int M, int N, int K, const void* A, int a_mn, const void* B,
-                  int b_mn) {
-  const int ra = a_mn ? make_map(map_a, A, K, M, BK) : make_map(map_a, A, M, K, BM);
-  const int rb = b_mn ? make_map(map_b, B, K, N, BK) : make_map(map_b, B, N, K, BN);
+                  int b_mn, int lda, int ldb) {
+  const int ra = a_mn ? make_map(map_a, A, K, M, BK, lda) : make_map(map_a, A, M, K, BM, lda);
+  const int rb = b_mn ? make_map(map_b, B, K, N, BK, ldb) : make_map(map_b, B, N, K, BN, ldb);
   return (ra || rb) ? -1 : 0;
 }
 
@@ -124,16 +126,37 @@ int gx_gemm_bf16_tn(int M, int N, int K, const void* A, const void* B, void* C, 
 // General form: a_mn != 0 means A is stored [K, M] row-major (M contiguous), likewise b_mn for B = [K, N].
 int gx_gemm_bf16(int M, int N, int K, const void* A, int a_mn, const void* B, int b_mn, void* C, int c_is_bf16,
                  int k_splits, void* stream) {
+  if (M > 0 && N > 0 && K > 0 && (M % BM || N % BN || K % BK || (k_splits >= 1 && (K / BK) % k_splits))) {
+    g_gemm_error = "gx_gemm_bf16_tn: M, N must be multiples of 128, K of 64 x k_splits (gx_gemm_bf16_ld takes any size)";
+    return GX_ERR_UNSUPPORTED;
+  }
+  return gx_gemm_bf16_ld(M, N, K, A, 0, a_mn, B, 0, b_mn, C, 0, c_is_bf16, k_splits, stream);
+}
+
+// True extents M, N, K of any size; lda / ldb / ldc are row strides in elements (0 = dense).  Operand rows must
+// start 16-byte aligned (strides multiples of 8 elements); C must be allocated "tile padded": at least
+// ceil(M/128)*128 rows of ldc >= ceil(N/128)*128 elements, because the epilogue writes whole 128-column tile rows
+// (rows beyond M are never written).  Out-of-range operand elements read as zero (TMA fill).
+int gx_gemm_bf16_ld(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C,
+                    int ldc, int c_is_bf16, int k_splits, void* stream) {
   if (M <= 0 || N <= 0 || K <= 0 || !A || !B || !C) {
     g_gemm_error = "gx_gemm_bf16_tn: bad argument";
     return GX_ERR_BAD_ARG;
   }
-  if (M % BM || N % BN || K % BK || k_splits < 1 || (K / BK) % k_splits || (k_splits > 1 && c_is_bf16)) {
-    g_gemm_error = "gx_gemm_bf16_tn: M, N must be multiples of 128, K of 64 x k_splits; split-K needs an fp32 C";
+  const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+  if (ldc == 0) ldc = N;
+  if (k_splits < 1 || (k_splits > 1 && c_is_bf16) || ldc % 4 || ldc < (N % BN ? tiles_n * BN : N)) {
+    g_gemm_error = "gx_gemm_bf16_tn: split-K needs an fp32 C; ldc must be a multiple of 4 and cover whole 128-column tiles";
+    return GX_ERR_UNSUPPORTED;
+  }
+  const int k_blocks = (K + BK - 1) / BK;
+  const int k_per_split = ((k_blocks + k_splits - 1) / k_splits) * BK;
+  if ((long long)k_per_split * (k_splits - 1) >= K && k_splits > 1) {
+    g_gemm_error = "gx_gemm_bf16_tn: more K splits than 64-wide K blocks";
     return GX_ERR_UNSUPPORTED;
   }
   CUtensorMap map_a, map_b;
-  if (gxg_make_maps(&map_a, &map_b, M, N, K, A, a_mn, B, b_mn)) {
+  if (gxg_make_maps(&map_a, &map_b, M, N, K, A, a_mn, B, b_mn, lda, ldb)) {
     g_gemm_error = "gx_gemm_bf16_tn: cuTensorMapEncodeTiled failed (pointers must be 16-byte aligned)";
     return GX_ERR_CUDA;
   }
@@ -162,17 +185,17 @@ int gx_gemm_bf16(int M, int N, int K, const void* A, int a_mn, const void* B, in
   args.M = M;
   args.N = N;
   args.K = K;
-  args.ldc = N;
+  args.ldc = ldc;
   args.epilogue = k_splits > 1 ? EPI_ATOMIC_F32 : (c_is_bf16 ? EPI_STORE_BF16 : EPI_STORE_F32);
-  args.k_per_split = K / k_splits;
+  args.k_per_split = k_per_split;
   args.a_mn = a_mn ? 1 : 0;
   args.b_mn = b_mn ? 1 : 0;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
-  cfg.gridDim = dim3(N / BN, M / BM, k_splits);
+  cfg.gridDim = dim3(tiles_n, tiles_m, k_splits);
   cfg.blockDim = dim3(kThreads);
   // a grid that fits the GPU once gets the deep ring (twice the bytes in flight per SM)
-  const bool deep = (long long)(N / BN) * (M / BM) * k_splits <= sm_count();
+  const bool deep = (long long)tiles_n * tiles_m * k_splits <= sm_count();
   cfg.dynamicSmemBytes = smem_bytes(deep ? kStagesDeep : kStagesShallow);
   cfg.stream = static_cast<cudaStream_t>(stream);
   cudaLaunchAttribute attr[1];
@@ -182,7 +205,7 @@ int gx_gemm_bf16(int M, int N, int K, const void* A, int a_mn, const void* B, in
   cfg.numAttrs = gemm_use_pdl() ? 1 : 0;
   void* params[] = {&map_a, &map_b, &args};
   // several waves of tiles: persistent CTAs (one per SM) with a double-buffered accumulator
-  const long long tiles = (long long)(N / BN) * (M / BM);
+  const long long tiles = (long long)tiles_n * tiles_m;
   const bool persistent = k_splits == 1 && tiles > 2LL * sm_count() && gemm_use_persistent();
   const void* fn = deep ? (const void*)gx_gemm_tn_kernel_deep : (const void*)gx_gemm_tn_kernel;
   if (persistent) {
@@ -191,7 +214,7 @@ int gx_gemm_bf16(int M, int N, int K, const void* A, int a_mn, const void* B, in
     fn = (const void*)gx_gemm_tn_kernel_persistent;
     if (N % 256 == 0 && tiles / 2 > 2LL * sm_count() && gemm_tile_n() == 256) {   // 128 x 256 tiles
       fn = (const void*)gx_gemm_tn_kernel_persistent_n256;
-      if (!b_mn && make_map(&map_b, B, N, K, 256)) {      // K-major B: one 256-row box per stage
+      if (!b_mn && make_map(&map_b, B, N, K, 256, ldb)) {      // K-major B: one 256-row box per stage
         g_gemm_error = "gx_gemm_bf16_tn: cuTensorMapEncodeTiled failed (256-row box)";
         return GX_ERR_CUDA;
       }

@@ -283,7 +283,8 @@ __device__ __forceinline__ void gx_gemm_body(const CUtensorMap& map_a, const CUt
   const int lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int k_begin = blockIdx.z * args.k_per_split;
-  const int num_k_blocks = (args.k_per_split + BK - 1) / BK;
+  const int k_len = args.K - k_begin < args.k_per_split ? args.K - k_begin : args.k_per_split;   // last split may be short
+  const int num_k_blocks = (k_len + BK - 1) / BK;
 
   if (warp == 0 && elect_one()) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -384,7 +385,7 @@ __device__ __forceinline__ void gx_gemm_body(const CUtensorMap& map_a, const CUt
 #pragma unroll
       for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
 #ifdef GX_GEMM_FUSED
-      gx_epi_chunk(epi, epi_state, tile, m_base, n0 + c, args.M, args.N, acc, lane);
+      gx_epi_chunk(epi, epi_state, tile, m_base, n0 + c, args.M, args.ldc, acc, lane);   // N parameter = row stride
 #else
       if (args.epilogue == EPI_STORE_F32)
         store_rows_f32(tile, acc, args.c_f32, args.ldc, m_base, args.M, n0 + c, lane);
@@ -453,7 +454,7 @@ __device__ __forceinline__ void gx_gemm_persistent_body(const CUtensorMap& map_a
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
-  const int tiles_m = args.M / BM, tiles_n = args.N / BNP, n_tiles = tiles_m * tiles_n;
+  const int tiles_m = (args.M + BM - 1) / BM, tiles_n = (args.N + BNP - 1) / BNP, n_tiles = tiles_m * tiles_n;
   const int num_k_blocks = (args.K + BK - 1) / BK;
 
   if (warp == 0 && elect_one()) {

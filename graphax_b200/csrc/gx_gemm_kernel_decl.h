@@ -14,4 +14,4 @@ struct GemmArgs {
 };
 }  // namespace gxg
 int gxg_make_maps(CUtensorMap* map_a, CUtensorMap* map_b, int M, int N, int K, const void* A, int a_mn, const void* B,
-                  int b_mn);
+                  int b_mn, int lda, int ldb);

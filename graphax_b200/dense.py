@@ -268,6 +268,14 @@ _GX_TANH = """__device__ __forceinline__ float gx_tanh(float x) {
 """
 
 
+def _padded(shape: Shape2) -> Shape2:
+    """Storage extents of a [rows, cols] tensor: every axis longer than 1 is rounded up to whole 128-element
+    tiles, so that kernels may read and write whole tile rows; the true extents go into the TMA tensor maps
+    (out-of-range operand elements read as zero) and into the row bounds of reductions."""
+    r, c = shape
+    return (r if r == 1 else -(-r // 128) * 128, c if c == 1 else -(-c // 128) * 128)
+
+
 class DenseExecutor:
     """Materialises the tensor DAG with the library's kernels: tcgen05 GEMMs and fused elementwise kernels
     compiled per plan (NVRTC).  torch supplies device memory and the stream only.
@@ -309,7 +317,7 @@ class DenseExecutor:
         self.fused_colsums: Dict[int, List[int]] = {}
         for n in sorted(reach):
             node = dag.nodes[n]
-            if node.kind == "colsum" and dag.nodes[node.args[0]].kind == "ew" and dag.nodes[node.args[0]].shape[1] % 4 == 0:
+            if node.kind == "colsum" and dag.nodes[node.args[0]].kind == "ew":
                 self.fused_colsums.setdefault(node.args[0], []).append(n)
         fused = {c for cs in self.fused_colsums.values() for c in cs}
         self.needs_bf16 = {a for n in reach if dag.nodes[n].kind == "gemm" for a in dag.nodes[n].args}
@@ -345,6 +353,7 @@ class DenseExecutor:
         def reserve(key, shape):
             nonlocal off
             if key not in self.arena_keys:
+                shape = _padded(shape)
                 self.arena_keys[key] = (off, shape)
                 off += (shape[0] * shape[1] + 3) // 4 * 4
         for n in sorted(reach):
@@ -356,9 +365,10 @@ class DenseExecutor:
             elif node.kind in ("colsum", "sumall"):
                 reserve((n, "f32"), node.shape)
                 if node.kind == "sumall":
-                    reserve((n, "part"), (1, 32))
+                    reserve((n, "part"), (1, dag.nodes[node.args[0]].shape[1]))
         self.arena_size = off
         self.arena = None
+        self.input_stage: Dict[Tuple[int, str], object] = {}
         self.concurrent = os.environ.get("GX_DENSE_STREAMS", "2") != "1"
         # kernels that add into the arena, and results that nothing downstream reads (side-stream candidates)
         self.arena_users = set()
@@ -407,7 +417,7 @@ class DenseExecutor:
         loads/stores) and strides over rows; optional outputs: fp32 copy, bf16 copy, column sums."""
         dag = self.plan.dag
         leaves, lines, result = self._leaves_and_expr(n)
-        rows, cols = dag.nodes[n].shape
+        rows, cols = _padded(dag.nodes[n].shape)      # kernels see the storage width; launches pass the true row count
         vec = 4 if cols % 4 == 0 else 1
         params, loads = [], []
         for i, leaf in enumerate(leaves):
@@ -475,12 +485,12 @@ class DenseExecutor:
         xs, ys = dag.nodes[node.args[0]].shape, dag.nodes[node.args[1]].shape
         m, k = xs[::-1] if node.tx else xs
         nn = ys[1] if node.ty else ys[0]
-        tiles = (m // 128) * (nn // 128)
+        tiles = -(-m // 128) * -(-nn // 128)
         splits = 1
         if tiles < 96:
             limit = int(os.environ.get("GX_SPLITK_CTAS", "160"))
             for sp in (16, 8, 4, 2):
-                if (k // 64) % sp == 0 and tiles * sp <= limit:
+                if -(-k // 64) >= 4 * sp and tiles * sp <= limit:      # at least four 64-wide K blocks per split
                     splits = sp
                     break
         return m, nn, k, splits
@@ -493,7 +503,7 @@ class DenseExecutor:
         pos = {n: i for i, n in enumerate(self.order)}
         for n in list(self.order):
             node = dag.nodes[n]
-            if node.kind != "ew" or node.shape[1] % 128 or node.shape[0] % 128:
+            if node.kind != "ew":
                 continue
             leaves = self._leaves_and_expr(n)[0]
             gemms = [l for l in leaves if dag.nodes[l].kind == "gemm" and dag.nodes[l].shape == node.shape]
@@ -623,10 +633,21 @@ class DenseExecutor:
             off, shape = self.arena_keys[key]
             self.buffers[key] = self.arena[off:off + shape[0] * shape[1]].view(shape)
         if key not in self.buffers:
-            r, c = self.plan.dag.nodes[n].shape
             dt = self.torch.float32 if kind == "f32" else self.torch.bfloat16
-            self.buffers[key] = self.torch.empty((r, c), dtype=dt, device=f"cuda:{self.device}")
+            self.buffers[key] = self.torch.zeros(_padded(self.plan.dag.nodes[n].shape), dtype=dt, device=f"cuda:{self.device}")
         return self.buffers[key]
+
+    def _stage_input(self, i: int, t, dtype):
+        """An argument in tile-padded storage of the given dtype (the tensor itself when it already is)."""
+        shape = tuple(t.shape)
+        if _padded(shape) == shape and t.dtype == dtype:
+            return t
+        key = (i, str(dtype))
+        buf = self.input_stage.get(key)
+        if buf is None:
+            buf = self.input_stage[key] = self.torch.zeros(_padded(shape), dtype=dtype, device=t.device)
+        buf[:shape[0], :shape[1]].copy_(t)
+        return buf
 
     def _bf16(self, n: int):
         """bf16 copy of node n as stored ([rows, cols] row-major); the GEMM reads it K-major or MN-major."""
@@ -654,8 +675,9 @@ class DenseExecutor:
                 else:
                     cs.append(0)
             block = (ctypes.c_void_p * (len(ptrs) + 3 * len(outs)))(*(ptrs + o32 + o16 + cs))
-            rc = self.lib.gx_gemm_fused_launch(self.fused_kernels[n], m, nn, k, a.data_ptr(), int(node.tx), b.data_ptr(),
-                                               int(node.ty), ctypes.cast(block, ctypes.c_void_p), stages, stream)
+            rc = self.lib.gx_gemm_fused_launch(self.fused_kernels[n], m, nn, k, a.data_ptr(), a.shape[1], int(node.tx),
+                                               b.data_ptr(), b.shape[1], int(node.ty), _padded(node.shape)[1],
+                                               ctypes.cast(block, ctypes.c_void_p), stages, stream)
             if rc != 0:
                 raise self.rt.GraphaxB200Error(self.lib.gx_last_error().decode())
             self.launches += 1
@@ -666,8 +688,11 @@ class DenseExecutor:
             x, y = node.args
             a, b = self._bf16(x), self._bf16(y)  # op(X) = X^T is read in place as an MN-major operand
             m, nn, k, splits = self._gemm_geometry(n)
-            out = self._buf(n, "f32")
-            self.rt.gemm_bf16_tn(a, b, out=out, k_splits=splits, a_mn=node.tx, b_mn=node.ty, zero=False)
+            out = self._buf(n, "f32")          # split-K accumulators live in the arena the step has already cleared
+            rc = self.lib.gx_gemm_bf16_ld(m, nn, k, a.data_ptr(), a.shape[1], int(node.tx), b.data_ptr(), b.shape[1],
+                                          int(node.ty), out.data_ptr(), out.shape[1], 0, splits, stream)
+            if rc != 0:
+                raise self.rt.GraphaxB200Error(self.lib.gx_gemm_last_error().decode())
             self.launches += 1
             if n in self.needs_bf16:
                 self._buf(n, "bf16").copy_(out)
@@ -675,21 +700,20 @@ class DenseExecutor:
         elif node.kind in ("colsum", "sumall"):
             src = data(node.args[0])
             out = self._buf(n, "f32")
-            r, c = dag.nodes[node.args[0]].shape
+            r, c = dag.nodes[node.args[0]].shape      # true extents: padding rows / columns stay out of the sums
+            ld = src.shape[1]
             if node.kind == "colsum":
-                rcs = [self.lib.gx_colsum_f32(src.data_ptr(), out.data_ptr(), r, c, stream)]
-            elif (r * c) % 32 == 0:             # all elements: [r*c/32, 32] column sums, then fold the 32 partials
+                rcs = [self.lib.gx_colsum_f32(src.data_ptr(), out.data_ptr(), r, ld, stream)]
+            else:                               # all elements: column sums over the true rows, then the true columns
                 part = self._buf(n, "part")
-                rcs = [self.lib.gx_colsum_f32(src.data_ptr(), part.data_ptr(), r * c // 32, 32, stream),
-                       self.lib.gx_colsum_f32(part.data_ptr(), out.data_ptr(), 32, 1, stream)]
-            else:
-                rcs = [self.lib.gx_colsum_f32(src.data_ptr(), out.data_ptr(), r * c, 1, stream)]
+                rcs = [self.lib.gx_colsum_f32(src.data_ptr(), part.data_ptr(), r, ld, stream),
+                       self.lib.gx_colsum_f32(part.data_ptr(), out.data_ptr(), c, 1, stream)]
             self.launches += len(rcs)
             if any(rcs):
                 raise self.rt.GraphaxB200Error(self.lib.gx_last_error().decode())
         else:
             leaves, vec = self._ew_meta[n]
-            r, c = node.shape
+            r, c = node.shape[0], _padded(node.shape)[1]      # true rows (column sums), padded width (= row stride)
             o32 = self._buf(n, "f32").data_ptr() if n in self.f32_read else 0
             o16 = self._buf(n, "bf16").data_ptr() if n in self.needs_bf16 else 0
             csum = self._buf(self.fused_colsums[n][0], "f32").data_ptr() if n in self.fused_colsums else 0
@@ -714,9 +738,9 @@ class DenseExecutor:
             t = t.reshape(self.plan.in_shapes[i]).contiguous()
             dts.append("bf16" if t.dtype == torch.bfloat16 else "f32")
             if t.dtype == torch.bfloat16:
-                self.inputs_bf16[i] = t
+                self.inputs_bf16[i] = self._stage_input(i, t, torch.bfloat16)
             else:
-                self.inputs_f32[i] = t.float()
+                self.inputs_f32[i] = self._stage_input(i, t, torch.float32)
         if self.input_dtypes != dts:
             self.input_dtypes = dts                 # elementwise kernels read inputs in their own dtype
             for n in list(self.kernels):
@@ -733,7 +757,7 @@ class DenseExecutor:
         for i in range(len(inputs)):                # GEMM operands must be bf16
             if i not in self.inputs_bf16 and any(dag.nodes[n].kind == "input" and dag.nodes[n].input_index == i
                                                  for n in self.needs_bf16):
-                self.inputs_bf16[i] = self.inputs_f32[i].bfloat16()
+                self.inputs_bf16[i] = self._stage_input(i, inputs[i].reshape(self.plan.in_shapes[i]), torch.bfloat16)
 
         def data(n: int):
             node = dag.nodes[n]
@@ -783,8 +807,9 @@ class DenseExecutor:
             if g is None:
                 grads.append(torch.zeros(shape, device=f"cuda:{self.device}"))
             else:
-                grads.append(data(g).float().reshape(shape))
-        return grads, (data(self.plan.primal).reshape(()) if self.with_primal else None)
+                r, c = dag.nodes[g].shape
+                grads.append(data(g)[:r, :c].float().reshape(shape))
+        return grads, (data(self.plan.primal)[0, 0].reshape(()) if self.with_primal else None)
 
 
 def dense_jacve(fun, order, argnums, *args, has_aux: bool = False, device: int = 0, _cache={}):

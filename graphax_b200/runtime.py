@@ -32,7 +32,7 @@ class GxInfo(ctypes.Structure):
 EXPORTS = ["gx_plan_create", "gx_plan_destroy", "gx_plan_info", "gx_plan_specialize", "gx_plan_specialize_opts",
            "gx_plan_select_kernel",
            "gx_jacve_launch", "gx_jacve_host", "gx_last_error", "gx_abi_version", "gx_aot_count", "gx_aot_key",
-           "gx_hash_bytes", "gx_gemm_bf16_tn", "gx_gemm_bf16", "gx_transpose_bf16", "gx_gemm_last_error",
+           "gx_hash_bytes", "gx_gemm_bf16_tn", "gx_gemm_bf16", "gx_gemm_bf16_ld", "gx_transpose_bf16", "gx_gemm_last_error",
            "gx_jit_compile", "gx_jit_destroy", "gx_jit_launch", "gx_colsum_f32", "gx_gemm_fused_launch"]
 
 _lib = None
@@ -93,8 +93,11 @@ def load_library() -> ctypes.CDLL:
         lib.gx_jit_destroy.restype = None
         lib.gx_jit_launch.argtypes = [vp, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint, ctypes.POINTER(vp), vp]
         lib.gx_jit_launch.restype = ctypes.c_int
-        lib.gx_gemm_fused_launch.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, vp,
-                                             ctypes.c_int, vp, ctypes.c_int, vp]
+        lib.gx_gemm_fused_launch.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int,
+                                             vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, vp]
+        lib.gx_gemm_bf16_ld.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, vp,
+                                        ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]
+        lib.gx_gemm_bf16_ld.restype = ctypes.c_int
         lib.gx_gemm_fused_launch.restype = ctypes.c_int
         lib.gx_colsum_f32.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, vp]
         lib.gx_colsum_f32.restype = ctypes.c_int

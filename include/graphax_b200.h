@@ -117,6 +117,11 @@ int gx_gemm_bf16_tn(int M, int N, int K, const void* A, const void* B, void* C, 
  * likewise b_mn for B stored [K, N]; no transposed copies are needed for g^T x style contractions. */
 int gx_gemm_bf16(int M, int N, int K, const void* A, int a_mn, const void* B, int b_mn, void* C, int c_is_bf16,
                  int k_splits, void* stream);
+/* Any M, N, K: the operand tensor maps carry the true extents (out-of-range elements read as zero); lda / ldb /
+ * ldc are row strides in elements (0 = dense; operand strides multiples of 8).  C must be tile padded: at least
+ * ceil(M/128)*128 rows of ldc >= ceil(N/128)*128 elements (whole 128-column tile rows are written, rows >= M never). */
+int gx_gemm_bf16_ld(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C,
+                    int ldc, int c_is_bf16, int k_splits, void* stream);
 int gx_transpose_bf16(int rows, int cols, const void* in, void* out, void* stream);
 const char* gx_gemm_last_error(void);
 
@@ -133,9 +138,10 @@ int gx_colsum_f32(const void* in, void* out, int rows, int cols, void* stream);
  * csrc/gx_gemm_kernel.cuh compiled by gx_jit_compile behind a generated `GxEpi` / `gx_epi_chunk` (dense.py) -
  * the reference's `_mixed_mul` followed by `_pure_broadcast_mul` / elemental partials (sparse/tensor.py:1062-1231,
  * 826-866) without the intermediate edge ever reaching HBM.  `epi` points to the kernel's GxEpi block; `stages` is
- * the operand-ring depth the kernel was compiled with (GX_GEMM_STAGES: 3, or 6 for grids of at most one CTA per SM). */
-int gx_gemm_fused_launch(gx_jit_kernel* kernel, int M, int N, int K, const void* A, int a_mn, const void* B, int b_mn,
-                         const void* epi, int stages, void* stream);
+ * the operand-ring depth the kernel was compiled with (GX_GEMM_STAGES: 3, or 6 for grids of at most one CTA per SM);
+ * M, N, K, lda, ldb as in gx_gemm_bf16_ld, `ldn` the row stride of every [M, N] epilogue operand and output. */
+int gx_gemm_fused_launch(gx_jit_kernel* kernel, int M, int N, int K, const void* A, int lda, int a_mn, const void* B,
+                         int ldb, int b_mn, int ldn, const void* epi, int stages, void* stream);
 
 const char* gx_last_error(void);
 int gx_abi_version(void);

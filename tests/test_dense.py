@@ -65,7 +65,7 @@ def test_tcgen05_gemm(built_library, m, n, k, splits):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("dtype", ["bf16", "f32"])
-@pytest.mark.parametrize("sizes", [(512, 128, 256, 128), (2048, 256, 1024, 768)])
+@pytest.mark.parametrize("sizes", [(512, 128, 256, 128), (2048, 256, 1024, 768), (500, 100, 300, 10), (3000, 784, 1000, 10)])
 def test_mlp_weight_jacobians(built_library, dtype, sizes, monkeypatch):
     """jacve(MLP_loss, 'rev', argnums=(W1, b1, W2, b2)) on the GPU vs the oracle.  The small case runs split-K
     contractions and separate elementwise kernels, the large one (>= 96 output tiles per contraction) the
@@ -93,7 +93,7 @@ def test_mlp_weight_jacobians(built_library, dtype, sizes, monkeypatch):
         assert np.abs(g - e).max() <= 2e-3 * scale       # same rounding points as the engine: tight
         assert np.abs(g - r).max() <= 3e-2 * scale       # vs exact arithmetic: bf16 operand rounding
     ex = [v for k, v in dense_jacve.__kwdefaults__["_cache"].items() if k[3] == tuple(a.shape for a in args)][-1]
-    assert bool(ex.gemm_fused) == (B >= 2048)            # the large case really took the fused path
+    assert ex.gemm_fused or B < 2048                     # the large cases really took the fused path
     if ex.gemm_fused:
         monkeypatch.setenv("GX_DENSE_FUSE", "0")
         dense_jacve.__kwdefaults__["_cache"].clear()
