@@ -381,6 +381,8 @@ def run_gpu_arm(args) -> None:
             "gpu_launches": int(launches) * world,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": recorded_traffic(args.order), "peak_source": peak_src,
+                         "frac_of_nominal_8TBs": achieved / 8000.0,
+                         "fp32_issue": recorded_traffic(args.order + ":fp32"),   # the co-bound
                          "algorithmic_bytes_per_jacobian": plan.bytes_per_jacobian,
                          "kernel_ms": ms_per_step},
             "clocks": sampler.summary(),
@@ -404,8 +406,10 @@ def run_gpu_arm(args) -> None:
                 torch.cuda.empty_cache()
                 tb = min(batch, 1 << 18)
                 tv, _ = torch_measure(w, tb, reps=3, device="cuda")
+                tc, _ = torch_measure(w, min(batch, 1 << 16), reps=3, device="cpu")
                 line["gpu_autodiff_baseline"] = {"value": tv, "unit": UNIT, "kind": "torch.func.vmap(jacrev(f)), eager, fp32",
-                                                 "sample": f"{tb} samples x 3 reps on cuda:0"}
+                                                 "sample": f"{tb} samples x 3 reps on cuda:0",
+                                                 "same_on_host_cpu": tc}
             except Exception as e:          # a baseline must never take the bench line down
                 line["gpu_autodiff_baseline"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
         sys.stdout.flush()
