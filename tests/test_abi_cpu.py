@@ -90,3 +90,20 @@ def test_lowering_needs_no_gpu():
     from graphax_b200.examples.orders import ROEFLUX_3D_VMAP_MIXED
     jf2 = gx.jacve(RoeFlux_3d, order=ROEFLUX_3D_VMAP_MIXED, argnums=w.argnums, order_numbering="vmap")
     assert jf2.lower(w.arg_shapes).key == plan.key
+
+
+def test_api_helpers_without_a_gpu():
+    """Host-side logic of the newer API paths: elementwise detection, vmap in_axes validation, nested tracing."""
+    import graphax_b200 as gx
+    from graphax_b200.examples import Simple, RoeFlux_1d
+    from graphax_b200.examples.economics import BlackScholes_Jacobian
+    from graphax_b200.tracer import make_jaxpr
+    jf = gx.jacve(Simple, order="rev", argnums=(0, 1))
+    assert jf._elementwise_scalar_jaxpr([(50, 50), (50, 50)]) is not None        # every equation maps [50,50] -> [50,50]
+    assert jf._elementwise_scalar_jaxpr([(50, 50), (50,)]) is None               # broadcasting: not elementwise
+    assert gx.jacve(RoeFlux_1d, order="rev", argnums=(0,))._elementwise_scalar_jaxpr([(8,)] * 6) is not None
+    with pytest.raises(NotImplementedError):
+        gx.vmap(jf, in_axes=(0, 1))
+    with pytest.raises(TypeError):
+        gx.vmap(lambda x: x)
+    assert len(make_jaxpr(BlackScholes_Jacobian, [()] * 5).outvars) == 5          # inner plan replayed on the outer trace

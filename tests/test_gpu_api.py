@@ -148,3 +148,21 @@ def test_elementwise_function_of_matrices(built_library, order):
     _, aux = gx.jacve(Simple, order=order, argnums=(0, 1), count_ops=True)(x, y)
     _, aux1 = gx.jacve(Simple, order=order, argnums=(0, 1), count_ops=True)(5., 7.)
     assert aux["num_muls"] == 2500 * aux1["num_muls"] and aux["num_adds"] == 2500 * aux1["num_adds"]
+
+
+@pytest.mark.gpu
+def test_reference_timing_script_form(built_library):
+    """performance_measurements.py:105-127 times jacve(RoeFlux_1d, order, argnums)(*six (600,) arrays): an
+    elementwise function of vectors, whose [600, 600] blocks are diagonal.  The diagonal must equal the batched
+    per-sample Jacobians."""
+    import torch
+    from graphax_b200.examples import RoeFlux_1d
+    w = WORKLOADS["roe1d"]
+    xs = [torch.from_numpy(x).cuda() for x in w.inputs(600)]
+    jac = gx.jacve(RoeFlux_1d, order="rev", argnums=list(range(6)))(*xs)
+    ref = gx.vmap(gx.jacve(RoeFlux_1d, order="rev", argnums=list(range(6))))(*xs)
+    assert len(jac) == 3 and len(jac[0]) == 6 and tuple(jac[0][0].shape) == (600, 600)
+    for o in range(3):
+        for a in range(6):
+            assert torch.equal(jac[o][a].diagonal(), ref[o][a])
+            assert float((jac[o][a] - torch.diag(jac[o][a].diagonal())).abs().max()) == 0.0

@@ -174,3 +174,30 @@ def test_sum_contraction_is_opt_in_and_stays_close():
         mx = np.abs(t64).max(axis=(1, 2), keepdims=True)
         rms = lambda e: float(np.sqrt(np.mean((e / mx) ** 2)))
         assert rms(b - t64) <= 1.02 * rms(a - t64)
+
+
+def test_launch_shape_fits_shared_memory_and_fast_math_heuristic():
+    """Wide tiles get fewer warps per CTA so that the per-warp staging fits in 227 KB; plans whose single warp
+    tile does not fit are refused (they stay on the interpreter); the checked fast reciprocal / sqrt path is
+    only generated for plans with enough of them."""
+    from graphax_b200.codegen import MAX_DYNAMIC_SMEM, checked_fast_math, launch_shape
+    from graphax_b200.examples.deep_learning import Encoder, EncoderDecoder
+    M = (4, 4)
+    enc = build_plan(make_jaxpr(Encoder, [M, (2, 4)] + [M] * 6 + [M, (2, 4), (4,), (2, 1)] + [()] * 4), "rev", range(2, 16))
+    threads, _, stages, spt = launch_shape(enc)
+    per_warp = 4 * (2 * enc.n_in_scalars * 32 + (enc.n_rows * enc.n_cols + enc.n_rows) * 32 + 4)
+    assert threads < 128 and (threads // 32) * per_warp <= MAX_DYNAMIC_SMEM
+    encdec = build_plan(make_jaxpr(EncoderDecoder, [M, (2, 4)] + [M] * 9 + [M, (2, 4), (4,), (2, 1)] + [()] * 6), "rev", range(2, 21))
+    with pytest.raises(ValueError):
+        launch_shape(encdec)
+    assert checked_fast_math(WORKLOADS["roe3d"].plan("rev")) and checked_fast_math(WORKLOADS["roe1d"].plan("rev"))
+    assert not checked_fast_math(WORKLOADS["readme"].plan("readme"))
+
+
+def test_generated_source_shares_sincos_and_uses_checked_reciprocals():
+    from graphax_b200.codegen import emit_source
+    src = emit_source(WORKLOADS["robotarm"].plan("rev"), nvrtc=True)
+    assert src.count("sincosf(") == 6                       # six joint angles, each needs sin and cos
+    src = emit_source(WORKLOADS["roe3d"].plan("mixed"), nvrtc=True)
+    assert src.count("gx_rcp<kPrecise>(") == 9 and src.count("gx_sqrt<kPrecise>(") == 3
+    assert "__frcp_rn(v" not in src.split("template <bool kPrecise>\n__device__ __forceinline__ unsigned gx_body")[1].split("return unsafe;")[0]

@@ -92,3 +92,18 @@ def test_unknown_primitive_raises_not_implemented():
         return x.trace.emit("cumsum", (x.var,), x.shape)
     with pytest.raises(NotImplementedError, match="does not have registered elemental partial"):
         build_plan(make_jaxpr(f, [(3,)]), "rev", (0,))
+
+
+def test_nn_helpers_lower_to_the_expected_primitives():
+    """softmax (without jax.nn's custom_jvp wrapper), mean, keepdims reductions, split and stop_gradient."""
+    from graphax_b200.tracer import jnn, jnp, lax, make_jaxpr
+    j = make_jaxpr(lambda a: jnn.softmax(a, axis=1), [(3, 4)])
+    assert [e.primitive for e in j.eqns] == ["reduce_max", "broadcast_in_dim", "stop_gradient", "sub", "exp",
+                                             "reduce_sum", "broadcast_in_dim", "div"]
+    assert j.outvars[0].shape == (3, 4)
+    j = make_jaxpr(lambda a: jnp.mean(a, axis=-1), [(3, 4)])
+    assert [e.primitive for e in j.eqns] == ["reduce_sum", "div"] and j.outvars[0].shape == (3,)
+    j = make_jaxpr(lambda a: jnp.split(a, [2, 4], axis=0), [(6, 3)])
+    assert [e.primitive for e in j.eqns] == ["slice"] * 3 and [o.shape for o in j.outvars] == [(2, 3)] * 3
+    j = make_jaxpr(lambda a: jnp.sqrt(2.) * lax.stop_gradient(a), [(2,)])
+    assert [e.primitive for e in j.eqns] == ["stop_gradient", "mul"]          # sqrt(2.) folds at trace time
