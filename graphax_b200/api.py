@@ -82,6 +82,7 @@ class JacveFunction:
         self.jit = jit
         self._plans: Dict[Tuple, Plan] = {}
         self._device_plans: Dict[Tuple, Any] = {}
+        self._elementwise_cache: Dict[Tuple, Any] = {}
         wraps(fun)(self)
 
     # ---- host side: trace + lower once per shape signature -------------------
@@ -158,6 +159,13 @@ class JacveFunction:
         itself; other operands are literals), its Jacobian blocks are diagonal - in the reference every edge
         is a pair of SparseDimensions sharing one val (primitives.py:42-107) - and their values are the
         Jacobians of the scalar function, one per element.  Returns the scalar function's jaxpr, else None."""
+        key = tuple(tuple(s) for s in shapes)
+        if key in self._elementwise_cache:
+            return self._elementwise_cache[key]
+        self._elementwise_cache[key] = result = self._detect_elementwise(key)
+        return result
+
+    def _detect_elementwise(self, shapes):
         common = shapes[0]
         if not common or any(tuple(s) != tuple(common) for s in shapes):
             return None
@@ -193,19 +201,19 @@ class JacveFunction:
             dp.launch(n, [t.reshape(n).data_ptr() for t in tensors], jac.data_ptr(),
                       primal.data_ptr() if primal is not None else None, torch.cuda.current_stream(device).cuda_stream)
             nd = len(common)
+            if not self.sparse_representation:       # one zero fill and one strided copy for all blocks
+                dense = torch.zeros((plan.n_rows, plan.n_cols, n, n), dtype=torch.float32, device=f"cuda:{device}")
+                dense.diagonal(dim1=2, dim2=3).copy_(jac.permute(1, 2, 0))
             blocks = []
             for oi in range(plan.n_rows):
                 row = []
                 for ai in range(len(self.argnums)):
-                    vals = jac[:, oi, ai]
                     if self.sparse_representation:
                         dims_o = [["sparse", d, common[d], d, nd + d] for d in range(nd)]
                         dims_p = [["sparse", nd + d, common[d], d, d] for d in range(nd)]
-                        row.append(SparseJacobian(dims_o, dims_p, list(common), vals.reshape(common)))
+                        row.append(SparseJacobian(dims_o, dims_p, list(common), jac[:, oi, ai].reshape(common)))
                     else:
-                        dense = torch.zeros((n, n), dtype=torch.float32, device=f"cuda:{device}")
-                        dense.diagonal().copy_(vals)
-                        row.append(dense.reshape(common + common))
+                        row.append(dense[oi, ai].reshape(common + common))
                 blocks.append(row)
         grads_tree, single = self._tree(blocks, len(shapes))
         if self.count_ops:
