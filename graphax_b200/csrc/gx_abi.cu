@@ -827,13 +827,20 @@ int gx_plan_specialize_opts(gx_plan* p, const char* src, size_t nbytes, const ch
   if (rt.CreateProgram(&prog, src, "gx_plan.cu", 0, nullptr, nullptr) != 0)
     return fail(GX_ERR_JIT, "nvrtcCreateProgram failed");
   std::string archopt = std::string("--gpu-architecture=") + (arch && *arch ? arch : "sm_100a");
-  char d_threads[48], d_blocks[48], d_stages[48], d_spt[48];
+  // two input stages per warp unless only one fits beside the output tile (same rule as codegen.input_stages)
+  const int tile = (int)(p->h.n_rows * p->h.n_cols + ((p->h.flags & GX_FLAG_HAS_PRIMAL) ? p->h.n_rows : 0));
+  auto smem_for = [&](int in_stages) {
+    return (threads / 32) * (in_stages * (int)p->h.n_in_scalars * 32 * spt + out_stages * tile * 32 * spt + 4) * 4;
+  };
+  const int in_stages = smem_for(2) <= 227 * 1024 ? 2 : 1;
+  char d_threads[48], d_blocks[48], d_stages[48], d_spt[48], d_in[48];
+  snprintf(d_in, sizeof d_in, "-DGX_IN_STAGES=%d", in_stages);
   snprintf(d_spt, sizeof d_spt, "-DGX_SPT=%d", spt);
   snprintf(d_threads, sizeof d_threads, "-DGX_THREADS=%d", threads);
   snprintf(d_blocks, sizeof d_blocks, "-DGX_MIN_BLOCKS=%d", min_blocks);
   snprintf(d_stages, sizeof d_stages, "-DGX_OUT_STAGES=%d", out_stages);
-  const char* opts[] = {archopt.c_str(), "-std=c++17", "-lineinfo", d_threads, d_blocks, d_stages, d_spt};
-  const int rc = rt.CompileProgram(prog, 7, opts);
+  const char* opts[] = {archopt.c_str(), "-std=c++17", "-lineinfo", d_threads, d_blocks, d_stages, d_spt, d_in};
+  const int rc = rt.CompileProgram(prog, 8, opts);
   if (rc != 0) {
     size_t n = 0;
     rt.GetProgramLogSize(prog, &n);
@@ -857,8 +864,7 @@ int gx_plan_specialize_opts(gx_plan* p, const char* src, size_t nbytes, const ch
     driver().ModuleUnload(mod);
     return fail(GX_ERR_JIT, "cuModuleGetFunction(gx_jacve_kernel): " + cu_err(r));
   }
-  const int tile = (int)(p->h.n_rows * p->h.n_cols + ((p->h.flags & GX_FLAG_HAS_PRIMAL) ? p->h.n_rows : 0));
-  const int smem = (threads / 32) * (2 * (int)p->h.n_in_scalars * 32 * spt + out_stages * tile * 32 * spt + 4) * 4;
+  const int smem = smem_for(in_stages);
   r = driver().FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, smem);
   int occ = 0, regs = 0;
   if (r == CUDA_SUCCESS) r = driver().OccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, smem);

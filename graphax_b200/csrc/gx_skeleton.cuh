@@ -33,6 +33,10 @@ typedef unsigned long long uint64_t;
 #endif
 
 #define GX_TILE (GX_N_ROWS * GX_N_COLS)
+#ifndef GX_IN_STAGES
+#define GX_IN_STAGES 2 /* 1: wide tiles whose second input stage would not fit; the next tile is then requested as soon
+                          as the current one has been copied to registers */
+#endif
 #ifndef GX_CHECKED_FAST_MATH
 #define GX_CHECKED_FAST_MATH 1
 #endif
@@ -120,7 +124,7 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 constexpr int kWarps = GX_THREADS / 32;
 constexpr int kInStageFloats = GX_N_IN * GX_WT;
 constexpr int kOutStageFloats = (GX_TILE + (GX_HAS_PRIMAL ? GX_N_ROWS : 0)) * GX_WT;
-constexpr int kWarpFloats = 2 * kInStageFloats + GX_OUT_STAGES * kOutStageFloats + 4;  // + 2 mbarriers
+constexpr int kWarpFloats = GX_IN_STAGES * kInStageFloats + GX_OUT_STAGES * kOutStageFloats + 4;  // + 2 mbarriers
 constexpr int kSmemBytes = kWarps * kWarpFloats * 4;
 
 }  // namespace gxk
@@ -136,7 +140,7 @@ GX_KERNEL_NAME(const __grid_constant__ GxLaunchArgs args) {
   // tile index, stage pointers, bulk-copy addresses) is warp-uniform and keeps it on the uniform datapath
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   float* in_stage = gx_smem + warp * kWarpFloats;
-  float* out_stage = in_stage + 2 * kInStageFloats;
+  float* out_stage = in_stage + GX_IN_STAGES * kInStageFloats;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_stage + GX_OUT_STAGES * kOutStageFloats);
 
   const long long n_tiles = (args.batch + GX_WT - 1) / GX_WT;
@@ -166,19 +170,20 @@ GX_KERNEL_NAME(const __grid_constant__ GxLaunchArgs args) {
   if (tile < n_bulk && elect_one()) issue_loads(tile, 0);
 
   for (int it = 0; tile < n_tiles; ++it, tile += stride) {
-    const int stage = it & 1;
+    const int stage = GX_IN_STAGES == 2 ? (it & 1) : 0;
+    const uint32_t in_parity = GX_IN_STAGES == 2 ? (uint32_t)((it >> 1) & 1) : (uint32_t)(it & 1);
     const int ostage = it % GX_OUT_STAGES;
     const bool bulk = tile < n_bulk;
     const long long next = tile + stride;
     // prefetch the next tile: its stage was last read one iteration ago, before the __syncwarp below
-    if (next < n_bulk && elect_one()) issue_loads(next, stage ^ 1);
+    if (GX_IN_STAGES == 2 && next < n_bulk && elect_one()) issue_loads(next, stage ^ 1);
 
     float* tile_s = out_stage + ostage * kOutStageFloats;
 #if GX_SPT == 1
     float x[GX_N_IN];
     const long long sample = tile * GX_WT + lane;
     if (bulk) {
-      mbar_wait(&full_bar[stage], (uint32_t)((it >> 1) & 1));
+      mbar_wait(&full_bar[stage], in_parity);
       const float* s = in_stage + stage * kInStageFloats;
 #define GX_RD_BULK(a, size, off) \
   _Pragma("unroll") for (int c = 0; c < (size); ++c) x[(off) + c] = s[(off) * GX_WT + lane * (size) + c];
@@ -194,6 +199,8 @@ GX_KERNEL_NAME(const __grid_constant__ GxLaunchArgs args) {
     // the out stage about to be written was handed to the TMA engine GX_OUT_STAGES iterations ago
     if (lane == 0) bulk_wait_read<GX_OUT_STAGES - 1>();
     __syncwarp();
+    // single input stage: every lane has its inputs in registers, the stage can take the next tile already
+    if (GX_IN_STAGES == 1 && next < n_bulk && elect_one()) issue_loads(next, 0);
 #if GX_CHECKED_FAST_MATH
     // branch-free reciprocals / square roots; a lane whose operand left their exact range flags the tile, which
     // is then re-evaluated with the IEEE intrinsics (identical results wherever both are defined)
@@ -207,7 +214,7 @@ GX_KERNEL_NAME(const __grid_constant__ GxLaunchArgs args) {
     float2 x[GX_N_IN];
     const long long sample = tile * GX_WT + lane;
     if (bulk) {
-      mbar_wait(&full_bar[stage], (uint32_t)((it >> 1) & 1));
+      mbar_wait(&full_bar[stage], in_parity);
       const float* s = in_stage + stage * kInStageFloats;
 #define GX_RD_BULK(a, size, off)                                                  \
   _Pragma("unroll") for (int c = 0; c < (size); ++c)                              \

@@ -81,10 +81,11 @@ def test_plan_replay_matches_oracle(name, order):
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,order", [("Perceptron", "fwd"), ("Perceptron", "rev"), ("Encoder", "rev"),
                                         ("EncoderDecoder", "rev")])
-def test_gpu_matches_plan_replay(built_library, name, order):
-    """Through the public API; the 23k-operation EncoderDecoder plan is above the run-time compilation
-    threshold and runs on the interpreter kernel."""
+def test_gpu_matches_plan_replay(built_library, name, order, monkeypatch):
+    """Through the public API.  The 23k-operation EncoderDecoder plan would take ~50 s to compile at run time
+    (tools/encdec_bench.py does that); here the threshold is lowered so that it runs on the interpreter."""
     import torch
+    monkeypatch.setenv("GX_JIT_MAX_OPS", "12000")
     from oracle import replay
     fn, shapes, argnums = CASES[name]
     xs = [x.astype(np.float32) for x in _inputs(name, 200)]

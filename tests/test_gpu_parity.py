@@ -259,3 +259,24 @@ def test_checked_fast_math_falls_back_exactly(built_library):
         for got, ref in ((jac, ref_j), (primal, ref_p)):
             same = (bits(got) == bits(ref)) | (np.isnan(got) & np.isnan(ref))
             assert same.all(), (kernel, np.argwhere(~same)[:5])
+
+
+@pytest.mark.gpu
+def test_wide_input_single_stage_kernel(built_library):
+    """400 inputs and a [3 x 400] tile: two input stages per warp no longer fit beside the output tile, so the
+    kernel runs with one (gx_skeleton.cuh GX_IN_STAGES) and requests the next tile as soon as the current one is
+    in registers.  Many tiles per warp, ragged tail."""
+    from graphax_b200.codegen import input_stages, launch_shape
+    from graphax_b200.plan import build_plan
+    from graphax_b200.tracer import jnp, make_jaxpr
+    from oracle import replay
+
+    def f(x):
+        return jnp.sum(x * x), jnp.sum(x), x[0] * x[399] + x[7]
+    plan = build_plan(make_jaxpr(f, [(400,)]), "rev", (0,))
+    assert input_stages(plan, launch_shape(plan)[0]) == 1
+    x = np.random.default_rng(3).uniform(-1, 1, (148 * 32 * 3 + 77, 400)).astype(np.float32)
+    jac, primal, used = run_engine(plan, [x], "jit")
+    assert used == "jit"
+    ref_j, ref_p = replay.replay(plan.blob, [x], plan.n_rows, plan.n_cols)
+    assert np.array_equal(bits(jac), bits(ref_j)) and np.array_equal(bits(primal), bits(ref_p))
