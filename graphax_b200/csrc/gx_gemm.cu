@@ -203,7 +203,9 @@ int gx_gemm_bf16_ld(int M, int N, int K, const void* A, int lda, int a_mn, const
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = gemm_use_pdl() ? 1 : 0;
+  CUtensorMap map_b_half = map_b;              // 128-row boxes of B: the half-width items of the persistent kernel
   void* params[] = {&map_a, &map_b, &args};
+  void* params_persistent[] = {&map_a, &map_b, &map_b_half, &args};
   // several waves of tiles: persistent CTAs (one per SM) with a double-buffered accumulator
   const long long tiles = (long long)tiles_n * tiles_m;
   const bool persistent = k_splits == 1 && tiles > 2LL * sm_count() && gemm_use_persistent();
@@ -220,7 +222,7 @@ int gx_gemm_bf16_ld(int M, int N, int K, const void* A, int lda, int a_mn, const
       }
     }
   }
-  cudaError_t e = cudaLaunchKernelExC(&cfg, fn, params);
+  cudaError_t e = cudaLaunchKernelExC(&cfg, fn, persistent ? params_persistent : params);
   if (e != cudaSuccess) {
     g_gemm_error = std::string("gx_gemm_tn_kernel launch: ") + cudaGetErrorString(e);
     return GX_ERR_CUDA;

@@ -434,9 +434,22 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 }  // namespace gxg
 
+// Work items of the persistent kernel.  With 256-wide tiles the tiles that do not fill a whole round of the grid
+// are cut into two 128-wide halves: 4096^3 is 512 tiles = 3.46 rounds of 148 CTAs, i.e. 4 rounds; with the last 68
+// tiles as 136 half tiles it is 3.5.  Item w < full: tile w, full width; else half (w - full) & 1 of tile
+// full + (w - full) / 2.
+struct GemmItem {
+  int tile, half, width;
+};
+template <int BNP>
+__device__ __forceinline__ GemmItem gemm_item(int w, int full) {
+  if (BNP == 128 || w < full) return {w, 0, BNP};
+  return {full + ((w - full) >> 1), (w - full) & 1, 128};
+}
+
 template <int BNP>   // tile width: 128, or 256 (A re-read half as often: 85 instead of 64 flop per operand byte)
 __device__ __forceinline__ void gx_gemm_persistent_body(const CUtensorMap& map_a, const CUtensorMap& map_b,
-                                                        const gxg::GemmArgs& args) {
+                                                        const CUtensorMap& map_b_half, const gxg::GemmArgs& args) {
   using namespace gxg;
   constexpr uint32_t kStageBytesB = BNP * BK * 2;                        // shadows the 128-wide constant
   constexpr int kStages = kRingBytesPersistent / (kStageBytesA + kStageBytesB);   // 6 or 4
@@ -456,6 +469,10 @@ __device__ __forceinline__ void gx_gemm_persistent_body(const CUtensorMap& map_a
   const int lane = threadIdx.x & 31;
   const int tiles_m = (args.M + BM - 1) / BM, tiles_n = (args.N + BNP - 1) / BNP, n_tiles = tiles_m * tiles_n;
   const int num_k_blocks = (args.K + BK - 1) / BK;
+  // tiles in whole rounds; the remainder is halved only if the halves still fit in one round (else nothing is won)
+  const int rounds_full = (n_tiles / (int)gridDim.x) * (int)gridDim.x;
+  const int full = (BNP == 128 || 2 * (n_tiles - rounds_full) > (int)gridDim.x) ? n_tiles : rounds_full;
+  const int n_items = full + 2 * (n_tiles - full);
 
   if (warp == 0 && elect_one()) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -487,14 +504,15 @@ __device__ __forceinline__ void gx_gemm_persistent_body(const CUtensorMap& map_a
     // ===== TMA producer: the ring position runs on across tiles =====
     if (elect_one()) {
       uint32_t it = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const GemmItem item = gemm_item<BNP>(w, full);
         int tm, tn;
-        tile_coords(t, tiles_m, tiles_n, tm, tn);
-        const int m0 = tm * BM, n0 = tn * BNP;
+        tile_coords(item.tile, tiles_m, tiles_n, tm, tn);
+        const int m0 = tm * BM, n0 = tn * BNP + item.half * 128;
         for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
           const int s = it % kStages;
           mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
-          mbar_expect_tx(&full_bar[s], kStageBytesA + kStageBytesB);
+          mbar_expect_tx(&full_bar[s], kStageBytesA + (uint32_t)item.width * BK * 2);
           const int k0 = kb * BK;
           if (!args.a_mn) {
             tma_load_2d(smem_a + s * kStageBytesA, &map_a, k0, m0, &full_bar[s]);
@@ -503,10 +521,9 @@ __device__ __forceinline__ void gx_gemm_persistent_body(const CUtensorMap& map_a
             tma_load_2d(smem_a + s * kStageBytesA + 8192, &map_a, m0 + 64, k0, &full_bar[s]);
           }
           if (!args.b_mn) {
-            tma_load_2d(smem_b + s * kStageBytesB, &map_b, k0, n0, &full_bar[s]);
+            tma_load_2d(smem_b + s * kStageBytesB, item.width == BNP ? &map_b : &map_b_half, k0, n0, &full_bar[s]);
           } else {
-#pragma unroll
-            for (int q = 0; q < BNP / 64; ++q)
+            for (int q = 0; q < item.width / 64; ++q)
               tma_load_2d(smem_b + s * kStageBytesB + q * 8192, &map_b, n0 + 64 * q, k0, &full_bar[s]);
           }
         }
@@ -515,7 +532,8 @@ __device__ __forceinline__ void gx_gemm_persistent_body(const CUtensorMap& map_a
   } else if (warp == 1) {
     // ===== MMA issuer: accumulator i & 1 =====
     uint32_t it = 0, i = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++i) {
+      const int width = gemm_item<BNP>(w, full).width;
       const uint32_t buf = i & 1;
       mbar_wait(&tmem_empty_bar[buf], ((i >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
       tc_fence_after();
@@ -528,7 +546,8 @@ __device__ __forceinline__ void gx_gemm_persistent_body(const CUtensorMap& map_a
           const uint64_t da = args.a_mn ? make_smem_desc_mn(sa) : make_smem_desc(sa);
           const uint64_t db = args.b_mn ? make_smem_desc_mn(sb) : make_smem_desc(sb);
           const uint32_t step_a = args.a_mn ? 128u : 2u, step_b = args.b_mn ? 128u : 2u;
-          const uint32_t idesc = kInstrDesc | (args.a_mn ? (1u << 15) : 0u) | (args.b_mn ? (1u << 16) : 0u);
+          const uint32_t idesc = ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(width >> 3) << 17) | ((BM >> 4) << 24)) |
+                                 (args.a_mn ? (1u << 15) : 0u) | (args.b_mn ? (1u << 16) : 0u);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k)
             umma_f16(tmem_base + buf * BNP, da + step_a * k, db + step_b * k, idesc, (kb | k) != 0 ? 1u : 0u);
@@ -541,18 +560,19 @@ __device__ __forceinline__ void gx_gemm_persistent_body(const CUtensorMap& map_a
   } else {
     // ===== epilogue =====
     const int quad = warp & 3;
-    const int c_begin = ((warp - 2) >> 2) * (BNP / 2);
     float* tile = staging + (warp - 2) * 1024;
     uint32_t i = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++i) {
+      const GemmItem item = gemm_item<BNP>(w, full);
       const uint32_t buf = i & 1;
       int tm, tn;
-      tile_coords(t, tiles_m, tiles_n, tm, tn);
-      const int m_base = tm * BM + quad * 32, n0 = tn * BNP;
+      tile_coords(item.tile, tiles_m, tiles_n, tm, tn);
+      const int m_base = tm * BM + quad * 32, n0 = tn * BNP + item.half * 128;
+      const int c_begin = ((warp - 2) >> 2) * (item.width / 2), c_end = c_begin + item.width / 2;
       mbar_wait(&tmem_full_bar[buf], (i >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = c_begin; c < c_begin + BNP / 2; c += 64) {
+      for (int c = c_begin; c < c_end; c += 64) {
         float acc[2][32];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -572,7 +592,7 @@ __device__ __forceinline__ void gx_gemm_persistent_body(const CUtensorMap& map_a
 #pragma unroll
           for (int j = 0; j < 32; ++j) acc[h][j] = __uint_as_float(v[j]);
         }
-        if (c + 64 >= c_begin + BNP / 2) {
+        if (c + 64 >= c_end) {
           // the last of this warp's columns is in registers: hand the TMEM buffer back before the global stores
           tc_fence_before();
           __syncwarp();
@@ -599,13 +619,13 @@ __device__ __forceinline__ void gx_gemm_persistent_body(const CUtensorMap& map_a
 
 extern "C" __global__ void __launch_bounds__(gxg::kThreads, 1)
 gx_gemm_tn_kernel_persistent(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                             const gxg::GemmArgs args) {
-  gx_gemm_persistent_body<128>(map_a, map_b, args);
+                             const __grid_constant__ CUtensorMap map_b_half, const gxg::GemmArgs args) {
+  gx_gemm_persistent_body<128>(map_a, map_b, map_b_half, args);
 }
 extern "C" __global__ void __launch_bounds__(gxg::kThreads, 1)
 gx_gemm_tn_kernel_persistent_n256(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                                  const gxg::GemmArgs args) {
-  gx_gemm_persistent_body<256>(map_a, map_b, args);
+                                  const __grid_constant__ CUtensorMap map_b_half, const gxg::GemmArgs args) {
+  gx_gemm_persistent_body<256>(map_a, map_b, map_b_half, args);
 }
 #endif  // !GX_NVRTC
 

@@ -122,3 +122,25 @@ def test_jacve_api_dispatches_matrix_arguments(built_library):
         assert float((g.double().cpu() - ti.grad).abs().max()) <= 3e-2 * float(ti.grad.abs().max())
     with pytest.raises(NotImplementedError):
         gx.jacve(MLP_loss, order="fwd", argnums=(1,))(*tens)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("m,n,k", [(4096, 4096, 512), (8192, 2048, 576), (4096, 3968, 512), (2560, 3840, 1024)])
+def test_persistent_gemm_variants(built_library, m, n, k):
+    """Grids of several waves run on the persistent kernels: 128 x 256 tiles with a double-buffered TMEM
+    accumulator (4096 x 4096: 512 tiles = 3 rounds of 148 CTAs + 68 tiles cut into 136 half-width items),
+    128 x 128 tiles when N is not a multiple of 256; every operand layout, fp32 and bf16 results."""
+    import torch
+    from graphax_b200 import runtime
+    torch.manual_seed(1)
+    A = (torch.randn(m, k, device="cuda") * 0.1).bfloat16()
+    B = (torch.randn(n, k, device="cuda") * 0.1).bfloat16()
+    ref = A.float() @ B.float().T
+    for a_mn in (False, True):
+        for b_mn in (False, True):
+            a = A.T.contiguous() if a_mn else A
+            b = B.T.contiguous() if b_mn else B
+            c32 = runtime.gemm_bf16_tn(a, b, out_dtype=torch.float32, a_mn=a_mn, b_mn=b_mn)
+            c16 = runtime.gemm_bf16_tn(a, b, out_dtype=torch.bfloat16, a_mn=a_mn, b_mn=b_mn)
+            assert float((c32 - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+            assert float((c16.float() - ref).abs().max()) <= 2 ** -8 * float(ref.abs().max())
