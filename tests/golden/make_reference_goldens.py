@@ -1,0 +1,199 @@
+"""Golden vectors from the reference's OWN code.
+
+Run once in the build container (where /root/reference exists):
+
+    python tests/golden/make_reference_goldens.py
+
+graphax is pure Python on top of JAX and JAX is not installed here, so this script
+puts `tests/golden/jaxlite` (a NumPy stand-in for the JAX API, see its `jax/_impl.py`)
+and `/root/reference/src` on `sys.path` and then runs the UNMODIFIED reference:
+`jax.make_jaxpr` of the reference's example functions, `graphax.core._build_graph`,
+`graphax.jacve(f, order, argnums, count_ops=True)` and
+`vertex_elimination_jaxpr(..., sparse_representation=True)`.
+
+What is recorded (tests/golden/reference_run.json + reference_run.npz):
+  * the jaxpr of every example function (primitive, operands, literals, parameters);
+  * the SparseTensor structure of every elemental edge (`core.py:314-412`);
+  * per order: the validated order, `num_muls`, `num_adds`, per-vertex `order_counts`,
+    the structure of every final Jacobian block (`sparse_representation=True`);
+  * float32 inputs, primal outputs and dense Jacobians at N points per (function, order).
+
+The arithmetic behind the values is NumPy float32, one call per primitive, in the
+order the reference's Python issues them; a real JAX run can differ from it only by
+XLA's fusion / FMA contraction of those same operations.
+"""
+import json
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+REPO = HERE.parent.parent
+REFERENCE = Path(sys.argv[1] if len(sys.argv) > 1 else "/root/reference/src")
+
+sys.path.insert(0, str(REPO))
+from graphax_b200.configs import WORKLOADS, EXTRA_WORKLOADS   # noqa: E402  (points and orders only)
+
+sys.path[:0] = [str(HERE / "jaxlite"), str(REFERENCE)]
+import jax                      # noqa: E402  (jaxlite)
+import jax.numpy as jnp         # noqa: E402
+import graphax                  # noqa: E402  (the reference)
+import graphax.core as gcore    # noqa: E402
+from graphax import examples as gex             # noqa: E402
+from graphax.sparse.tensor import SparseDimension   # noqa: E402
+
+assert jax.__version__.endswith("jaxlite") and str(REFERENCE) in graphax.__file__
+
+N_POINTS = {"roe3d": 96, "roe1d": 96, "robotarm": 96}
+
+# workload name (graphax_b200.configs) -> the reference's own function
+FUNCTIONS = {
+    "roe3d": gex.RoeFlux_3d, "roe1d": gex.RoeFlux_1d, "robotarm": gex.RobotArm_6DOF,
+    "simple": gex.Simple, "lighthouse": gex.Lighthouse, "hole": gex.Hole, "helmholtz": gex.Helmholtz,
+}
+
+
+def dims(ds):
+    return [["S" if isinstance(d, SparseDimension) else "D", d.id, d.size, d.val_dim,
+             d.other_id if isinstance(d, SparseDimension) else None] for d in ds]
+
+
+def describe(t):
+    if t is None:
+        return None
+    return {"out_dims": dims(t.out_dims), "primal_dims": dims(t.primal_dims),
+            "val_shape": None if t.val is None else list(np.shape(t.val)),
+            "n_pre_transforms": len(t.pre_transforms), "n_post_transforms": len(t.post_transforms)}
+
+
+def jsonable(v):
+    if isinstance(v, (tuple, list)):
+        return [jsonable(x) for x in v]
+    if isinstance(v, np.dtype):
+        return v.name
+    if isinstance(v, np.generic):
+        return v.item()
+    return v
+
+
+def dump_jaxpr(jaxpr):
+    key = {}
+    for i, v in enumerate(jaxpr.invars):
+        key[v] = -(i + 1)
+    eqns = []
+    for n, eqn in enumerate(jaxpr.eqns, start=1):
+        key[eqn.outvars[0]] = n
+        ops = [["lit", float(a.val)] if isinstance(a, jax.core.Literal) else ["var", key[a]] for a in eqn.invars]
+        eqns.append({"primitive": eqn.primitive.name, "operands": ops, "shape": list(eqn.outvars[0].aval.shape),
+                     "params": {k: jsonable(v) for k, v in eqn.params.items() if v is not None}})
+    return key, {"n_eqns": len(eqns), "eqns": eqns, "outvars": [key[v] for v in jaxpr.outvars],
+                 "in_shapes": [list(v.aval.shape) for v in jaxpr.invars]}
+
+
+def pack(out, n_rows_each, n_cols_each):
+    """The reference's tuple-of-tuples of blocks -> one [rows, cols] matrix (row-major blocks)."""
+    rows = []
+    for o, row in zip(n_rows_each, out):
+        row = row if isinstance(row, tuple) else (row,)
+        rows.append(np.concatenate([np.asarray(b, dtype=np.float32).reshape(o, c) for b, c in zip(row, n_cols_each)], axis=1))
+    return np.concatenate(rows, axis=0)
+
+
+def run_workload(name, w, fun, n_points):
+    argnums = tuple(w.argnums)
+    base = [np.asarray(w.base[sum(w.sizes[:i]):sum(w.sizes[:i + 1])], np.float32).reshape(s) for i, s in enumerate(w.arg_shapes)]
+    pts = w.inputs(n_points - 1)
+    points = [[jnp.array(b)] + [jnp.array(p[k]) for k in range(n_points - 1)] for b, p in zip(base, pts)]
+    args0 = [p[0] for p in points]
+
+    closed = jax.make_jaxpr(fun)(*args0)
+    jaxpr = closed.jaxpr
+    key, rec = dump_jaxpr(jaxpr)
+    rec["function"] = f"graphax.examples.{fun.__name__}"
+    rec["point0"] = [np.asarray(a).reshape(-1).tolist() for a in args0]
+
+    env, graph, tgraph, vo = gcore._build_graph(jaxpr, args0, closed.literals)
+    rec["vo_vertices"] = sorted(int(v) for v in vo)
+    rec["elemental"] = [[key[src], key[dst], describe(t)] for src in graph for dst, t in graph[src].items()]
+
+    out_sizes = [int(np.prod(v.aval.shape, dtype=np.int64)) for v in jaxpr.outvars]
+    in_sizes = [int(np.prod(jaxpr.invars[a].aval.shape, dtype=np.int64)) for a in argnums]
+    arrays = {"inputs": np.stack([np.concatenate([np.asarray(p[k]).reshape(-1) for p in points]) for k in range(n_points)]).astype(np.float32)}
+    prim = []
+    for k in range(n_points):
+        vals = fun(*[p[k] for p in points])
+        vals = vals if isinstance(vals, (tuple, list)) else (vals,)
+        prim.append(np.concatenate([np.asarray(v, np.float32).reshape(-1) for v in vals]))
+    arrays["primal"] = np.stack(prim)
+
+    rec["orders"] = {}
+    for oname in w.order_names():
+        order = w.order(oname)
+        order = order if isinstance(order, str) else [int(v) for v in order]
+        t0 = time.time()
+        jacs = []
+        for k in range(n_points):
+            out, aux = graphax.jacve(fun, order=order, argnums=argnums, count_ops=True)(*[p[k] for p in points])
+            if len(jaxpr.outvars) == 1:
+                out = (out,)
+            if len(argnums) == 1:
+                out = tuple((b,) for b in out)
+            jacs.append(pack(out, out_sizes, in_sizes))
+            if k == 0:
+                aux0 = aux
+            else:
+                assert aux["num_muls"] == aux0["num_muls"] and aux["order_counts"] == aux0["order_counts"]
+        sparse = gcore.vertex_elimination_jaxpr(jaxpr, order, closed.literals, *args0, argnums=argnums,
+                                                sparse_representation=True)
+        if len(argnums) > 1:
+            sparse = [t for row in sparse for t in row]
+        n_a = len(argnums)
+        rec["orders"][oname] = {
+            "order": order, "eliminated": [int(v) for v, _ in aux0["order_counts"]],
+            "num_muls": int(aux0["num_muls"]), "num_adds": int(aux0["num_adds"]),
+            "order_counts": [[int(v), int(c)] for v, c in aux0["order_counts"]],
+            "blocks": {f"{i // n_a},{i % n_a}": describe(t) for i, t in enumerate(sparse)},
+        }
+        arrays[f"jac/{oname}"] = np.stack(jacs)
+        print(f"  {name}:{oname}: muls {aux0['num_muls']} adds {aux0['num_adds']}  "
+              f"{n_points} points in {time.time() - t0:.1f} s", flush=True)
+    return rec, arrays
+
+
+def run_g():
+    """The reference's only literal known answers: `# fwd: 632, rev: 566` (`examples/randoms.py:91`)."""
+    rng = np.random.default_rng(7)
+    xs = [jnp.array(np.float32(x)) for x in rng.uniform(0.5, 1.5, 15)]
+    rec = {"function": "graphax.examples.g", "n_eqns": len(jax.make_jaxpr(gex.g)(*xs).jaxpr.eqns), "orders": {}}
+    for order in ("fwd", "rev"):
+        _, aux = graphax.jacve(gex.g, order=order, argnums=tuple(range(15)), count_ops=True)(*xs)
+        rec["orders"][order] = {"num_muls": int(aux["num_muls"]), "num_adds": int(aux["num_adds"]),
+                                "order_counts": [[int(v), int(c)] for v, c in aux["order_counts"]]}
+        print(f"  g:{order}: muls {aux['num_muls']} (reference comment: {'632' if order == 'fwd' else '566'})")
+    return rec
+
+
+def main():
+    out = {"generator": "tests/golden/make_reference_goldens.py",
+           "reference": "jamielohoff/graphax, unmodified sources under /root/reference/src, on tests/golden/jaxlite",
+           "arithmetic": "NumPy float32, one call per primitive", "workloads": {}}
+    arrays = {}
+    for name, fun in FUNCTIONS.items():
+        w = WORKLOADS.get(name) or EXTRA_WORKLOADS[name]
+        print(name, flush=True)
+        rec, arr = run_workload(name, w, fun, N_POINTS.get(name, 8))
+        out["workloads"][name] = rec
+        for k, v in arr.items():
+            arrays[f"{name}/{k}"] = v
+    print("g", flush=True)
+    out["workloads"]["g"] = run_g()
+    (HERE / "reference_run.json").write_text(json.dumps(out, separators=(",", ":")))
+    np.savez_compressed(HERE / "reference_run.npz", **arrays)
+    print("wrote", HERE / "reference_run.json", (HERE / "reference_run.json").stat().st_size, "bytes;",
+          HERE / "reference_run.npz", (HERE / "reference_run.npz").stat().st_size, "bytes")
+
+
+if __name__ == "__main__":
+    main()

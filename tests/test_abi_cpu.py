@@ -107,3 +107,13 @@ def test_api_helpers_without_a_gpu():
     with pytest.raises(TypeError):
         gx.vmap(lambda x: x)
     assert len(make_jaxpr(BlackScholes_Jacobian, [()] * 5).outvars) == 5          # inner plan replayed on the outer trace
+
+
+def test_product_never_imports_test_infrastructure():
+    """oracle/ and the JAX stand-in under tests/golden/jaxlite are checkers: nothing in the package may import them."""
+    import re
+    from pathlib import Path
+    pkg = Path(__file__).resolve().parent.parent / "graphax_b200"
+    for f in pkg.rglob("*.py"):
+        text = f.read_text()
+        assert not re.search(r"^\s*(from|import)\s+(oracle|jaxlite|jax)\b", text, re.M), f

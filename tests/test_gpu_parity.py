@@ -82,6 +82,42 @@ def test_engine_matches_reference_order_oracle(built_library, name, order, divis
     assert aux["num_muls"] == plan.stats["num_muls"] and aux["num_adds"] == plan.stats["num_adds"]
 
 
+def _reference_run():
+    import json
+    from helpers import GOLDEN
+    run = json.loads((GOLDEN / "reference_run.json").read_text())
+    return run, np.load(GOLDEN / "reference_run.npz")
+
+
+REF_CASES = [(n, o) for n in ("roe3d", "roe1d", "robotarm") for o in WORKLOADS[n].order_names()]
+
+
+@pytest.mark.parametrize("name,order", REF_CASES)
+@pytest.mark.parametrize("division", DIVISIONS)
+@pytest.mark.parametrize("kernel", ["aot", "interpreter"])
+def test_kernels_match_reference_run(built_library, name, order, division, kernel):
+    """CUDA kernels against float32 Jacobians computed by the reference's own code (unmodified graphax sources on
+    the NumPy stand-in for JAX, tests/golden/make_reference_goldens.py) at the committed points: north-star
+    tolerance rtol 1e-5 in the form |dJ| <= 1e-5 max|J_sample| + 1e-5 |J| (the kernels contract mul+add into FMA
+    and, in `reciprocal` mode, replace x/y by x*(1/y) with one correction step)."""
+    run, arr = _reference_run()
+    w = WORKLOADS[name]
+    flat = arr[f"{name}/inputs"]
+    xs, off = [], 0
+    for shape, size in zip(w.arg_shapes, w.sizes):
+        xs.append(np.ascontiguousarray(flat[:, off:off + size].reshape((len(flat),) + tuple(shape))))
+        off += size
+    plan = w.plan(order, division=division)
+    assert plan.structure["order"] == run["workloads"][name]["orders"][order]["eliminated"]
+    jac, primal, used = run_engine(plan, xs, kernel)
+    assert used == kernel
+    ref = arr[f"{name}/jac/{order}"].astype(np.float64)
+    bound = parity_bound(ref)
+    assert np.isfinite(jac).all()
+    assert (np.abs(jac - ref) <= bound).all(), float((np.abs(jac - ref) / bound).max())
+    np.testing.assert_allclose(primal, arr[f"{name}/primal"], rtol=2e-6, atol=1e-6)
+
+
 @pytest.mark.parametrize("batch", [0, 1, 127, 128, 129, 300])
 @pytest.mark.parametrize("kernel", ["aot", "interpreter"])
 def test_ragged_batches(built_library, batch, kernel):

@@ -1,0 +1,126 @@
+"""Pin oracle and engine against a run of the reference's OWN code.
+
+`tests/golden/reference_run.{json,npz}` come from `tests/golden/make_reference_goldens.py`: the unmodified
+graphax sources (`core.py`, `primitives.py`, `sparse/tensor.py`, `examples/*.py`) executed on `tests/golden/jaxlite`,
+a NumPy stand-in for the JAX API (JAX is not installed in this image).  The stand-in + reference pair reproduces
+the reference's only literal known answers (`count_ops` 632 / 566 for `g`, `examples/randoms.py:91`).
+
+Checked here, on the CPU:
+  * jaxpr: the engine's tracer lowers its copies of the workloads to the same equations, operands, literals
+    and parameters as the reference's own example functions traced by the stand-in;
+  * structure: every elemental edge, every final Jacobian block, the eliminated vertices, `num_muls`,
+    `num_adds` and the per-vertex counts are identical (oracle and plan builder alike);
+  * values: the NumPy oracle reproduces the reference's float32 Jacobians BIT FOR BIT; the plan replay
+    (FMA-contracted, reciprocal division) stays inside the parity bound of BASELINE.md section 5.
+The GPU half is `tests/test_gpu_parity.py::test_kernels_match_reference_run`.
+"""
+import json
+
+import numpy as np
+import pytest
+
+from graphax_b200.configs import get_workload
+from helpers import GOLDEN, bits, pack_blocks, parity_bound
+from oracle import replay, ve_numpy as vo
+
+RUN = json.loads((GOLDEN / "reference_run.json").read_text())
+ARR = np.load(GOLDEN / "reference_run.npz")
+CASES = [(n, o) for n, rec in RUN["workloads"].items() if n != "g" for o in rec["orders"]]
+NAMES = [n for n in RUN["workloads"] if n != "g"]
+
+
+def split_inputs(w, flat):
+    out, off = [], 0
+    for shape, size in zip(w.arg_shapes, w.sizes):
+        out.append(np.ascontiguousarray(flat[:, off:off + size].reshape((len(flat),) + tuple(shape))))
+        off += size
+    return out
+
+
+def strip(desc):
+    """Structure fields both sides describe the same way (transforms are closures in the reference)."""
+    return None if desc is None else {k: desc[k] for k in ("out_dims", "primal_dims", "val_shape")}
+
+
+def test_reference_run_reproduces_the_reference_known_answers():
+    g = RUN["workloads"]["g"]
+    assert g["n_eqns"] == 105
+    assert g["orders"]["fwd"]["num_muls"] == 632 and g["orders"]["rev"]["num_muls"] == 566   # randoms.py:91
+    assert RUN["workloads"]["roe3d"]["n_eqns"] == 138 and RUN["workloads"]["roe3d"]["outvars"] == [134, 136, 138]
+    assert RUN["workloads"]["roe1d"]["n_eqns"] == 101 and RUN["workloads"]["roe1d"]["outvars"] == [97, 99, 101]
+    assert RUN["workloads"]["robotarm"]["n_eqns"] == 114
+    assert sorted(RUN["workloads"]["robotarm"]["outvars"]) == [62, 66, 68, 85, 102, 114]
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_tracer_lowers_to_the_jaxpr_of_the_reference_example(name):
+    from graphax_b200.tracer import Literal
+    w, rec = get_workload(name), RUN["workloads"][name]
+    jaxpr = w.jaxpr()
+    assert [list(v.shape) for v in jaxpr.invars] == rec["in_shapes"]
+    assert len(jaxpr.eqns) == rec["n_eqns"]
+    key = lambda v: -(v.input_index + 1) if v.input_index is not None else v.eqn_index + 1
+    assert [key(v) for v in jaxpr.outvars] == rec["outvars"]
+    for n, (mine, ref) in enumerate(zip(jaxpr.eqns, rec["eqns"]), start=1):
+        assert mine.primitive == ref["primitive"], n
+        ops = [["lit", float(np.float32(a.val))] if isinstance(a, Literal) else ["var", key(a)] for a in mine.invars]
+        assert ops == ref["operands"], (n, mine)
+        assert list(mine.outvar.shape) == ref["shape"], n
+        for k, v in ref["params"].items():
+            if k in ("precision", "preferred_element_type", "sharding", "strides"):
+                continue
+            got = mine.params[k]
+            norm = lambda x: [norm(y) for y in x] if isinstance(x, (list, tuple)) else x
+            assert norm(got) == norm(v), (n, k)
+
+
+@pytest.mark.parametrize("name,order", CASES)
+def test_oracle_equals_reference_run(name, order):
+    w, rec = get_workload(name), RUN["workloads"][name]
+    ro = rec["orders"][order]
+    xs = split_inputs(w, ARR[f"{name}/inputs"])
+    jac, primal, aux = vo.jacve(w.jaxpr(), w.order(order), w.argnums, xs, np.float32)
+    # structure
+    assert aux["structure"]["order"] == ro["eliminated"]
+    mine = {(s, d): strip(desc) for s, d, desc in aux["structure"]["elemental"]}
+    ref = {(s, d): strip(desc) for s, d, desc in rec["elemental"]}
+    assert mine == ref
+    for s, d, desc in aux["structure"]["elemental"]:
+        r = next(x for x in rec["elemental"] if x[0] == s and x[1] == d)[2]
+        assert len(desc["pre_transforms"]) == r["n_pre_transforms"] + r["n_post_transforms"]
+    assert {k: strip(v) for k, v in aux["structure"]["blocks"].items()} == {k: strip(v) for k, v in ro["blocks"].items()}
+    # count_ops
+    assert (aux["num_muls"], aux["num_adds"]) == (ro["num_muls"], ro["num_adds"])
+    assert [list(c) for c in aux["order_counts"]] == ro["order_counts"]
+    # values: same operations in the same order on the same float32 inputs
+    J = pack_blocks(jac, len(xs[0]), w.sizes)
+    assert (bits(J) == bits(ARR[f"{name}/jac/{order}"])).all()
+    p = np.concatenate([q.reshape(len(xs[0]), -1) for q in primal], axis=1)
+    assert (bits(p) == bits(ARR[f"{name}/primal"])).all()
+
+
+@pytest.mark.parametrize("name,order", CASES)
+def test_plan_structure_equals_reference_run(name, order):
+    w, rec = get_workload(name), RUN["workloads"][name]
+    ro = rec["orders"][order]
+    plan = w.plan(order)
+    assert plan.structure["order"] == ro["eliminated"]
+    assert {(s, d): strip(x) for s, d, x in plan.structure["elemental"]} == {(s, d): strip(x) for s, d, x in rec["elemental"]}
+    assert {k: strip(v) for k, v in plan.structure["blocks"].items()} == {k: strip(v) for k, v in ro["blocks"].items()}
+    assert (plan.stats["num_muls"], plan.stats["num_adds"]) == (ro["num_muls"], ro["num_adds"])
+    assert [list(c) for c in plan.stats["order_counts"]] == ro["order_counts"]
+
+
+@pytest.mark.parametrize("division", ["reciprocal", "ieee"])
+@pytest.mark.parametrize("name,order", CASES)
+def test_plan_replay_within_parity_bound_of_reference_run(name, order, division):
+    """The arithmetic the kernels execute (plan blob, replayed by the C interpreter) against the reference's
+    float32 Jacobians: |dJ| <= 1e-5 max|J_sample| + 1e-5 |J| (accumulation order / FMA contraction differ)."""
+    w = get_workload(name)
+    xs = split_inputs(w, ARR[f"{name}/inputs"])
+    plan = w.plan(order, division=division)
+    rep, prim = replay.replay(plan.blob, xs, plan.n_rows, plan.n_cols)
+    ref = ARR[f"{name}/jac/{order}"].astype(np.float64)
+    assert np.isfinite(rep).all()
+    assert (np.abs(rep - ref) <= parity_bound(ref)).all(), float((np.abs(rep - ref) / parity_bound(ref)).max())
+    np.testing.assert_allclose(prim, ARR[f"{name}/primal"], rtol=2e-6, atol=1e-7)
