@@ -249,6 +249,8 @@ class Primitive:
         return Array(out)
 
     def bind(self, *args, **params):
+        if any(isinstance(a, BatchTracer) for a in args):
+            return _batch_bind(self, args, params)
         if not _TRACES:
             return self._eval(args, params)
         # Inside make_jaxpr every bind is staged (JAX >= 0.4.36 has one current trace), constants included.
@@ -426,7 +428,7 @@ select_n_p = Primitive("select_n", _select_n_impl)
 
 
 def _is_value(x) -> bool:
-    return isinstance(x, (Array, Tracer))
+    return isinstance(x, (Array, Tracer, BatchTracer))
 
 
 def _shape_of(x) -> Tuple[int, ...]:
@@ -954,7 +956,131 @@ def _unavailable(name):
     return fn
 
 
-vmap = _unavailable("vmap")
+
+# ------------------------------------------------------------------------------------------------
+# vmap: the batching rules of the primitives the reference's vmapped tests reach (batch axis kept in front)
+# ------------------------------------------------------------------------------------------------
+
+
+class BatchTracer(_Ops):
+    """A value with a hidden leading batch axis; `aval` is the per-sample view, as inside `jax.vmap`."""
+
+    def __init__(self, val):
+        self.val = val
+        self.aval = ShapedArray(val.shape[1:], val.dtype)
+
+    def __repr__(self):
+        return f"Batched<{self.aval}>"
+
+
+def _ndim(x) -> int:
+    return len(_shape_of(x))
+
+
+def _broadcast_batcher(prim, args, params):
+    """jax.interpreters.batching.broadcast_batcher: equal shapes (and scalars) bind directly; otherwise unbatched
+    arrays get a unit batch axis and lower-rank operands trailing unit axes (`lax.expand_dims`), the primitive's
+    own broadcasting does the rest."""
+    vals = [a.val if isinstance(a, BatchTracer) else a for a in args]
+    shapes = {_shape_of(v) for v in vals if _ndim(v)}
+    if len(shapes) > 1 or any(_ndim(a) and not isinstance(a, BatchTracer) for a in args):
+        vals = [v if isinstance(a, BatchTracer) or not _ndim(v) else _expand_leading(v, 1) for a, v in zip(args, vals)]
+        nd = builtins.max(_ndim(v) for v in vals)
+        vals = [v if not isinstance(a, BatchTracer) or _ndim(v) == nd else expand_dims(v, tuple(range(_ndim(v), nd)))
+                for a, v in zip(args, vals)]
+    return BatchTracer(prim.bind(*vals, **params))
+
+
+def _batch_bind(prim, args, params):
+    name = prim.name
+    B = next(a.val.shape[0] for a in args if isinstance(a, BatchTracer))
+    if len(args) == 1 and name not in _BATCH_RULES:
+        return BatchTracer(prim.bind(args[0].val, **params))         # elementwise unary
+    if name in ("add", "add_any", "sub", "mul", "div", "atan2", "pow", "max", "min", "eq", "gt", "lt"):
+        return _broadcast_batcher(prim, args, params)
+    if name in _BATCH_RULES:
+        return _BATCH_RULES[name](prim, args, params, B)
+    raise NotImplementedError(f"jaxlite: no batching rule for {name}")
+
+
+def _b_reduce(prim, args, params, B):
+    return BatchTracer(prim.bind(args[0].val, axes=tuple(a + 1 for a in params["axes"])))
+
+
+def _b_dot_general(prim, args, params, B):
+    lhs, rhs = args
+    (lc, rc), (lb, rb) = params["dimension_numbers"]
+    if not (isinstance(lhs, BatchTracer) and isinstance(rhs, BatchTracer)):
+        if isinstance(lhs, BatchTracer) and not lb:      # the batch axis is the first free axis of lhs
+            dn = ((tuple(i + 1 for i in lc), rc), ((), ()))
+            return BatchTracer(prim.bind(lhs.val, rhs, **dict(params, dimension_numbers=dn)))
+        raise NotImplementedError("jaxlite: dot_general with a batched right operand only")
+    sh = lambda t: tuple(i + 1 for i in t)
+    dn = ((sh(lc), sh(rc)), ((0,) + sh(lb), (0,) + sh(rb)))
+    return BatchTracer(prim.bind(lhs.val, rhs.val, **dict(params, dimension_numbers=dn)))
+
+
+def _b_slice(prim, args, params, B):
+    strides = params.get("strides")
+    return BatchTracer(prim.bind(args[0].val, start_indices=(0,) + tuple(params["start_indices"]),
+                                 limit_indices=(B,) + tuple(params["limit_indices"]),
+                                 strides=None if strides is None else (1,) + tuple(strides)))
+
+
+def _b_concatenate(prim, args, params, B):
+    vals = []
+    for a in args:
+        if isinstance(a, BatchTracer):
+            vals.append(a.val)
+        else:       # lax.broadcast(op, (size,))
+            shape = (B,) + _shape_of(a)
+            vals.append(broadcast_in_dim_p.bind(a, shape=shape, broadcast_dimensions=tuple(range(1, len(shape))), sharding=None))
+    return BatchTracer(prim.bind(*vals, dimension=params["dimension"] + 1))
+
+
+def _b_broadcast_in_dim(prim, args, params, B):
+    return BatchTracer(prim.bind(args[0].val, shape=(B,) + tuple(params["shape"]), sharding=None,
+                                 broadcast_dimensions=(0,) + tuple(d + 1 for d in params["broadcast_dimensions"])))
+
+
+def _b_transpose(prim, args, params, B):
+    return BatchTracer(prim.bind(args[0].val, permutation=(0,) + tuple(p + 1 for p in params["permutation"])))
+
+
+def _b_reshape(prim, args, params, B):
+    return BatchTracer(prim.bind(args[0].val, new_sizes=(B,) + tuple(params["new_sizes"]), dimensions=None, sharding=None))
+
+
+def _b_squeeze(prim, args, params, B):
+    return BatchTracer(prim.bind(args[0].val, dimensions=tuple(d + 1 for d in params["dimensions"])))
+
+
+_BATCH_RULES = {"reduce_sum": _b_reduce, "reduce_max": _b_reduce, "reduce_min": _b_reduce, "dot_general": _b_dot_general,
+                "slice": _b_slice, "concatenate": _b_concatenate, "broadcast_in_dim": _b_broadcast_in_dim,
+                "transpose": _b_transpose, "reshape": _b_reshape, "squeeze": _b_squeeze}
+
+
+def vmap(fun, in_axes=0, out_axes=0):
+    """`jax.vmap` for `in_axes` of 0 / None and `out_axes=0`."""
+    if out_axes != 0:
+        raise NotImplementedError("jaxlite: vmap out_axes")
+
+    def batched(*args):
+        axes = in_axes if isinstance(in_axes, (tuple, list)) else (in_axes,) * len(args)
+        if any(a not in (0, None) for a in axes):
+            raise NotImplementedError("jaxlite: vmap in_axes other than 0 / None")
+        args = [a if _is_value(a) else Array(a) for a in args]
+        B = next(a.shape[0] for a, ax in zip(args, axes) if ax == 0)
+        outs = fun(*[BatchTracer(a) if ax == 0 else a for a, ax in zip(args, axes)])
+
+        def unwrap(o):
+            if isinstance(o, BatchTracer):
+                return o.val
+            shape = (B,) + _shape_of(o)       # an unbatched output is broadcast along the new axis
+            return broadcast_in_dim_p.bind(_lift(o), shape=shape, broadcast_dimensions=tuple(range(1, len(shape))), sharding=None)
+        return tree_map(unwrap, outs)
+    return batched
+
 jacfwd = _unavailable("jacfwd")
 jacrev = _unavailable("jacrev")
 grad = _unavailable("grad")

@@ -175,6 +175,37 @@ def run_g():
     return rec
 
 
+def run_roe3d_vmapped(batch=4):
+    """The form the reference's own test uses: `jacve(jax.vmap(RoeFlux_3d), order)` with orders written against
+    the 146-equation vmapped jaxpr (`tests/examples/example_test.py:146-166`)."""
+    from graphax_b200.examples import orders as ref_orders
+    w = WORKLOADS["roe3d"]
+    xs = [jnp.array(x) for x in w.inputs(batch)]
+    vf = jax.vmap(gex.RoeFlux_3d)
+    jaxpr = jax.make_jaxpr(vf)(*xs).jaxpr
+    pads = [n for n, e in enumerate(jaxpr.eqns, 1)
+            if e.primitive.name == "broadcast_in_dim" and not isinstance(e.invars[0], jax.core.Literal)]
+    rec = {"function": "jax.vmap(graphax.examples.RoeFlux_3d)", "batch": batch, "n_eqns": len(jaxpr.eqns),
+           "identity_pads": pads, "primitives": [e.primitive.name for e in jaxpr.eqns], "orders": {}}
+    arrays = {"inputs": np.concatenate([np.asarray(x).reshape(batch, -1) for x in xs], axis=1).astype(np.float32)}
+    orders = {"fwd": "fwd", "rev": "rev", "mixed": list(ref_orders.ROEFLUX_3D_VMAP_MIXED),
+              "mixed2": list(ref_orders.ROEFLUX_3D_VMAP_MIXED2)}
+    for oname, order in orders.items():
+        out, aux = graphax.jacve(vf, order=order, argnums=tuple(range(6)), count_ops=True)(*xs)
+        rows = []
+        for row in out:      # blocks [B, out, B, in]
+            rows.append(np.concatenate([np.asarray(b, np.float32).reshape(batch, -1, batch, c) for b, c in zip(row, w.sizes)], axis=3))
+        full = np.concatenate(rows, axis=1)                       # [B, 5, B, 10]
+        off = full.copy()
+        for b in range(batch):
+            off[b, :, b, :] = 0
+        rec["orders"][oname] = {"order": order, "num_muls": int(aux["num_muls"]), "num_adds": int(aux["num_adds"]),
+                                "off_diagonal_max": float(np.abs(off).max())}
+        arrays[f"jac/{oname}"] = np.stack([full[b, :, b, :] for b in range(batch)])
+        print(f"  roe3d_vmap:{oname}: muls {aux['num_muls']} adds {aux['num_adds']} off-diagonal max {np.abs(off).max()}")
+    return rec, arrays
+
+
 def main():
     out = {"generator": "tests/golden/make_reference_goldens.py",
            "reference": "jamielohoff/graphax, unmodified sources under /root/reference/src, on tests/golden/jaxlite",
@@ -187,6 +218,11 @@ def main():
         out["workloads"][name] = rec
         for k, v in arr.items():
             arrays[f"{name}/{k}"] = v
+    print("roe3d_vmap", flush=True)
+    rec, arr = run_roe3d_vmapped()
+    out["workloads"]["roe3d_vmap"] = rec
+    for k, v in arr.items():
+        arrays[f"roe3d_vmap/{k}"] = v
     print("g", flush=True)
     out["workloads"]["g"] = run_g()
     (HERE / "reference_run.json").write_text(json.dumps(out, separators=(",", ":")))
