@@ -6,13 +6,17 @@ argnums))``.  Only ``tests/``, ``__graft_entry__.smoke()`` and
 ``bench.py``'s CPU-baseline legs may import this module; nothing under
 ``graphax_b200/`` does.
 
-PARITY UNPINNED BY A RUNNABLE REFERENCE: graphax needs JAX, which is not in this
-image, so this restatement could not be run against the reference itself.  It is
-pinned instead by (tests/test_oracle.py): the reference's only literal known
-answers (count_ops 632 / 566 for ``g``, ``examples/randoms.py:91``), the vertex
-sets implied by every elimination order in the reference's tests, the einsum
-identities of ``tests/core/*_mul_test.py`` (rank <= 1 cases), and fp64 Jacobians
-from an independent autodiff (``tests/golden/``).
+PINNED AGAINST A RUN OF THE REFERENCE'S OWN CODE (tests/test_reference_goldens.py): graphax
+needs JAX, which is not in this image, so the unmodified reference sources were run here on
+a NumPy stand-in for the JAX API (``tests/golden/jaxlite``, generator
+``tests/golden/make_reference_goldens.py``; that pair reproduces the reference's literal
+known answers, count_ops 632 / 566 for ``g``, ``examples/randoms.py:91``).  Against the
+committed vectors of that run this module gives identical edge / block structures,
+elimination orders and count_ops numbers, and float32 Jacobians that are equal BIT FOR BIT
+for all 21 (function, order) pairs.  XLA's own arithmetic (fusion, FMA contraction) remains
+unpinned: no JAX to run.  Further pins (tests/test_oracle.py): the vertex sets implied by
+every elimination order in the reference's tests, the einsum identities of
+``tests/core/*_mul_test.py`` (rank <= 1 cases), fp64 Jacobians from an independent autodiff.
 
 What follows the reference, function by function (file:line into /root/reference/src/graphax):
 

@@ -206,6 +206,47 @@ def run_roe3d_vmapped(batch=4):
     return rec, arrays
 
 
+RANK_N = {   # per-sample shapes and argnums of the reference's own tests (tests/examples/example_test.py:168-349)
+    "NeuralNetwork": ([(4,), (8, 4), (8,), (4, 8), (4,), (4,)], (1, 2, 3, 4)),
+    "Perceptron": ([(4,), (4,), (8, 4), (8,), (4, 8), (4,), (), ()], tuple(range(8))),
+    "Encoder": ([(4, 4), (2, 4)] + [(4, 4)] * 6 + [(4, 4), (2, 4), (4,), (2, 1)] + [()] * 4, tuple(range(2, 16))),
+    "EncoderDecoder": ([(4, 4), (2, 4)] + [(4, 4)] * 9 + [(4, 4), (2, 4), (4,), (2, 1)] + [()] * 6, tuple(range(2, 21))),
+}
+
+
+def NeuralNetwork(x, W1, b1, W2, b2, y):
+    """The function defined inside the reference's `test_NeuralNetwork` (example_test.py:170-179)."""
+    a1 = jnp.tanh(W1 @ x + b1)
+    a2 = jnp.tanh(W2 @ a1 + b2)
+    d = a2 - y
+    return .5*jnp.sum(d**2)
+
+
+def run_rank_n(name, n_points=2):
+    """Matrix-valued vertices (`_mixed_mul`, dot_general / transpose / reduce_max edges): values, counts, equations."""
+    shapes, argnums = RANK_N[name]
+    fun = NeuralNetwork if name == "NeuralNetwork" else getattr(gex, name)
+    rng = np.random.default_rng(11)
+    pts = [rng.normal(0.0, 0.6, (n_points,) + s) if s else rng.uniform(0.5, 1.5, (n_points,)) for s in shapes]
+    pts = [p.astype(np.float32) for p in pts]
+    jaxpr = jax.make_jaxpr(fun)(*[jnp.array(p[0]) for p in pts]).jaxpr
+    rec = {"function": name, "in_shapes": [list(s) for s in shapes], "argnums": list(argnums), "n_eqns": len(jaxpr.eqns),
+           "primitives": [e.primitive.name for e in jaxpr.eqns], "out_shapes": [list(v.aval.shape) for v in jaxpr.outvars],
+           "orders": {}}
+    arrays = {f"in{i}": p for i, p in enumerate(pts)}
+    for order in ("fwd", "rev"):
+        vals = []
+        for k in range(n_points):
+            out, aux = graphax.jacve(fun, order=order, argnums=argnums, count_ops=True)(*[jnp.array(p[k]) for p in pts])
+            rows = out if len(jaxpr.outvars) > 1 else (out,)
+            vals.append(np.concatenate([np.concatenate([np.asarray(b, np.float32).reshape(-1, int(np.prod(shapes[a], dtype=np.int64)))
+                                                        for b, a in zip(row, argnums)], axis=1) for row in rows], axis=0))
+        rec["orders"][order] = {"num_muls": int(aux["num_muls"]), "num_adds": int(aux["num_adds"])}
+        arrays[f"jac/{order}"] = np.stack(vals)
+        print(f"  {name}:{order}: muls {aux['num_muls']} adds {aux['num_adds']} tile {vals[0].shape}")
+    return rec, arrays
+
+
 def main():
     out = {"generator": "tests/golden/make_reference_goldens.py",
            "reference": "jamielohoff/graphax, unmodified sources under /root/reference/src, on tests/golden/jaxlite",
@@ -218,6 +259,13 @@ def main():
         out["workloads"][name] = rec
         for k, v in arr.items():
             arrays[f"{name}/{k}"] = v
+    out["rank_n"] = {}
+    for name in RANK_N:
+        print(name, flush=True)
+        rec, arr = run_rank_n(name)
+        out["rank_n"][name] = rec
+        for k, v in arr.items():
+            arrays[f"rank_n/{name}/{k}"] = v
     print("roe3d_vmap", flush=True)
     rec, arr = run_roe3d_vmapped()
     out["workloads"]["roe3d_vmap"] = rec

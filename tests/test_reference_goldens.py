@@ -157,3 +157,54 @@ def test_vmapped_reference_form_and_order_translation(order):
         assert (bits(J) != bits(ref)).mean() < 0.1
     else:
         assert (bits(J) == bits(ref)).all(), float(np.abs(J - ref).max())
+
+
+# ---- matrix-valued vertices: the reference's own NeuralNetwork / Perceptron / Encoder / EncoderDecoder tests ----------
+def _rank_n_case(name):
+    from graphax_b200.examples.deep_learning import Encoder, EncoderDecoder, Perceptron
+    from graphax_b200.tracer import jnp
+
+    def NeuralNetwork(x, W1, b1, W2, b2, y):          # reference tests/examples/example_test.py:170-179
+        a1 = jnp.tanh(W1 @ x + b1)
+        a2 = jnp.tanh(W2 @ a1 + b2)
+        d = a2 - y
+        return .5 * jnp.sum(d ** 2)
+    return {"NeuralNetwork": NeuralNetwork, "Perceptron": Perceptron, "Encoder": Encoder,
+            "EncoderDecoder": EncoderDecoder}[name]
+
+
+@pytest.mark.parametrize("name", list(RUN["rank_n"]))
+def test_rank_n_graphs_against_reference_run(name):
+    """Same equations as the reference traces, and the reference's float32 Jacobians reproduced by the dense-matrix
+    oracle (`oracle/dense_ve.py`) and by the engine's plan (C replay), forward and reverse."""
+    from graphax_b200.plan import build_plan
+    from graphax_b200.tracer import make_jaxpr
+    from oracle import dense_ve
+    rec = RUN["rank_n"][name]
+    shapes, argnums = [tuple(s) for s in rec["in_shapes"]], tuple(rec["argnums"])
+    jaxpr = make_jaxpr(_rank_n_case(name), shapes)
+    assert [e.primitive for e in jaxpr.eqns] == rec["primitives"]
+    assert [list(v.shape) for v in jaxpr.outvars] == rec["out_shapes"]
+    xs = [ARR[f"rank_n/{name}/in{i}"] for i in range(len(shapes))]
+    n = len(xs[0])
+    # The reference's own forward and reverse results disagree on some entries of the two attention examples:
+    # `_swap_axes` (`sparse/tensor.py:529-569`) decides by comparing shapes, which is ambiguous for the square 4x4
+    # matrices of these tests (reverse mode of sum(tanh(x)*x, axis=0) is wrong for a 4x4 x and right for a 3x4 x).
+    # Entries the reference computes consistently in both modes are the golden values.
+    r_fwd = ARR[f"rank_n/{name}/jac/fwd"].astype(np.float64)
+    r_rev = ARR[f"rank_n/{name}/jac/rev"].astype(np.float64)
+    scale = np.abs(r_rev).max(axis=(1, 2), keepdims=True)
+    agree = np.abs(r_fwd - r_rev) <= 1e-5 * scale
+    expect_all = {"NeuralNetwork": True, "Perceptron": True, "Encoder": False, "EncoderDecoder": False}[name]
+    assert agree.all() == expect_all and agree.mean() > 0.15
+    for order in ("fwd", "rev"):
+        ref = ARR[f"rank_n/{name}/jac/{order}"].astype(np.float64)
+        jac, _ = dense_ve.jacve(jaxpr, order, argnums, xs, np.float32)
+        tile = np.concatenate([np.concatenate([b.reshape(n, max(1, o.size), -1) for b in row], axis=2)
+                               for o, row in zip(jaxpr.outvars, jac)], axis=1)
+        assert ((np.abs(tile - ref) / scale)[agree]).max() < 2e-5, (name, order)
+        if name == "EncoderDecoder" and order == "fwd":
+            continue                                   # a 100k-operation plan: covered by the reverse order
+        plan = build_plan(jaxpr, order, argnums)
+        rep, _ = replay.replay(plan.blob, xs, plan.n_rows, plan.n_cols)
+        assert ((np.abs(rep - ref) / scale)[agree]).max() < 2e-5, (name, order)
