@@ -12,7 +12,7 @@ def ElementalZoo(x, y, v):
     c = jnp.maximum(v, y) - jnp.minimum(v, x)
     d = jnp.arctan(a) + jnp.sinh(x) * jnp.cosh(y)
     e = jnp.arcsin(x * .5) + jnp.arccos(y * .25) + jnp.tan(x)
-    f = jnp.log1p(b * b) + jnp.erf(c)
+    f = jnp.log1p(jnp.square(b)) + jnp.erf(c)
     g = jnp.power(y, x) + jnp.square(v) + jnp.arcsinh(v) + jnp.arctanh(x * .3) + jnp.arccosh(y + 1.)
     h = jnp.abs(v - 1.5) + jnp.sqrt(y) + (-v) ** 3 / y
     return d + e, f * g + h, jnp.sum(c) * a

@@ -206,6 +206,46 @@ def run_roe3d_vmapped(batch=4):
     return rec, arrays
 
 
+def run_zoo(n_points=16):
+    """Every elementwise elemental rule (`primitives.py:150-239`) through the reference, on the engine's coverage
+    function `graphax_b200/examples/zoo.py` (its source is executed here against jaxlite's `jnp`).  Recorded twice:
+    with the reference's rules as they are, and with the `asinh` rule replaced through the reference's own extension
+    point (`defelemental`): `primitives.py:172` registers sqrt(1 + x^2), the reciprocal of the derivative."""
+    import types
+    import jax.lax as lax
+    from graphax.primitives import defelemental, elemental_rules
+    ns = types.SimpleNamespace(**{k: getattr(jnp, k) for k in dir(jnp) if not k.startswith("_")})
+    ns.sigmoid, ns.erf = lax.logistic, jax.scipy.special.erf          # conveniences of the engine's jnp shim
+    scope = {"jnp": ns}
+    exec((REPO / "graphax_b200" / "examples" / "zoo.py").read_text().replace("from ..tracer import jnp", ""), scope)
+    zoo = scope["ElementalZoo"]
+    w = EXTRA_WORKLOADS["zoo"]
+    pts = w.inputs(n_points)
+    rec = {"function": "graphax_b200.examples.zoo.ElementalZoo (engine fixture, reference rules)", "orders": {}}
+    arrays = {"inputs": np.concatenate([p.reshape(n_points, -1) for p in pts], axis=1)}
+    jaxpr = jax.make_jaxpr(zoo)(*[jnp.array(p[0]) for p in pts]).jaxpr
+    rec["primitives"] = [e.primitive.name for e in jaxpr.eqns]
+    original = elemental_rules[lax.asinh_p]
+    for variant in ("reference_rules", "asinh_corrected"):
+        if variant == "asinh_corrected":
+            defelemental(lax.asinh_p, lambda x: 1. / jnp.sqrt(1. + x**2))
+        for order in ("fwd", "rev"):
+            vals = []
+            for k in range(n_points):
+                out, aux = graphax.jacve(zoo, order=order, argnums=(0, 1, 2), count_ops=True)(*[jnp.array(p[k]) for p in pts])
+                vals.append(pack(out, [1, 3, 1], w.sizes))
+            arrays[f"{variant}/jac/{order}"] = np.stack(vals)
+            rec["orders"][order] = {"num_muls": int(aux["num_muls"]), "num_adds": int(aux["num_adds"])}
+    elemental_rules[lax.asinh_p] = original
+    # a second quirk, recorded as a known answer: both partials of `x*x` land on the same graph edge
+    # (`core.py:376-378` assigns graph[invar][outvar] twice), so the reference returns x instead of 2x
+    dup = graphax.jacve(lambda x: x * x, order="fwd", argnums=(0,))(jnp.array(3.0))
+    rec["quirks"] = {"d(x*x)/dx at x=3": float(np.asarray(dup[0] if isinstance(dup, (tuple, list)) else dup))}
+    d = np.abs(arrays["reference_rules/jac/rev"] - arrays["asinh_corrected/jac/rev"]).max()
+    print(f"  zoo: muls {rec['orders']} ; asinh rule changes the Jacobian by up to {d:.3f}")
+    return rec, arrays
+
+
 RANK_N = {   # per-sample shapes and argnums of the reference's own tests (tests/examples/example_test.py:168-349)
     "NeuralNetwork": ([(4,), (8, 4), (8,), (4, 8), (4,), (4,)], (1, 2, 3, 4)),
     "Perceptron": ([(4,), (4,), (8, 4), (8,), (4, 8), (4,), (), ()], tuple(range(8))),
@@ -266,6 +306,11 @@ def main():
         out["rank_n"][name] = rec
         for k, v in arr.items():
             arrays[f"rank_n/{name}/{k}"] = v
+    print("zoo", flush=True)
+    rec, arr = run_zoo()
+    out["zoo"] = rec
+    for k, v in arr.items():
+        arrays[f"zoo/{k}"] = v
     print("roe3d_vmap", flush=True)
     rec, arr = run_roe3d_vmapped()
     out["workloads"]["roe3d_vmap"] = rec

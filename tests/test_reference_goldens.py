@@ -208,3 +208,36 @@ def test_rank_n_graphs_against_reference_run(name):
         plan = build_plan(jaxpr, order, argnums)
         rep, _ = replay.replay(plan.blob, xs, plan.n_rows, plan.n_cols)
         assert ((np.abs(rep - ref) / scale)[agree]).max() < 2e-5, (name, order)
+
+
+def test_every_elementwise_rule_against_reference_run():
+    """`graphax_b200/examples/zoo.py` touches every elementwise rule of `primitives.py:150-239`.  Through the
+    reference's rules the engine's Jacobian agrees once the reference's `asinh` rule is corrected via its own
+    extension point: `primitives.py:172` registers sqrt(1 + x^2), the reciprocal of d asinh / dx.  The engine
+    implements the derivative, which this test documents by also checking the mismatch."""
+    w, rec = get_workload("zoo"), RUN["zoo"]
+    assert [e.primitive for e in w.jaxpr().eqns] == rec["primitives"]
+    xs = split_inputs(w, ARR["zoo/inputs"])
+    for order in ("fwd", "rev"):
+        plan = w.plan(order)
+        assert (plan.stats["num_muls"], plan.stats["num_adds"]) == (rec["orders"][order]["num_muls"], rec["orders"][order]["num_adds"])
+        rep, _ = replay.replay(plan.blob, xs, plan.n_rows, plan.n_cols)
+        jac, _, _ = vo.jacve(w.jaxpr(), order, w.argnums, xs, np.float32)
+        J = pack_blocks(jac, len(xs[0]), w.sizes)
+        good = ARR[f"zoo/asinh_corrected/jac/{order}"].astype(np.float64)
+        assert (np.abs(J - good) <= parity_bound(good)).all()
+        assert (np.abs(rep - good) <= parity_bound(good)).all()
+        as_is = ARR[f"zoo/reference_rules/jac/{order}"].astype(np.float64)
+        bad = np.abs(rep - as_is) > parity_bound(as_is)
+        assert bad.any() and not bad[:, 0, :].any() and not bad[:, 4, :].any()    # only the rows fed by arcsinh(v)
+
+
+def test_duplicate_operand_deviation():
+    """Deliberate deviation: for `x*x` the reference writes both partials to the same graph edge
+    (`core.py:376-378`, the second assignment overwrites the first) and returns x; the engine sums them (2x)."""
+    from graphax_b200.plan import build_plan
+    from graphax_b200.tracer import make_jaxpr
+    assert RUN["zoo"]["quirks"]["d(x*x)/dx at x=3"] == 3.0
+    plan = build_plan(make_jaxpr(lambda x: x * x, [()]), "fwd", (0,))
+    rep, _ = replay.replay(plan.blob, [np.array([3.0], np.float32)], plan.n_rows, plan.n_cols)
+    assert rep.reshape(-1)[0] == 6.0
