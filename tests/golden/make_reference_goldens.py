@@ -246,6 +246,45 @@ def run_zoo(n_points=16):
     return rec, arrays
 
 
+PYTREE_CASES = {   # name: (source of the function over `jnp`, per-sample shapes, argnums)
+    "1out_1in": ("lambda x: jnp.sin(x) * x", [(3,)], (0,)),
+    "1out_2in_both": ("lambda x, y: jnp.sin(x) * y", [(3,), (3,)], (0, 1)),
+    "1out_2in_first": ("lambda x, y: jnp.sin(x) * y", [(3,), (3,)], (0,)),
+    "1out_2in_second": ("lambda x, y: jnp.sin(x) * y", [(3,), (3,)], (1,)),
+    "2out_1in": ("lambda x: (jnp.sin(x), jnp.sum(x * 2.))", [(3,)], (0,)),
+    "2out_2in_both": ("lambda x, y: (jnp.sin(x) * y, jnp.sum(x) * jnp.cos(y))", [(3,), ()], (0, 1)),
+    "2out_2in_first": ("lambda x, y: (jnp.sin(x) * y, jnp.sum(x) * jnp.cos(y))", [(3,), ()], (0,)),
+    "scalar_1out_1in": ("lambda x: jnp.sin(x) * x", [()], (0,)),
+    "independent_block": ("lambda x, y: (jnp.sin(x), jnp.cos(y))", [(3,), (2,)], (0, 1)),
+}
+
+
+def tree_shape(t):
+    if isinstance(t, tuple):
+        return {"tuple": [tree_shape(c) for c in t]}
+    if isinstance(t, list):
+        return {"list": [tree_shape(c) for c in t]}
+    if isinstance(t, dict):
+        return {"dict": sorted(t)}
+    return list(np.shape(t))
+
+
+def run_pytree_cases():
+    """Result conventions of `jacve` / `jacfun` (`core.py:60-93`, `:555-581`): nesting and block shapes for every
+    combination of output count, argument count and `argnums`, without and with `has_aux` / `count_ops`."""
+    out = {}
+    for name, (src, shapes, argnums) in PYTREE_CASES.items():
+        fun = eval(src, {"jnp": jnp})
+        args = [jnp.array(np.linspace(0.3, 0.9, int(np.prod(s, dtype=np.int64)) if s else 1).reshape(s).astype(np.float32)) for s in shapes]
+        rec = {"source": src, "in_shapes": [list(s) for s in shapes], "argnums": list(argnums)}
+        rec["plain"] = tree_shape(graphax.jacve(fun, order="rev", argnums=argnums)(*args))
+        rec["has_aux"] = tree_shape(graphax.jacve(fun, order="rev", argnums=argnums, has_aux=True)(*args))
+        rec["count_ops"] = tree_shape(graphax.jacve(fun, order="rev", argnums=argnums, count_ops=True)(*args))
+        out[name] = rec
+        print(f"  {name}: {rec['plain']}")
+    return out
+
+
 RANK_N = {   # per-sample shapes and argnums of the reference's own tests (tests/examples/example_test.py:168-349)
     "NeuralNetwork": ([(4,), (8, 4), (8,), (4, 8), (4,), (4,)], (1, 2, 3, 4)),
     "Perceptron": ([(4,), (4,), (8, 4), (8,), (4, 8), (4,), (), ()], tuple(range(8))),
@@ -306,6 +345,8 @@ def main():
         out["rank_n"][name] = rec
         for k, v in arr.items():
             arrays[f"rank_n/{name}/{k}"] = v
+    print("pytree conventions", flush=True)
+    out["pytree"] = run_pytree_cases()
     print("zoo", flush=True)
     rec, arr = run_zoo()
     out["zoo"] = rec

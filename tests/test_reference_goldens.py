@@ -241,3 +241,31 @@ def test_duplicate_operand_deviation():
     plan = build_plan(make_jaxpr(lambda x: x * x, [()]), "fwd", (0,))
     rep, _ = replay.replay(plan.blob, [np.array([3.0], np.float32)], plan.n_rows, plan.n_cols)
     assert rep.reshape(-1)[0] == 6.0
+
+
+def _tree_shape(t):
+    if isinstance(t, tuple):
+        return {"tuple": [_tree_shape(c) for c in t]}
+    if isinstance(t, list):
+        return {"list": [_tree_shape(c) for c in t]}
+    if isinstance(t, dict):
+        return {"dict": sorted(t)}
+    return list(np.shape(t))
+
+
+@pytest.mark.parametrize("name", list(RUN["pytree"]))
+def test_result_pytree_conventions_match_reference_run(name):
+    """`jacve` result nesting and block shapes (`core.py:60-93, 555-581`) for every combination of output count,
+    argument count and `argnums`, plain / `has_aux` / `count_ops` - packaging only, on a host tile."""
+    import graphax_b200 as gx
+    from graphax_b200.tracer import jnp
+    rec = RUN["pytree"][name]
+    fun = eval(rec["source"], {"jnp": jnp})
+    shapes = [tuple(s) for s in rec["in_shapes"]]
+    for mode in ("plain", "has_aux", "count_ops"):
+        jf = gx.jacve(fun, order="rev", argnums=tuple(rec["argnums"]), has_aux=mode == "has_aux",
+                      count_ops=mode == "count_ops")
+        plan = jf.lower(shapes)
+        tile = np.zeros((1, plan.n_rows, plan.n_cols), np.float32)
+        got = jf._package(plan, tile, np.zeros((1, plan.n_rows), np.float32), shapes, 1, False)
+        assert _tree_shape(got) == rec[mode], (name, mode)
