@@ -36,15 +36,21 @@ REFERENCE = Path(sys.argv[1] if len(sys.argv) > 1 else "/root/reference/src")
 sys.path.insert(0, str(REPO))
 from graphax_b200.configs import WORKLOADS, EXTRA_WORKLOADS   # noqa: E402  (points and orders only)
 
-sys.path[:0] = [str(HERE / "jaxlite"), str(REFERENCE)]
-import jax                      # noqa: E402  (jaxlite)
+try:                                     # a box that has the real thing: same script, real JAX / XLA arithmetic
+    import jax as _real_jax              # noqa: F401
+    BACKEND = f"jax {_real_jax.__version__}"
+    sys.path.insert(0, str(REFERENCE))
+except ImportError:
+    BACKEND = "jaxlite (tests/golden/jaxlite: NumPy float32, one call per primitive)"
+    sys.path[:0] = [str(HERE / "jaxlite"), str(REFERENCE)]
+import jax                      # noqa: E402  (jaxlite unless JAX is installed)
 import jax.numpy as jnp         # noqa: E402
 import graphax                  # noqa: E402  (the reference)
 import graphax.core as gcore    # noqa: E402
 from graphax import examples as gex             # noqa: E402
 from graphax.sparse.tensor import SparseDimension   # noqa: E402
 
-assert jax.__version__.endswith("jaxlite") and str(REFERENCE) in graphax.__file__
+assert str(REFERENCE) in graphax.__file__, "graphax must be the reference's own sources"
 
 N_POINTS = {"roe3d": 96, "roe1d": 96, "robotarm": 96}
 
@@ -328,8 +334,8 @@ def run_rank_n(name, n_points=2):
 
 def main():
     out = {"generator": "tests/golden/make_reference_goldens.py",
-           "reference": "jamielohoff/graphax, unmodified sources under /root/reference/src, on tests/golden/jaxlite",
-           "arithmetic": "NumPy float32, one call per primitive", "workloads": {}}
+           "reference": "jamielohoff/graphax, unmodified sources under /root/reference/src",
+           "backend": BACKEND, "workloads": {}}
     arrays = {}
     for name, fun in FUNCTIONS.items():
         w = WORKLOADS.get(name) or EXTRA_WORKLOADS[name]

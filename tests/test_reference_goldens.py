@@ -269,3 +269,15 @@ def test_result_pytree_conventions_match_reference_run(name):
         tile = np.zeros((1, plan.n_rows, plan.n_cols), np.float32)
         got = jf._package(plan, tile, np.zeros((1, plan.n_rows), np.float32), shapes, 1, False)
         assert _tree_shape(got) == rec[mode], (name, mode)
+
+
+def test_fixture_points_are_the_configured_synthetic_inputs():
+    """The reference run was taken at the reference's own test point followed by the first samples of the synthetic
+    batch bench.py uses (`configs.Workload.inputs`), so the fixtures can be regenerated and compared anywhere."""
+    assert RUN["backend"].startswith("jaxlite") or RUN["backend"].startswith("jax ")
+    for name in ("roe3d", "roe1d", "robotarm"):
+        w = get_workload(name)
+        flat = ARR[f"{name}/inputs"]
+        assert np.array_equal(flat[0], np.asarray(w.base, np.float32))
+        synth = np.concatenate([x.reshape(len(flat) - 1, -1) for x in w.inputs(len(flat) - 1)], axis=1)
+        assert np.array_equal(bits(flat[1:]), bits(synth))
