@@ -67,8 +67,9 @@ class JacveFunction:
 
     def __init__(self, fun: Callable, order: EliminationOrder, argnums: Sequence[int], has_aux: bool,
                  count_ops: bool, sparse_representation: bool, order_numbering: str, device: Optional[int],
-                 jit: bool, contract_sums: bool = False):
+                 jit: bool, contract_sums: bool = False, frontend: str = "auto"):
         self.fun = fun
+        self.frontend = frontend
         self.contract_sums = bool(contract_sums)
         self.order = order if isinstance(order, str) else [int(o) for o in order]
         self.argnums = tuple(int(a) for a in (argnums if isinstance(argnums, (tuple, list, range)) else (argnums,)))
@@ -91,7 +92,7 @@ class JacveFunction:
         key = tuple(tuple(s) for s in arg_shapes)
         plan = self._plans.get(key)
         if plan is None:
-            jaxpr = make_jaxpr(self.fun, key)
+            jaxpr = make_jaxpr(self.fun, key, self.frontend)
             order = self.order
             if not isinstance(order, str) and self.order_numbering == "vmap":
                 order = jaxpr.translate_vmap_order(order)
@@ -170,8 +171,8 @@ class JacveFunction:
         if not common or any(tuple(s) != tuple(common) for s in shapes):
             return None
         try:
-            full = make_jaxpr(self.fun, shapes)
-            scalar = make_jaxpr(self.fun, [()] * len(shapes))
+            full = make_jaxpr(self.fun, shapes, self.frontend)
+            scalar = make_jaxpr(self.fun, [()] * len(shapes), self.frontend)
         except Exception:
             return None
         if len(full.eqns) != len(scalar.eqns) or len(full.outvars) != len(scalar.outvars):
@@ -335,7 +336,7 @@ class JacveFunction:
         if self.sparse_representation:
             raise NotImplementedError("sparse_representation inside a traced function")
         shapes = [tuple(a.shape) if isinstance(a, Tracer) else tuple(np.shape(a)) for a in args]
-        jaxpr = make_jaxpr(self.fun, shapes)
+        jaxpr = make_jaxpr(self.fun, shapes, self.frontend)
         order = self.order
         if not isinstance(order, str) and self.order_numbering == "vmap":
             order = jaxpr.translate_vmap_order(order)
@@ -433,7 +434,8 @@ class JacveFunction:
 
 def jacve(fun: Callable, order: EliminationOrder, argnums: Sequence[int] = (0,), has_aux: bool = False,
           count_ops: bool = False, sparse_representation: bool = False, *, order_numbering: str = "per_sample",
-          device: Optional[int] = None, jit: bool = True, contract_sums: bool = False) -> JacveFunction:
+          device: Optional[int] = None, jit: bool = True, contract_sums: bool = False,
+          frontend: str = "auto") -> JacveFunction:
     """Jacobian of ``fun`` w.r.t. ``argnums`` by vertex elimination in the given ``order``.
 
     ``order``: ``"fwd"``/``"forward"``, ``"rev"``/``"reverse"`` or a sequence of 1-based vertex ids
@@ -441,9 +443,11 @@ def jacve(fun: Callable, order: EliminationOrder, argnums: Sequence[int] = (0,),
     accepts ids written against ``jacve(jax.vmap(fun))`` (reference ``example_test.py:150-166``).
     ``contract_sums=True`` trades the reference's association of the edge sums for 6-12 % fewer instructions
     (``plan._contract_sums``); off by default so results follow the reference's summation order.
+    ``frontend``: ``"native"`` traces ``fun`` with the engine's own ``jnp`` stand-in, ``"jax"`` with
+    ``jax.make_jaxpr`` (functions written against the real ``jax.numpy``; needs JAX), ``"auto"`` tries both.
     """
     return JacveFunction(fun, order, argnums, has_aux, count_ops, sparse_representation, order_numbering,
-                         device, jit, contract_sums)
+                         device, jit, contract_sums, frontend)
 
 
 def vmap(jacfun: JacveFunction, in_axes: int = 0) -> Callable:

@@ -579,8 +579,35 @@ class _JnpShim:
 jnp = _JnpShim()
 
 
-def make_jaxpr(fun: Callable, arg_shapes: Sequence[Shape]) -> Jaxpr:
-    """Trace ``fun`` on per-sample avals of the given shapes (f32)."""
+FRONTENDS = ("auto", "native", "jax")
+
+
+def make_jaxpr(fun: Callable, arg_shapes: Sequence[Shape], frontend: str = "auto") -> Jaxpr:
+    """Trace ``fun`` on per-sample avals of the given shapes (f32).
+
+    ``frontend="native"`` runs ``fun`` on this module's tracers (functions written against ``graphax_b200.jnp``);
+    ``"jax"`` traces with ``jax.make_jaxpr`` and converts the result (``jax_frontend.py``: functions written against
+    the real ``jax.numpy``, needs JAX); ``"auto"`` tries the native tracers and falls back to JAX when the function
+    rejects them and JAX is installed."""
+    if frontend not in FRONTENDS:
+        raise ValueError(f"frontend must be one of {FRONTENDS}")
+    if frontend == "jax":
+        from . import jax_frontend
+        return jax_frontend.make_jaxpr(fun, arg_shapes)
+    try:
+        return _make_jaxpr_native(fun, arg_shapes)
+    except (TypeError, AttributeError) as e:
+        if frontend == "auto":
+            from . import jax_frontend
+            if jax_frontend.available():
+                try:
+                    return jax_frontend.make_jaxpr(fun, arg_shapes)
+                except (TypeError, AttributeError):
+                    raise e from None      # the function takes neither kind of tracer: report the native error
+        raise
+
+
+def _make_jaxpr_native(fun: Callable, arg_shapes: Sequence[Shape]) -> Jaxpr:
     trace = _Trace()
     invars = [Var(tuple(s), input_index=i) for i, s in enumerate(arg_shapes)]
     _ACTIVE.append(trace)

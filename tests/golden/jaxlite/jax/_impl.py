@@ -817,12 +817,20 @@ def scatter(operand, scatter_indices, updates, dimension_numbers, indices_are_so
 # ------------------------------------------------------------------------------------------------
 
 
+class ShapeDtypeStruct:
+    def __init__(self, shape, dtype):
+        self.shape, self.dtype = tuple(shape), _canon_dtype(dtype)
+
+
 def make_jaxpr(fun: Callable) -> Callable:
     def traced(*args, **kwargs):
         flat, _ = tree_flatten(args)
         trace = _Trace()
         invars = []
         for a in flat:
+            if isinstance(a, ShapeDtypeStruct):
+                invars.append(Var(ShapedArray(a.shape, a.dtype)))
+                continue
             v = np.asarray(_raw(a))
             invars.append(Var(ShapedArray(v.shape, v.dtype)))
         tracers = [Tracer(trace, v) for v in invars]

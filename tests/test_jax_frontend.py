@@ -1,0 +1,85 @@
+"""`frontend="jax"`: functions written against `jax.numpy` are traced by `jax.make_jaxpr` and converted
+(graphax_b200/jax_frontend.py).  JAX is not installed in this image, so the conversion runs against
+tests/golden/jaxlite - the NumPy stand-in for the JAX API that also carries the reference run - in a child process
+(so that the stand-in's `jax` never shadows anything in the test session)."""
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+
+CHILD = r'''
+import json, sys
+from pathlib import Path
+root = Path(sys.argv[1])
+sys.path[:0] = [str(root), str(root / "tests" / "golden" / "jaxlite")]
+import jax, jax.numpy as jnp            # jaxlite
+import graphax_b200 as gx
+from graphax_b200 import jax_frontend
+from graphax_b200.configs import WORKLOADS, EXTRA_WORKLOADS
+from graphax_b200.plan import build_plan
+from graphax_b200.tracer import Literal, make_jaxpr
+
+assert jax.__version__.endswith("jaxlite") and jax_frontend.available()
+sources = {"roe3d": ("roe_flux.py", "RoeFlux_3d"), "roe1d": ("roe_flux.py", "RoeFlux_1d"),
+           "robotarm": ("robot_arm.py", "RobotArm_6DOF"), "simple": ("simple.py", "Simple"),
+           "lighthouse": ("simple.py", "Lighthouse"), "helmholtz": ("simple.py", "Helmholtz")}
+out = {}
+for name, (file, fn) in sources.items():
+    w = WORKLOADS.get(name) or EXTRA_WORKLOADS[name]
+    text = (root / "graphax_b200" / "examples" / file).read_text().replace("from ..tracer import jnp", "import jax.numpy as jnp")
+    scope = {}
+    exec(text, scope)
+    fun = scope[fn]                       # the same source, now a function of jax.numpy
+    via_jax = make_jaxpr(fun, w.arg_shapes, "jax")
+    auto = make_jaxpr(fun, w.arg_shapes, "auto")      # the native tracers are rejected -> falls back to JAX
+    native = w.jaxpr()
+    key = lambda v: ("lit", v.val) if isinstance(v, Literal) else ("in", v.input_index) if v.input_index is not None else ("v", v.eqn_index)
+    same = len(via_jax.eqns) == len(native.eqns) == len(auto.eqns)
+    for a, b in zip(via_jax.eqns, native.eqns):
+        same &= a.primitive == b.primitive and [key(x) for x in a.invars] == [key(x) for x in b.invars] \
+            and a.outvar.shape == b.outvar.shape
+        same &= all(tuple(a.params[k]) == tuple(b.params[k]) if isinstance(b.params[k], (tuple, list)) else a.params[k] == b.params[k]
+                    for k in a.params if k in b.params and b.params[k] is not None)
+    same &= via_jax.vmap_pads == native.vmap_pads and [key(v) for v in via_jax.outvars] == [key(v) for v in native.outvars]
+    blobs = all(build_plan(via_jax, w.order(o), w.argnums).blob == w.plan(o, with_primal=True).blob for o in w.order_names())
+    out[name] = {"same_jaxpr": bool(same), "same_plans": bool(blobs), "n_eqns": len(via_jax.eqns)}
+
+# unknown primitives are refused like in the reference (core.py:396-398)
+try:
+    make_jaxpr(lambda x: jnp.tile(x, 2), [(3,)], "jax")
+    out["refuses_untraceable"] = False
+except NotImplementedError:
+    out["refuses_untraceable"] = True
+# the public API takes the jax.numpy function unchanged (lowering only: no GPU in this process)
+jf = gx.jacve(scope_fun := (lambda x, y: jnp.sin(x) * y), order="rev", argnums=(0, 1))
+plan = jf.lower([(3,), (3,)])
+out["api_lowers"] = [plan.n_rows, plan.n_cols, len(plan.jaxpr.eqns)]
+print(json.dumps(out))
+'''
+
+
+def test_jax_frontend_reproduces_the_native_tracer_on_a_jax_numpy_function():
+    r = subprocess.run([sys.executable, "-c", CHILD, str(ROOT)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out.pop("refuses_untraceable") is True
+    assert out.pop("api_lowers") == [3, 6, 2]
+    assert out["roe3d"]["n_eqns"] == 138 and out["roe1d"]["n_eqns"] == 101 and out["robotarm"]["n_eqns"] == 114
+    for name, rec in out.items():
+        assert rec["same_jaxpr"] and rec["same_plans"], (name, rec)
+
+
+def test_jax_frontend_needs_jax():
+    """Without JAX the explicit frontend fails loudly, and functions of the native jnp keep working."""
+    import pytest
+    from graphax_b200 import jax_frontend
+    from graphax_b200.tracer import jnp, make_jaxpr
+    if jax_frontend.available():
+        pytest.skip("JAX (or a stand-in) is importable in this session")
+    with pytest.raises(ImportError):
+        make_jaxpr(lambda x: x * x, [()], "jax")
+    assert len(make_jaxpr(lambda x: jnp.sin(x) * x, [()], "auto").eqns) == 2
+    with pytest.raises(ValueError):
+        make_jaxpr(lambda x: x, [()], "xla")
