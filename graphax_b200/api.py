@@ -122,7 +122,14 @@ class JacveFunction:
         tensors = []
         for a in args:
             if not isinstance(a, torch.Tensor):
-                a = torch.as_tensor(np.asarray(a, dtype=np.float32))
+                # device arrays of other libraries (jax.Array, cupy) come in through DLPack without a copy
+                if hasattr(a, "__dlpack__") and not isinstance(a, np.ndarray):
+                    try:
+                        a = torch.from_dlpack(a)
+                    except Exception:
+                        a = torch.as_tensor(np.asarray(a, dtype=np.float32))
+                else:
+                    a = torch.as_tensor(np.asarray(a, dtype=np.float32))
             tensors.append(a.to(device=f"cuda:{device}", dtype=torch.float32).contiguous())
         if batched:
             batch = tensors[0].shape[0]
