@@ -311,8 +311,14 @@ _CONST_UNARY = {"sqrt": np.sqrt, "abs": np.abs, "neg": np.negative, "exp": np.ex
 def _unary(prim: str):
     def fn(x: Any) -> Tracer:
         if not isinstance(x, Tracer):
-            if isinstance(x, (int, float, np.floating, np.integer)) and prim in _CONST_UNARY:
-                return float(np.float32(_CONST_UNARY[prim](np.float32(x))))   # constants fold at trace time
+            if isinstance(x, (int, float, np.floating, np.integer)):
+                if _ACTIVE:
+                    # inside a traced function JAX stages every operation, constants included:
+                    # jnp.sqrt(2.) is the equation `sqrt 2.0` - a vertex without in-edges (it still counts
+                    # in the numbering and must appear in a custom order, like jnp.zeros)
+                    return _current().emit(prim, (Literal(float(x)),), ())
+                if prim in _CONST_UNARY:
+                    return float(np.float32(_CONST_UNARY[prim](np.float32(x))))
             raise TypeError(f"{prim} expects a traced value")
         return x.trace.emit(prim, (x.var,), x.shape)
     fn.__name__ = prim

@@ -252,6 +252,48 @@ def run_zoo(n_points=16):
     return rec, arrays
 
 
+def run_examples(n_points=4):
+    """The remaining scalar examples of the reference (`examples/easy.py`, `minpack.py`, `economics.py`): jaxpr,
+    `count_ops` and Jacobians, forward and reverse.  The tests rebuild each function from its recorded jaxpr."""
+    from graphax.examples import minpack
+    cases = {
+        "KerrSenn_metric": (gex.KerrSenn_metric, [1.0, 2.0, 0.7, 0.3]),
+        "FreeEnergy": (gex.FreeEnergy, [[0.05, 0.15, 0.25, 0.35]]),
+        "CloudSchemes_step": (gex.CloudSchemes_step, [0.8, 1.1, 0.9, 1.2, 0.7, 1.3, 0.6, 1.4, 0.5, 1.5, 1.05]),
+        "PropaneCombustion": (gex.PropaneCombustion, [0.9, 1.1, 1.3, 0.7, 1.2, 0.8, 1.4, 0.6, 1.5, 0.5, 2.0]),
+        "HumanHeartDipole": (gex.HumanHeartDipole, [0.3, 0.7, 0.4, 0.6, 1.1, 0.9, 1.3, 0.8]),
+        "SteadyStateCombustion": (minpack.SteadyStateCombustion, [0.1, 0.2, 0.3, 0.4]),
+        "BlackScholes": (gex.BlackScholes, [1.0, 0.9, 0.05, 0.3, 1.5]),
+    }
+    out, arrays = {}, {}
+    rng = np.random.default_rng(5)
+    for name, (fun, base) in cases.items():
+        base = [np.asarray(b, np.float32) for b in base]
+        pts = [[jnp.array(b * (1 + 0.02 * rng.uniform(-1, 1, b.shape)).astype(np.float32)) for b in base] for _ in range(n_points)]
+        closed = jax.make_jaxpr(fun)(*pts[0])
+        _, rec = dump_jaxpr(closed.jaxpr)
+        rec["function"] = f"graphax.examples.{fun.__name__}"
+        argnums = tuple(range(len(base)))
+        out_sizes = [int(np.prod(v.aval.shape, dtype=np.int64)) for v in closed.jaxpr.outvars]
+        in_sizes = [int(b.size) for b in base]
+        arrays[f"examples/{name}/inputs"] = np.stack([np.concatenate([np.asarray(a).reshape(-1) for a in p]) for p in pts])
+        rec["orders"] = {}
+        for order in ("fwd", "rev"):
+            jacs = []
+            for p in pts:
+                res, aux = graphax.jacve(fun, order=order, argnums=argnums, count_ops=True)(*p)
+                if len(out_sizes) == 1:
+                    res = (res,)
+                if len(argnums) == 1:
+                    res = tuple(r if isinstance(r, tuple) else (r,) for r in res)
+                jacs.append(pack(res, out_sizes, in_sizes))
+            rec["orders"][order] = {"num_muls": int(aux["num_muls"]), "num_adds": int(aux["num_adds"])}
+            arrays[f"examples/{name}/jac/{order}"] = np.stack(jacs)
+        out[name] = rec
+        print(f"  {name}: {rec['n_eqns']} eqns, {rec['orders']}")
+    return out, arrays
+
+
 PYTREE_CASES = {   # name: (source of the function over `jnp`, per-sample shapes, argnums)
     "1out_1in": ("lambda x: jnp.sin(x) * x", [(3,)], (0,)),
     "1out_2in_both": ("lambda x, y: jnp.sin(x) * y", [(3,), (3,)], (0, 1)),
@@ -351,6 +393,9 @@ def main():
         out["rank_n"][name] = rec
         for k, v in arr.items():
             arrays[f"rank_n/{name}/{k}"] = v
+    print("further examples", flush=True)
+    out["examples"], arr = run_examples()
+    arrays.update(arr)
     print("pytree conventions", flush=True)
     out["pytree"] = run_pytree_cases()
     print("zoo", flush=True)

@@ -124,3 +124,20 @@ def torch_eval_jaxpr(jaxpr, args):
             raise NotImplementedError(p)
         env[id(e.outvar)] = r
     return tuple(env[id(o)] for o in jaxpr.outvars)
+
+
+def jaxpr_from_record(rec):
+    """Rebuild an engine jaxpr from the equations recorded by tests/golden/make_reference_goldens.py (`dump_jaxpr`):
+    the function exactly as the reference traced it, without needing its source."""
+    from graphax_b200.tracer import Eqn, Jaxpr, Literal, Var
+    env = {-(i + 1): Var(tuple(s), input_index=i) for i, s in enumerate(rec["in_shapes"])}
+    eqns = []
+    for n, e in enumerate(rec["eqns"], start=1):
+        ins = tuple(Literal(float(v)) if kind == "lit" else env[v] for kind, v in e["operands"])
+        out = Var(tuple(e["shape"]), eqn_index=n - 1)
+        env[n] = out
+        tup = lambda v: tuple(tup(x) for x in v) if isinstance(v, list) else v
+        params = {k: tup(v) for k, v in e["params"].items() if k not in ("precision", "preferred_element_type", "sharding")}
+        eqns.append(Eqn(e["primitive"], ins, out, params))
+    return Jaxpr([env[-(i + 1)] for i in range(len(rec["in_shapes"]))], eqns, [env[k] for k in rec["outvars"]],
+                 [0] * len(eqns), True)

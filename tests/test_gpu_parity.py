@@ -118,6 +118,38 @@ def test_kernels_match_reference_run(built_library, name, order, division, kerne
     np.testing.assert_allclose(primal, arr[f"{name}/primal"], rtol=2e-6, atol=1e-6)
 
 
+def _example_names():
+    import json
+    from helpers import GOLDEN
+    return list(json.loads((GOLDEN / "reference_run.json").read_text())["examples"])
+
+
+@pytest.mark.parametrize("name", _example_names())
+@pytest.mark.parametrize("order", ["fwd", "rev"])
+def test_further_reference_examples_on_the_gpu(built_library, name, order):
+    """KerrSenn_metric, FreeEnergy, CloudSchemes_step, PropaneCombustion, HumanHeartDipole, SteadyStateCombustion and
+    BlackScholes, each rebuilt from the jaxpr the reference traced, through run-time specialised kernels against
+    the Jacobians the reference computed (tests/golden/make_reference_goldens.py)."""
+    from graphax_b200.plan import build_plan
+    from helpers import jaxpr_from_record
+    run, arr = _reference_run()
+    rec = run["examples"][name]
+    jaxpr = jaxpr_from_record(rec)
+    flat = arr[f"examples/{name}/inputs"]
+    xs, off = [], 0
+    for shape in rec["in_shapes"]:
+        size = int(np.prod(shape, dtype=np.int64)) if shape else 1
+        xs.append(np.ascontiguousarray(flat[:, off:off + size].reshape((len(flat),) + tuple(shape))))
+        off += size
+    plan = build_plan(jaxpr, order, tuple(range(len(xs))))
+    jac, _, used = run_engine(plan, xs, "jit")
+    assert used == "jit"
+    ref = arr[f"examples/{name}/jac/{order}"].astype(np.float64)
+    bound = parity_bound(ref)
+    assert np.isfinite(jac).all()
+    assert (np.abs(jac - ref) <= bound).all(), float((np.abs(jac - ref) / bound).max())
+
+
 @pytest.mark.parametrize("batch", [0, 1, 127, 128, 129, 300])
 @pytest.mark.parametrize("kernel", ["aot", "interpreter"])
 def test_ragged_batches(built_library, batch, kernel):

@@ -27,7 +27,7 @@ def _torch_hessian(xs, b):
 def test_inner_plan_becomes_outer_equations():
     jaxpr = make_jaxpr(BlackScholes_Jacobian, ARGS5)
     assert len(jaxpr.outvars) == 5 and all(o.shape == () for o in jaxpr.outvars)
-    assert len(jaxpr.eqns) > 3 * len(make_jaxpr(BlackScholes, ARGS5).eqns)     # primal + partials + products
+    assert len(jaxpr.eqns) > 2.5 * len(make_jaxpr(BlackScholes, ARGS5).eqns)   # primal + partials + products
     prims = {e.primitive for e in jaxpr.eqns}
     assert {"erf", "exp", "log", "sqrt", "div", "mul"} <= prims
 

@@ -281,3 +281,27 @@ def test_fixture_points_are_the_configured_synthetic_inputs():
         assert np.array_equal(flat[0], np.asarray(w.base, np.float32))
         synth = np.concatenate([x.reshape(len(flat) - 1, -1) for x in w.inputs(len(flat) - 1)], axis=1)
         assert np.array_equal(bits(flat[1:]), bits(synth))
+
+
+@pytest.mark.parametrize("name", list(RUN["examples"]))
+def test_further_reference_examples(name):
+    """The other scalar examples of the reference (`examples/easy.py`, `minpack.py`, `economics.py`), each rebuilt
+    from the jaxpr the reference traced: same `count_ops`, Jacobians within the parity bound, forward and reverse."""
+    from graphax_b200.plan import build_plan
+    from helpers import jaxpr_from_record
+    rec = RUN["examples"][name]
+    jaxpr = jaxpr_from_record(rec)
+    flat = ARR[f"examples/{name}/inputs"]
+    xs, off = [], 0
+    for shape in rec["in_shapes"]:
+        size = int(np.prod(shape, dtype=np.int64)) if shape else 1
+        xs.append(np.ascontiguousarray(flat[:, off:off + size].reshape((len(flat),) + tuple(shape))))
+        off += size
+    argnums = tuple(range(len(xs)))
+    for order in ("fwd", "rev"):
+        plan = build_plan(jaxpr, order, argnums)
+        assert (plan.stats["num_muls"], plan.stats["num_adds"]) == (rec["orders"][order]["num_muls"], rec["orders"][order]["num_adds"])
+        rep, _ = replay.replay(plan.blob, xs, plan.n_rows, plan.n_cols)
+        ref = ARR[f"examples/{name}/jac/{order}"].astype(np.float64)
+        assert np.isfinite(rep).all()
+        assert (np.abs(rep - ref) <= parity_bound(ref)).all(), float((np.abs(rep - ref) / parity_bound(ref)).max())
