@@ -374,6 +374,35 @@ def run_rank_n(name, n_points=2):
     return rec, arrays
 
 
+def run_f(n_points=2):
+    """`examples/randoms.py:f` (80 equations on vectors and matrices: dot_general in four layouts, transpose, reshape,
+    squeeze, reduce_max / reduce_min, slice, stop_gradient; its test is commented out in the reference).  It calls
+    arcsinh twice, so it is run with the `asinh` rule corrected through `defelemental` (see `run_zoo`)."""
+    import jax.lax as lax
+    from graphax.primitives import defelemental, elemental_rules
+    shapes = [(4,), (2, 3), (4, 4), (4, 1)]
+    rng = np.random.default_rng(3)
+    pts = [rng.uniform(0.2, 0.8, (n_points,) + s).astype(np.float32) for s in shapes]
+    closed = jax.make_jaxpr(gex.f)(*[jnp.array(p[0]) for p in pts])
+    _, rec = dump_jaxpr(closed.jaxpr)
+    rec["function"] = "graphax.examples.f (asinh rule corrected)"
+    arrays = {f"in{i}": p for i, p in enumerate(pts)}
+    original = elemental_rules[lax.asinh_p]
+    defelemental(lax.asinh_p, lambda x: 1. / jnp.sqrt(1. + x**2))
+    rec["orders"] = {}
+    for order in ("fwd", "rev"):
+        vals = []
+        for k in range(n_points):
+            out, aux = graphax.jacve(gex.f, order=order, argnums=(0, 1, 2, 3), count_ops=True)(*[jnp.array(p[k]) for p in pts])
+            vals.append(np.concatenate([np.concatenate([np.asarray(b, np.float32).reshape(max(1, int(np.prod(o.aval.shape, dtype=np.int64))), -1)
+                                                        for b in row], axis=1) for o, row in zip(closed.jaxpr.outvars, out)], axis=0))
+        rec["orders"][order] = {"num_muls": int(aux["num_muls"]), "num_adds": int(aux["num_adds"])}
+        arrays[f"jac/{order}"] = np.stack(vals)
+    elemental_rules[lax.asinh_p] = original
+    print(f"  f: {rec['n_eqns']} eqns {rec['orders']}")
+    return rec, arrays
+
+
 def main():
     out = {"generator": "tests/golden/make_reference_goldens.py",
            "reference": "jamielohoff/graphax, unmodified sources under /root/reference/src",
@@ -403,6 +432,11 @@ def main():
     out["zoo"] = rec
     for k, v in arr.items():
         arrays[f"zoo/{k}"] = v
+    print("f", flush=True)
+    rec, arr = run_f()
+    out["rank_n_recorded"] = {"f": rec}
+    for k, v in arr.items():
+        arrays[f"rank_n_recorded/f/{k}"] = v
     print("roe3d_vmap", flush=True)
     rec, arr = run_roe3d_vmapped()
     out["workloads"]["roe3d_vmap"] = rec

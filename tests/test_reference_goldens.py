@@ -305,3 +305,26 @@ def test_further_reference_examples(name):
         ref = ARR[f"examples/{name}/jac/{order}"].astype(np.float64)
         assert np.isfinite(rep).all()
         assert (np.abs(rep - ref) <= parity_bound(ref)).all(), float((np.abs(rep - ref) / parity_bound(ref)).max())
+
+
+def test_random_tensor_function_f_against_reference_run():
+    """`examples/randoms.py:f`: 80 equations on vectors and matrices (dot_general in four layouts, transpose, reshape,
+    squeeze, reduce_max / reduce_min, slice, stop_gradient), rebuilt from the jaxpr the reference traced.  Reference
+    values are taken where its forward and reverse results agree (8 of 720 entries do not, cf. the `_swap_axes` note
+    above); the engine's forward and reverse plans agree everywhere."""
+    from graphax_b200.plan import build_plan
+    from helpers import jaxpr_from_record
+    rec = RUN["rank_n_recorded"]["f"]
+    assert rec["n_eqns"] == 80
+    jaxpr = jaxpr_from_record(rec)
+    xs = [ARR[f"rank_n_recorded/f/in{i}"] for i in range(4)]
+    r_fwd, r_rev = ARR["rank_n_recorded/f/jac/fwd"].astype(np.float64), ARR["rank_n_recorded/f/jac/rev"].astype(np.float64)
+    scale = np.abs(r_rev).max(axis=(1, 2), keepdims=True)
+    agree = np.abs(r_fwd - r_rev) <= 1e-4 * scale
+    assert 0.98 < agree.mean() < 1.0
+    reps = {}
+    for order in ("fwd", "rev"):
+        plan = build_plan(jaxpr, order, (0, 1, 2, 3))
+        reps[order], _ = replay.replay(plan.blob, xs, plan.n_rows, plan.n_cols)
+        assert ((np.abs(reps[order] - r_rev) / scale)[agree]).max() < 5e-5, order
+    assert (np.abs(reps["fwd"] - reps["rev"]) / scale).max() < 5e-5
