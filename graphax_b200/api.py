@@ -389,6 +389,9 @@ class JacveFunction:
                 raise NotImplementedError(f"nested jacve: constant sub-expression ({op.op}) left to the device")
             elif op.op == "fma":
                 vals[op.dst] = xs[0] * xs[1] + xs[2]
+            elif op.op == "select":
+                which = xs[0] if isinstance(xs[0], Tracer) else tjnp.zeros(()) + xs[0]
+                vals[op.dst] = tjnp.where(which > 0.5, xs[1], xs[2])
             elif op.op in unary:
                 vals[op.dst] = unary[op.op](xs[0])
             else:

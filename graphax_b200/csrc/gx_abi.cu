@@ -90,7 +90,7 @@ namespace {
 __host__ __device__ __forceinline__ bool gx_is_binary(unsigned op) {
   return op == GX_OP_ADD || op == GX_OP_SUB || op == GX_OP_MUL || op == GX_OP_DIV || op == GX_OP_FMA ||
          op == GX_OP_ATAN2 || op == GX_OP_POW || op == GX_OP_MAX || op == GX_OP_MIN || op == GX_OP_GT ||
-         op == GX_OP_LT || op == GX_OP_EQ;
+         op == GX_OP_LT || op == GX_OP_EQ || op == GX_OP_SELECT;
 }
 
 __device__ __forceinline__ float gx_apply(unsigned op, float a, float b, float c) {
@@ -124,6 +124,7 @@ __device__ __forceinline__ float gx_apply(unsigned op, float a, float b, float c
     case GX_OP_LOGISTIC: return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-a)));
     case GX_OP_MAX: return fmaxf(a, b);
     case GX_OP_MIN: return fminf(a, b);
+    case GX_OP_SELECT: return a != 0.0f ? b : c;
     case GX_OP_GT: return a > b ? 1.0f : 0.0f;
     case GX_OP_LT: return a < b ? 1.0f : 0.0f;
     case GX_OP_EQ: return a == b ? 1.0f : 0.0f;
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(T) gx_interp_kernel(const __grid_constant__ Gx
       } else {
         const float va = fetch(oa);
         const float vb = gx_is_binary(op) ? fetch(ob) : 0.0f;
-        const float vc = op == GX_OP_FMA ? fetch(oc) : 0.0f;
+        const float vc = (op == GX_OP_FMA || op == GX_OP_SELECT) ? fetch(oc) : 0.0f;
         s_slots[dst * T + tid] = gx_apply(op, va, vb, vc);
       }
     }
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(T) gx_interp_large_kernel(const __grid_constan
       } else {
         const float va = fetch(oa);
         const float vb = gx_is_binary(op) ? fetch(ob) : 0.0f;
-        const float vc = op == GX_OP_FMA ? fetch(oc) : 0.0f;
+        const float vc = (op == GX_OP_FMA || op == GX_OP_SELECT) ? fetch(oc) : 0.0f;
         slots[(size_t)dst * T + tid] = gx_apply(op, va, vb, vc);
       }
     }
@@ -501,7 +502,7 @@ int validate_blob(const void* blob, size_t nbytes, gx_plan* p) {
     if (rc) return rc;
     const bool binary = gx_is_binary(o.op);
     if (binary && (rc = check_operand(o.b, i))) return rc;
-    if (o.op == GX_OP_FMA && (rc = check_operand(o.c, i))) return rc;
+    if ((o.op == GX_OP_FMA || o.op == GX_OP_SELECT) && (rc = check_operand(o.c, i))) return rc;
     if (o.op == GX_OP_STORE_JAC) {
       if (o.dst >= tile) return fail(GX_ERR_BAD_BLOB, "plan blob: store_jac outside the Jacobian tile");
       if (stored[o.dst]++) return fail(GX_ERR_BAD_BLOB, "plan blob: Jacobian tile entry stored twice");

@@ -10,7 +10,8 @@
   X(TANH, tanh) X(SINH, sinh) X(COSH, cosh) X(ASIN, asin) X(ACOS, acos) X(ATAN, atan) \
   X(ASINH, asinh) X(ACOSH, acosh) X(ATANH, atanh) X(ERF, erf) X(POW, pow) X(LOGISTIC, logistic) \
   X(STORE_JAC, store_jac) X(STORE_PRIMAL, store_primal) \
-  X(MAX, max) X(MIN, min) X(GT, gt) X(LT, lt) X(EQ, eq)
+  X(MAX, max) X(MIN, min) X(GT, gt) X(LT, lt) X(EQ, eq) \
+  X(SELECT, select)
 
 enum gx_opcode {
 #define GX_ENUM(NAME, name) GX_OP_##NAME,
@@ -38,5 +39,8 @@ struct gx_blob_header {
 struct gx_op {
   unsigned short op, dst, a, b, c, pad;
 };
+
+// select: dst = a != 0 ? b : c   (lax.select_n(which, case0, case1) with b = case1, c = case0)
+#define GX_OP_IS_TERNARY(op) ((op) == GX_OP_FMA || (op) == GX_OP_SELECT)
 
 #endif

@@ -33,6 +33,7 @@ OPCODES = [
     "asin", "acos", "atan", "asinh", "acosh", "atanh", "erf", "pow", "logistic",
     "store_jac", "store_primal",
     "max", "min", "gt", "lt", "eq",
+    "select",                     # select(which, on_true, on_false): which != 0 ? on_true : on_false
 ]
 OP = {name: i for i, name in enumerate(OPCODES)}
 _UNARY = {"neg", "abs", "sqrt", "sin", "cos", "tan", "exp", "log", "log1p", "tanh", "sinh", "cosh",
@@ -121,6 +122,12 @@ class Dag:
     def emit(self, op: str, *a: int) -> int:
         if op == "neg" and self.op[a[0]] == "neg":
             return self.args[a[0]][0]
+        if op == "select":
+            which, on_true, on_false = a
+            if on_true == on_false:
+                return on_true
+            if self.op[which] == "const":
+                return on_true if float(self.cval[which]) != 0.0 else on_false
         if op == "mul":
             x, y = a
             if self._is(y, 1.0):
@@ -303,6 +310,25 @@ def lower_eqn(dag: Dag, eqn: Eqn, read, division: str = "ieee") -> Tuple[Vec, Li
         first = ew.binary("gt" if prim == "max" else "lt", x, y)          # 1.0 where x wins, else 0.0
         second = ew.sub(ew.lit(1.0), first)
         return edges(out, (first, second))
+    if prim == "select_n":
+        # lax.select_n(which, case0, case1) (jnp.where(c, x, y) = select_n(c, y, x)).  The reference's rule
+        # (primitives.py:225-234) returns one zero Jacobian per case and none for the predicate, i.e. fewer partials
+        # than traced operands, so it writes no edge at all (core.py:405-410) and the derivative through a `where`
+        # is lost.  Here the selected case passes its derivative: masks `which` / `1 - which` (comparisons produce
+        # exactly 1.0 / 0.0), and the predicate gets a zero partial.
+        if len(ops) != 3:
+            raise NotImplementedError("select_n with more than two cases")
+        which, case0, case1 = ops
+        shape = _bshape(_bshape(which.shape, case0.shape), case1.shape)
+        iw, i0, i1 = (_bcast_index(v, shape) for v in (which, case0, case1))
+        out = Vec(shape, [dag.emit("select", which.nodes[a], case1.nodes[c], case0.nodes[b]) for a, b, c in zip(iw, i0, i1)])
+        on = Vec(shape, [dag.emit("select", which.nodes[a], dag.const(1.0), dag.const(0.0)) for a in iw])
+        off = Vec(shape, [dag.emit("select", which.nodes[a], dag.const(0.0), dag.const(1.0)) for a in iw])
+        zero = Vec(shape, [dag.const(0.0)] * len(iw))
+        partials = (zero, off, on)
+        return out, [(eqn.invars[i],) + _parallel_jacobian(ops[i], out, partials[i], 2) for i in traced]
+    if prim == "convert_element_type":   # primitives.py:1236-1255: one floating-point type here, the value passes through
+        return edges(ops[0], (ew.ones_like(ops[0]),))
     if prim in ("gt", "lt", "eq"):   # primitives.py:218-223: comparisons carry zero partials
         x, y = ops
         out = ew.binary(prim, x, y)

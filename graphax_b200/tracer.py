@@ -231,6 +231,10 @@ class Tracer:
     def __neg__(self) -> "Tracer":
         return self.trace.emit("neg", (self.var,), self.shape)
 
+    # comparisons (values 1.0 / 0.0: the tracer has one dtype); `==` stays identity for dict / list use
+    __gt__ = lambda s, o: s._binary("gt", o)
+    __lt__ = lambda s, o: s._binary("lt", o)
+
     def __pow__(self, y: Any) -> "Tracer":
         if isinstance(y, (int, np.integer)) and not isinstance(y, bool):
             return self.trace.emit("integer_pow", (self.var,), self.shape, y=int(y))
@@ -436,6 +440,18 @@ def _mean(x: Tracer, axis=None) -> Tracer:
     return _reduce_sum(x, axis) / float(n)
 
 
+def _where(cond: Any, x: Any, y: Any) -> Tracer:
+    """``jnp.where(cond, x, y)`` = ``lax.select(cond, x, y)`` = ``select_n(cond, y, x)``; scalars broadcast."""
+    if not isinstance(cond, Tracer):
+        raise TypeError("where expects a traced condition")
+    trace = cond.trace
+    atoms = [_atom(cond), _atom(y), _atom(x)]
+    shape = ()
+    for a in atoms:
+        shape = _bcast_shape(shape, a.shape)
+    return trace.emit("select_n", tuple(atoms), shape)
+
+
 def _stop_gradient(x: Tracer) -> Tracer:
     return x.trace.emit("stop_gradient", (x.var,), x.shape)
 
@@ -555,6 +571,7 @@ class _JnpShim:
         return x.reshape(shape)
     zeros = staticmethod(_zeros)
     concatenate = staticmethod(_concatenate)
+    where = staticmethod(_where)
 
     @staticmethod
     def split(x, indices_or_sections, axis: int = 0):

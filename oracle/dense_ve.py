@@ -28,6 +28,16 @@ def _apply(eqn, vals: List[np.ndarray], batched: List[bool]):
     x = [v if b or not lead else v[None] for v, b in zip(vals, batched)]
     if p == "stop_gradient":
         return x[0]
+    if p == "convert_element_type":
+        return x[0]
+    if p == "select_n":       # lax.select_n(which, case0, case1)
+        nd = max(a.ndim for a in x)
+        w, c0, c1 = [v.reshape(v.shape[:1] + (1,) * (nd - v.ndim) + v.shape[1:]) if lead else v for v in x]
+        return np.where(w != 0, c1, c0)
+    if p in ("gt", "lt", "eq"):
+        nd = max(a.ndim for a in x)
+        a, b = [v.reshape(v.shape[:1] + (1,) * (nd - v.ndim) + v.shape[1:]) if lead else v for v in x]
+        return {"gt": np.greater, "lt": np.less, "eq": np.equal}[p](a, b).astype(np.result_type(a, b))
     if p in ("add", "sub", "mul", "div", "atan2", "pow", "max", "min"):
         nd = max(a.ndim for a in x)
         a, b = [v.reshape(v.shape[:1] + (1,) * (nd - v.ndim) + v.shape[1:]) if v.ndim > 1 or lead else v for v in x]
@@ -134,6 +144,13 @@ def _elemental_jacobians(eqn, vals, out, is_var, dtype):
         elif p in ("max", "min"):
             first = full(x[0]) > full(x[1]) if p == "max" else full(x[0]) < full(x[1])
             part = np.where(first, 1., 0.) if i == 0 else np.where(first, 0., 1.)
+        elif p in ("gt", "lt", "eq"):
+            part = np.zeros(bshape, dtype=dtype)
+        elif p == "select_n":       # the selected case passes its derivative, the predicate none
+            w = full(x[0]) != 0
+            part = np.zeros(bshape, dtype=dtype) if i == 0 else np.where(w, 0., 1.) if i == 1 else np.where(w, 1., 0.)
+        elif p == "convert_element_type":
+            part = np.ones(bshape, dtype=dtype)
         elif p == "integer_pow":
             y = int(eqn.params["y"])
             part = y * _ipow(x[0], y - 1)

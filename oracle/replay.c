@@ -26,7 +26,7 @@
 enum {
   OP_INPUT, OP_CONST, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_FMA, OP_NEG, OP_ABS, OP_SQRT, OP_SIN, OP_COS, OP_TAN,
   OP_ATAN2, OP_EXP, OP_LOG, OP_LOG1P, OP_TANH, OP_SINH, OP_COSH, OP_ASIN, OP_ACOS, OP_ATAN, OP_ASINH, OP_ACOSH,
-  OP_ATANH, OP_ERF, OP_POW, OP_LOGISTIC, OP_STORE_JAC, OP_STORE_PRIMAL, OP_MAX, OP_MIN, OP_GT, OP_LT, OP_EQ, OP_COUNT
+  OP_ATANH, OP_ERF, OP_POW, OP_LOGISTIC, OP_STORE_JAC, OP_STORE_PRIMAL, OP_MAX, OP_MIN, OP_GT, OP_LT, OP_EQ, OP_SELECT, OP_COUNT
 };
 
 typedef struct {
@@ -52,7 +52,7 @@ typedef struct {
 static const char* opcode_names[OP_COUNT] = {
   "input", "const", "add", "sub", "mul", "div", "fma", "neg", "abs", "sqrt", "sin", "cos", "tan", "atan2", "exp",
   "log", "log1p", "tanh", "sinh", "cosh", "asin", "acos", "atan", "asinh", "acosh", "atanh", "erf", "pow",
-  "logistic", "store_jac", "store_primal", "max", "min", "gt", "lt", "eq"};
+  "logistic", "store_jac", "store_primal", "max", "min", "gt", "lt", "eq", "select"};
 
 int gxo_opcode_count(void) { return OP_COUNT; }
 const char* gxo_opcode_name(int i) { return i >= 0 && i < OP_COUNT ? opcode_names[i] : ""; }
@@ -97,9 +97,9 @@ static void run_block(const job_t* j, int64_t s0, int n, float* slots, float* in
     const float* c = a;
     if (o->op == OP_ADD || o->op == OP_SUB || o->op == OP_MUL || o->op == OP_DIV || o->op == OP_FMA ||
         o->op == OP_ATAN2 || o->op == OP_POW || o->op == OP_MAX || o->op == OP_MIN || o->op == OP_GT ||
-        o->op == OP_LT || o->op == OP_EQ)
+        o->op == OP_LT || o->op == OP_EQ || o->op == OP_SELECT)
       b = operand(j, o->b, slots, cb, inbuf);
-    if (o->op == OP_FMA) c = operand(j, o->c, slots, cc, inbuf);
+    if (o->op == OP_FMA || o->op == OP_SELECT) c = operand(j, o->c, slots, cc, inbuf);
     float t[LANES];
     float* d = t; /* operands may alias the destination slot: compute into a temporary row */
     switch (o->op) {
@@ -135,6 +135,7 @@ static void run_block(const job_t* j, int64_t s0, int n, float* slots, float* in
       case OP_GT: BINARY(x > y ? 1.0f : 0.0f);
       case OP_LT: BINARY(x < y ? 1.0f : 0.0f);
       case OP_EQ: BINARY(x == y ? 1.0f : 0.0f);
+      case OP_SELECT: for (int l = 0; l < LANES; ++l) d[l] = a[l] != 0.0f ? b[l] : c[l]; break;
       default: for (int l = 0; l < LANES; ++l) d[l] = 0.0f; break;
     }
     memcpy(slots + (size_t)o->dst * LANES, t, sizeof t);

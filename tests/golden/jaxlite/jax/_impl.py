@@ -766,10 +766,20 @@ def diagonal(x, offset=0, axis1=0, axis2=1):
     return Array(np.diagonal(_raw(x), offset, axis1, axis2).copy())
 
 
-@_concrete
 def where(c, x, y):
-    # jnp.where(cond, 1, 0) yields weak int32
-    return Array(_f(np.where(_raw(c), _raw(x), _raw(y))))
+    """`jnp.where(c, x, y)` = `lax.select(c, x, y)` = `select_n(c, y, x)`; eager calls keep jnp's weak int32 result
+    for `where(cond, 1, 0)`."""
+    if not _TRACES and not any(isinstance(v, BatchTracer) for v in (c, x, y)):
+        return Array(_f(np.where(_raw(c), _raw(x), _raw(y))))
+    c, x, y = _lift(c), _lift(x), _lift(y)
+    if _is_scalar_const(x):
+        x = _weak(x, y)
+    if _is_scalar_const(y):
+        y = _weak(y, x)
+    shape = np.broadcast_shapes(_shape_of(c), _shape_of(x), _shape_of(y))
+    full = lambda v: v if _shape_of(v) == shape or not _shape_of(v) and _is_scalar_const(v) and False else \
+        broadcast_in_dim(v, shape, tuple(range(len(shape) - len(_shape_of(v)), len(shape))))
+    return select_n_p.bind(full(c), full(y), full(x))
 
 
 @_concrete

@@ -247,6 +247,13 @@ def run_zoo(n_points=16):
     # (`core.py:376-378` assigns graph[invar][outvar] twice), so the reference returns x instead of 2x
     dup = graphax.jacve(lambda x: x * x, order="fwd", argnums=(0,))(jnp.array(3.0))
     rec["quirks"] = {"d(x*x)/dx at x=3": float(np.asarray(dup[0] if isinstance(dup, (tuple, list)) else dup))}
+    # a third: the `select_n` rule (`primitives.py:225-234`) builds an inconsistent SparseTensor, so the reference
+    # cannot differentiate through `jnp.where` at all
+    try:
+        graphax.jacve(lambda x: jnp.where(x > 0., x, 0.1 * x), order="rev", argnums=(0,))(jnp.array([0.5, -0.3, 1.2]))
+        rec["quirks"]["jnp.where"] = "ok"
+    except Exception as e:       # noqa: BLE001
+        rec["quirks"]["jnp.where"] = type(e).__name__
     d = np.abs(arrays["reference_rules/jac/rev"] - arrays["asinh_corrected/jac/rev"]).max()
     print(f"  zoo: muls {rec['orders']} ; asinh rule changes the Jacobian by up to {d:.3f}")
     return rec, arrays
