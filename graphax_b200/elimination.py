@@ -167,11 +167,28 @@ def _product_entries(dag: Dag, post: Entries, pre: Entries, existing: Optional[E
     return out
 
 
+def _count_terms(post: Entries, pre: Entries, existing: Optional[Entries]) -> Tuple[int, int]:
+    """(scalar products, scalar additions onto an existing edge) of one J[s,p] (+)= J[s,v] J[v,p]."""
+    by_k: Dict[int, List[int]] = {}
+    for (i, k) in post:
+        by_k.setdefault(k, []).append(i)
+    n_mul, hit = 0, set()
+    for (k, j) in pre:
+        rows = by_k.get(k)
+        if rows:
+            n_mul += len(rows)
+            if existing is not None:
+                hit.update((i, j) for i in rows)
+    return n_mul, (sum(1 for ij in hit if ij in existing) if existing is not None else 0)
+
+
 @dataclass
 class StepStats:
     vertex: int
     num_muls: int = 0
     num_adds: int = 0
+    scalar_muls: int = 0          # structurally non-zero scalar products / additions: defined at any rank
+    scalar_adds: int = 0
     pairs: int = 0
     classes: Dict[str, int] = field(default_factory=dict)
     structure_complete: bool = True
@@ -188,6 +205,9 @@ def eliminate(g: Graph, vertex: int) -> StepStats:
             pre = g.bwd[v][p]
             stats.pairs += 1
             old = g.fwd[p].get(s)
+            m, a = _count_terms(post.entries, pre.entries, None if old is None else old.entries)
+            stats.scalar_muls += m
+            stats.scalar_adds += a
             if post.struct is None or pre.struct is None or (old is not None and old.struct is None):
                 stats.structure_complete = False
                 entries = _product_entries(dag, post.entries, pre.entries, None if old is None else old.entries)
@@ -257,6 +277,14 @@ class Accumulated:
     @property
     def num_adds(self) -> int:
         return sum(s.num_adds for s in self.steps)
+
+    @property
+    def scalar_muls(self) -> int:
+        return sum(s.scalar_muls for s in self.steps)
+
+    @property
+    def scalar_adds(self) -> int:
+        return sum(s.scalar_adds for s in self.steps)
 
 
 def accumulate(jaxpr: Jaxpr, order: Order, argnums: Sequence[int], division: str = "ieee") -> Accumulated:

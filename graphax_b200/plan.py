@@ -466,6 +466,10 @@ def _collect_stats(plan: Plan, acc: Accumulated) -> None:
         "num_muls": acc.num_muls if acc.structure_complete else None,
         "num_adds": acc.num_adds if acc.structure_complete else None,
         "order_counts": [(s.vertex, s.num_muls) for s in acc.steps] if acc.structure_complete else None,
+        # structurally non-zero scalar products / additions: what the kernels execute before x1 / +0 are dropped;
+        # defined at any rank (for vertices of rank <= 1 see num_muls / num_adds, the reference's own cost model)
+        "scalar_muls": acc.scalar_muls, "scalar_adds": acc.scalar_adds,
+        "scalar_order_counts": [(s.vertex, s.scalar_muls) for s in acc.steps],
         "pairs": sum(s.pairs for s in acc.steps),
         "max_pairs_per_step": max((s.pairs for s in acc.steps), default=0),
         "product_classes": classes,

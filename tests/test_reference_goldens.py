@@ -328,3 +328,22 @@ def test_random_tensor_function_f_against_reference_run():
         reps[order], _ = replay.replay(plan.blob, xs, plan.n_rows, plan.n_cols)
         assert ((np.abs(reps[order] - r_rev) / scale)[agree]).max() < 5e-5, order
     assert (np.abs(reps["fwd"] - reps["rev"]) / scale).max() < 5e-5
+
+
+@pytest.mark.parametrize("name", list(RUN["rank_n"]))
+def test_scalar_product_counts_for_matrix_valued_graphs(name):
+    """`count_ops` above rank 1 reports structurally non-zero scalar products (the reference's tensor-level cost model,
+    `tensor.py:1414-1493`, is not restated).  Against the reference run: identical for its NeuralNetwork test, within
+    5 % for Perceptron / Encoder / EncoderDecoder; on vertices of rank <= 1 the exact model is used (other tests)."""
+    from graphax_b200.plan import build_plan
+    from graphax_b200.tracer import make_jaxpr
+    rec = RUN["rank_n"][name]
+    jaxpr = make_jaxpr(_rank_n_case(name), [tuple(s) for s in rec["in_shapes"]])
+    for order in ("rev",) if name == "EncoderDecoder" else ("fwd", "rev"):
+        stats = build_plan(jaxpr, order, tuple(rec["argnums"])).stats
+        assert stats["num_muls"] is None                     # no tensor-level structure above rank 1
+        ref = rec["orders"][order]["num_muls"]
+        assert abs(stats["scalar_muls"] - ref) <= 0.05 * ref, (order, stats["scalar_muls"], ref)
+        if name == "NeuralNetwork":
+            assert (stats["scalar_muls"], stats["scalar_adds"]) == (ref, rec["orders"][order]["num_adds"])
+        assert sum(c for _, c in stats["scalar_order_counts"]) == stats["scalar_muls"]
