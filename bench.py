@@ -91,7 +91,8 @@ def run_reference_arm(args) -> None:
     if rank != 0:
         return
     cores = len(os.sched_getaffinity(0))
-    reference_note = "graphax needs jax, which is not installed in this image; timing the oracle port"
+    reference_note = ("graphax needs jax, which is not installed in this image; timing the oracle port (bit-exact with a "
+                      "run of the reference's own sources on a NumPy stand-in for JAX, tests/golden/reference_run.*)")
     try:  # honour a per-pod reference install if one ever exists
         sys.path.insert(0, str(ROOT / "baseline" / "_ref"))
         import jax  # noqa: F401
