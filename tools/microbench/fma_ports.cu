@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(1024, 1) kern(float* out, const float* in, lon
   for (int it = 0; it < ITERS; ++it) {
 #pragma unroll
     for (int i = 0; i < ACC; ++i) {
+      if (MODE >= 8) break;
       if (MODE == 0) a[i] = __fmaf_rn(a[i], b[i], c[i]);                 // 3 distinct registers
       if (MODE == 1) a[i] = __fmaf_rn(s, a[i], c[i]);                    // shared multiplier (reuse cache)
       if (MODE == 2) a[i] = __fmul_rn(a[i], b[i]);                       // 2 registers
@@ -31,6 +32,18 @@ __global__ void __launch_bounds__(1024, 1) kern(float* out, const float* in, lon
       if (MODE == 5) a[i] = __fmaf_rn(a[i], b[i], a[i]);                 // 2 distinct registers
       if (MODE == 6) a[i] = __fmaf_rn(s, a[i], t);                       // shared multiplier and addend
       if (MODE == 7) { a[i] = __fmul_rn(a[i], b[i]); c[i] = __fadd_rn(c[i], b[i]); }   // 2 x 2-register
+    }
+    if (MODE >= 8) {      // packed f32x2: ACC / 2 instructions, each two operations
+#pragma unroll
+      for (int i = 0; i < ACC; i += 2) {
+        float2 pa = make_float2(a[i], a[i + 1]), pb = make_float2(b[i], b[i + 1]), pc = make_float2(c[i], c[i + 1]), r;
+        if (MODE == 8) r = __ffma2_rn(pa, pb, pc);                          // three register pairs
+        if (MODE == 9) r = __ffma2_rn(make_float2(s, s), pa, pc);           // broadcast multiplier, two pairs
+        if (MODE == 10) r = __fmul2_rn(pa, pb);                             // two pairs
+        if (MODE == 11) r = __fmul2_rn(make_float2(s, s), pa);              // broadcast, one pair
+        if (MODE == 12) r = __ffma2_rn(make_float2(s, s), pa, make_float2(t, t));
+        a[i] = r.x; a[i + 1] = r.y;
+      }
     }
   }
   const long long t1 = clock64();
@@ -53,7 +66,8 @@ void run(const char* name, int warps_per_smsp, float* out, float* in, long long*
   double avg = 0;
   for (int i = 0; i < 148; ++i) avg += h[i];
   avg /= 148;
-  const double inst = (double)ITERS * ACC * (MODE == 7 ? 2 : 1) * warps_per_smsp;   // warp instructions per scheduler
+  const double inst = (double)ITERS * ACC * (MODE == 7 ? 2 : 1) * warps_per_smsp;   // scalar operations per scheduler
+  // (packed modes: ACC / 2 instructions of two operations each; the figure stays "cycles per operation")
   printf("%-44s warps/scheduler %d: %.3f cycles per warp instruction\n", name, warps_per_smsp, avg / inst);
 }
 
@@ -64,7 +78,7 @@ int main() {
   cudaMalloc(&in, 16384 * 4);
   cudaMalloc(&cyc, 148 * 8);
   cudaMemset(in, 0, 16384 * 4);
-  for (int w : {1, 2, 4, 8}) {
+  for (int w : {2, 4, 8}) {
     run<0>("FFMA a=a*b+c (3 registers)", w, out, in, cyc);
     run<1>("FFMA a=s*a+c (shared multiplier)", w, out, in, cyc);
     run<6>("FFMA a=s*a+t (shared multiplier, addend)", w, out, in, cyc);
@@ -73,6 +87,11 @@ int main() {
     run<2>("FMUL a=a*b", w, out, in, cyc);
     run<3>("FADD a=a+b", w, out, in, cyc);
     run<7>("FMUL + FADD pair", w, out, in, cyc);
+    run<8>("FFMA2 three pairs            [per op]", w, out, in, cyc);
+    run<9>("FFMA2 s.F32 * pair + pair    [per op]", w, out, in, cyc);
+    run<12>("FFMA2 s.F32 * pair + t.F32   [per op]", w, out, in, cyc);
+    run<10>("FMUL2 pair * pair            [per op]", w, out, in, cyc);
+    run<11>("FMUL2 s.F32 * pair           [per op]", w, out, in, cyc);
   }
   printf("%s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;
