@@ -1,0 +1,80 @@
+#!/usr/bin/env python
+"""Register-port cost of a plan-specialised kernel's SASS (no GPU needed).
+
+    python tools/sass_port_model.py roe3d mixed rev fwd mixed2
+
+Model (measured in tools/microbench/fma_ports.cu, profiles/microbench_r01_fma_operand_ports.txt): the register file
+has two banks (register index mod 2) that each deliver one operand per cycle; an FFMA / FMUL / FADD occupies its
+scheduler for as many cycles as its most loaded bank, operands held in the reuse cache (flagged `.reuse` by the
+previous instruction in the same slot) and immediates are free, every other instruction costs one cycle.  Prints
+the modelled cycles of the hot loop per 32-sample tile; measured cycles per tile = kernel time x SM clock /
+(tiles per scheduler), e.g. 58.0 us x 1.92 GHz / 55.35 = 2012 for the mixed order.
+"""
+import re
+import subprocess
+import sys
+import tempfile
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+from graphax_b200 import codegen                      # noqa: E402
+from graphax_b200.configs import get_workload         # noqa: E402
+
+
+def sass_of(plan):
+    src = codegen.emit_source(plan, nvrtc=False)
+    with tempfile.TemporaryDirectory() as d:
+        cu = Path(d) / "k.cu"
+        cu.write_text(src)
+        subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-I", str(codegen.CSRC), "-cubin",
+                        "-o", f"{d}/k.cubin", str(cu)], check=True, capture_output=True)
+        out = subprocess.run(["cuobjdump", "-sass", f"{d}/k.cubin"], capture_output=True, text=True).stdout
+    return [m.group(1).strip() for m in (re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(.*?);", l) for l in out.splitlines()) if m]
+
+
+def cost(instructions, banks=2):
+    total, prev = 0, {}
+    stats = {"ffma": 0, "ffma_two_cycles": 0, "fmul_fadd_two_cycles": 0}
+    for s in instructions:
+        m = re.match(r"(@!?U?P\d+\s+)?([A-Z0-9_.]+)\s*(.*)", s)
+        base, rest = m.group(2).split(".")[0], m.group(3)
+        c, cur = 1, {}
+        if base in ("FFMA", "FMUL", "FADD"):
+            load = {}
+            for slot, o in enumerate([o.strip() for o in rest.split(",")][1:]):
+                r = re.match(r"[-|]*R(\d+)(\.reuse)?", o)
+                if not r:
+                    continue                      # immediate, constant bank, RZ
+                idx = int(r.group(1))
+                if r.group(2):
+                    cur[slot] = idx
+                if prev.get(slot) == idx:
+                    continue                      # served by the reuse cache
+                load[idx % banks] = load.get(idx % banks, 0) + 1
+            c = max([1] + list(load.values()))
+            if base == "FFMA":
+                stats["ffma"] += 1
+                stats["ffma_two_cycles"] += c > 1
+            else:
+                stats["fmul_fadd_two_cycles"] += c > 1
+        prev = cur
+        total += c
+    return total, stats
+
+
+def main():
+    workload, orders = sys.argv[1], sys.argv[2:]
+    for order in orders:
+        ins = sass_of(get_workload(workload).plan(order))
+        # the hot loop: from the tile's input reads to the end of the fast body (the exact fallback follows the vote)
+        start = next(i for i, s in enumerate(ins) if "LDS" in s) - 5
+        end = next((i for i, s in enumerate(ins) if "VOTE.ANY" in s), len(ins) - 40) + 40
+        loop = ins[start:end]
+        cycles, stats = cost(loop)
+        print(f"{workload}:{order}: {len(loop)} instructions per tile, modelled {cycles} cycles  {stats}")
+
+
+if __name__ == "__main__":
+    main()
