@@ -46,6 +46,17 @@ for name, (file, fn) in sources.items():
     blobs = all(build_plan(via_jax, w.order(o), w.argnums).blob == w.plan(o, with_primal=True).blob for o in w.order_names())
     out[name] = {"same_jaxpr": bool(same), "same_plans": bool(blobs), "n_eqns": len(via_jax.eqns)}
 
+# the stand-in's vmap reproduces jax.vmap's identity pads for RoeFlux_3d (SURVEY.md A.1 rule 5)
+text = (root / "graphax_b200" / "examples" / "roe_flux.py").read_text().replace("from ..tracer import jnp", "import jax.numpy as jnp")
+scope = {}
+exec(text, scope)
+w = WORKLOADS["roe3d"]
+batched = [jnp.array(x) for x in w.inputs(3)]
+vj = jax.make_jaxpr(jax.vmap(scope["RoeFlux_3d"]))(*batched).jaxpr
+out["vmap_eqns"] = len(vj.eqns)
+out["vmap_pads"] = [n for n, e in enumerate(vj.eqns, 1)
+                    if e.primitive.name == "broadcast_in_dim" and not isinstance(e.invars[0], jax.core.Literal)]
+
 # unknown primitives are refused like in the reference (core.py:396-398)
 try:
     make_jaxpr(lambda x: jnp.tile(x, 2), [(3,)], "jax")
@@ -66,6 +77,7 @@ def test_jax_frontend_reproduces_the_native_tracer_on_a_jax_numpy_function():
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out.pop("refuses_untraceable") is True
     assert out.pop("api_lowers") == [3, 6, 2]
+    assert out.pop("vmap_eqns") == 146 and out.pop("vmap_pads") == [24, 33, 48, 55, 59, 82, 91, 133]
     assert out["roe3d"]["n_eqns"] == 138 and out["roe1d"]["n_eqns"] == 101 and out["robotarm"]["n_eqns"] == 114
     for name, rec in out.items():
         assert rec["same_jaxpr"] and rec["same_plans"], (name, rec)
