@@ -783,6 +783,21 @@ def where(c, x, y):
 
 
 @_concrete
+def einsum(subscripts, *operands, **kwargs):
+    return Array(_f(np.einsum(subscripts, *[np.asarray(_raw(o)) for o in operands])))
+
+
+@_concrete
+def diag(v, k=0):
+    return Array(np.diag(_raw(v), k))
+
+
+@_concrete
+def all(a, axis=None):      # noqa: A001
+    return Array(np.all(_raw(a), axis=axis))
+
+
+@_concrete
 def allclose(a, b, rtol=1e-5, atol=1e-8, equal_nan=False):
     return Array(np.allclose(np.asarray(_raw(a), np.float64), np.asarray(_raw(b), np.float64), rtol=rtol, atol=atol, equal_nan=equal_nan))
 
@@ -838,7 +853,7 @@ def make_jaxpr(fun: Callable) -> Callable:
         trace = _Trace()
         invars = []
         for a in flat:
-            if isinstance(a, ShapeDtypeStruct):
+            if isinstance(a, (ShapeDtypeStruct, Tracer)):      # a Tracer: make_jaxpr inside an outer trace
                 invars.append(Var(ShapedArray(a.shape, a.dtype)))
                 continue
             v = np.asarray(_raw(a))

@@ -4,7 +4,7 @@ from ._impl import (add, subtract, multiply, divide, true_divide, arctan2, maxim
                     power, negative, abs, absolute, sqrt, exp, log, log1p, sin, cos, tan, arcsin, arccos, arctan,
                     sinh, cosh, tanh, arcsinh, arccosh, arctanh, square, sum, max, min, amax, amin, mean, dot, matmul,
                     transpose, reshape, squeeze, expand_dims, concatenate, zeros, ones, zeros_like, ones_like, full,
-                    split, array, asarray, eye, tile, diagonal, where, allclose, logical_and, arange, Array as ndarray)
+                    split, array, asarray, eye, tile, diagonal, where, allclose, logical_and, arange, einsum, diag, all, Array as ndarray)
 
 float32 = _np.float32
 float64 = _np.float64
