@@ -145,6 +145,9 @@ class _Ops:
     def reshape(s, *shape): return reshape(s, shape[0] if len(shape) == 1 and not isinstance(shape[0], (int, np.integer)) else shape)
     def sum(s, axis=None, keepdims=False): return sum(s, axis=axis, keepdims=keepdims)
     def astype(s, dtype): return convert_element_type(s, dtype)
+    def mean(s, axis=None): return mean(s, axis)
+    def max(s, axis=None, keepdims=False): return max(s, axis=axis, keepdims=keepdims)
+    def min(s, axis=None, keepdims=False): return min(s, axis=axis, keepdims=keepdims)
     def squeeze(s, axis=None): return squeeze(s, axis)
     def transpose(s, *axes): return transpose(s, axes[0] if len(axes) == 1 and not isinstance(axes[0], int) else (axes or None))
     T = property(lambda s: transpose(s))
@@ -478,6 +481,14 @@ def _binary(prim):
             x = _weak(x, y)
         elif _is_scalar_const(y) and not _is_scalar_const(x):
             y = _weak(y, x)
+        if _is_value(x) and (_is_value(y) or _is_scalar_const(y)) or _is_value(y) and _is_scalar_const(x):
+            dx, dy = np.asarray(x).dtype if _is_scalar_const(x) else x.dtype, np.asarray(y).dtype if _is_scalar_const(y) else y.dtype
+            if prim.name not in ("eq", "gt", "lt") or dx != dy:
+                to = _canon_dtype(np.result_type(dx, dy))
+                if _is_value(x) and x.dtype != to:
+                    x = convert_element_type(x, to)
+                if _is_value(y) and y.dtype != to:
+                    y = convert_element_type(y, to)
         x, y = _promote_ranks(x, y)
         return prim.bind(x, y)
     fn.__name__ = prim.name
@@ -733,9 +744,9 @@ def split(x, indices_or_sections, axis=0):
 
 def _concrete(fn):
     def wrapped(*args, **kwargs):
-        if _TRACES:
+        if any(isinstance(a, (Tracer, BatchTracer)) for a in args):
             raise NotImplementedError(f"jaxlite: {fn.__name__} is not traceable")
-        return fn(*args, **kwargs)
+        return fn(*args, **kwargs)      # inside a trace the result is a constant (JAX would stage iota / eq / ...)
     wrapped.__name__ = fn.__name__
     return wrapped
 
@@ -756,9 +767,17 @@ def eye(n, m=None, dtype=None):
     return Array(np.eye(int(n), None if m is None else int(m), dtype=_canon_dtype(dtype or np.float32)))
 
 
-@_concrete
 def tile(x, reps):
-    return Array(np.tile(_raw(x), reps))
+    reps = (reps,) if isinstance(reps, (int, np.integer)) else tuple(int(r) for r in reps)
+    if not isinstance(x, (Tracer, BatchTracer)):
+        return Array(np.tile(_raw(x), reps))
+    reps = (1,) * (x.ndim - len(reps)) + reps
+    if builtins.all(r == 1 for r in reps):
+        return x if len(reps) == x.ndim else reshape(x, (1,) * (len(reps) - x.ndim) + tuple(x.shape))
+    shape = (1,) * (len(reps) - x.ndim) + tuple(x.shape)
+    inter = tuple(v for r, d in zip(reps, shape) for v in (r, d))
+    y = broadcast_in_dim(reshape(x, shape), inter, tuple(range(1, 2 * len(shape), 2)))
+    return reshape(y, tuple(r * d for r, d in zip(reps, shape)))
 
 
 @_concrete
@@ -815,13 +834,8 @@ class ScatterDimensionNumbers:
         self.scatter_dims_to_operand_dims = tuple(scatter_dims_to_operand_dims)
 
 
-@_concrete
-def scatter(operand, scatter_indices, updates, dimension_numbers, indices_are_sorted=False, unique_indices=False,
-            mode=None):
-    """`lax.scatter` for the one form the reference uses (`primitives.py:744-749, 1062-1067, 1114-1117`):
-    a single index vector and no inserted window dimensions, i.e. the update block replaces the window of
-    `operand` that starts at the given offsets."""
-    op, idx, upd = np.array(_raw(operand)), np.asarray(_raw(scatter_indices)), np.asarray(_raw(updates))
+def _scatter_impl(operand, scatter_indices, updates, dimension_numbers, **_):
+    op, idx, upd = np.array(operand), np.asarray(scatter_indices), np.asarray(updates)
     dn = dimension_numbers
     if idx.ndim != 1 or dn.inserted_window_dims or len(dn.update_window_dims) != upd.ndim:
         raise NotImplementedError("jaxlite: general scatter")
@@ -830,11 +844,21 @@ def scatter(operand, scatter_indices, updates, dimension_numbers, indices_are_so
     start = [0] * op.ndim
     for k, d in enumerate(dn.scatter_dims_to_operand_dims):
         start[d] = int(idx[k])
-    window = tuple(slice(s, s + n) for s, n in zip(start, upd.shape))
     if any(s + n > m for s, n, m in zip(start, upd.shape, op.shape)):
-        return Array(op)                                   # out-of-bounds windows are dropped
-    op[window] = upd.astype(op.dtype)
-    return Array(op)
+        return op                                          # out-of-bounds windows are dropped
+    op[tuple(slice(s, s + n) for s, n in zip(start, upd.shape))] = upd.astype(op.dtype)
+    return op
+
+
+scatter_p = Primitive("scatter", _scatter_impl)
+
+
+def scatter(operand, scatter_indices, updates, dimension_numbers, indices_are_sorted=False, unique_indices=False,
+            mode=None):
+    """`lax.scatter` for the one form the reference uses (`primitives.py:744-749, 1062-1067, 1114-1117`):
+    a single index vector and no inserted window dimensions, i.e. the update block replaces the window of
+    `operand` that starts at the given offsets."""
+    return scatter_p.bind(_lift(operand), _lift(scatter_indices), _lift(updates), dimension_numbers=dimension_numbers)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -853,7 +877,7 @@ def make_jaxpr(fun: Callable) -> Callable:
         trace = _Trace()
         invars = []
         for a in flat:
-            if isinstance(a, (ShapeDtypeStruct, Tracer)):      # a Tracer: make_jaxpr inside an outer trace
+            if isinstance(a, (ShapeDtypeStruct, Tracer, BatchTracer)):   # tracers: make_jaxpr inside a trace / vmap
                 invars.append(Var(ShapedArray(a.shape, a.dtype)))
                 continue
             v = np.asarray(_raw(a))
@@ -1047,7 +1071,13 @@ def _b_dot_general(prim, args, params, B):
         if isinstance(lhs, BatchTracer) and not lb:      # the batch axis is the first free axis of lhs
             dn = ((tuple(i + 1 for i in lc), rc), ((), ()))
             return BatchTracer(prim.bind(lhs.val, rhs, **dict(params, dimension_numbers=dn)))
-        raise NotImplementedError("jaxlite: dot_general with a batched right operand only")
+        if isinstance(rhs, BatchTracer) and not lb:      # the batch axis is the first free axis of rhs: move it to the front
+            dn = ((lc, tuple(i + 1 for i in rc)), ((), ()))
+            out = prim.bind(lhs, rhs.val, **dict(params, dimension_numbers=dn))
+            pos = _ndim(lhs) - len(lc)
+            perm = (pos,) + tuple(i for i in range(_ndim(out)) if i != pos)
+            return BatchTracer(out if pos == 0 else transpose_p.bind(out, permutation=perm))
+        raise NotImplementedError("jaxlite: dot_general with batch dimensions and one batched operand")
     sh = lambda t: tuple(i + 1 for i in t)
     dn = ((sh(lc), sh(rc)), ((0,) + sh(lb), (0,) + sh(rb)))
     return BatchTracer(prim.bind(lhs.val, rhs.val, **dict(params, dimension_numbers=dn)))

@@ -12,4 +12,5 @@ int32 = _np.int32
 int64 = _np.int64
 bool_ = _np.bool_
 pi = _np.pi
+newaxis = None
 inf = _np.inf

@@ -58,8 +58,10 @@ out["vmap_pads"] = [n for n, e in enumerate(vj.eqns, 1)
                     if e.primitive.name == "broadcast_in_dim" and not isinstance(e.invars[0], jax.core.Literal)]
 
 # unknown primitives are refused like in the reference (core.py:396-398)
+import jax.lax as lax
+dn = lax.ScatterDimensionNumbers((0,), (), (0,))
 try:
-    make_jaxpr(lambda x: jnp.tile(x, 2), [(3,)], "jax")
+    build_plan(make_jaxpr(lambda x, i: lax.scatter(x, i, x * 2., dn), [(3,), (1,)], "jax"), "rev", (0,))
     out["refuses_untraceable"] = False
 except NotImplementedError:
     out["refuses_untraceable"] = True
