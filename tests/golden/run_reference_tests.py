@@ -18,7 +18,7 @@ HERE = Path(__file__).resolve().parent
 REF = Path(sys.argv[1] if len(sys.argv) > 1 else "/root/reference")
 FILES = ["tests/core/sparse_mul_test.py", "tests/core/dense_mul_test.py", "tests/core/mixed_mul_test.py",
          "tests/core/replication_test.py", "tests/core/primitive_test.py", "tests/core/multi_output_primitives_test.py",
-         "tests/examples/example_test.py"]
+         "tests/examples/example_test.py", "tests/examples/hessian_test.py"]
 KNOWN = {
     "PrimitveTest::test_squeezing": "reference: primitives.py:927 calls list.index(int) on a list of Dimension objects (ValueError)",
     "MultiOutputTest::test_split": "stand-in: make_jaxpr THROUGH jacve (printing the emitted program) needs traceable index arrays",
