@@ -97,3 +97,46 @@ def test_jax_frontend_needs_jax():
     assert len(make_jaxpr(lambda x: jnp.sin(x) * x, [()], "auto").eqns) == 2
     with pytest.raises(ValueError):
         make_jaxpr(lambda x: x, [()], "xla")
+
+
+GPU_CHILD = r'''
+import json, sys
+from pathlib import Path
+root = Path(sys.argv[1])
+sys.path[:0] = [str(root), str(root / "tests"), str(root / "tests" / "golden" / "jaxlite")]
+import numpy as np, torch
+import jax, jax.numpy as jnp            # jaxlite
+import graphax_b200 as gx
+from graphax_b200.configs import WORKLOADS
+
+text = (root / "graphax_b200" / "examples" / "roe_flux.py").read_text().replace("from ..tracer import jnp", "import jax.numpy as jnp")
+scope = {}
+exec(text, scope)
+w = WORKLOADS["roe3d"]
+xs = w.inputs(4096)
+jf = gx.jacve(scope["RoeFlux_3d"], order=list(w.vmap_orders["mixed"]), argnums=tuple(range(6)), order_numbering="vmap")
+jac = gx.vmap(jf)(*[jnp.array(x) for x in xs])          # stand-in arrays in, torch CUDA tensors out
+got = np.concatenate([np.concatenate([b.reshape(4096, b.shape[1], -1).cpu().numpy() for b in row], axis=2) for row in jac], axis=1)
+native = gx.jacve(w.fun, order=list(w.vmap_orders["mixed"]), argnums=tuple(range(6)), order_numbering="vmap")
+ref = gx.vmap(native)(*[torch.from_numpy(x).cuda() for x in xs])
+ref = np.concatenate([np.concatenate([b.reshape(4096, b.shape[1], -1).cpu().numpy() for b in row], axis=2) for row in ref], axis=1)
+print(json.dumps({"bit_equal": bool(np.array_equal(got.view(np.uint32), ref.view(np.uint32))), "shape": list(got.shape),
+                  "kernel": next(iter(jf._device_plans.values())).kernel}))
+'''
+
+
+def test_gpu_call_with_a_jax_numpy_function():
+    """End to end on the GPU: RoeFlux_3d written against `jax.numpy` (stand-in), the reference's mixed order in its
+    own 146-numbering, arrays of the other library as inputs - same plan, same ahead-of-time kernel, same bits as the
+    native path."""
+    import pytest
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    r = subprocess.run([sys.executable, "-c", GPU_CHILD, str(ROOT)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out == {"bit_equal": True, "shape": [4096, 5, 10], "kernel": "aot"}
+
+
+test_gpu_call_with_a_jax_numpy_function = __import__("pytest").mark.gpu(test_gpu_call_with_a_jax_numpy_function)
