@@ -168,6 +168,38 @@ def run_workload(name, w, fun, n_points):
     return rec, arrays
 
 
+def run_random_orders(n_orders=3, n_points=8):
+    """The caller-given order is arbitrary: seeded random permutations of the eliminable vertices of the three named
+    workloads, through the reference (count_ops, per-vertex counts, block structures, Jacobians)."""
+    out, arrays = {}, {}
+    for name in ("roe3d", "roe1d", "robotarm"):
+        w, fun = WORKLOADS[name], FUNCTIONS[name]
+        base = [np.asarray(w.base[sum(w.sizes[:i]):sum(w.sizes[:i + 1])], np.float32).reshape(s) for i, s in enumerate(w.arg_shapes)]
+        pts = w.inputs(n_points, start=1000)
+        jaxpr = jax.make_jaxpr(fun)(*[jnp.array(b) for b in base]).jaxpr
+        outs = {id(v) for v in jaxpr.outvars}
+        eliminable = [i for i, e in enumerate(jaxpr.eqns, 1) if id(e.outvars[0]) not in outs]
+        argnums = tuple(w.argnums)
+        out_sizes = [int(np.prod(v.aval.shape, dtype=np.int64)) for v in jaxpr.outvars]
+        arrays[f"random_orders/{name}/inputs"] = np.concatenate([p.reshape(n_points, -1) for p in pts], axis=1)
+        out[name] = {}
+        for k in range(n_orders):
+            order = [int(v) for v in np.random.default_rng(100 * k + len(eliminable)).permutation(eliminable)]
+            jacs = []
+            for b in range(n_points):
+                res, aux = graphax.jacve(fun, order=order, argnums=argnums, count_ops=True)(*[jnp.array(p[b]) for p in pts])
+                jacs.append(pack(res, out_sizes, w.sizes))
+            sparse = gcore.vertex_elimination_jaxpr(jaxpr, order, [], *[jnp.array(p[0]) for p in pts], argnums=argnums,
+                                                    sparse_representation=True)
+            sparse = [t for row in sparse for t in row]
+            out[name][f"random{k}"] = {"order": order, "num_muls": int(aux["num_muls"]), "num_adds": int(aux["num_adds"]),
+                                       "order_counts": [[int(v), int(c)] for v, c in aux["order_counts"]],
+                                       "blocks": {f"{i // len(argnums)},{i % len(argnums)}": describe(t) for i, t in enumerate(sparse)}}
+            arrays[f"random_orders/{name}/jac/random{k}"] = np.stack(jacs)
+            print(f"  {name}:random{k}: muls {aux['num_muls']} adds {aux['num_adds']}")
+    return out, arrays
+
+
 def run_g():
     """The reference's only literal known answers: `# fwd: 632, rev: 566` (`examples/randoms.py:91`)."""
     rng = np.random.default_rng(7)
@@ -429,6 +461,9 @@ def main():
         out["rank_n"][name] = rec
         for k, v in arr.items():
             arrays[f"rank_n/{name}/{k}"] = v
+    print("random orders", flush=True)
+    out["random_orders"], arr = run_random_orders()
+    arrays.update(arr)
     print("further examples", flush=True)
     out["examples"], arr = run_examples()
     arrays.update(arr)

@@ -150,6 +150,36 @@ def test_further_reference_examples_on_the_gpu(built_library, name, order):
     assert (np.abs(jac - ref) <= bound).all(), float((np.abs(jac - ref) / bound).max())
 
 
+def _random_cases():
+    import json
+    from helpers import GOLDEN
+    run = json.loads((GOLDEN / "reference_run.json").read_text())
+    return [(n, k) for n, rec in run["random_orders"].items() for k in rec]
+
+
+@pytest.mark.parametrize("name,key", _random_cases())
+def test_random_orders_on_the_gpu(built_library, name, key):
+    """Arbitrary caller-given orders: seeded random permutations, run-time specialised kernels against the Jacobians
+    the reference computed for the same order (bound widened by the order's own fp32 noise, see the CPU test)."""
+    from graphax_b200.plan import build_plan
+    from oracle import ve_numpy
+    run, arr = _reference_run()
+    w, ro = WORKLOADS[name], run["random_orders"][name][key]
+    flat = arr[f"random_orders/{name}/inputs"]
+    xs, off = [], 0
+    for shape, size in zip(w.arg_shapes, w.sizes):
+        xs.append(np.ascontiguousarray(flat[:, off:off + size].reshape((len(flat),) + tuple(shape))))
+        off += size
+    plan = build_plan(w.jaxpr(), ro["order"], w.argnums)
+    jac, _, used = run_engine(plan, xs, "jit")
+    assert used == "jit"
+    ref = arr[f"random_orders/{name}/jac/{key}"].astype(np.float64)
+    j64, _, _ = ve_numpy.jacve(w.jaxpr(), ro["order"], w.argnums, [x.astype(np.float64) for x in xs], np.float64)
+    noise = np.abs(ref - pack_blocks(j64, len(flat), w.sizes)).max(axis=(1, 2), keepdims=True)
+    assert np.isfinite(jac).all()
+    assert (np.abs(jac - ref) <= parity_bound(ref) + 2 * noise).all()
+
+
 @pytest.mark.parametrize("batch", [0, 1, 127, 128, 129, 300])
 @pytest.mark.parametrize("kernel", ["aot", "interpreter"])
 def test_ragged_batches(built_library, batch, kernel):

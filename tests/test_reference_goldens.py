@@ -361,3 +361,34 @@ def test_reference_test_suite_on_the_stand_in():
     assert rec["files"]["tests/examples/example_test.py"]["passed"] >= 12
     for f in rec["files"].values():
         assert all(reason != "unexplained" for reason in f["failed"].values()), f
+
+
+RANDOM_CASES = [(n, k) for n, rec in RUN["random_orders"].items() for k in rec]
+
+
+@pytest.mark.parametrize("name,key", RANDOM_CASES)
+def test_random_elimination_orders_against_reference_run(name, key):
+    """The caller-given order is arbitrary: seeded random permutations of the eliminable vertices, through the
+    reference.  Same checks as for the named orders: structure of every final block, count_ops totals and per-vertex
+    counts identical, oracle values bit-exact, plan replay inside the parity bound."""
+    from graphax_b200.plan import build_plan
+    w, ro = get_workload(name), RUN["random_orders"][name][key]
+    xs = split_inputs(w, ARR[f"random_orders/{name}/inputs"])
+    order = ro["order"]
+    jac, _, aux = vo.jacve(w.jaxpr(), order, w.argnums, xs, np.float32)
+    assert (aux["num_muls"], aux["num_adds"]) == (ro["num_muls"], ro["num_adds"])
+    assert [list(c) for c in aux["order_counts"]] == ro["order_counts"]
+    assert {k: strip(v) for k, v in aux["structure"]["blocks"].items()} == {k: strip(v) for k, v in ro["blocks"].items()}
+    ref32 = ARR[f"random_orders/{name}/jac/{key}"]
+    assert (bits(pack_blocks(jac, len(xs[0]), w.sizes)) == bits(ref32)).all()
+    plan = build_plan(w.jaxpr(), order, w.argnums)
+    assert (plan.stats["num_muls"], plan.stats["num_adds"]) == (ro["num_muls"], ro["num_adds"])
+    assert [list(c) for c in plan.stats["order_counts"]] == ro["order_counts"]
+    assert {k: strip(v) for k, v in plan.structure["blocks"].items()} == {k: strip(v) for k, v in ro["blocks"].items()}
+    rep, _ = replay.replay(plan.blob, xs, plan.n_rows, plan.n_cols)
+    ref = ref32.astype(np.float64)
+    # a random order is not a well-conditioned one: both fp32 evaluations carry the order's own rounding noise
+    j64, _, _ = vo.jacve(w.jaxpr(), order, w.argnums, [x.astype(np.float64) for x in xs], np.float64)
+    t64 = pack_blocks(j64, len(xs[0]), w.sizes)
+    noise = np.abs(ref - t64).max(axis=(1, 2), keepdims=True)
+    assert (np.abs(rep - ref) <= parity_bound(ref) + 2 * noise).all()
