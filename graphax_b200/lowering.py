@@ -329,6 +329,12 @@ def lower_eqn(dag: Dag, eqn: Eqn, read, division: str = "ieee") -> Tuple[Vec, Li
         return out, [(eqn.invars[i],) + _parallel_jacobian(ops[i], out, partials[i], 2) for i in traced]
     if prim == "convert_element_type":   # primitives.py:1236-1255: one floating-point type here, the value passes through
         return edges(ops[0], (ew.ones_like(ops[0]),))
+    if prim in ("ge", "le", "ne"):   # complements of lt / gt / eq (a NaN operand compares as true here)
+        x, y = ops
+        base = ew.binary({"ge": "lt", "le": "gt", "ne": "eq"}[prim], x, y)
+        out = Vec(base.shape, [dag.emit("select", n, dag.const(0.0), dag.const(1.0)) for n in base.nodes])
+        zero = Vec(out.shape, [dag.const(0.0)] * out.size)
+        return edges(out, (zero, zero))
     if prim in ("gt", "lt", "eq"):   # primitives.py:218-223: comparisons carry zero partials
         x, y = ops
         out = ew.binary(prim, x, y)

@@ -234,6 +234,8 @@ class Tracer:
     # comparisons (values 1.0 / 0.0: the tracer has one dtype); `==` stays identity for dict / list use
     __gt__ = lambda s, o: s._binary("gt", o)
     __lt__ = lambda s, o: s._binary("lt", o)
+    __ge__ = lambda s, o: s._binary("ge", o)
+    __le__ = lambda s, o: s._binary("le", o)
 
     def __pow__(self, y: Any) -> "Tracer":
         if isinstance(y, (int, np.integer)) and not isinstance(y, bool):
@@ -478,6 +480,7 @@ class _NnShim:
     softmax = staticmethod(lambda x, axis=-1: _softmax(x, axis))
     sigmoid = staticmethod(lambda x: _unary("logistic")(x))
     tanh = staticmethod(lambda x: _unary("tanh")(x))
+    relu = staticmethod(lambda x: _binary_fn("max")(x, 0.0))      # jax.nn.relu = maximum(x, 0)
 
 
 jnn = _NnShim()

@@ -34,10 +34,11 @@ def _apply(eqn, vals: List[np.ndarray], batched: List[bool]):
         nd = max(a.ndim for a in x)
         w, c0, c1 = [v.reshape(v.shape[:1] + (1,) * (nd - v.ndim) + v.shape[1:]) if lead else v for v in x]
         return np.where(w != 0, c1, c0)
-    if p in ("gt", "lt", "eq"):
+    if p in ("gt", "lt", "eq", "ge", "le", "ne"):
         nd = max(a.ndim for a in x)
         a, b = [v.reshape(v.shape[:1] + (1,) * (nd - v.ndim) + v.shape[1:]) if lead else v for v in x]
-        return {"gt": np.greater, "lt": np.less, "eq": np.equal}[p](a, b).astype(np.result_type(a, b))
+        return {"gt": np.greater, "lt": np.less, "eq": np.equal, "ge": np.greater_equal, "le": np.less_equal,
+                "ne": np.not_equal}[p](a, b).astype(np.result_type(a, b))
     if p in ("add", "sub", "mul", "div", "atan2", "pow", "max", "min"):
         nd = max(a.ndim for a in x)
         a, b = [v.reshape(v.shape[:1] + (1,) * (nd - v.ndim) + v.shape[1:]) if v.ndim > 1 or lead else v for v in x]
@@ -144,7 +145,7 @@ def _elemental_jacobians(eqn, vals, out, is_var, dtype):
         elif p in ("max", "min"):
             first = full(x[0]) > full(x[1]) if p == "max" else full(x[0]) < full(x[1])
             part = np.where(first, 1., 0.) if i == 0 else np.where(first, 0., 1.)
-        elif p in ("gt", "lt", "eq"):
+        elif p in ("gt", "lt", "eq", "ge", "le", "ne"):
             part = np.zeros(bshape, dtype=dtype)
         elif p == "select_n":       # the selected case passes its derivative, the predicate none
             w = full(x[0]) != 0

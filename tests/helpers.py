@@ -95,7 +95,8 @@ def torch_eval_jaxpr(jaxpr, args):
         elif p == "max": r = torch.maximum(x[0], x[1])
         elif p == "min": r = torch.minimum(x[0], x[1])
         elif p == "integer_pow": r = x[0] ** prm["y"]
-        elif p in ("gt", "lt", "eq"): r = {"gt": torch.gt, "lt": torch.lt, "eq": torch.eq}[p](x[0], x[1]).to(torch.float64)
+        elif p in ("gt", "lt", "eq", "ge", "le", "ne"):
+            r = {"gt": torch.gt, "lt": torch.lt, "eq": torch.eq, "ge": torch.ge, "le": torch.le, "ne": torch.ne}[p](x[0], x[1]).to(torch.float64)
         elif p == "select_n": r = torch.where(x[0] != 0, x[2], x[1])
         elif p == "convert_element_type": r = x[0]
         elif p in un: r = un[p](x[0])

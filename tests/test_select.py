@@ -72,6 +72,30 @@ def test_select_of_unselected_nan_branch_keeps_the_value_finite():
     assert prim.reshape(-1)[0] == -3.0 and np.isclose(prim.reshape(-1)[1], np.log(2.0))
 
 
+def test_ge_le_and_relu():
+    import torch
+    from graphax_b200.tracer import jnn
+    from oracle import dense_ve, replay
+
+    def f(x, y):
+        clipped = jnp.where(x >= y, y, x)                 # min(x, y) through >=
+        return jnn.relu(clipped - 0.2) * jnp.where(x <= 0.5, x * x, x)
+    jaxpr = make_jaxpr(f, [(5,), (5,)])
+    assert "ge" in [e.primitive for e in jaxpr.eqns] and "le" in [e.primitive for e in jaxpr.eqns]
+    rng = np.random.default_rng(4)
+    xs = [rng.uniform(-1, 2, (32, 5)).astype(np.float32) for _ in range(2)]
+    plan = build_plan(jaxpr, "rev", (0, 1))
+    rep, _ = replay.replay(plan.blob, xs, plan.n_rows, plan.n_cols)
+    j64, _ = dense_ve.jacve(jaxpr, "rev", (0, 1), [x.astype(np.float64) for x in xs], np.float64)
+    t64 = _tile(jaxpr, j64, 32)
+    assert np.abs(rep - t64).max() < 1e-5
+    for b in range(4):
+        args = [torch.tensor(x[b], dtype=torch.float64, requires_grad=True) for x in xs]
+        out = torch_eval_jaxpr(jaxpr, args)[0]
+        rows = [torch.cat([g.reshape(-1) for g in torch.autograd.grad(out[r], args, retain_graph=True)]) for r in range(5)]
+        assert np.abs(torch.stack(rows).numpy() - t64[b]).max() < 1e-12
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("kernel", ["jit", "interpreter"])
 @pytest.mark.parametrize("order", ["fwd", "rev"])
