@@ -121,3 +121,21 @@ def test_product_never_imports_test_infrastructure():
         assert "golden/" not in text.replace("tests/golden/jaxlite``", "") or f.name == "jax_frontend.py", f   # no fixture paths in the product
         if re.search(r"^(from|import)\s+jax\b", text, re.M):
             raise AssertionError(f"{f}: JAX must stay an optional, function-local import")
+
+
+def test_jax_ffi_shim_is_guarded_and_matches_the_header():
+    """The `jax.ffi` binding (unverifiable here: no JAX) must import without JAX, say so, and its C++ handler may only
+    use entry points the C ABI header declares."""
+    import re
+    from pathlib import Path
+    from graphax_b200 import jax_ffi
+    root = Path(__file__).resolve().parent.parent
+    if not jax_ffi.available():
+        import pytest
+        with pytest.raises(ImportError):
+            jax_ffi.build_handler()
+    header = (root / "include" / "graphax_b200.h").read_text()
+    handler = (root / "graphax_b200" / "csrc" / "gx_xla_ffi.cc").read_text()
+    for sym in set(re.findall(r"\b(gx_[a-z_]+)\s*\(", handler)):
+        assert re.search(rf"\b{sym}\s*\(", header), sym
+    assert "XLA_FFI_DEFINE_HANDLER_SYMBOL(GxJacve" in handler and "PlatformStream<cudaStream_t>" in handler
