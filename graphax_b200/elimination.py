@@ -100,7 +100,7 @@ def build_graph(jaxpr: Jaxpr, division: str = "ieee") -> Graph:
                 for ij, n in entries.items():
                     merged[ij] = dag.add(n, merged[ij]) if ij in merged else n
                 both = struct is not None and old.struct is not None
-                edge = Edge(st.add(struct, old.struct) if both else None, merged)
+                edge = Edge(_try(st.add, struct, old.struct) if both else None, merged)
             else:
                 edge = Edge(struct, entries)
             g.fwd[src][v] = edge
@@ -136,6 +136,16 @@ def checkify_order(order: Order, g: Graph) -> List[int]:
     if len(set(order)) != len(order):
         raise ValueError("Supplied order eliminates a vertex more than once!")
     return order
+
+
+def _try(fn, *structs):
+    """Structure algebra outside what the reference's SparseTensor rules cover (a value-less shape-op edge that
+    reaches an output, the same variable concatenated twice - the reference itself raises or returns a wrongly shaped
+    block there): the scalar entries stay exact, the descriptor is dropped (``None`` = not tracked)."""
+    try:
+        return fn(*structs)
+    except AssertionError:
+        return None
 
 
 def _strip(s: st.Struct) -> st.Struct:
@@ -194,6 +204,41 @@ class StepStats:
     structure_complete: bool = True
 
 
+
+def _structured_product(g: Graph, stats: StepStats, post: Edge, pre: Edge, old: Optional[Edge], p: int, s: int) -> None:
+    """One J[s,p] (+)= J[s,v] J[v,p] with the reference's SparseTensor structure rules (core.py:198-262)."""
+    dag = g.dag
+    pre_s = pre.struct
+    if post.struct.pre and pre.struct.has_val:
+        # unload_pre_transforms: shape-op Jacobians pending on the outgoing edge act on the incoming one
+        pre_s = _strip(pre_s)
+        for t in post.struct.pre:
+            pre_s = st.apply_transform(t, pre_s)
+    if pre.struct.has_val and post.struct.has_val:
+        lhs, rhs = _strip(post.struct), _strip(pre_s)
+        cls = st.mul_class(lhs, rhs)
+        key = f"{post.struct.sparsity_class()}x{pre.struct.sparsity_class()}:{cls}"
+        stats.classes[key] = stats.classes.get(key, 0) + 1
+        out_s = st.mul(lhs, rhs)
+        stats.num_muls += st.num_muls(lhs, rhs)
+        pending = pre.struct.pre
+    elif pre.struct.has_val:
+        out_s, pending = _strip(pre_s), pre.struct.pre
+    else:
+        out_s, pending = _strip(post.struct), pre.struct.pre + post.struct.pre
+    out_s = replace(out_s, pre=pending)
+
+    if old is not None:
+        # fill-in onto an existing edge: flush deferred transforms on both, then add
+        new_m, old_m = st.materialise(out_s), st.materialise(old.struct)
+        out_s = st.add(new_m, old_m)
+        stats.num_adds += st.num_adds(out_s, old_m)
+    entries = _product_entries(dag, post.entries, pre.entries, None if old is None else old.entries)
+    edge = Edge(out_s, entries)
+    g.fwd[p][s] = edge
+    g.bwd[s][p] = edge
+
+
 def eliminate(g: Graph, vertex: int) -> StepStats:
     """Eliminate one vertex (core.py:155-272). Returns the reference's op counts."""
     stats = StepStats(vertex)
@@ -215,35 +260,15 @@ def eliminate(g: Graph, vertex: int) -> StepStats:
                 g.fwd[p][s] = edge
                 g.bwd[s][p] = edge
                 continue
-            pre_s = pre.struct
-            if post.struct.pre and pre.struct.has_val:
-                # unload_pre_transforms: shape-op Jacobians pending on the outgoing edge act on the incoming one
-                pre_s = _strip(pre_s)
-                for t in post.struct.pre:
-                    pre_s = st.apply_transform(t, pre_s)
-            if pre.struct.has_val and post.struct.has_val:
-                lhs, rhs = _strip(post.struct), _strip(pre_s)
-                cls = st.mul_class(lhs, rhs)
-                key = f"{post.struct.sparsity_class()}x{pre.struct.sparsity_class()}:{cls}"
-                stats.classes[key] = stats.classes.get(key, 0) + 1
-                out_s = st.mul(lhs, rhs)
-                stats.num_muls += st.num_muls(lhs, rhs)
-                pending = pre.struct.pre
-            elif pre.struct.has_val:
-                out_s, pending = _strip(pre_s), pre.struct.pre
-            else:
-                out_s, pending = _strip(post.struct), pre.struct.pre + post.struct.pre
-            out_s = replace(out_s, pre=pending)
-
-            if old is not None:
-                # fill-in onto an existing edge: flush deferred transforms on both, then add
-                new_m, old_m = st.materialise(out_s), st.materialise(old.struct)
-                out_s = st.add(new_m, old_m)
-                stats.num_adds += st.num_adds(out_s, old_m)
-            entries = _product_entries(dag, post.entries, pre.entries, None if old is None else old.entries)
-            edge = Edge(out_s, entries)
-            g.fwd[p][s] = edge
-            g.bwd[s][p] = edge
+            try:
+                _structured_product(g, stats, post, pre, old, p, s)
+            except AssertionError:      # outside the reference's structure rules: keep the exact entries only
+                stats.structure_complete = False
+                entries = _product_entries(dag, post.entries, pre.entries, None if old is None else old.entries)
+                edge = Edge(None, entries)
+                g.fwd[p][s] = edge
+                g.bwd[s][p] = edge
+            continue
 
     keep_in_edges = v in g.vo_vertices
     if not keep_in_edges:
@@ -303,5 +328,5 @@ def accumulate(jaxpr: Jaxpr, order: Order, argnums: Sequence[int], division: str
             if edge is None:
                 blocks[(oi, ai)] = (None, {})
             else:
-                blocks[(oi, ai)] = (st.materialise(edge.struct) if edge.struct is not None else None, edge.entries)
+                blocks[(oi, ai)] = (_try(st.materialise, edge.struct) if edge.struct is not None else None, edge.entries)
     return Accumulated(g, vertices, steps, blocks)
