@@ -91,3 +91,71 @@ def test_outputs_that_are_bare_shape_operations(case):
         plan = build_plan(jaxpr, order, tuple(range(len(shapes))))
         rep, _ = replay.replay(plan.blob, xs, plan.n_rows, plan.n_cols)
         assert np.array_equal(rep[0], _autograd(jaxpr, xs, 0))
+
+
+# ---- matrices: matmul, transposes, axis reductions, reshapes, N-D slices / concatenations -----------------------------
+def _random_matrix_function(seed, n_ops):
+    def fn(*xs):
+        r = np.random.default_rng(seed)
+        vals = list(xs)
+        for _ in range(n_ops):
+            kind = r.choice(['un','bi','matmul','T','sum','max','reshape','where','slice','concat','expand','squeeze'])
+            a = vals[r.integers(len(vals))]
+            b = vals[r.integers(len(vals))]
+            v = None
+            if kind == 'un': v = [jnp.tanh, jnp.sin, lambda t: jnp.exp(t*0.3), lambda t: jnp.sqrt(jnp.square(t)+1.)][r.integers(4)](a)
+            elif kind == 'bi':
+                if a.shape == b.shape: v = [lambda p,q:p+q, lambda p,q:p*q, lambda p,q:p-q, lambda p,q: p/(jnp.square(q)+1.), jnp.maximum][r.integers(5)](a,b)
+                elif b.ndim == 0: v = a * b
+                elif a.ndim == 2 and b.ndim == 1 and a.shape[1] == b.shape[0]: v = a + b
+            elif kind == 'matmul':
+                if a.ndim >= 1 and b.ndim >= 1 and a.ndim <= 2 and b.ndim <= 2 and a.shape[-1] == b.shape[0]: v = a @ b
+            elif kind == 'T':
+                if a.ndim == 2: v = a.T
+            elif kind == 'sum':
+                if a.ndim >= 1: v = jnp.sum(a, axis=int(r.integers(a.ndim)))
+            elif kind == 'max':
+                if a.ndim >= 1: v = jnp.max(a, axis=int(r.integers(a.ndim)))
+            elif kind == 'reshape':
+                if a.ndim == 2: v = a.reshape(a.shape[0]*a.shape[1])
+                elif a.ndim == 1 and a.shape[0] % 2 == 0: v = a.reshape(2, a.shape[0]//2)
+            elif kind == 'where':
+                if a.shape == b.shape: v = jnp.where(a > b * 0.9 + 0.05, a * b, a - 2. * b)
+            elif kind == 'slice':
+                if a.ndim == 2 and a.shape[0] >= 2: v = a[1:, :]
+                elif a.ndim == 1 and a.shape[0] >= 2: v = a[:-1]
+            elif kind == 'concat':
+                if a.ndim == b.ndim == 1: v = jnp.concatenate([a, b])
+                elif a.ndim == b.ndim == 2 and a.shape[1] == b.shape[1]: v = jnp.concatenate([a, b], axis=0)
+            elif kind == 'expand':
+                if a.ndim == 1: v = jnp.expand_dims(a, 0)
+            elif kind == 'squeeze':
+                if a.ndim == 2 and 1 in a.shape: v = jnp.squeeze(a)
+            if v is not None and v.size <= 40: vals.append(v)
+        outs = [v for v in vals[len(xs):]][-2:]
+        return tuple(outs)
+    return fn
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_matrix_function_random_order(seed):
+    from oracle import replay
+    rng = np.random.default_rng(5000 + seed)
+    shapes = [(3, 4), (4,), (4, 3), ()][:rng.integers(2, 5)]
+    jaxpr = make_jaxpr(_random_matrix_function(seed, int(rng.integers(6, 22))), shapes)
+    outs = {getattr(o, "eqn_index", None) for o in jaxpr.outvars}
+    if not jaxpr.outvars or None in outs or len(outs) < len(jaxpr.outvars):
+        pytest.skip("degenerate draw: an input or the same value returned twice")
+    eliminable = [i + 1 for i in range(len(jaxpr.eqns)) if i not in outs]
+    xs = [rng.uniform(0.3, 1.5, (4,) + s).astype(np.float32) for s in shapes]
+    for order in ("fwd", "rev", [int(v) for v in rng.permutation(eliminable)]):
+        try:
+            plan = build_plan(jaxpr, order, tuple(range(len(shapes))))
+        except ValueError:
+            assert not isinstance(order, str)
+            continue
+        rep, _ = replay.replay(plan.blob, xs, plan.n_rows, plan.n_cols)
+        for b in range(2):
+            ref = _autograd(jaxpr, xs, b)
+            assert np.isfinite(rep[b]).all()
+            assert np.abs(rep[b] - ref).max() <= 3e-4 * max(1.0, np.abs(ref).max()), (seed, order)
