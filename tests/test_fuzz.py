@@ -159,3 +159,33 @@ def test_random_matrix_function_random_order(seed):
             ref = _autograd(jaxpr, xs, b)
             assert np.isfinite(rep[b]).all()
             assert np.abs(rep[b] - ref).max() <= 3e-4 * max(1.0, np.abs(ref).max()), (seed, order)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,seed", [("vector", s) for s in range(10)] + [("matrix", s) for s in range(8)])
+def test_random_plans_on_the_gpu(built_library, kind, seed):
+    """The same random plans through the run-time specialised and the interpreter kernels against the C replay
+    (libm functions differ by a few ulp between CUDA and glibc)."""
+    from helpers import run_engine
+    from oracle import replay
+    if kind == "vector":
+        rng = np.random.default_rng(1000 + seed)
+        shapes = [(), (3,), (3,), ()][:rng.integers(2, 5)]
+        jaxpr = make_jaxpr(_random_function(seed, int(rng.integers(8, 28))), shapes)
+    else:
+        rng = np.random.default_rng(5000 + seed)
+        shapes = [(3, 4), (4,), (4, 3), ()][:rng.integers(2, 5)]
+        jaxpr = make_jaxpr(_random_matrix_function(seed, int(rng.integers(6, 22))), shapes)
+    outs = {getattr(o, "eqn_index", None) for o in jaxpr.outvars}
+    if not jaxpr.outvars or None in outs or len(outs) < len(jaxpr.outvars):
+        pytest.skip("degenerate draw")
+    xs = [rng.uniform(0.3, 1.5, (300,) + s).astype(np.float32) for s in shapes]
+    plan = build_plan(jaxpr, "rev", tuple(range(len(shapes))))
+    ref_j, ref_p = replay.replay(plan.blob, xs, plan.n_rows, plan.n_cols)
+    ok = np.isfinite(ref_j).all(axis=(1, 2))
+    scale = np.abs(ref_j).max(axis=(1, 2), keepdims=True) + 1e-30
+    for kernel in ("jit", "interpreter"):
+        jac, primal, used = run_engine(plan, xs, kernel)
+        assert used == kernel
+        assert (np.abs(jac - ref_j) / scale)[ok].max() <= 1e-5, (kind, seed, kernel)
+        np.testing.assert_allclose(primal[ok], ref_p[ok], rtol=1e-5, atol=1e-6)
