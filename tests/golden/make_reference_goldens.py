@@ -200,6 +200,88 @@ def run_random_orders(n_orders=3, n_points=8):
     return out, arrays
 
 
+def _random_vector_function(seed, n_ops):
+    """A seeded random function of scalars, (1,) and (3,) vectors: elementwise rules, sum, dot, slices, concatenate."""
+    def fn(*xs):
+        r = np.random.default_rng(seed)
+        vals = list(xs)
+        for _ in range(n_ops):
+            kind = r.choice(["un", "bi", "bi", "sum", "dot", "slice", "concat", "pow2"])
+            a, b = vals[r.integers(len(vals))], vals[r.integers(len(vals))]
+            v = None
+            if kind == "un":
+                v = [jnp.sin, jnp.cos, jnp.sqrt, jnp.abs, lambda t: -t, jnp.exp, jnp.tanh][r.integers(7)](a)
+            elif kind == "bi":
+                if a is b:
+                    continue
+                if a.shape == b.shape or a.ndim == 0 or b.ndim == 0 or (a.ndim == b.ndim == 1 and 1 in (a.shape[0], b.shape[0])):
+                    v = [lambda p, q: p + q, lambda p, q: p * q, lambda p, q: p - q, lambda p, q: p / q][r.integers(4)](a, b)
+            elif kind == "sum":
+                if a.ndim == 1:
+                    v = jnp.sum(a)
+            elif kind == "dot":
+                if a is not b and a.ndim == b.ndim == 1 and a.shape == b.shape and a.shape[0] > 1:
+                    v = jnp.dot(a, b)
+            elif kind == "slice":
+                if a.ndim == 1 and a.shape[0] == 3:
+                    v = a[int(r.integers(0, 2)):int(r.integers(2, 4))]
+            elif kind == "concat":
+                if a is not b and a.ndim == b.ndim == 1 and a.shape[0] + b.shape[0] <= 4:
+                    v = jnp.concatenate([a, b])
+            elif kind == "pow2":
+                v = a**2
+            if v is not None:
+                vals.append(v)
+        return tuple(vals[len(xs):][-2:])
+    return fn
+
+
+def run_random_functions(wanted=16, n_points=4):
+    """Random functions through the reference, forward and reverse: jaxpr, count_ops, Jacobians.  Draws on which the
+    reference raises (its slice / concatenate rules do for many graphs) or returns wrongly shaped blocks are skipped
+    and counted."""
+    out, arrays, skipped, trial = {}, {}, 0, 0
+    while len(out) < wanted and trial < 400:
+        trial += 1
+        rng = np.random.default_rng(7000 + trial)
+        shapes = [(1,), (3,), (3,), (1,), ()][:rng.integers(2, 6)]
+        fun = _random_vector_function(trial, int(rng.integers(5, 18)))
+        pts = [rng.uniform(0.5, 1.5, (n_points,) + s).astype(np.float32) for s in shapes]
+        args0 = [jnp.array(p[0]) for p in pts]
+        closed = jax.make_jaxpr(fun)(*args0)
+        outvars = closed.jaxpr.outvars
+        produced = {id(e.outvars[0]) for e in closed.jaxpr.eqns}
+        if len(outvars) < 2 or len({id(v) for v in outvars}) < len(outvars) or any(id(v) not in produced for v in outvars):
+            continue
+        argnums = tuple(range(len(shapes)))
+        out_sizes = [int(np.prod(v.aval.shape, dtype=np.int64)) for v in outvars]
+        in_sizes = [int(np.prod(s, dtype=np.int64)) if s else 1 for s in shapes]
+        rec_orders, jac = {}, {}
+        try:
+            for order in ("fwd", "rev"):
+                vals = []
+                for k in range(n_points):
+                    res, aux = graphax.jacve(fun, order=order, argnums=argnums, count_ops=True)(*[jnp.array(p[k]) for p in pts])
+                    vals.append(pack(res, out_sizes, in_sizes))
+                rec_orders[order] = {"num_muls": int(aux["num_muls"]), "num_adds": int(aux["num_adds"]),
+                                     "order_counts": [[int(v), int(c)] for v, c in aux["order_counts"]]}
+                jac[order] = np.stack(vals)
+        except Exception:      # noqa: BLE001  (the reference's own limits)
+            skipped += 1
+            continue
+        if not all(np.isfinite(v).all() for v in jac.values()):
+            continue
+        _, rec = dump_jaxpr(closed.jaxpr)
+        rec["orders"] = rec_orders
+        name = f"seed{trial}"
+        out[name] = rec
+        arrays[f"random_functions/{name}/inputs"] = np.concatenate([p.reshape(n_points, -1) for p in pts], axis=1)
+        for order, v in jac.items():
+            arrays[f"random_functions/{name}/jac/{order}"] = v
+    print(f"  {len(out)} random functions recorded, {skipped} draws skipped because the reference raises on them")
+    return {"functions": out, "skipped_reference_raises": skipped, "draws": trial}, arrays
+
+
 def run_g():
     """The reference's only literal known answers: `# fwd: 632, rev: 566` (`examples/randoms.py:91`)."""
     rng = np.random.default_rng(7)
@@ -463,6 +545,9 @@ def main():
             arrays[f"rank_n/{name}/{k}"] = v
     print("random orders", flush=True)
     out["random_orders"], arr = run_random_orders()
+    arrays.update(arr)
+    print("random functions", flush=True)
+    out["random_functions"], arr = run_random_functions()
     arrays.update(arr)
     print("further examples", flush=True)
     out["examples"], arr = run_examples()

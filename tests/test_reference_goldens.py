@@ -392,3 +392,36 @@ def test_random_elimination_orders_against_reference_run(name, key):
     t64 = pack_blocks(j64, len(xs[0]), w.sizes)
     noise = np.abs(ref - t64).max(axis=(1, 2), keepdims=True)
     assert (np.abs(rep - ref) <= parity_bound(ref) + 2 * noise).all()
+
+
+@pytest.mark.parametrize("name", list(RUN["random_functions"]["functions"]))
+def test_random_functions_against_reference_run(name):
+    """Seeded random functions of scalars and small vectors (elementwise rules, sum, dot, slices, concatenate), rebuilt
+    from the jaxpr the reference traced: `count_ops` totals and per-vertex counts identical, oracle values bit-exact,
+    plan replay inside the parity bound, forward and reverse."""
+    from graphax_b200.plan import build_plan
+    from helpers import jaxpr_from_record
+    rec = RUN["random_functions"]["functions"][name]
+    jaxpr = jaxpr_from_record(rec)
+    flat = ARR[f"random_functions/{name}/inputs"]
+    xs, sizes, off = [], [], 0
+    for shape in rec["in_shapes"]:
+        size = int(np.prod(shape, dtype=np.int64)) if shape else 1
+        xs.append(np.ascontiguousarray(flat[:, off:off + size].reshape((len(flat),) + tuple(shape))))
+        sizes.append(size)
+        off += size
+    argnums = tuple(range(len(xs)))
+    for order in ("fwd", "rev"):
+        ro = rec["orders"][order]
+        ref32 = ARR[f"random_functions/{name}/jac/{order}"]
+        jac, _, aux = vo.jacve(jaxpr, order, argnums, xs, np.float32)
+        assert (aux["num_muls"], aux["num_adds"]) == (ro["num_muls"], ro["num_adds"])
+        assert [list(c) for c in aux["order_counts"]] == ro["order_counts"]
+        # bit for bit up to the sign of exact zeros (a structurally zero entry the oracle computes as -0.0 * x)
+        assert (bits(pack_blocks(jac, len(flat), sizes) + 0.0) == bits(ref32 + 0.0)).all()
+        plan = build_plan(jaxpr, order, argnums)
+        assert (plan.stats["num_muls"], plan.stats["num_adds"]) == (ro["num_muls"], ro["num_adds"])
+        assert [list(c) for c in plan.stats["order_counts"]] == ro["order_counts"]
+        rep, _ = replay.replay(plan.blob, xs, plan.n_rows, plan.n_cols)
+        ref = ref32.astype(np.float64)
+        assert (np.abs(rep - ref) <= 3 * parity_bound(ref)).all(), float((np.abs(rep - ref) / parity_bound(ref)).max())
