@@ -202,7 +202,7 @@ def run_gpu_arm(args) -> None:
     import torch.distributed as dist
     import graphax_b200 as gx
     from graphax_b200 import runtime
-    from graphax_b200.sharding import init_process_group
+    from graphax_b200.sharding import bind_to_local_numa_node, init_process_group
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device. graphax_b200 has no CPU fallback (use --impl reference for the CPU arm).")
@@ -213,6 +213,7 @@ def run_gpu_arm(args) -> None:
     os.dup2(2, 1)
     rank, local_rank, world = init_process_group("nccl")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_local_numa_node(local_rank) if world > 1 and os.environ.get("GX_NUMA_BIND", "1") == "1" else "off"
     dev = f"cuda:{local_rank}"
     w = WORKLOADS[WORKLOAD]
     batch = args.batch                                   # per GPU (weak scaling)
@@ -379,7 +380,8 @@ def run_gpu_arm(args) -> None:
                        "cache": f"{N_BUFFER_SETS} rotating input/output sets "
                                 f"({N_BUFFER_SETS * plan.bytes_per_jacobian * batch / 1e6:.0f} MB) larger than the 126 MB L2",
                        "launch": (f"CUDA graph of {per_graph} steps per replay" if graph is not None else "one host call per step"),
-                       "parallelism": f"batch sharded over {world} GPU(s), no collective"},
+                       "parallelism": f"batch sharded over {world} GPU(s), no collective",
+                       "host_affinity": numa},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * plan.n_in_scalars * batch,
                     "d2h_bytes_per_step": 4 * plan.n_rows * plan.n_cols * batch, "steps": e2e_steps,
                     "api": f"graphax_b200.vmap(jacve({TITLES[WORKLOAD]}, order, argnums))(*pinned_host_arrays, out=pinned_result)",

@@ -28,6 +28,35 @@ def env_rank() -> Tuple[int, int, int]:
             int(os.environ.get("WORLD_SIZE", "1")))
 
 
+def bind_to_local_numa_node(device: int) -> str:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE pinned host buffers are allocated:
+    page-locked memory is then node-local (first touch), and host<->device copies of the ranks of one box stop
+    crossing the socket interconnect.  Returns a one-line description; a no-op when the topology is not exposed."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(device)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:                 # nvml prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return "numa node unknown (single node or not exposed)"
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return f"numa node {node}: none of its CPUs is available to this process"
+        os.sched_setaffinity(0, allowed)
+        return f"numa node {node}, {len(allowed)} CPUs"
+    except Exception as e:      # noqa: BLE001  (topology files missing in a container, no NVML, ...)
+        return f"not bound ({type(e).__name__})"
+
+
 def init_process_group(backend: str = "nccl"):
     import torch.distributed as dist
     rank, local_rank, world = env_rank()
