@@ -4,7 +4,7 @@ N=${1:-8}
 nvidia-smi topo -m 2>/dev/null | head -14
 for b in 1 0; do
   GX_NUMA_BIND=$b python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
-    --master-port 2951$b bench.py --gpus $N --steps 200 --warmup 5 --other-orders 0 2>/dev/null > /tmp/numa_$b.json
+    --master-port 2951$b bench.py --gpus $N --steps 200 --warmup 5 --no-other-orders 2>/dev/null > /tmp/numa_$b.json
   python - "$b" <<'PY'
 import json, sys
 d = json.loads(open(f"/tmp/numa_{sys.argv[1]}.json").read().strip().splitlines()[-1])
