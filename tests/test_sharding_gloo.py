@@ -53,3 +53,13 @@ def test_two_rank_sharding_reassembles_the_batch(tmp_path):
     ref, _ = replay.replay(plan.blob, w.inputs(batch), plan.n_rows, plan.n_cols, n_threads=1)
     got = np.load(tmp_path / "gathered.npy")
     assert got.shape == ref.shape and np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+def test_numa_binding_is_a_safe_no_op_without_topology():
+    """No NVML / no sysfs topology (this container): the helper reports why and leaves the affinity alone."""
+    import os
+    from graphax_b200.sharding import bind_to_local_numa_node
+    before = os.sched_getaffinity(0)
+    msg = bind_to_local_numa_node(0)
+    assert isinstance(msg, str) and msg
+    assert os.sched_getaffinity(0) <= before and os.sched_getaffinity(0)
