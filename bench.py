@@ -213,7 +213,7 @@ def run_gpu_arm(args) -> None:
     os.dup2(2, 1)
     rank, local_rank, world = init_process_group("nccl")
     torch.cuda.set_device(local_rank)
-    numa = bind_to_local_numa_node(local_rank) if world > 1 and os.environ.get("GX_NUMA_BIND", "1") == "1" else "off"
+    numa = bind_to_local_numa_node(local_rank) if world > 1 and os.environ.get("GX_NUMA_BIND", "0") == "1" else "off"
     dev = f"cuda:{local_rank}"
     w = WORKLOADS[WORKLOAD]
     batch = args.batch                                   # per GPU (weak scaling)
