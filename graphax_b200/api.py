@@ -67,9 +67,15 @@ class JacveFunction:
 
     def __init__(self, fun: Callable, order: EliminationOrder, argnums: Sequence[int], has_aux: bool,
                  count_ops: bool, sparse_representation: bool, order_numbering: str, device: Optional[int],
-                 jit: bool, contract_sums: bool = False, frontend: str = "auto"):
+                 jit: bool, contract_sums: bool = False, frontend: str = "auto", rounding: Optional[str] = None):
+        from .plan import DEFAULT_ROUNDING
         self.fun = fun
         self.frontend = frontend
+        self.rounding = DEFAULT_ROUNDING if rounding is None else rounding
+        if self.rounding not in ("fma", "reference"):
+            raise ValueError("rounding must be 'fma' or 'reference'")
+        if contract_sums and self.rounding == "reference":
+            raise ValueError("contract_sums changes the association of the edge sums: use rounding='fma' with it")
         self.contract_sums = bool(contract_sums)
         self.order = order if isinstance(order, str) else [int(o) for o in order]
         self.argnums = tuple(int(a) for a in (argnums if isinstance(argnums, (tuple, list, range)) else (argnums,)))
@@ -96,7 +102,8 @@ class JacveFunction:
             order = self.order
             if not isinstance(order, str) and self.order_numbering == "vmap":
                 order = jaxpr.translate_vmap_order(order)
-            plan = build_plan(jaxpr, order, self.argnums, with_primal=True, contract=self.contract_sums)
+            plan = build_plan(jaxpr, order, self.argnums, with_primal=True, contract=self.contract_sums,
+                              rounding=self.rounding)
             plan.jaxpr = jaxpr
             self._plans[key] = plan
         return plan
@@ -449,19 +456,23 @@ class JacveFunction:
 def jacve(fun: Callable, order: EliminationOrder, argnums: Sequence[int] = (0,), has_aux: bool = False,
           count_ops: bool = False, sparse_representation: bool = False, *, order_numbering: str = "per_sample",
           device: Optional[int] = None, jit: bool = True, contract_sums: bool = False,
-          frontend: str = "auto") -> JacveFunction:
+          frontend: str = "auto", rounding: Optional[str] = None) -> JacveFunction:
     """Jacobian of ``fun`` w.r.t. ``argnums`` by vertex elimination in the given ``order``.
 
     ``order``: ``"fwd"``/``"forward"``, ``"rev"``/``"reverse"`` or a sequence of 1-based vertex ids
     (positions of the equations of the traced function, as in the reference).  ``order_numbering="vmap"``
     accepts ids written against ``jacve(jax.vmap(fun))`` (reference ``example_test.py:150-166``).
+    ``rounding``: ``"reference"`` evaluates the reference's own sequence of rounded float32 operations (separate
+    multiply and add per ``J[s,p] += J[s,v] J[v,p]``, IEEE divisions): bit-identical to the unfused reference
+    algorithm; ``"fma"`` contracts product-and-add pairs into FMAs and divides through one reciprocal (fewer
+    instructions, a few ulp per operation away from the reference).  Default: ``plan.DEFAULT_ROUNDING``.
     ``contract_sums=True`` trades the reference's association of the edge sums for 6-12 % fewer instructions
     (``plan._contract_sums``); off by default so results follow the reference's summation order.
     ``frontend``: ``"native"`` traces ``fun`` with the engine's own ``jnp`` stand-in, ``"jax"`` with
     ``jax.make_jaxpr`` (functions written against the real ``jax.numpy``; needs JAX), ``"auto"`` tries both.
     """
     return JacveFunction(fun, order, argnums, has_aux, count_ops, sparse_representation, order_numbering,
-                         device, jit, contract_sums, frontend)
+                         device, jit, contract_sums, frontend, rounding)
 
 
 def vmap(jacfun: JacveFunction, in_axes: int = 0) -> Callable:

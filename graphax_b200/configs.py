@@ -63,8 +63,13 @@ class Workload:
     def order_names(self) -> List[str]:
         return list(self.orders) + list(self.vmap_orders)
 
-    def plan(self, order_key: str, with_primal: bool = True, division: str = "reciprocal") -> Plan:
-        return _plan(self.name, order_key, with_primal, division)
+    def plan(self, order_key: str, with_primal: bool = True, division: str = None, rounding: str = None) -> Plan:
+        if rounding is None:
+            from .plan import DEFAULT_ROUNDING
+            rounding = "fma" if division == "reciprocal" else DEFAULT_ROUNDING
+        if division is None:
+            division = "ieee" if rounding == "reference" else "reciprocal"
+        return _plan(self.name, order_key, with_primal, division, rounding)
 
     def inputs(self, batch: int, start: int = 0, seed: int = SEED) -> List[np.ndarray]:
         """float32 arrays [batch, *shape] (rank-0 arguments -> [batch])."""
@@ -123,9 +128,10 @@ def _jaxpr(name: str) -> Jaxpr:
 
 
 @lru_cache(maxsize=None)
-def _plan(name: str, order_key: str, with_primal: bool, division: str) -> Plan:
+def _plan(name: str, order_key: str, with_primal: bool, division: str, rounding: str = "fma") -> Plan:
     w = get_workload(name)
-    return build_plan(w.jaxpr(), w.order(order_key), w.argnums, with_primal=with_primal, division=division)
+    return build_plan(w.jaxpr(), w.order(order_key), w.argnums, with_primal=with_primal, division=division,
+                      rounding=rounding)
 
 
 def named_plans() -> List[Tuple[str, Plan]]:
@@ -135,4 +141,5 @@ def named_plans() -> List[Tuple[str, Plan]]:
         for key in w.order_names():
             for division in ("reciprocal", "ieee"):
                 out.append((f"{w.name}:{key}:{division}", w.plan(key, division=division)))
+            out.append((f"{w.name}:{key}:reference", w.plan(key, rounding="reference")))
     return out

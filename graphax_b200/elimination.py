@@ -58,8 +58,8 @@ class Graph:
         return -(var.input_index + 1) if var.input_index is not None else var.eqn_index + 1
 
 
-def build_graph(jaxpr: Jaxpr, division: str = "ieee") -> Graph:
-    dag = Dag()
+def build_graph(jaxpr: Jaxpr, division: str = "ieee", fuse: bool = True) -> Graph:
+    dag = Dag(fuse=fuse)
     env: Dict[int, Vec] = {}
     k = 0
     for var in jaxpr.invars:
@@ -312,9 +312,11 @@ class Accumulated:
         return sum(s.scalar_adds for s in self.steps)
 
 
-def accumulate(jaxpr: Jaxpr, order: Order, argnums: Sequence[int], division: str = "ieee") -> Accumulated:
-    """``vertex_elimination_jaxpr`` minus densification (core.py:522-562)."""
-    g = build_graph(jaxpr, division)
+def accumulate(jaxpr: Jaxpr, order: Order, argnums: Sequence[int], division: str = "ieee",
+               fuse: bool = True) -> Accumulated:
+    """``vertex_elimination_jaxpr`` minus densification (core.py:522-562).  ``fuse=False``: no FMA nodes, every
+    ``J[s,p] += J[s,v] J[v,p]`` is a rounded product followed by a rounded sum (the reference's own rounding)."""
+    g = build_graph(jaxpr, division, fuse)
     for o in jaxpr.outvars:
         if not isinstance(o, Var) or o.eqn_index is None:
             raise NotImplementedError("outputs that are inputs or constants are not supported")

@@ -61,7 +61,10 @@ def _f32_from_fraction(x: Fraction) -> np.float32:
 class Dag:
     """Hash-consed scalar expression DAG. Node ids are dense ints."""
 
-    def __init__(self) -> None:
+    def __init__(self, fuse: bool = True) -> None:
+        # fuse=False ("reference" rounding): every product-and-add is two rounded operations, mul then add, like
+        # the reference's separate jnp multiply and add (core.py:210, 262-272); no FMA node is ever created
+        self.fuse = bool(fuse)
         self.op: List[str] = []
         self.args: List[Tuple[int, ...]] = []
         self.cval: List[Optional[np.float32]] = []     # value for const nodes
@@ -138,6 +141,8 @@ class Dag:
                 return self.emit("neg", x)
             if self._is(x, -1.0):
                 return self.emit("neg", y)
+        if op == "fma" and not self.fuse:
+            return self.emit("add", self.emit("mul", a[0], a[1]), a[2])
         if op == "fma":
             x, y, c = a
             for p, q in ((x, y), (y, x)):

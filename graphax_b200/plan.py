@@ -38,6 +38,9 @@ from .elimination import Accumulated, Graph, accumulate
 from .lowering import OP, Dag
 from .tracer import Jaxpr, Var
 
+# Where plans round unless the caller says otherwise (see build_plan): "reference" = the reference's own sequence of
+# rounded operations, "fma" = contracted.
+DEFAULT_ROUNDING = "fma"
 MAGIC = 0x4C505847
 VERSION = 1
 FLAG_HAS_PRIMAL = 1
@@ -76,6 +79,7 @@ class Plan:
     stats: Dict[str, object] = field(default_factory=dict)
     structure: Dict[str, object] = field(default_factory=dict)
     division: str = "reciprocal"
+    rounding: str = "fma"
 
     @property
     def key(self) -> str:
@@ -311,17 +315,38 @@ def _reschedule_for_ilp(dag: Dag, sched: List[int], limit: int, window: int) -> 
 
 
 def build_plan(jaxpr: Jaxpr, order, argnums: Sequence[int], with_primal: bool = True,
-               division: str = "reciprocal", schedule: str = "pressure", contract: bool = False) -> Plan:
-    """Lower (jaxpr, order, argnums) to a plan. ``division`` selects how x/y and its partials are
-    evaluated (``lowering.lower_eqn``): "reciprocal" (default, one IEEE reciprocal + multiplies) or
-    "ieee" (the reference's formulas verbatim, three IEEE divisions).  ``contract=True`` additionally folds
-    additions into the multiply chains feeding them (``_contract_sums``): 6-12 % fewer instructions, but a
-    different association of the sums than the reference's, so it is opt-in."""
+               division: Optional[str] = None, schedule: str = "pressure", contract: bool = False,
+               rounding: Optional[str] = None) -> Plan:
+    """Lower (jaxpr, order, argnums) to a plan.
+
+    ``rounding`` fixes where the plan rounds:
+
+    * ``"reference"`` - the reference's own sequence of rounded operations: every ``J[s,p] += J[s,v] J[v,p]`` is a
+      rounded product followed by a rounded sum (``post_val * pre_val`` then ``+=``, core.py:210, 262-272; no FMA
+      contraction), contractions sum their products in ascending index order, and ``x/y`` with its partials is the
+      three IEEE divisions of primitives.py:197-199.  Results are bit-identical to the unfused float32 evaluation
+      of the reference algorithm (``oracle/ve_numpy.py``) up to the sign of exact zeros.
+    * ``"fma"`` - product-and-add pairs are contracted into FMAs (one rounding instead of two) and, by default,
+      ``x/y`` is lowered through one reciprocal (``division="reciprocal"``).  Fewer operations; agrees with the
+      reference to a few ulp per operation, which an ill-conditioned elimination order can amplify.
+
+    ``division`` ("reciprocal" | "ieee", ``lowering.lower_eqn``) defaults to "reciprocal" for ``rounding="fma"`` and
+    must be "ieee" for ``rounding="reference"``.  ``contract=True`` additionally folds additions into the multiply
+    chains feeding them (``_contract_sums``): 6-12 % fewer instructions, but a different association of the sums
+    than the reference's, so it is opt-in (``rounding="fma"`` only)."""
+    if rounding is None:
+        rounding = "fma" if (contract or division == "reciprocal") else DEFAULT_ROUNDING
+    if rounding not in ("fma", "reference"):
+        raise ValueError("rounding must be 'fma' or 'reference'")
+    if division is None:
+        division = "ieee" if rounding == "reference" else "reciprocal"
+    if rounding == "reference" and (division != "ieee" or contract):
+        raise ValueError("rounding='reference' implies division='ieee' and contract=False")
     argnums = [int(a) for a in argnums]
     for a in argnums:
         if not 0 <= a < len(jaxpr.invars):
             raise ValueError(f"argnum {a} out of range for a function of {len(jaxpr.invars)} arguments")
-    acc = accumulate(jaxpr, order, argnums, division)
+    acc = accumulate(jaxpr, order, argnums, division, fuse=(rounding == "fma"))
     g, dag = acc.graph, acc.graph.dag
 
     in_sizes = [v.size for v in jaxpr.invars]
@@ -381,6 +406,7 @@ def build_plan(jaxpr: Jaxpr, order, argnums: Sequence[int], with_primal: bool = 
 
     plan = Plan(in_sizes, out_sizes, argnums, n_rows, n_cols, list(acc.order), dag, ssa, tile, primal_nodes)
     plan.division = division
+    plan.rounding = rounding
     _allocate_and_serialise(plan, with_primal)
     _collect_stats(plan, acc)
     return plan

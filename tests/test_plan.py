@@ -199,6 +199,16 @@ def test_generated_source_shares_sincos_and_uses_checked_reciprocals():
     from graphax_b200.codegen import emit_source
     src = emit_source(WORKLOADS["robotarm"].plan("rev"), nvrtc=True)
     assert src.count("sincosf(") == 6                       # six joint angles, each needs sin and cos
-    src = emit_source(WORKLOADS["roe3d"].plan("mixed"), nvrtc=True)
-    assert src.count("gx_rcp<kPrecise>(") == 9 and src.count("gx_sqrt<kPrecise>(") == 3
-    assert "__frcp_rn(v" not in src.split("template <bool kPrecise>\n__device__ __forceinline__ unsigned gx_body")[1].split("return unsafe;")[0]
+    src = emit_source(WORKLOADS["roe3d"].plan("mixed", rounding="fma"), nvrtc=True)
+    body = src.split("template <bool kPrecise>\n__device__ __forceinline__ unsigned gx_body")[1].split("return (kPrecise")[0]
+    assert body.count("gx_rcp<kPrecise>(") == 9 and body.count("gx_sqrt<kPrecise>(") == 3
+    assert "__frcp_rn(v" not in body and "__fdiv_rn(" not in body
+    # every operand of a checked operation is folded into the running range exactly once, two per instruction
+    # (squares of an already checked denominator need no check of their own)
+    assert 8 <= 2 * body.count("gx_chk2(") + body.count("gx_chk1(") <= 12
+    # the reference rounding: no FMA outside the division / square-root sequences, three divisions per x/y,
+    # one shared reciprocal per denominator
+    src = emit_source(WORKLOADS["roe3d"].plan("mixed", rounding="reference"), nvrtc=True)
+    body = src.split("template <bool kPrecise>\n__device__ __forceinline__ unsigned gx_body")[1].split("return (kPrecise")[0]
+    assert "__fmaf_rn(" not in body and "__fdiv_rn(" not in body
+    assert body.count("gx_div<kPrecise>(") == 39 and body.count("gx_rcp<kPrecise>(") == 16

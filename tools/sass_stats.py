@@ -24,10 +24,15 @@ def main():
     ap.add_argument("--min-blocks", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--keep", default="")
+    ap.add_argument("--rounding", default="fma", choices=["fma", "reference"])
+    ap.add_argument("--checked-fast", type=int, default=-1)
     args = ap.parse_args()
     from graphax_b200 import codegen
     from graphax_b200.configs import get_workload
-    plan = get_workload(args.workload).plan(args.order)
+    plan = get_workload(args.workload).plan(args.order, rounding=args.rounding)
+    if args.checked_fast >= 0:
+        import os
+        os.environ["GX_CHECKED_FAST"] = str(args.checked_fast)
     src = codegen.emit_source(plan, nvrtc=False, threads=args.threads, min_blocks=args.min_blocks)
     with tempfile.TemporaryDirectory() as d:
         cu = Path(d) / "k.cu"

@@ -44,7 +44,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workloads", default="roe3d")
     ap.add_argument("--orders", default="")
-    ap.add_argument("--divisions", default="reciprocal,ieee")
+    ap.add_argument("--divisions", default="reciprocal,ieee",
+                    help="comma list of reciprocal / ieee (fma rounding) / reference (the reference's own rounding)")
     ap.add_argument("--threads", default="64,128,256")
     ap.add_argument("--min-blocks", default="2,3,4,5,6")
     ap.add_argument("--out-stages", default="2,1")
@@ -66,10 +67,14 @@ def main():
             for division, sched in [(d, sc) for d in args.divisions.split(",") for sc in (args.schedules.split(",") if args.schedules else [""])]:
                 if sched or args.contract:
                     from graphax_b200.plan import build_plan
-                    plan = build_plan(w.jaxpr(), w.order(order), w.argnums, division=division,
-                                      schedule=sched or "pressure", contract=bool(args.contract))
+                    plan = build_plan(w.jaxpr(), w.order(order), w.argnums, schedule=sched or "pressure",
+                                      contract=bool(args.contract),
+                                      **({"rounding": "reference"} if division == "reference" else
+                                         {"division": division, "rounding": "fma"}))
+                elif division == "reference":
+                    plan = w.plan(order, rounding="reference")
                 else:
-                    plan = w.plan(order, division=division)
+                    plan = w.plan(order, division=division, rounding="fma")
                 nsets = 4
                 sets = [([torch.from_numpy(x).cuda() for x in host],
                          torch.empty((batch, plan.n_rows, plan.n_cols), device="cuda")) for _ in range(nsets)]
@@ -133,7 +138,10 @@ def main():
     Path(args.out).parent.mkdir(parents=True, exist_ok=True)
     Path(args.out).write_text(json.dumps({"results": results, "best": best}, indent=1))
     if args.write:
-        (ROOT / "graphax_b200" / "tuning.json").write_text(json.dumps(best, indent=1))
+        path = ROOT / "graphax_b200" / "tuning.json"
+        merged = json.loads(path.read_text()) if path.exists() else {}
+        merged.update(best)
+        path.write_text(json.dumps(merged, indent=1))
 
 
 if __name__ == "__main__":
