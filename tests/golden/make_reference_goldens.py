@@ -495,6 +495,50 @@ def run_rank_n(name, n_points=2):
     return rec, arrays
 
 
+def run_mlp_batched(batch=12, widths=(6, 10, 4)):
+    """The batched MLP of the reference's `test_vmap_NeuralNetwork` (example_test.py:204-215: the per-sample network
+    under `jax.vmap(in_axes=(0, None, None, None, None, 0))`, summed to a scalar loss) at NON-SQUARE widths, so that
+    the shape comparisons in the reference's `_swap_axes` (sparse/tensor.py:529-569) are unambiguous: weight
+    Jacobians of a scalar loss through `_mixed_mul` contractions over the batch.  This pins the tensor-valued path
+    (graphax_b200/dense.py + oracle/dense_numpy.py) to a run of the reference's own code."""
+    from functools import partial
+    n_in, n_hidden, n_out = widths
+
+    @partial(jax.vmap, in_axes=(0, None, None, None, None, 0))
+    def NeuralNetwork(x, W1, b1, W2, b2, y):
+        y1 = W1 @ x
+        z1 = y1 + b1
+        a1 = jnp.tanh(z1)
+        y2 = W2 @ a1
+        z2 = y2 + b2
+        return 0.5*(jnp.tanh(z2) - y)**2
+
+    def f(x, W1, b1, W2, b2, y):
+        out = NeuralNetwork(x, W1, b1, W2, b2, y)
+        return out.sum()
+
+    rng = np.random.default_rng(23)
+    shapes = [(batch, n_in), (n_hidden, n_in), (n_hidden,), (n_out, n_hidden), (n_out,), (batch, n_out)]
+    args = [(rng.standard_normal(sh) * sc).astype(np.float32) for sh, sc in
+            zip(shapes, (1.0, n_in ** -0.5, 0.1, n_hidden ** -0.5, 0.1, 1.0))]
+    argnums = (1, 2, 3, 4)
+    closed = jax.make_jaxpr(f)(*[jnp.array(a) for a in args])
+    rec = {"function": "sum(vmap(NeuralNetwork, in_axes=(0, None, None, None, None, 0))) (example_test.py:204-215)",
+           "in_shapes": [list(sh) for sh in shapes], "argnums": list(argnums), "n_eqns": len(closed.jaxpr.eqns),
+           "primitives": [e.primitive.name for e in closed.jaxpr.eqns], "orders": {}}
+    arrays = {f"in{i}": a for i, a in enumerate(args)}
+    for order in ("fwd", "rev"):
+        (loss, grads), = [graphax.jacve(f, order=order, argnums=argnums, has_aux=True)(*[jnp.array(a) for a in args])]
+        _, aux = graphax.jacve(f, order=order, argnums=argnums, count_ops=True)(*[jnp.array(a) for a in args])
+        rec["orders"][order] = {"num_muls": int(aux["num_muls"]), "num_adds": int(aux["num_adds"])}
+        arrays[f"loss/{order}"] = np.asarray(loss, np.float32)
+        for a, g in zip(argnums, grads):
+            assert tuple(np.shape(g)) == tuple(shapes[a]), (np.shape(g), shapes[a])
+            arrays[f"grad{a}/{order}"] = np.asarray(g, np.float32)
+        print(f"  mlp_batched:{order}: muls {aux['num_muls']} adds {aux['num_adds']} loss {float(loss):.6f}")
+    return rec, arrays
+
+
 def run_f(n_points=2):
     """`examples/randoms.py:f` (80 equations on vectors and matrices: dot_general in four layouts, transpose, reshape,
     squeeze, reduce_max / reduce_min, slice, stop_gradient; its test is commented out in the reference).  It calls
@@ -564,6 +608,11 @@ def main():
     out["rank_n_recorded"] = {"f": rec}
     for k, v in arr.items():
         arrays[f"rank_n_recorded/f/{k}"] = v
+    print("mlp_batched", flush=True)
+    rec, arr = run_mlp_batched()
+    out["mlp_batched"] = rec
+    for k, v in arr.items():
+        arrays[f"mlp_batched/{k}"] = v
     print("roe3d_vmap", flush=True)
     rec, arr = run_roe3d_vmapped()
     out["workloads"]["roe3d_vmap"] = rec

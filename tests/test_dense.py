@@ -29,6 +29,38 @@ def test_dense_oracle_matches_independent_autodiff():
         assert np.abs(g - ti.grad.numpy()).max() < 1e-12
 
 
+def _reference_mlp():
+    """Weight Jacobians computed by the reference's own code for the batched MLP of its test_vmap_NeuralNetwork
+    (example_test.py:204-215) at non-square widths 6 -> 10 -> 4, batch 12 (tests/golden/make_reference_goldens.py)."""
+    import json
+    from helpers import GOLDEN
+    arr = np.load(GOLDEN / "reference_run.npz")
+    rec = json.loads((GOLDEN / "reference_run.json").read_text())["mlp_batched"]
+    args = [arr[f"mlp_batched/in{i}"] for i in range(6)]
+    ref = {o: ([arr[f"mlp_batched/grad{a}/{o}"] for a in (1, 2, 3, 4)], float(arr[f"mlp_batched/loss/{o}"]))
+           for o in ("fwd", "rev")}
+    return rec, args, ref
+
+
+def test_dense_oracle_matches_reference_run():
+    """The tensor-level oracle against the reference run: same loss bit for bit, weight Jacobians within float32
+    summation-order noise (3e-7 of max|J|) of BOTH the reference's forward and reverse results, which the fp64
+    evaluation of the oracle confirms to the same level."""
+    from oracle import dense_numpy as dn
+    rec, args, ref = _reference_mlp()
+    assert rec["primitives"].count("dot_general") == 2 and rec["argnums"] == [1, 2, 3, 4]
+    jaxpr = make_jaxpr(MLP_loss, [a.shape for a in args])
+    g32, l32 = dn.jacve_rev(jaxpr, (1, 2, 3, 4), args, np.float32)
+    g64, _ = dn.jacve_rev(jaxpr, (1, 2, 3, 4), [a.astype(np.float64) for a in args], np.float64)
+    for order in ("fwd", "rev"):
+        grads, loss = ref[order]
+        assert np.float32(l32) == np.float32(loss)
+        for r, g, gg in zip(grads, g32, g64):
+            scale = np.abs(r).max()
+            assert np.abs(r - g.reshape(r.shape)).max() <= 5e-7 * scale
+            assert np.abs(r - gg.reshape(r.shape)).max() <= 5e-7 * scale
+
+
 def test_dense_plan_structure():
     from graphax_b200.dense import build_dense_plan
     jaxpr = make_jaxpr(MLP_loss, [(256, 128), (256, 128), (256,), (128, 256), (128,), (256, 128)])
