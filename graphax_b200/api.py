@@ -67,8 +67,12 @@ class JacveFunction:
 
     def __init__(self, fun: Callable, order: EliminationOrder, argnums: Sequence[int], has_aux: bool,
                  count_ops: bool, sparse_representation: bool, order_numbering: str, device: Optional[int],
-                 jit: bool, contract_sums: bool = False, frontend: str = "auto", rounding: Optional[str] = None):
+                 jit: bool, contract_sums: bool = False, frontend: str = "auto", rounding: Optional[str] = None,
+                 precision: Optional[str] = None):
         from .plan import DEFAULT_ROUNDING
+        if precision not in (None, "bf16", "fp32"):
+            raise ValueError("precision must be 'bf16', 'fp32' or None")
+        self.precision = precision
         self.fun = fun
         self.frontend = frontend
         self.rounding = DEFAULT_ROUNDING if rounding is None else rounding
@@ -159,7 +163,8 @@ class JacveFunction:
         device = self.device if self.device is not None else torch.cuda.current_device()
         tensors = [a if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a, dtype=np.float32)) for a in args]
         tensors = [t.to(f"cuda:{device}") for t in tensors]
-        out = dense_jacve(self.fun, self.order, self.argnums, *tensors, has_aux=self.has_aux, device=device)
+        out = dense_jacve(self.fun, self.order, self.argnums, *tensors, has_aux=self.has_aux, device=device,
+                          precision=self.precision, frontend=self.frontend)
         if self.has_aux:
             primal, grads = out
             return primal, (grads if len(self.argnums) > 1 else grads[0])
@@ -456,7 +461,7 @@ class JacveFunction:
 def jacve(fun: Callable, order: EliminationOrder, argnums: Sequence[int] = (0,), has_aux: bool = False,
           count_ops: bool = False, sparse_representation: bool = False, *, order_numbering: str = "per_sample",
           device: Optional[int] = None, jit: bool = True, contract_sums: bool = False,
-          frontend: str = "auto", rounding: Optional[str] = None) -> JacveFunction:
+          frontend: str = "auto", rounding: Optional[str] = None, precision: Optional[str] = None) -> JacveFunction:
     """Jacobian of ``fun`` w.r.t. ``argnums`` by vertex elimination in the given ``order``.
 
     ``order``: ``"fwd"``/``"forward"``, ``"rev"``/``"reverse"`` or a sequence of 1-based vertex ids
@@ -466,13 +471,18 @@ def jacve(fun: Callable, order: EliminationOrder, argnums: Sequence[int] = (0,),
     multiply and add per ``J[s,p] += J[s,v] J[v,p]``, IEEE divisions): bit-identical to the unfused reference
     algorithm; ``"fma"`` contracts product-and-add pairs into FMAs and divides through one reciprocal (fewer
     instructions, a few ulp per operation away from the reference).  Default: ``plan.DEFAULT_ROUNDING``.
+    ``precision`` applies to the tensor-valued path only (non-batched calls with matrix arguments of >= 4096
+    elements, ``dense.py``): ``"fp32"`` contracts float32 operands to float32 accuracy (three-term bf16 split on the
+    tensor cores), ``"bf16"`` rounds the operands of every contraction to bf16 (BASELINE config 5; error up to 3e-2
+    of max|J|).  ``None``: "bf16" only when every matrix argument already is a bf16 tensor.  That path supports
+    ``order="rev"``, a scalar output, ``has_aux``; ``count_ops`` / ``sparse_representation`` raise there.
     ``contract_sums=True`` trades the reference's association of the edge sums for 6-12 % fewer instructions
     (``plan._contract_sums``); off by default so results follow the reference's summation order.
     ``frontend``: ``"native"`` traces ``fun`` with the engine's own ``jnp`` stand-in, ``"jax"`` with
     ``jax.make_jaxpr`` (functions written against the real ``jax.numpy``; needs JAX), ``"auto"`` tries both.
     """
     return JacveFunction(fun, order, argnums, has_aux, count_ops, sparse_representation, order_numbering,
-                         device, jit, contract_sums, frontend, rounding)
+                         device, jit, contract_sums, frontend, rounding, precision)
 
 
 def vmap(jacfun: JacveFunction, in_axes: int = 0) -> Callable:

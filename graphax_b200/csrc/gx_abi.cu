@@ -397,6 +397,11 @@ struct gx_plan {
   int interp_ctas_per_sm = 1;
   bool interp_large = false;   // program / live values exceed shared memory: gx_interp_large_kernel
   float* d_scratch = nullptr;
+  // the scratch area is shared by every launch of this plan: launches on different streams (the two slots of the
+  // host pipeline, or a caller using several streams) are chained through this event
+  std::mutex scratch_mu;
+  cudaEvent_t scratch_free = nullptr;
+  bool scratch_used = false;
   int* d_in_map = nullptr;
   // AOT kernel
   const GxAotKernel* aot = nullptr;
@@ -411,7 +416,7 @@ struct gx_plan {
   int jit_ctas_per_sm = 0;
   int jit_regs = 0;
 
-  int kernel_kind = GX_KERNEL_INTERPRETER;
+  std::atomic<int> kernel_kind{GX_KERNEL_INTERPRETER};   // read by concurrent launches, set by select / specialize
   std::atomic<uint64_t> launches{0};
 
   // host pipeline resources (lazily created, guarded by host_mu)
@@ -442,7 +447,7 @@ int validate_blob(const void* blob, size_t nbytes, gx_plan* p) {
   if (h.version != GX_BLOB_VERSION) return fail(GX_ERR_BAD_BLOB, "plan blob: unsupported version");
   if (h.total_bytes != nbytes) return fail(GX_ERR_BAD_BLOB, "plan blob: size field does not match buffer length");
   if (h.n_in_arrays == 0 || h.n_in_arrays > GX_MAX_ARRAYS || h.n_out_arrays == 0 || h.n_out_arrays > GX_MAX_ARRAYS)
-    return fail(GX_ERR_BAD_BLOB, "plan blob: between 1 and 16 input and output arrays are supported");
+    return fail(GX_ERR_BAD_BLOB, "plan blob: between 1 and 32 (GX_MAX_ARRAYS) input and output arrays are supported");
   const size_t need = sizeof(gx_blob_header) + 4ull * (2 * h.n_in_arrays + h.n_out_arrays) + 4ull * h.n_consts +
                       sizeof(gx_op) * (size_t)h.n_ops;
   if (need != nbytes) return fail(GX_ERR_BAD_BLOB, "plan blob: section sizes do not add up to the buffer length");
@@ -555,7 +560,7 @@ void fill_args(const gx_plan* p, GxLaunchArgs& a, int64_t batch, const void* con
 
 int launch_on(gx_plan* p, int64_t batch, const void* const* in_ptrs, void* jac, void* primal, cudaStream_t stream) {
   if (batch == 0) return GX_OK;
-  const int kind = p->kernel_kind;
+  const int kind = p->kernel_kind.load(std::memory_order_acquire);
   if (kind == GX_KERNEL_AOT && p->aot) {
     GxLaunchArgs a;
     const int wt = 32 * p->aot->samples_per_thread;
@@ -629,9 +634,21 @@ int launch_on(gx_plan* p, int64_t batch, const void* const* in_ptrs, void* jac, 
     const int grid = (int)std::min<long long>(tiles, (long long)p->sm_count * p->interp_ctas_per_sm);
     a.scratch = p->d_scratch;
     a.in_map = p->d_in_map;
-    if (p->interp_large)
+    if (p->interp_large) {
+      // live values of CTA b sit in scratch[b]: two launches of one plan must not overlap.  Outside stream capture
+      // (a captured stream orders its own launches) every launch waits for the previous one's completion event.
+      std::lock_guard<std::mutex> lock(p->scratch_mu);
+      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(stream, &cap);
+      const bool chain = cap == cudaStreamCaptureStatusNone && p->scratch_free != nullptr;
+      if (chain && p->scratch_used) GX_CUDA(cudaStreamWaitEvent(stream, p->scratch_free, 0));
       gx_interp_large_kernel<GX_LARGE_T><<<grid, GX_LARGE_T, 0, stream>>>(a);
-    else if (T == 128)
+      GX_CUDA(cudaGetLastError());
+      if (chain) {
+        GX_CUDA(cudaEventRecord(p->scratch_free, stream));
+        p->scratch_used = true;
+      }
+    } else if (T == 128)
       gx_interp_kernel<128><<<grid, 128, p->interp_smem, stream>>>(a);
     else if (T == 64)
       gx_interp_kernel<64><<<grid, 64, p->interp_smem, stream>>>(a);
@@ -705,6 +722,7 @@ int gx_plan_create(const void* blob, size_t nbytes, int device, gx_plan** out) {
     p->interp_ctas_per_sm = GX_LARGE_CTAS_PER_SM;
     const size_t ctas = (size_t)p->sm_count * GX_LARGE_CTAS_PER_SM;
     GX_CUDA_P(cudaMalloc(&p->d_scratch, std::max<size_t>(4 * ctas * p->h.n_slots * GX_LARGE_T, 16)));
+    GX_CUDA_P(cudaEventCreateWithFlags(&p->scratch_free, cudaEventDisableTiming));
     std::vector<int> in_map(2 * (size_t)p->h.n_in_scalars);
     size_t k = 0;
     for (unsigned arr = 0; arr < p->h.n_in_arrays; ++arr)
@@ -758,6 +776,7 @@ void gx_plan_destroy(gx_plan* p) {
   if (p->d_ops) cudaFree(p->d_ops);
   if (p->d_consts) cudaFree(p->d_consts);
   if (p->d_scratch) cudaFree(p->d_scratch);
+  if (p->scratch_free) cudaEventDestroy(p->scratch_free);
   if (p->d_in_map) cudaFree(p->d_in_map);
   delete p;
 }
@@ -774,13 +793,14 @@ int gx_plan_info(const gx_plan* p, gx_info* out) {
   out->n_ops = p->h.n_ops;
   out->n_slots = p->h.n_slots;
   out->has_primal = (p->h.flags & GX_FLAG_HAS_PRIMAL) ? 1 : 0;
-  out->kernel_kind = (uint32_t)p->kernel_kind;
-  if (p->kernel_kind == GX_KERNEL_AOT && p->aot) {
+  const int kind_now = p->kernel_kind.load(std::memory_order_acquire);
+  out->kernel_kind = (uint32_t)kind_now;
+  if (kind_now == GX_KERNEL_AOT && p->aot) {
     out->threads = p->aot->threads;
     out->smem_bytes = p->aot->smem_bytes;
     out->ctas_per_sm = p->aot_ctas_per_sm;
     out->regs_per_thread = p->aot_regs;
-  } else if (p->kernel_kind == GX_KERNEL_JIT && p->jit_func) {
+  } else if (kind_now == GX_KERNEL_JIT && p->jit_func) {
     out->threads = p->jit_threads;
     out->smem_bytes = p->jit_smem;
     out->ctas_per_sm = p->jit_ctas_per_sm;

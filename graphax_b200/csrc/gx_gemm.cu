@@ -137,15 +137,79 @@ int gx_gemm_bf16(int M, int N, int K, const void* A, int a_mn, const void* B, in
 // start 16-byte aligned (strides multiples of 8 elements); C must be allocated "tile padded": at least
 // ceil(M/128)*128 rows of ldc >= ceil(N/128)*128 elements, because the epilogue writes whole 128-column tile rows
 // (rows beyond M are never written).  Out-of-range operand elements read as zero (TMA fill).
+static int gemm_launch(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C,
+                       int ldc, int c_is_bf16, int k_splits, bool accumulate, void* stream);
+
 int gx_gemm_bf16_ld(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C,
                     int ldc, int c_is_bf16, int k_splits, void* stream) {
+  return gemm_launch(M, N, K, A, lda, a_mn, B, ldb, b_mn, C, ldc, c_is_bf16, k_splits, false, stream);
+}
+
+// fp32-accurate contraction of fp32 matrices on the bf16 tensor cores.  Every operand is split into three bf16
+// terms, x = x0 + x1 + x2 with x0 = bf16(x), x1 = bf16(x - x0), x2 = bf16(x - x0 - x1) (gx_split3_bf16: 8 + 8 + 8
+// significant bits, the residual is below 2^-24 |x|), and C += sum over i + j <= 2 of A_i B_j^T: six tensor-core
+// products whose bf16 x bf16 terms are exact in the fp32 accumulator; the dropped terms are below 2^-24 |a||b|.
+// C is fp32, caller-zeroed (all six launches add with fp32 reductions); operands as in gx_gemm_bf16_ld.
+int gx_gemm_bf16x3_ld(int M, int N, int K, const void* const* A3, int lda, int a_mn, const void* const* B3, int ldb,
+                      int b_mn, void* C, int ldc, int k_splits, void* stream) {
+  if (!A3 || !B3) {
+    g_gemm_error = "gx_gemm_bf16x3_ld: bad argument";
+    return GX_ERR_BAD_ARG;
+  }
+  static const int terms[6][2] = {{2, 0}, {1, 1}, {0, 2}, {1, 0}, {0, 1}, {0, 0}};   // small contributions first
+  for (int t = 0; t < 6; ++t) {
+    const int rc = gemm_launch(M, N, K, A3[terms[t][0]], lda, a_mn, B3[terms[t][1]], ldb, b_mn, C, ldc, 0,
+                               k_splits < 1 ? 1 : k_splits, true, stream);
+    if (rc != GX_OK) return rc;
+  }
+  return GX_OK;
+}
+
+namespace {
+__global__ void gx_split3_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ o0,
+                                      __nv_bfloat16* __restrict__ o1, __nv_bfloat16* __restrict__ o2, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float x = in[i];
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(h0);              // exact: both share the leading bits
+    const __nv_bfloat16 h1 = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(h1);             // exact
+    o0[i] = h0;
+    o1[i] = h1;
+    o2[i] = __float2bfloat16_rn(r2);
+  }
+}
+}  // namespace
+
+// x (fp32, n elements) -> three bf16 arrays with x0 + x1 + x2 = x up to 2^-24 |x| (see gx_gemm_bf16x3_ld)
+int gx_split3_bf16(const void* in, void* out0, void* out1, void* out2, long long n, void* stream) {
+  if (!in || !out0 || !out1 || !out2 || n <= 0) {
+    g_gemm_error = "gx_split3_bf16: bad argument";
+    return GX_ERR_BAD_ARG;
+  }
+  const int threads = 256;
+  const long long want = (n + threads - 1) / threads;
+  const int blocks = (int)(want < 148LL * 16 ? want : 148LL * 16);
+  gx_split3_bf16_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const float*>(in), static_cast<__nv_bfloat16*>(out0), static_cast<__nv_bfloat16*>(out1),
+      static_cast<__nv_bfloat16*>(out2), n);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    g_gemm_error = std::string("gx_split3_bf16 launch: ") + cudaGetErrorString(e);
+    return GX_ERR_CUDA;
+  }
+  return GX_OK;
+}
+
+static int gemm_launch(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C,
+                       int ldc, int c_is_bf16, int k_splits, bool accumulate, void* stream) {
   if (M <= 0 || N <= 0 || K <= 0 || !A || !B || !C) {
     g_gemm_error = "gx_gemm_bf16_tn: bad argument";
     return GX_ERR_BAD_ARG;
   }
   const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
   if (ldc == 0) ldc = N;
-  if (k_splits < 1 || (k_splits > 1 && c_is_bf16) || ldc % 4 || ldc < (N % BN ? tiles_n * BN : N)) {
+  if (k_splits < 1 || ((k_splits > 1 || accumulate) && c_is_bf16) || ldc % 4 || ldc < (N % BN ? tiles_n * BN : N)) {
     g_gemm_error = "gx_gemm_bf16_tn: split-K needs an fp32 C; ldc must be a multiple of 4 and cover whole 128-column tiles";
     return GX_ERR_UNSUPPORTED;
   }
@@ -186,7 +250,7 @@ int gx_gemm_bf16_ld(int M, int N, int K, const void* A, int lda, int a_mn, const
   args.N = N;
   args.K = K;
   args.ldc = ldc;
-  args.epilogue = k_splits > 1 ? EPI_ATOMIC_F32 : (c_is_bf16 ? EPI_STORE_BF16 : EPI_STORE_F32);
+  args.epilogue = (k_splits > 1 || accumulate) ? EPI_ATOMIC_F32 : (c_is_bf16 ? EPI_STORE_BF16 : EPI_STORE_F32);
   args.k_per_split = k_per_split;
   args.a_mn = a_mn ? 1 : 0;
   args.b_mn = b_mn ? 1 : 0;
@@ -208,7 +272,7 @@ int gx_gemm_bf16_ld(int M, int N, int K, const void* A, int lda, int a_mn, const
   void* params_persistent[] = {&map_a, &map_b, &map_b_half, &args};
   // several waves of tiles: persistent CTAs (one per SM) with a double-buffered accumulator
   const long long tiles = (long long)tiles_n * tiles_m;
-  const bool persistent = k_splits == 1 && tiles > 2LL * sm_count() && gemm_use_persistent();
+  const bool persistent = k_splits == 1 && !accumulate && tiles > 2LL * sm_count() && gemm_use_persistent();
   const void* fn = deep ? (const void*)gx_gemm_tn_kernel_deep : (const void*)gx_gemm_tn_kernel;
   if (persistent) {
     cfg.gridDim = dim3(sm_count());

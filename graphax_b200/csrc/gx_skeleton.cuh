@@ -196,8 +196,10 @@ GX_KERNEL_NAME(const __grid_constant__ GxLaunchArgs args) {
       GX_FOREACH_ARRAY(GX_RD_DIRECT)
 #undef GX_RD_DIRECT
     }
-    // the out stage about to be written was handed to the TMA engine GX_OUT_STAGES iterations ago
-    if (lane == 0) bulk_wait_read<GX_OUT_STAGES - 1>();
+    // the out stage about to be written was handed to the TMA engine GX_OUT_STAGES iterations ago.  Bulk async-groups
+    // are per-thread state and elect.sync does not promise which lane issued (and committed) the stores, so every
+    // lane waits: a lane without outstanding groups falls straight through.
+    bulk_wait_read<GX_OUT_STAGES - 1>();
     __syncwarp();
     // single input stage: every lane has its inputs in registers, the stage can take the next tile already
     if (GX_IN_STAGES == 1 && next < n_bulk && elect_one()) issue_loads(next, 0);
@@ -230,7 +232,7 @@ GX_KERNEL_NAME(const __grid_constant__ GxLaunchArgs args) {
       GX_FOREACH_ARRAY(GX_RD_DIRECT)
 #undef GX_RD_DIRECT
     }
-    if (lane == 0) bulk_wait_read<GX_OUT_STAGES - 1>();
+    bulk_wait_read<GX_OUT_STAGES - 1>();
     __syncwarp();
     gx_body(x, tile_s + lane * GX_TILE, tile_s + (lane + 32) * GX_TILE,
             tile_s + GX_WT * GX_TILE + lane * GX_N_ROWS, tile_s + GX_WT * GX_TILE + (lane + 32) * GX_N_ROWS);
@@ -261,7 +263,7 @@ GX_KERNEL_NAME(const __grid_constant__ GxLaunchArgs args) {
       __syncwarp();  // the stage may be rewritten by the next iteration
     }
   }
-  if (lane == 0) bulk_wait_all();  // shared memory must outlive the stores that read it
+  bulk_wait_all();  // shared memory must outlive the stores that read it (every lane: see bulk_wait_read above)
 }
 
 #ifndef GX_NVRTC

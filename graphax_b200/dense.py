@@ -15,8 +15,12 @@ space the named config needs - a scalar output eliminated in reverse order - at 
 * times a broadcast (bias) edge it is a contraction over the broadcast axis -> column sum;
 * fill-in on an existing edge is ``_sparse_add`` of two dense edges -> fused into the elementwise kernels.
 
-Precision: matrix operands of the contractions are bf16, accumulation and all elementwise arithmetic fp32
-("bf16-in / fp32-accumulate" of BASELINE.json); results (weight Jacobians) are fp32.
+Precision (``precision=``): ``"bf16"`` rounds the matrix operands of every contraction to bf16, accumulation and
+all elementwise arithmetic are fp32 ("bf16-in / fp32-accumulate" of BASELINE.json) - the default when every matrix
+argument already IS a bf16 tensor.  ``"fp32"`` (the default otherwise) keeps the reference's float32 semantics on
+the same tensor cores: every operand is split into three bf16 terms and the contraction is the sum of the six
+leading term products (``gx_gemm_bf16x3_ld``), so results agree with a float32 evaluation to summation-order
+noise instead of bf16 operand rounding (3e-2 of max|J|).  Results (weight Jacobians) are fp32 either way.
 
 Anything else (other orders, vector outputs, rank > 2, batch dimensions) raises ``NotImplementedError``.
 """
@@ -286,10 +290,16 @@ class DenseExecutor:
     round trip.  The contraction of a cotangent with a broadcast (bias) edge, a column sum, is folded into the
     kernel that produces the cotangent (per-thread partial sums + one atomicAdd per column)."""
 
-    def __init__(self, plan: DensePlan, device: int = 0, with_primal: bool = False):
+    def __init__(self, plan: DensePlan, device: int = 0, with_primal: bool = False, precision: str = "bf16"):
         import torch
         from . import runtime
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
         self.plan, self.device, self.rt, self.torch = plan, device, runtime, torch
+        # fp32: contractions run as six products of bf16 split terms (gx_gemm_bf16x3_ld) on fp32 copies of their
+        # operands; no fused epilogues and a single stream (the split terms of a tensor are shared by its readers)
+        self.split = precision == "fp32"
+        self.precision = precision
         self.lib = runtime.load_library()
         self.with_primal = with_primal
         dag = plan.dag
@@ -328,7 +338,7 @@ class DenseExecutor:
         self.launches = 0
         self._ew_meta: Dict[int, tuple] = {}
         self.input_dtypes: Optional[List[str]] = None     # elementwise kernels are compiled once these are known
-        self.fuse = os.environ.get("GX_DENSE_FUSE", "1") != "0"
+        self.fuse = os.environ.get("GX_DENSE_FUSE", "1") != "0" and not self.split
         self.gemm_fused: Dict[int, List[int]] = {}      # gemm node -> elementwise nodes evaluated in its epilogue
         self.fused_into: Dict[int, int] = {}
         if self.fuse:
@@ -343,6 +353,8 @@ class DenseExecutor:
                 self.f32_read.update(l for l in self._leaves_and_expr(n)[0] if l != self.fused_into.get(n))
             elif node.kind in ("colsum", "sumall"):
                 self.f32_read.add(node.args[0])
+        if self.split:
+            self.f32_read.update(self.needs_bf16)
         self.order = [n for n in self.order if n not in self.fused_into]
         self.fused_kernels: Dict[int, object] = {}
         self._fused_meta: Dict[int, tuple] = {}
@@ -360,7 +372,7 @@ class DenseExecutor:
             node = dag.nodes[n]
             if n not in self.materialised:
                 continue
-            if node.kind == "gemm" and n in self.order and self._gemm_geometry(n)[3] > 1:
+            if node.kind == "gemm" and n in self.order and (self._gemm_geometry(n)[3] > 1 or self.split):
                 reserve((n, "f32"), node.shape)
             elif node.kind in ("colsum", "sumall"):
                 reserve((n, "f32"), node.shape)
@@ -369,7 +381,9 @@ class DenseExecutor:
         self.arena_size = off
         self.arena = None
         self.input_stage: Dict[Tuple[int, str], object] = {}
-        self.concurrent = os.environ.get("GX_DENSE_STREAMS", "2") != "1"
+        self.concurrent = os.environ.get("GX_DENSE_STREAMS", "2") != "1" and not self.split
+        self._split_bufs: Dict[int, list] = {}
+        self._split_done: set = set()
         # kernels that add into the arena, and results that nothing downstream reads (side-stream candidates)
         self.arena_users = set()
         for n in self.order:
@@ -654,6 +668,22 @@ class DenseExecutor:
         node = self.plan.dag.nodes[n]
         return self.inputs_bf16[node.input_index] if node.kind == "input" else self._buf(n, "bf16")
 
+    def _split3(self, n: int, stream) -> list:
+        """The three bf16 terms of node n's fp32 value (computed once per step, right before its first reader)."""
+        bufs = self._split_bufs.get(n)
+        src = self._data(n)
+        if bufs is None:
+            bufs = self._split_bufs[n] = [self.torch.zeros(tuple(src.shape), dtype=self.torch.bfloat16, device=src.device)
+                                          for _ in range(3)]
+        if n not in self._split_done:
+            rc = self.lib.gx_split3_bf16(src.data_ptr(), bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr(),
+                                         src.numel(), stream)
+            if rc != 0:
+                raise self.rt.GraphaxB200Error(self.lib.gx_gemm_last_error().decode())
+            self._split_done.add(n)
+            self.launches += 1
+        return bufs
+
     def _launch_node(self, n: int) -> None:
         """Enqueue the kernel(s) that materialise node n on the current stream."""
         torch, dag = self.torch, self.plan.dag
@@ -684,6 +714,18 @@ class DenseExecutor:
             for o in outs[1:]:
                 for extra in self.fused_colsums.get(o, [])[1:]:
                     self._buf(extra, "f32").copy_(self._buf(self.fused_colsums[o][0], "f32"))
+        elif node.kind == "gemm" and self.split:
+            x, y = node.args
+            a3, b3 = self._split3(x, stream), self._split3(y, stream)
+            m, nn, k, splits = self._gemm_geometry(n)
+            out = self._buf(n, "f32")          # in the arena: cleared at the start of the step, all six products add
+            vp = ctypes.c_void_p
+            rc = self.lib.gx_gemm_bf16x3_ld(m, nn, k, (vp * 3)(*[t.data_ptr() for t in a3]), a3[0].shape[1], int(node.tx),
+                                            (vp * 3)(*[t.data_ptr() for t in b3]), b3[0].shape[1], int(node.ty),
+                                            out.data_ptr(), out.shape[1], splits, stream)
+            if rc != 0:
+                raise self.rt.GraphaxB200Error(self.lib.gx_gemm_last_error().decode())
+            self.launches += 6
         elif node.kind == "gemm":
             x, y = node.args
             a, b = self._bf16(x), self._bf16(y)  # op(X) = X^T is read in place as an MN-major operand
@@ -715,7 +757,7 @@ class DenseExecutor:
             leaves, vec = self._ew_meta[n]
             r, c = node.shape[0], _padded(node.shape)[1]      # true rows (column sums), padded width (= row stride)
             o32 = self._buf(n, "f32").data_ptr() if n in self.f32_read else 0
-            o16 = self._buf(n, "bf16").data_ptr() if n in self.needs_bf16 else 0
+            o16 = self._buf(n, "bf16").data_ptr() if (n in self.needs_bf16 and not self.split) else 0
             csum = self._buf(self.fused_colsums[n][0], "f32").data_ptr() if n in self.fused_colsums else 0
             vals = [ctypes.c_void_p(data(l).data_ptr()) for l in leaves]
             vals += [ctypes.c_void_p(o32), ctypes.c_void_p(o16), ctypes.c_void_p(csum), ctypes.c_int(r), ctypes.c_int(c)]
@@ -733,9 +775,12 @@ class DenseExecutor:
         torch, dag = self.torch, self.plan.dag
         stream = torch.cuda.current_stream(self.device).cuda_stream
         self.inputs_f32, self.inputs_bf16 = {}, {}
+        self._split_done = set()
         dts = []
         for i, t in enumerate(inputs):
             t = t.reshape(self.plan.in_shapes[i]).contiguous()
+            if self.split and t.dtype != torch.float32:
+                t = t.float()
             dts.append("bf16" if t.dtype == torch.bfloat16 else "f32")
             if t.dtype == torch.bfloat16:
                 self.inputs_bf16[i] = self._stage_input(i, t, torch.bfloat16)
@@ -755,7 +800,7 @@ class DenseExecutor:
             for g in self.gemm_fused:
                 self._compile_fused(g)
         for i in range(len(inputs)):                # GEMM operands must be bf16
-            if i not in self.inputs_bf16 and any(dag.nodes[n].kind == "input" and dag.nodes[n].input_index == i
+            if not self.split and i not in self.inputs_bf16 and any(dag.nodes[n].kind == "input" and dag.nodes[n].input_index == i
                                                  for n in self.needs_bf16):
                 self.inputs_bf16[i] = self._stage_input(i, inputs[i].reshape(self.plan.in_shapes[i]), torch.bfloat16)
 
@@ -812,14 +857,25 @@ class DenseExecutor:
         return grads, (data(self.plan.primal)[0, 0].reshape(()) if self.with_primal else None)
 
 
-def dense_jacve(fun, order, argnums, *args, has_aux: bool = False, device: int = 0, _cache={}):
+def default_precision(args) -> str:
+    """"bf16" when every matrix argument already is a bf16 tensor (nothing is lost by bf16 operands), else "fp32"."""
+    import torch
+    mats = [a for a in args if getattr(a, "ndim", 0) >= 2]
+    return "bf16" if mats and all(isinstance(a, torch.Tensor) and a.dtype == torch.bfloat16 for a in mats) else "fp32"
+
+
+def dense_jacve(fun, order, argnums, *args, has_aux: bool = False, device: int = 0, precision: Optional[str] = None,
+                frontend: str = "auto", _cache={}):
     """``jacve`` for a scalar function of matrices (reverse order): returns the weight Jacobians as fp32
-    tensors of the arguments' shapes (tuple over ``argnums``; with ``has_aux`` also the function value)."""
+    tensors of the arguments' shapes (tuple over ``argnums``; with ``has_aux`` also the function value).
+    ``precision``: "bf16" (operands of the contractions rounded to bf16) or "fp32" (three-term bf16 split, float32
+    accuracy); default: "bf16" only if every matrix argument is a bf16 tensor."""
     shapes = tuple(tuple(a.shape) for a in args)
-    key = (fun, str(order), tuple(argnums), shapes, device, has_aux)
+    precision = precision or default_precision(args)
+    key = (fun, str(order), tuple(argnums), shapes, device, has_aux, precision)
     if key not in _cache:
-        plan = build_dense_plan(make_jaxpr(fun, shapes), order, argnums)
-        _cache[key] = DenseExecutor(plan, device, with_primal=has_aux)
+        plan = build_dense_plan(make_jaxpr(fun, shapes, frontend), order, argnums)
+        _cache[key] = DenseExecutor(plan, device, with_primal=has_aux, precision=precision)
     ex = _cache[key]
     grads, primal = ex.run(args)
     return (primal, tuple(grads)) if has_aux else tuple(grads)

@@ -33,7 +33,8 @@ EXPORTS = ["gx_plan_create", "gx_plan_destroy", "gx_plan_info", "gx_plan_special
            "gx_plan_select_kernel",
            "gx_jacve_launch", "gx_jacve_host", "gx_last_error", "gx_abi_version", "gx_aot_count", "gx_aot_key",
            "gx_hash_bytes", "gx_gemm_bf16_tn", "gx_gemm_bf16", "gx_gemm_bf16_ld", "gx_transpose_bf16", "gx_gemm_last_error",
-           "gx_jit_compile", "gx_jit_destroy", "gx_jit_launch", "gx_colsum_f32", "gx_gemm_fused_launch"]
+           "gx_jit_compile", "gx_jit_destroy", "gx_jit_launch", "gx_colsum_f32", "gx_gemm_fused_launch",
+           "gx_split3_bf16", "gx_gemm_bf16x3_ld"]
 
 _lib = None
 _lock = threading.Lock()
@@ -101,6 +102,12 @@ def load_library() -> ctypes.CDLL:
         lib.gx_gemm_fused_launch.restype = ctypes.c_int
         lib.gx_colsum_f32.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, vp]
         lib.gx_colsum_f32.restype = ctypes.c_int
+        lib.gx_split3_bf16.argtypes = [vp, vp, vp, vp, ctypes.c_longlong, vp]
+        lib.gx_split3_bf16.restype = ctypes.c_int
+        lib.gx_gemm_bf16x3_ld.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp), ctypes.c_int,
+                                          ctypes.c_int, ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, vp, ctypes.c_int,
+                                          ctypes.c_int, vp]
+        lib.gx_gemm_bf16x3_ld.restype = ctypes.c_int
         _lib = lib
         return lib
 

@@ -83,7 +83,11 @@ int gx_plan_specialize(gx_plan* plan, const char* cuda_source, size_t nbytes, co
  * thread (2 = both samples packed into FFMA2/FMUL2/FADD2 f32x2 instructions). */
 int gx_plan_specialize_opts(gx_plan* plan, const char* cuda_source, size_t nbytes, const char* arch, int threads,
                             int min_blocks, int out_stages, int samples_per_thread);
-/* Force a kernel kind for subsequent launches (GX_KERNEL_INTERPRETER is always valid). */
+/* Force a kernel kind for subsequent launches (GX_KERNEL_INTERPRETER is always valid).  Launching is thread-safe;
+ * gx_plan_specialize* and gx_plan_select_kernel reconfigure the plan and must not run concurrently with launches
+ * of the same plan (configure once, then launch from as many threads / streams as needed).  Plans too large for
+ * shared memory run on an interpreter with one private scratch area per plan: their launches are chained with an
+ * event, i.e. two streams never run the same such plan at the same time. */
 int gx_plan_select_kernel(gx_plan* plan, int kernel_kind);
 
 /* Replaces: the run-time half of `jax.vmap(graphax.jacve(f, order, argnums))(*xs)`, i.e. every
@@ -123,6 +127,13 @@ int gx_gemm_bf16(int M, int N, int K, const void* A, int a_mn, const void* B, in
 int gx_gemm_bf16_ld(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C,
                     int ldc, int c_is_bf16, int k_splits, void* stream);
 int gx_transpose_bf16(int rows, int cols, const void* in, void* out, void* stream);
+/* fp32-accurate contraction for fp32 callers (the reference's parity predicate is rtol 1e-4 / atol 1e-5,
+ * core.py:17-20, which bf16 operand rounding cannot meet): gx_split3_bf16 writes x = x0 + x1 + x2 as three bf16
+ * arrays (residual below 2^-24 |x|), gx_gemm_bf16x3_ld adds sum_{i+j<=2} A_i B_j^T into a caller-zeroed fp32 C
+ * (A3 / B3: the three terms of each operand, same layout rules as gx_gemm_bf16_ld).  Six tensor-core products. */
+int gx_split3_bf16(const void* in, void* out0, void* out1, void* out2, long long n, void* stream);
+int gx_gemm_bf16x3_ld(int M, int N, int K, const void* const* A3, int lda, int a_mn, const void* const* B3, int ldb,
+                      int b_mn, void* C, int ldc, int k_splits, void* stream);
 const char* gx_gemm_last_error(void);
 
 /* Fused elementwise kernels of the tensor-valued path are emitted per plan (graphax_b200/dense.py) and

@@ -96,26 +96,43 @@ def test_tcgen05_gemm(built_library, m, n, k, splits):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("dtype", ["bf16", "f32"])
+@pytest.mark.parametrize("mode", ["bf16", "f32_as_bf16", "fp32"])
 @pytest.mark.parametrize("sizes", [(512, 128, 256, 128), (2048, 256, 1024, 768), (500, 100, 300, 10), (3000, 784, 1000, 10)])
-def test_mlp_weight_jacobians(built_library, dtype, sizes, monkeypatch):
-    """jacve(MLP_loss, 'rev', argnums=(W1, b1, W2, b2)) on the GPU vs the oracle.  The small case runs split-K
-    contractions and separate elementwise kernels, the large one (>= 96 output tiles per contraction) the
-    run-time compiled contractions with fused epilogues; both must also agree with the unfused execution."""
+def test_mlp_weight_jacobians(built_library, mode, sizes, monkeypatch):
+    """jacve(MLP_loss, 'rev', argnums=(W1, b1, W2, b2)) on the GPU vs the oracle.
+
+    * ``bf16``: bf16 matrix arguments (config 5), ``f32_as_bf16``: float32 arguments with ``precision="bf16"``
+      requested explicitly - operands of the contractions are rounded to bf16: tight against the oracle run with
+      the same rounding points, 3e-2 of max|J| against exact arithmetic.  The small cases run split-K contractions
+      and separate elementwise kernels, the large ones (>= 96 output tiles per contraction) the run-time compiled
+      contractions with fused epilogues; both must also agree with the unfused execution.
+    * ``fp32``: float32 arguments, default precision: three-term bf16 split contractions; within the parity bound
+      |dJ| <= 1e-5 max|J| + 1e-5 |J| of the float64 oracle, i.e. float32 accuracy."""
     import torch
-    from graphax_b200 import dense
     from graphax_b200.dense import dense_jacve
     from oracle import dense_numpy as dn
     B, I, H, O = sizes
     args = _mlp_args(B, I, H, O)
     tens = [torch.from_numpy(a).cuda() for a in args]
-    if dtype == "bf16":
+    if mode == "bf16":
         tens = [t.bfloat16() if t.ndim == 2 else t for t in tens]
         args = [t.float().cpu().numpy() for t in tens]              # the oracle sees the same rounded inputs
+    kw = {"precision": "bf16"} if mode == "f32_as_bf16" else {}
     jaxpr = make_jaxpr(MLP_loss, [a.shape for a in args])
-    loss, grads = dense_jacve(MLP_loss, "rev", (1, 2, 3, 4), *tens, has_aux=True)
+    loss, grads = dense_jacve(MLP_loss, "rev", (1, 2, 3, 4), *tens, has_aux=True, **kw)
     torch.cuda.synchronize()
     ref64, loss64 = dn.jacve_rev(jaxpr, (1, 2, 3, 4), [a.astype(np.float64) for a in args], np.float64)
+    ex = [v for k, v in dense_jacve.__kwdefaults__["_cache"].items() if k[3] == tuple(a.shape for a in args)][-1]
+    if mode == "fp32":
+        assert ex.precision == "fp32" and not ex.gemm_fused
+        assert abs(float(loss) - float(loss64)) <= 2e-5 * abs(float(loss64))
+        for g, r in zip(grads, ref64):
+            g = g.cpu().numpy()
+            assert g.shape == r.shape
+            bound = 1e-5 * np.abs(r).max() + 1e-5 * np.abs(r)
+            assert (np.abs(g - r) <= bound).all(), float((np.abs(g - r) / bound).max())
+        return
+    assert ex.precision == "bf16"
     emu, loss_emu = dn.jacve_rev(jaxpr, (1, 2, 3, 4), args, np.float32, bf16_operands=True)
     assert abs(float(loss) - float(loss_emu)) <= 2e-3 * abs(float(loss_emu))
     for g, e, r in zip(grads, emu, ref64):
@@ -124,16 +141,75 @@ def test_mlp_weight_jacobians(built_library, dtype, sizes, monkeypatch):
         scale = np.abs(r).max()
         assert np.abs(g - e).max() <= 2e-3 * scale       # same rounding points as the engine: tight
         assert np.abs(g - r).max() <= 3e-2 * scale       # vs exact arithmetic: bf16 operand rounding
-    ex = [v for k, v in dense_jacve.__kwdefaults__["_cache"].items() if k[3] == tuple(a.shape for a in args)][-1]
     assert ex.gemm_fused or B < 2048                     # the large cases really took the fused path
     if ex.gemm_fused:
         monkeypatch.setenv("GX_DENSE_FUSE", "0")
         dense_jacve.__kwdefaults__["_cache"].clear()
-        _, plain = dense_jacve(MLP_loss, "rev", (1, 2, 3, 4), *tens, has_aux=True)
+        _, plain = dense_jacve(MLP_loss, "rev", (1, 2, 3, 4), *tens, has_aux=True, **kw)
         dense_jacve.__kwdefaults__["_cache"].clear()
         for g, p in zip(grads, plain):
             # same rounding points; only the summation order of column sums / split-K partials differs
             assert float((g - p).abs().max()) <= 1e-4 * float(p.abs().max())
+
+
+@pytest.mark.gpu
+def test_tensor_path_matches_the_reference_run(built_library):
+    """The tcgen05 path against weight Jacobians computed by the reference's own code (batched MLP of the
+    reference's test_vmap_NeuralNetwork at widths 6 -> 10 -> 4, batch 12): float32 arguments take the three-term
+    split contractions and must sit within |dJ| <= 1e-5 max|J| + 1e-5 |J| of the reference's forward AND reverse
+    results; with ``precision="bf16"`` the same call is only good to bf16 operand rounding."""
+    import torch
+    from graphax_b200.dense import dense_jacve
+    rec, args, ref = _reference_mlp()
+    tens = [torch.from_numpy(a).cuda() for a in args]
+    loss, grads = dense_jacve(MLP_loss, "rev", (1, 2, 3, 4), *tens, has_aux=True)
+    torch.cuda.synchronize()
+    for order in ("fwd", "rev"):
+        r_grads, r_loss = ref[order]
+        assert abs(float(loss) - r_loss) <= 1e-5 * abs(r_loss)
+        for g, r in zip(grads, r_grads):
+            g, r = g.cpu().numpy().astype(np.float64), r.astype(np.float64)
+            assert g.shape == r.shape
+            bound = 1e-5 * np.abs(r).max() + 1e-5 * np.abs(r)
+            assert (np.abs(g - r) <= bound).all(), float((np.abs(g - r) / bound).max())
+    _, coarse = dense_jacve(MLP_loss, "rev", (1, 2, 3, 4), *tens, has_aux=True, precision="bf16")
+    worst = max(float(np.abs(g.cpu().numpy() - r).max() / np.abs(r).max()) for g, r in zip(coarse, ref["rev"][0]))
+    assert 1e-5 < worst < 3e-2
+
+
+@pytest.mark.gpu
+def test_split3_contraction(built_library):
+    """gx_split3_bf16 + gx_gemm_bf16x3_ld: C = A B^T of float32 matrices to float32 accuracy on the bf16 tensor cores."""
+    import ctypes
+    import torch
+    from graphax_b200 import runtime
+    lib = runtime.load_library()
+    torch.manual_seed(5)
+    m, n, k = 256, 384, 1000
+    a = torch.randn(m, k, device="cuda")
+    b = torch.randn(n, k, device="cuda") * 3.0
+    stream = torch.cuda.current_stream().cuda_stream
+    parts = []
+    for t in (a, b):
+        p3 = [torch.empty_like(t, dtype=torch.bfloat16) for _ in range(3)]
+        assert lib.gx_split3_bf16(t.data_ptr(), p3[0].data_ptr(), p3[1].data_ptr(), p3[2].data_ptr(), t.numel(), stream) == 0
+        torch.cuda.synchronize()
+        resid = (t.double() - sum(p.double() for p in p3)).abs().max()
+        assert float(resid) <= 2.0 ** -23 * float(t.abs().max())
+        parts.append(p3)
+    c = torch.zeros(m, n, device="cuda")
+    vp = ctypes.c_void_p
+    rc = lib.gx_gemm_bf16x3_ld(m, n, k, (vp * 3)(*[p.data_ptr() for p in parts[0]]), k, 0,
+                               (vp * 3)(*[p.data_ptr() for p in parts[1]]), k, 0, c.data_ptr(), n, 1, stream)
+    assert rc == 0, lib.gx_gemm_last_error()
+    torch.cuda.synchronize()
+    ref = a.double() @ b.double().T
+    err = float((c.double() - ref).abs().max())
+    assert err <= 2e-6 * float(ref.abs().max()), err          # float32 accumulation of 1000 products
+    one = torch.zeros(m, n, device="cuda")
+    assert lib.gx_gemm_bf16_ld(m, n, k, parts[0][0].data_ptr(), k, 0, parts[1][0].data_ptr(), k, 0, one.data_ptr(), n, 0, 1, stream) == 0
+    torch.cuda.synchronize()
+    assert float((one.double() - ref).abs().max()) > 100 * err  # a single bf16 product is two orders worse
 
 
 @pytest.mark.gpu
@@ -144,7 +220,7 @@ def test_jacve_api_dispatches_matrix_arguments(built_library):
     import graphax_b200 as gx
     args = _mlp_args(256, 128, 128, 128, seed=3)
     tens = [torch.from_numpy(a).cuda() for a in args]
-    loss, grads = gx.jacve(MLP_loss, order="rev", argnums=(1, 2, 3, 4), has_aux=True)(*tens)
+    loss, grads = gx.jacve(MLP_loss, order="rev", argnums=(1, 2, 3, 4), has_aux=True, precision="bf16")(*tens)
     t = [torch.tensor(a, dtype=torch.float64, requires_grad=True) for a in args]
     L = .5 * ((torch.tanh(torch.tanh(t[0] @ t[1].T + t[2]) @ t[3].T + t[4]) - t[5]) ** 2).sum()
     L.backward()

@@ -65,15 +65,17 @@ def cost(instructions, banks=2):
 
 
 def main():
-    workload, orders = sys.argv[1], sys.argv[2:]
+    argv = [a for a in sys.argv[1:] if not a.startswith("--")]
+    rounding = "reference" if "--reference" in sys.argv else "fma"
+    workload, orders = argv[0], argv[1:]
     for order in orders:
-        ins = sass_of(get_workload(workload).plan(order))
+        ins = sass_of(get_workload(workload).plan(order, rounding=rounding))
         # the hot loop: from the tile's input reads to the end of the fast body (the exact fallback follows the vote)
         start = next(i for i, s in enumerate(ins) if "LDS" in s) - 5
         end = next((i for i, s in enumerate(ins) if "VOTE.ANY" in s), len(ins) - 40) + 40
         loop = ins[start:end]
         cycles, stats = cost(loop)
-        print(f"{workload}:{order}: {len(loop)} instructions per tile, modelled {cycles} cycles  {stats}")
+        print(f"{workload}:{order}:{rounding}: {len(loop)} instructions per tile, modelled {cycles} cycles  {stats}")
 
 
 if __name__ == "__main__":

@@ -122,6 +122,8 @@ def main():
                             except runtime.GraphaxB200Error as e:
                                 rows.append(dict(cfg, error=str(e)[:300]))
                 ok = [r for r in rows if "us" in r and r["variant"] == "jit"]
+                if not ok:
+                    raise SystemExit(f"{name}: every variant failed, first error: {rows[-1].get('error')}")
                 b = min(ok, key=lambda r: r["us"])
                 best[plan.key] = {"name": name, "threads": b["threads"], "min_blocks": b["min_blocks"],
                                   "out_stages": b["out_stages"], "samples_per_thread": b["samples_per_thread"],
