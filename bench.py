@@ -8,8 +8,11 @@ no collective on the data path).  `value` is whole-job throughput with inputs re
 with CUDA events (max over ranks); `e2e` is the same metric through the public API with HOST buffers
 (pinned host -> device copies and the device -> host read of the Jacobians inside the timed region);
 `roofline` relates the kernel to the measured HBM copy bandwidth over the compulsory 240 B/Jacobian;
-`cpu_baseline` / `--impl reference` time the oracle's NumPy port of the reference algorithm on the
-host cores (the reference itself needs JAX, which this image does not have).
+`cpu_baseline` / `--impl reference` time the reference on the host cores: graphax's OWN sources (the
+`baseline/_ref` install) in the scalable form `jax.vmap(graphax.jacve(f, order, argnums))`, with JAX - which this
+image does not have - replaced by the NumPy stand-in `tests/golden/jaxlite`; if that install is missing, the
+oracle's NumPy port of the algorithm.  The headline runs the default plan (`rounding="reference"`: bit-identical
+to that reference arithmetic); the contracted `rounding="fma"` plan is reported beside it with its parity record.
 """
 from __future__ import annotations
 
@@ -69,6 +72,52 @@ def cpu_port_throughput(order_key: str, sample: int, reps: int, cores: int):
     return sample / float(np.median(times)), times
 
 
+def _reference_available() -> bool:
+    return (ROOT / "baseline" / "_ref" / "graphax" / "core.py").exists() and \
+        (ROOT / "tests" / "golden" / "jaxlite" / "jax" / "__init__.py").exists()
+
+
+def _ref_chunk(bounds):
+    """One chunk through the reference's own `jax.vmap(graphax.jacve(RoeFlux, order, argnums))` (worker process)."""
+    if "fun" not in _CPU_CTX:
+        sys.path[:0] = [str(ROOT / "tests" / "golden" / "jaxlite"), str(ROOT / "baseline" / "_ref")]
+        import jax
+        import jax.numpy as jnp
+        import graphax
+        from graphax import examples as gex
+        assert "jaxlite" in jax.__file__ and "_ref" in graphax.__file__
+        w = WORKLOADS[WORKLOAD]
+        fun = {"roe3d": gex.RoeFlux_3d, "roe1d": gex.RoeFlux_1d, "robotarm": gex.RobotArm_6DOF}[WORKLOAD]
+        order = _CPU_CTX["order"]
+        _CPU_CTX["fun"] = jax.vmap(graphax.jacve(fun, order=order if isinstance(order, str) else list(order),
+                                                 argnums=tuple(w.argnums)))
+        _CPU_CTX["jnp"] = jnp
+    lo, hi = bounds
+    jnp = _CPU_CTX["jnp"]
+    out = _CPU_CTX["fun"](*[jnp.array(x[lo:hi]) for x in _CPU_CTX["xs"]])
+    return float(sum(np.abs(np.asarray(b)).sum() for row in out for b in row))
+
+
+def cpu_reference_throughput(order_key: str, sample: int, reps: int, cores: int, warmup: int = 1):
+    """Jacobians/s of graphax's own sources on the NumPy stand-in for JAX, `cores` worker processes."""
+    w = WORKLOADS[WORKLOAD]
+    _CPU_CTX.pop("fun", None)
+    _CPU_CTX["xs"] = w.inputs(sample)
+    _CPU_CTX["order"] = w.order(order_key)
+    chunk = 1 << 15
+    bounds = [(lo, min(lo + chunk, sample)) for lo in range(0, sample, chunk)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        for _ in range(max(1, warmup)):
+            pool.map(_ref_chunk, bounds, chunksize=1)
+        times = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            pool.map(_ref_chunk, bounds, chunksize=1)
+            times.append(time.perf_counter() - t0)
+    return sample / float(np.median(times)), times
+
+
 def cpu_replay_throughput(order_key: str, sample: int, reps: int, cores: int):
     """Jacobians/s of the oracle's C plan replay (fused, vectorised across samples, pthreads)."""
     from oracle import replay
@@ -85,35 +134,35 @@ def cpu_replay_throughput(order_key: str, sample: int, reps: int, cores: int):
 
 
 def run_reference_arm(args) -> None:
-    """--impl reference: the reference's CPU implementation of the path. graphax itself cannot run here
-    (it imports jax), so this times the oracle's port of it on all host cores."""
+    """--impl reference: the reference's CPU implementation of the path on all host cores, same workload, batch,
+    order and metric as the GPU arm.  graphax needs JAX, which this image does not have: its own sources (the
+    `baseline/_ref` install, unmodified) run on the NumPy stand-in `tests/golden/jaxlite` (kind "reference"); if the
+    install is missing, the oracle's NumPy port of the algorithm is timed instead (kind "port")."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = len(os.sched_getaffinity(0))
-    reference_note = ("graphax needs jax, which is not installed in this image; timing the oracle port (bit-exact with a "
-                      "run of the reference's own sources on a NumPy stand-in for JAX, tests/golden/reference_run.*)")
-    try:  # honour a per-pod reference install if one ever exists
-        sys.path.insert(0, str(ROOT / "baseline" / "_ref"))
-        import jax  # noqa: F401
-        import graphax  # noqa: F401
-        reference_note = "jax+graphax importable but not wired up; timing the oracle port"
-    except Exception:
-        pass
-    finally:
-        sys.path.pop(0)
-    sample = 1 << 18
+    sample = args.batch
     steps = max(1, min(args.steps, 20))
+    warmup = max(1, min(args.warmup, 5))
     t0 = time.perf_counter()
-    value, times = cpu_port_throughput(args.order, sample, steps + max(0, min(args.warmup, 2)), cores)
+    if _reference_available():
+        kind = "reference"
+        how = ("graphax's own sources (baseline/_ref, unmodified) as jax.vmap(graphax.jacve(f, order, argnums)), JAX "
+               "replaced by the NumPy stand-in tests/golden/jaxlite (JAX itself is not installed in this image)")
+        value, times = cpu_reference_throughput(args.order, sample, steps, cores, warmup)
+    else:
+        kind = "port"
+        how = "oracle/ve_numpy.py: NumPy port of the reference algorithm (baseline/_ref not present)"
+        value, times = cpu_port_throughput(args.order, sample, steps + warmup, cores)
+        times = times[warmup:]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * float(np.median(times)),
+        "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * float(np.median(times)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{TITLES[WORKLOAD]} order={args.order}, NumPy port of the reference algorithm, "
-                               f"{sample} samples per step (bounded sample of the 2^20 batch)",
-                   "note": reference_note},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+        "config": {"workload": f"{TITLES[WORKLOAD]} jacve order={args.order}, vmap batch {sample}, fp32 on the host CPU",
+                   "batch_per_gpu": sample, "order": args.order, "implementation": how},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": f"{sample} samples x {steps} steps, fp32, {cores} processes"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
@@ -197,12 +246,167 @@ def recorded_traffic(order_key: str):
     return None
 
 
+def parity_record(order_key: str, rounding: str):
+    """Full-batch parity of this (order, rounding) against the float32 oracle, from the committed record of
+    tests/test_gpu_full_parity.py (profiles/parity_full_r02.json); None if that order was not recorded."""
+    path = ROOT / "profiles" / "parity_full_r02.json"
+    if not path.exists():
+        return None
+    try:
+        rec = json.loads(path.read_text())
+    except Exception:
+        return None
+    key = f"{WORKLOAD}:{order_key}:reference" if rounding == "reference" else f"{WORKLOAD}:{order_key}:fma:reciprocal"
+    return rec.get(key)
+
+
+def _time_launches(launch, steps: int, stream, world: int, dist, dev) -> float:
+    """ms per step of `launch(i)` over `steps` back-to-back steps (CUDA events, max over ranks)."""
+    import torch
+    for i in range(5):
+        launch(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(steps):
+        launch(i)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def _graph_time(enqueue, per_graph: int, replays: int, dev) -> float:
+    """ms per step when `per_graph` consecutive steps are captured into one CUDA graph and replayed `replays` times."""
+    import torch
+    cap = torch.cuda.Stream(device=dev)
+    cap.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(cap):
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=cap):
+            cs = torch.cuda.current_stream()
+            for i in range(per_graph):
+                enqueue(i, cs.cuda_stream)
+    torch.cuda.current_stream().wait_stream(cap)
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(replays):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / (replays * per_graph)
+
+
+def measure_other_configs(local_rank: int, peak_gbs: float) -> dict:
+    """The other named configs of BASELINE.json on this GPU (N = 1 only; reported, not the headline):
+    config 2 RoeFlux_1d 2^16 'rev', config 4 RobotArm_6DOF 2^22 'rev' and Markowitz, config 5 the MLP
+    512 -> 1024 -> 512 weight-Jacobian step at batch 4096 (bf16 operands, fp32 accumulate)."""
+    import torch
+    import graphax_b200 as gx
+    dev = f"cuda:{local_rank}"
+    out = {}
+    stream = torch.cuda.current_stream()
+    for name, wname, order_key in (("RoeFlux_1d 2^16 rev", "roe1d", "rev"), ("RobotArm_6DOF 2^22 rev", "robotarm", "rev"),
+                                   ("RobotArm_6DOF 2^22 markowitz", "robotarm", "markowitz")):
+        try:
+            w = WORKLOADS[wname]
+            batch = w.batch
+            host = w.inputs(batch)
+            rec = {}
+            for rounding in ("reference", "fma"):
+                jf = gx.jacve(w.fun, order=w.order(order_key), argnums=w.argnums, rounding=rounding)
+                plan = jf.lower(w.arg_shapes)
+                dp = jf._device_plan(plan, local_rank)
+                nsets = 4 if plan.bytes_per_jacobian * batch * 4 < (8 << 30) else 2
+                sets = [([torch.from_numpy(x).to(dev) for x in host],
+                         torch.empty((batch, plan.n_rows, plan.n_cols), device=dev)) for _ in range(nsets)]
+
+                def enqueue(i, cuda_stream, dp=dp, sets=sets, batch=batch):
+                    ins, o = sets[i % len(sets)]
+                    dp.launch(batch, [t.data_ptr() for t in ins], o.data_ptr(), None, cuda_stream)
+                if plan.bytes_per_jacobian * batch < (64 << 20):      # launch-bound: replay from a CUDA graph
+                    ms, how = _graph_time(enqueue, 40, 25, dev), "CUDA graph of 40 steps"
+                else:
+                    ms = _time_launches(lambda i: enqueue(i, stream.cuda_stream), 100, stream, 1, None, dev)
+                    how = "one host call per step"
+                gbs = plan.bytes_per_jacobian * batch / (ms * 1e-3) / 1e9
+                rec[rounding] = {"value": batch / (ms * 1e-3), "unit": UNIT, "us_per_step": ms * 1e3,
+                                 "roofline_frac": gbs / peak_gbs, "achieved_gbs": gbs, "kernel": dp.kernel, "launch": how}
+                del sets
+                torch.cuda.empty_cache()
+            out[name] = dict(rec["reference"], bound="hbm", batch=batch, bytes_per_jacobian=plan.bytes_per_jacobian,
+                             fma_rounding=rec["fma"])
+        except Exception as e:                               # a side measurement must never take the bench line down
+            out[name] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    try:
+        from graphax_b200.dense import DenseExecutor, build_dense_plan
+        from graphax_b200.examples import MLP_loss
+        from graphax_b200.tracer import make_jaxpr
+        B, I, H, O = 4096, 512, 1024, 512
+        g = torch.Generator(device=dev).manual_seed(0)
+        margs = (torch.randn(B, I, device=dev, generator=g).bfloat16(),
+                 (torch.randn(H, I, device=dev, generator=g) * I ** -0.5).bfloat16(),
+                 torch.randn(H, device=dev, generator=g) * 0.1,
+                 (torch.randn(O, H, device=dev, generator=g) * H ** -0.5).bfloat16(),
+                 torch.randn(O, device=dev, generator=g) * 0.1,
+                 torch.randn(B, O, device=dev, generator=g).bfloat16())
+        ex = DenseExecutor(build_dense_plan(make_jaxpr(MLP_loss, [tuple(t.shape) for t in margs]), "rev", (1, 2, 3, 4)),
+                           local_rank, precision="bf16")
+        for _ in range(3):
+            ex.run(margs)
+        torch.cuda.synchronize()
+        l0 = ex.launches
+        ex.run(margs)
+        per_step = ex.launches - l0
+        side = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(side):
+            ex.run(margs)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                ex.run(margs)
+        for _ in range(5):
+            graph.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(200):
+            graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / 200 * 1e3
+        flops = 2 * B * (2 * I * H + 3 * H * O)
+        peak_tf = 1667.8
+        try:
+            peak_tf = float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["bf16_tflops"])
+        except Exception:
+            pass
+        out["MLP 512-1024-512 weight Jacobians, batch 4096, bf16 operands / fp32 accumulate, rev"] = {
+            "value": 1e6 / us, "unit": "steps/s", "us_per_step": us, "tflops": flops / us / 1e6, "bound": "tensor",
+            "roofline_frac": flops / us / 1e6 / peak_tf, "peak_tflops": peak_tf, "launches_per_step": per_step,
+            "launch": "CUDA graph of one step", "flops_per_step": flops}
+    except Exception as e:
+        out["MLP 512-1024-512 weight Jacobians"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    return out
+
+
 def run_gpu_arm(args) -> None:
     import torch
     import torch.distributed as dist
     import graphax_b200 as gx
     from graphax_b200 import runtime
-    from graphax_b200.sharding import bind_to_local_numa_node, init_process_group
+    from graphax_b200.plan import DEFAULT_ROUNDING
+    from graphax_b200.sharding import bind_to_local_numa_node, gather_for_verification, init_process_group
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device. graphax_b200 has no CPU fallback (use --impl reference for the CPU arm).")
@@ -218,12 +422,14 @@ def run_gpu_arm(args) -> None:
     w = WORKLOADS[WORKLOAD]
     batch = args.batch                                   # per GPU (weak scaling)
     order = w.order(args.order)
-    jacfun = gx.jacve(w.fun, order=order, argnums=w.argnums)
+    rounding = args.rounding or DEFAULT_ROUNDING
+    jacfun = gx.jacve(w.fun, order=order, argnums=w.argnums, rounding=rounding)
     plan = jacfun.lower(w.arg_shapes)
     dp = jacfun._device_plan(plan, local_rank)
     if args.kernel != "auto":
         dp.select_kernel({"interpreter": 0, "aot": 1, "jit": 2}[args.kernel])
     info = dp.info()
+    peak, peak_src = measured_peak_gbs()
 
     # synthetic inputs of this rank's shard; pinned on the host (for e2e) and resident in HBM (for value)
     host_in = [torch.from_numpy(x).pin_memory() for x in w.inputs(batch, start=rank * batch)]
@@ -243,6 +449,13 @@ def run_gpu_arm(args) -> None:
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     for i in range(max(args.warmup, 3)):
         step(i)
@@ -307,11 +520,43 @@ def run_gpu_arm(args) -> None:
             i += 1
         torch.cuda.synchronize()
     sampler.stop()
-    if world > 1:
-        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
+    elapsed_ms = max_over_ranks(elapsed_ms)
     sync_all()
+
+    # ---- verification: every rank contributes a window of its shard's result through an NCCL all-gather; rank 0
+    # compares all of them with the oracle on the same global sample indices -----------------------------------
+    verify = None
+    if not args.no_verify:
+        rows = 1024
+        lo = (batch - rows) // 2 if batch > rows else 0
+        n = min(rows, batch)
+        ins, out_t = sets[0]
+        dp.launch(batch, [t.data_ptr() for t in ins], out_t.data_ptr(), None, stream.cuda_stream)
+        torch.cuda.synchronize()
+        window = out_t[lo:lo + n].contiguous()
+        gathered = gather_for_verification(window, [n] * world)          # NCCL all-gather at world > 1
+        torch.cuda.synchronize()
+        if rank == 0:
+            from oracle import replay as oracle_replay
+            from oracle import ve_numpy
+            got = gathered.cpu().numpy().reshape(world, n, plan.n_rows, plan.n_cols)
+            bit_exact = values_equal_reference = True
+            for r in range(world):
+                xs = w.inputs(n, start=r * batch + lo)
+                ref_j, _ = oracle_replay.replay(plan.blob, xs, plan.n_rows, plan.n_cols)
+                bit_exact &= bool(np.array_equal(got[r].view(np.uint32), ref_j.view(np.uint32)))
+                if rounding == "reference":
+                    j32, _, _ = ve_numpy.jacve(w.jaxpr(), order, w.argnums, xs, np.float32)
+                    t32 = np.concatenate([np.concatenate([np.asarray(b).reshape(n, -1, sz) for b, sz in zip(row, w.sizes)], axis=2)
+                                          for row in j32], axis=1)
+                    values_equal_reference &= bool(np.array_equal(got[r], t32))
+            verify = {"ranks": world, "rows": world * n, "window_per_rank": [lo, lo + n],
+                      "collective": "NCCL all_gather" if world > 1 else "none (single rank)",
+                      "bit_exact": bit_exact, "against": "oracle/replay.c on the plan blob (uint32 compare)"}
+            if rounding == "reference":
+                verify["equal_to_reference_arithmetic"] = values_equal_reference
+                verify["reference_arithmetic"] = "oracle/ve_numpy.py float32 (bit-exact with the reference run, tests/golden)"
+        sync_all()
 
     # ---- e2e: public API, host buffers, H2D + kernel + D2H inside the timed region --------------------
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
@@ -323,49 +568,83 @@ def run_gpu_arm(args) -> None:
     for _ in range(e2e_steps):
         out = jacfun.batched(*host_in, out=host_out)
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * batch * e2e_steps / e2e_s
     checksum = float(host_out[:4096].double().abs().sum())                         # touch the result on the host
+    # the floor of that call on this box: the same bytes as raw pinned copies (H2D of the inputs on one stream, D2H
+    # of the result on another), all ranks at the same time, no kernel
+    sync_all()
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    d_in = [torch.empty_like(t, device=dev) for t in host_in]
+    d_out = sets[0][1]
 
+    def raw_copies():
+        with torch.cuda.stream(s_in):
+            for h, d in zip(host_in, d_in):
+                d.copy_(h, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            host_out.copy_(d_out, non_blocking=True)
+    for _ in range(2):
+        raw_copies()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        raw_copies()
+    torch.cuda.synchronize()
+    floor_s = max_over_ranks(time.perf_counter() - t0)
+    floor_value = world * batch * e2e_steps / floor_s
+    copy_bytes = 4 * (plan.n_in_scalars + plan.n_rows * plan.n_cols) * batch
+    del d_in
+    sync_all()
+
+    def time_variant(jf2, k2: int) -> float:
+        dp2 = jf2._device_plan(jf2.lower(w.arg_shapes), local_rank)
+
+        def launch(i):
+            ins, out_t = sets[i % N_BUFFER_SETS]
+            dp2.launch(batch, [t.data_ptr() for t in ins], out_t.data_ptr(), None, stream.cuda_stream)
+        return _time_launches(launch, k2, stream, world, dist, dev)
+
+    def summary(ms: float) -> dict:
+        gbs = plan.bytes_per_jacobian * batch / (ms * 1e-3) / 1e9
+        return {"value": world * batch / (ms * 1e-3), "ms_per_step": ms, "roofline_frac": gbs / peak}
+
+    # both roundings of the headline order, with their full-batch parity records
+    k2 = max(20, args.steps // 4)
+    modes = {}
+    if args.other_orders:
+        for r in ("reference", "fma"):
+            ms = elapsed_ms / args.steps if r == rounding else \
+                time_variant(gx.jacve(w.fun, order=order, argnums=w.argnums, rounding=r), k2)
+            modes[r] = dict(summary(ms), parity_full_batch=parity_record(args.order, r),
+                            what=("the reference's own sequence of rounded float32 operations (separate multiply and add, "
+                                  "IEEE divisions): results equal the reference arithmetic" if r == "reference" else
+                                  "product-and-add pairs contracted into FMAs, x/y through one reciprocal: fewer "
+                                  "instructions, a few ulp per operation away from the reference"))
     # the other elimination orders of the config ("mixed ... vs fwd/rev"), same batch, fewer steps
     other = {}
     if args.other_orders and WORKLOAD == "roe3d":
-        # "+contract_sums": the opt-in plan variant that folds edge sums into FMA chains (plan._contract_sums);
-        # compiled at run time with NVRTC, reported for information, never the headline
-        for key, contract in [(k, c) for c in (False, True) for k in w.order_names()]:
-            if key == args.order and not contract:
+        for key in w.order_names():
+            if key == args.order:
                 continue
-            jf2 = gx.jacve(w.fun, order=w.order(key), argnums=w.argnums, contract_sums=contract)
-            dp2 = jf2._device_plan(jf2.lower(w.arg_shapes), local_rank)
-            k2 = max(20, args.steps // 4)
-            for i in range(5):
-                ins, out_t = sets[i % N_BUFFER_SETS]
-                dp2.launch(batch, [t.data_ptr() for t in ins], out_t.data_ptr(), None, stream.cuda_stream)
-            sync_all()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            for i in range(k2):
-                ins, out_t = sets[i % N_BUFFER_SETS]
-                dp2.launch(batch, [t.data_ptr() for t in ins], out_t.data_ptr(), None, stream.cuda_stream)
-            e1.record(stream)
-            torch.cuda.synchronize()
-            ms2 = e0.elapsed_time(e1) / k2
-            if world > 1:
-                t = torch.tensor([ms2], device=dev, dtype=torch.float64)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                ms2 = float(t.item())
-            other[key + ("+contract_sums" if contract else "")] = {"value": world * batch / (ms2 * 1e-3), "ms_per_step": ms2, "steps": k2,
-                          "roofline_frac": plan.bytes_per_jacobian * batch / (ms2 * 1e-3) / 1e9 / measured_peak_gbs()[0]}
-            sync_all()
+            rec = {}
+            for r in ("reference", "fma"):
+                rec[r] = summary(time_variant(gx.jacve(w.fun, order=w.order(key), argnums=w.argnums, rounding=r), k2))
+            other[key] = dict(rec[rounding], steps=k2, other_rounding=rec["fma" if rounding == "reference" else "reference"])
+        # "+contract_sums": the opt-in fma variant that also folds edge sums into FMA chains (plan._contract_sums)
+        ms = time_variant(gx.jacve(w.fun, order=order, argnums=w.argnums, contract_sums=True), k2)
+        other[args.order + "+contract_sums (fma)"] = dict(summary(ms), steps=k2)
+    sync_all()
+
+    other_configs = None
+    if world == 1 and args.other_configs and WORKLOAD == "roe3d":
+        del sets
+        torch.cuda.empty_cache()
+        other_configs = measure_other_configs(local_rank, peak)
 
     if rank == 0:
         ms_per_step = elapsed_ms / args.steps
         value = world * batch / (ms_per_step * 1e-3)
-        peak, peak_src = measured_peak_gbs()
         achieved = plan.bytes_per_jacobian * batch / (ms_per_step * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -374,7 +653,8 @@ def run_gpu_arm(args) -> None:
             "config": {"workload": f"{TITLES[WORKLOAD]} ({plan.stats['n_vertices']} vertices) jacve order={args.order}, "
                                    f"vmap batch {batch} per GPU, fp32, argnums all {len(w.argnums)} inputs -> "
                                    f"[{plan.n_rows}x{plan.n_cols}] Jacobian",
-                       "batch_per_gpu": batch, "order": args.order, "kernel": runtime.KERNEL_NAMES[info.kernel_kind],
+                       "batch_per_gpu": batch, "order": args.order, "rounding": rounding,
+                       "kernel": runtime.KERNEL_NAMES[info.kernel_kind],
                        "plan_ops": plan.stats["n_ops"], "threads_per_cta": info.threads,
                        "ctas_per_sm": info.ctas_per_sm, "regs_per_thread": info.regs_per_thread,
                        "cache": f"{N_BUFFER_SETS} rotating input/output sets "
@@ -385,32 +665,54 @@ def run_gpu_arm(args) -> None:
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * plan.n_in_scalars * batch,
                     "d2h_bytes_per_step": 4 * plan.n_rows * plan.n_cols * batch, "steps": e2e_steps,
                     "api": f"graphax_b200.vmap(jacve({TITLES[WORKLOAD]}, order, argnums))(*pinned_host_arrays, out=pinned_result)",
-                    "checksum": checksum},
+                    "checksum": checksum,
+                    "floor": {"value": floor_value, "unit": UNIT, "ms_per_step": 1e3 * floor_s / e2e_steps,
+                              "gbs_per_gpu": copy_bytes * e2e_steps / floor_s / 1e9,
+                              "gbs_all_gpus": world * copy_bytes * e2e_steps / floor_s / 1e9,
+                              "what": f"raw pinned H2D of the inputs + D2H of the result ({copy_bytes / 1e6:.0f} MB per GPU and "
+                                      f"step) on two streams, {world} rank(s) concurrently, no kernel"},
+                    "frac_of_floor": e2e_value / floor_value},
             "gpu_launches": int(launches) * world,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": recorded_traffic(args.order), "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": recorded_traffic(f"{args.order}:{rounding}") or
+                         (recorded_traffic(args.order) if rounding == "fma" else None), "peak_source": peak_src,
                          "frac_of_nominal_8TBs": achieved / 8000.0,
-                         "fp32_issue": recorded_traffic(args.order + ":fp32"),   # the co-bound
+                         "fp32_issue": recorded_traffic(f"{args.order}:{rounding}:fp32"),   # the co-bound
                          "algorithmic_bytes_per_jacobian": plan.bytes_per_jacobian,
                          "kernel_ms": ms_per_step},
             "clocks": sampler.summary(),
         }
+        if verify is not None:
+            line["verify"] = verify
+        if modes:
+            line["rounding_modes"] = modes
         if other:
             line["other_orders"] = other
+        if other_configs:
+            line["other_configs"] = other_configs
         if world == 1 and not args.no_cpu_baseline:
             cores = len(os.sched_getaffinity(0))
-            sample = 1 << 19
-            v, _ = cpu_port_throughput(args.order, sample, 3, cores)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{sample} samples x 3 reps, NumPy port of the reference algorithm, "
-                                              f"fp32, {cores} processes",
-                                    "c_replay_value": cpu_replay_throughput(args.order, 1 << 18, 3, cores)}
+            if _reference_available():
+                sample = 1 << 20
+                v, _ = cpu_reference_throughput(args.order, sample, 5, cores)
+                line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
+                                        "sample": f"{sample} samples x 5 reps, fp32, {cores} processes: graphax's own sources "
+                                                  f"(baseline/_ref) as jax.vmap(graphax.jacve(f, order, argnums)) on the NumPy "
+                                                  f"stand-in for JAX (tests/golden/jaxlite)"}
+            else:
+                sample = 1 << 19
+                v, _ = cpu_port_throughput(args.order, sample, 3, cores)
+                line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                        "sample": f"{sample} samples x 3 reps, NumPy port of the reference algorithm, "
+                                                  f"fp32, {cores} processes"}
+            line["cpu_baseline"]["numpy_port_value"] = cpu_port_throughput(args.order, 1 << 18, 3, cores)[0]
+            line["cpu_baseline"]["c_replay_value"] = cpu_replay_throughput(args.order, 1 << 18, 3, cores)
             # generic autodiff on the same GPU (stand-in for the reference's XLA-on-one-B200 run, JAX
             # not being installed): torch.func.vmap(jacrev(f)), eager.  Reported for context only.
             try:
                 sys.path.insert(0, str(ROOT / "tools"))
                 from torch_baseline import measure as torch_measure
-                del sets
+                sets = None
                 torch.cuda.empty_cache()
                 tb = min(batch, 1 << 18)
                 tv, _ = torch_measure(w, tb, reps=3, device="cuda")
@@ -443,6 +745,11 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-orders", dest="other_orders", action="store_false")
     ap.add_argument("--workload", default="roe3d", choices=list(WORKLOADS))
+    ap.add_argument("--rounding", default="", choices=["", "reference", "fma"],
+                    help="plan rounding of the headline (default: plan.DEFAULT_ROUNDING = reference)")
+    ap.add_argument("--no-other-configs", dest="other_configs", action="store_false",
+                    help="skip the other named configs (RoeFlux_1d, RobotArm_6DOF, MLP) reported at N = 1")
+    ap.add_argument("--no-verify", action="store_true", help="skip the all-gather verification after the timed region")
     args = ap.parse_args()
     global WORKLOAD, METRIC
     WORKLOAD = args.workload

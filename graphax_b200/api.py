@@ -75,7 +75,7 @@ class JacveFunction:
         self.precision = precision
         self.fun = fun
         self.frontend = frontend
-        self.rounding = DEFAULT_ROUNDING if rounding is None else rounding
+        self.rounding = ("fma" if contract_sums else DEFAULT_ROUNDING) if rounding is None else rounding
         if self.rounding not in ("fma", "reference"):
             raise ValueError("rounding must be 'fma' or 'reference'")
         if contract_sums and self.rounding == "reference":

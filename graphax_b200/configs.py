@@ -66,7 +66,7 @@ class Workload:
     def plan(self, order_key: str, with_primal: bool = True, division: str = None, rounding: str = None) -> Plan:
         if rounding is None:
             from .plan import DEFAULT_ROUNDING
-            rounding = "fma" if division == "reciprocal" else DEFAULT_ROUNDING
+            rounding = "fma" if division is not None else DEFAULT_ROUNDING
         if division is None:
             division = "ieee" if rounding == "reference" else "reciprocal"
         return _plan(self.name, order_key, with_primal, division, rounding)

@@ -39,8 +39,9 @@ from .lowering import OP, Dag
 from .tracer import Jaxpr, Var
 
 # Where plans round unless the caller says otherwise (see build_plan): "reference" = the reference's own sequence of
-# rounded operations, "fma" = contracted.
-DEFAULT_ROUNDING = "fma"
+# rounded operations (bit-identical results), "fma" = contracted (fewer instructions, a few ulp per operation away).
+# An explicit ``division=`` or ``contract=True`` selects "fma": both are options of that mode.
+DEFAULT_ROUNDING = "reference"
 MAGIC = 0x4C505847
 VERSION = 1
 FLAG_HAS_PRIMAL = 1
@@ -335,7 +336,7 @@ def build_plan(jaxpr: Jaxpr, order, argnums: Sequence[int], with_primal: bool = 
     chains feeding them (``_contract_sums``): 6-12 % fewer instructions, but a different association of the sums
     than the reference's, so it is opt-in (``rounding="fma"`` only)."""
     if rounding is None:
-        rounding = "fma" if (contract or division == "reciprocal") else DEFAULT_ROUNDING
+        rounding = "fma" if (contract or division is not None) else DEFAULT_ROUNDING
     if rounding not in ("fma", "reference"):
         raise ValueError("rounding must be 'fma' or 'reference'")
     if division is None:

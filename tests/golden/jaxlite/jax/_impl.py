@@ -1118,7 +1118,26 @@ def _b_squeeze(prim, args, params, B):
     return BatchTracer(prim.bind(args[0].val, dimensions=tuple(d + 1 for d in params["dimensions"])))
 
 
-_BATCH_RULES = {"reduce_sum": _b_reduce, "reduce_max": _b_reduce, "reduce_min": _b_reduce, "dot_general": _b_dot_general,
+def _b_scatter(prim, args, params, B):
+    """The windowed-assignment form of `_scatter_impl` with a leading batch axis on operand and / or updates (static
+    indices): the batch axis becomes one more window dimension that starts at 0 - `jax.vmap(graphax.jacve(f))`
+    reaches it through the slice / concatenate transforms (`primitives.py:744-749, 1062-1067`)."""
+    operand, idx, upd = args
+    if isinstance(idx, BatchTracer):
+        raise NotImplementedError("jaxlite: scatter with batched indices")
+
+    def lead(a):
+        if isinstance(a, BatchTracer):
+            return a.val
+        shape = (B,) + _shape_of(a)
+        return broadcast_in_dim_p.bind(_lift(a), shape=shape, broadcast_dimensions=tuple(range(1, len(shape))), sharding=None)
+    dn = params["dimension_numbers"]
+    new = ScatterDimensionNumbers((0,) + tuple(d + 1 for d in dn.update_window_dims), (),
+                                  tuple(d + 1 for d in dn.scatter_dims_to_operand_dims))
+    return BatchTracer(prim.bind(lead(operand), idx, lead(upd), dimension_numbers=new))
+
+
+_BATCH_RULES = {"scatter": _b_scatter, "reduce_sum": _b_reduce, "reduce_max": _b_reduce, "reduce_min": _b_reduce, "dot_general": _b_dot_general,
                 "slice": _b_slice, "concatenate": _b_concatenate, "broadcast_in_dim": _b_broadcast_in_dim,
                 "transpose": _b_transpose, "reshape": _b_reshape, "squeeze": _b_squeeze}
 

@@ -9,7 +9,13 @@ pytestmark = pytest.mark.gpu
 
 EXACT = {"roe1d", "roe3d"}           # plans made only of correctly rounded ops: bit-exact vs the replay
 CASES = [(w.name, k) for w in WORKLOADS.values() for k in w.order_names()]
-DIVISIONS = ["reciprocal", "ieee"]     # how x/y and its partials are lowered (lowering.lower_eqn)
+# plan variants: the reference's own rounding (default), and the contracted ("fma") rounding with x/y lowered through a
+# reciprocal or through the reference's three IEEE divisions (plan.build_plan, lowering.lower_eqn)
+DIVISIONS = ["reference", "reciprocal", "ieee"]
+
+
+def _plan(w, order, mode):
+    return w.plan(order, rounding="reference") if mode == "reference" else w.plan(order, division=mode)
 
 
 def _tile64(w, order, xs):
@@ -25,7 +31,7 @@ def _tile64(w, order, xs):
 def test_kernel_matches_plan_replay(built_library, name, order, kernel, division):
     from oracle import replay
     w = WORKLOADS[name]
-    plan = w.plan(order, division=division)
+    plan = _plan(w, order, division)
     batch = 4096 + 37                                  # full tiles + ragged tail
     xs = w.inputs(batch)
     jac, primal, used = run_engine(plan, xs, kernel)
@@ -66,7 +72,7 @@ def test_engine_matches_reference_order_oracle(built_library, name, order, divis
     the reference's division formulas) within |dJ| <= 1e-5 max|J| + 1e-5 |J|; both also against fp64."""
     from oracle import ve_numpy
     w = WORKLOADS[name]
-    plan = w.plan(order, division=division)
+    plan = _plan(w, order, division)
     batch = 2048
     xs = w.inputs(batch)
     jac, primal, _ = run_engine(plan, xs, "aot")
@@ -75,6 +81,8 @@ def test_engine_matches_reference_order_oracle(built_library, name, order, divis
     t64, p64 = _tile64(w, order, xs)
     bound = parity_bound(t64)
     assert (np.abs(jac - t32) <= bound).all(), float((np.abs(jac - t32) / bound).max())
+    if division == "reference" and name in EXACT:
+        assert np.array_equal(jac, t32) and np.array_equal(primal, np.concatenate([p.reshape(batch, -1) for p in p32], 1))
     mx = np.abs(t64).max(axis=(1, 2), keepdims=True)
     err_engine, err_oracle = (np.abs(jac - t64) / mx).max(), (np.abs(t32 - t64) / mx).max()
     assert err_engine < 3e-5 and err_oracle < 3e-5, (err_engine, err_oracle)
@@ -107,7 +115,7 @@ def test_kernels_match_reference_run(built_library, name, order, division, kerne
     for shape, size in zip(w.arg_shapes, w.sizes):
         xs.append(np.ascontiguousarray(flat[:, off:off + size].reshape((len(flat),) + tuple(shape))))
         off += size
-    plan = w.plan(order, division=division)
+    plan = _plan(w, order, division)
     assert plan.structure["order"] == run["workloads"][name]["orders"][order]["eliminated"]
     jac, primal, used = run_engine(plan, xs, kernel)
     assert used == kernel
