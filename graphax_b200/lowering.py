@@ -278,8 +278,13 @@ def _parallel_jacobian(primal: Vec, out: Vec, partial: Vec, n_operands: int) -> 
     return st.diag(n), {(i, i): partial.nodes[i] for i in range(n)}
 
 
-def lower_eqn(dag: Dag, eqn: Eqn, read, division: str = "ieee") -> Tuple[Vec, List[Tuple[Var, st.Struct, Entries]]]:
+def lower_eqn(dag: Dag, eqn: Eqn, read, division: str = "ieee",
+              _use_registry: bool = True) -> Tuple[Vec, List[Tuple[Var, st.Struct, Entries]]]:
     """Primal value and elemental edges of one equation.
+
+    User-defined primitives and user-registered rules (``graphax_b200.primitives``: ``elemental_rules``,
+    ``defelemental``, ``defelemental2`` - the reference's extension point, primitives.py:110-146) take precedence
+    over the built-in rules below.
 
     Returns ``(out, [(operand_var, structure, entries), ...])`` with one edge per
     non-literal operand, or no edge at all when the rule yields fewer partials
@@ -294,6 +299,12 @@ def lower_eqn(dag: Dag, eqn: Eqn, read, division: str = "ieee") -> Tuple[Vec, Li
     reciprocal and a few FMAs instead of three IEEE divisions; the partial w.r.t. the
     denominator carries two roundings in both forms.
     """
+    if _use_registry:
+        from . import primitives as _registry
+        entry = _registry.lookup(eqn.primitive)
+        if entry is not None:
+            return _registry.lower_custom(dag, eqn, read, division, entry,
+                                          lambda: lower_eqn(dag, eqn, read, division, _use_registry=False))
     ew = _Ew(dag)
     recip = division == "reciprocal"
     if division not in ("ieee", "reciprocal"):

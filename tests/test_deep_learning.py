@@ -122,7 +122,7 @@ def test_large_plan_interpreter(built_library):
     torch.cuda.synchronize()
     ref_j, ref_p = replay.replay(plan.blob, xs, plan.n_rows, plan.n_cols)
     scale = np.abs(ref_j).max(axis=(1, 2), keepdims=True) + 1e-30
-    assert (np.abs(out.cpu().numpy() - ref_j) / scale).max() <= 5e-6
+    assert (np.abs(out.cpu().numpy() - ref_j) / scale).max() <= 2e-5      # libm (exp / log / tanh): host vs device
     rev = _plan("Encoder", "rev")
     rev_j, _ = replay.replay(rev.blob, xs, rev.n_rows, rev.n_cols)
     assert (np.abs(ref_j - rev_j) / scale).max() <= 1e-4
