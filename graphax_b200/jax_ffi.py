@@ -1,5 +1,6 @@
-"""`jax.ffi` binding of the jacve launch - the boundary BASELINE.json names.  UNVERIFIED IN THIS IMAGE: it needs JAX,
-jaxlib's XLA FFI headers and a GPU at the same time; nothing here is imported by the rest of the package.
+"""`jax.ffi` binding of the jacve launch - the boundary BASELINE.json names.  EXPERIMENTAL: never compiled or run (it
+needs JAX, jaxlib's XLA FFI headers and a GPU at the same time; this image has no JAX); nothing here is imported by
+the rest of the package, and jit / vmap composition is the design intent, not a tested property.
 
 With JAX installed::
 
@@ -59,12 +60,17 @@ def register() -> None:
     _registered = True
 
 
-def jacve(fun: Callable, order, argnums: Sequence[int] = (0,)) -> Callable:
-    """Batched Jacobian of `fun` (arguments carry a leading batch axis) as a jit / vmap composable JAX function;
-    result pytree as `graphax.jacve` (tuple per output of tuple per argnum), blocks `[batch, *out, *in]`."""
+def jacve(fun: Callable, order, argnums: Sequence[int] = (0,), device: int = None) -> Callable:
+    """Batched Jacobian of `fun` (arguments carry a leading batch axis) as a JAX function built on one
+    `jax.ffi.ffi_call`; result pytree as `graphax.jacve` (tuple per output of tuple per argnum), blocks
+    `[batch, *out, *in]`.  `device` is the CUDA device the plan is uploaded to (default: JAX's first GPU); it is
+    fixed HERE, outside any trace - under `jax.jit` the arguments are tracers and carry no device."""
     from .api import JacveFunction
     host = JacveFunction(fun, order, argnums, False, False, False, "per_sample", None, True, False, "jax")
     plans: Dict[Tuple, object] = {}
+    if device is None:
+        import jax
+        device = jax.devices("gpu")[0].id
 
     def batched(*xs):
         import jax
@@ -72,7 +78,6 @@ def jacve(fun: Callable, order, argnums: Sequence[int] = (0,)) -> Callable:
         register()
         shapes = [tuple(x.shape[1:]) for x in xs]
         plan = host.lower(shapes)
-        device = next(iter(xs[0].devices())).id
         dp = plans.setdefault((plan.key, device), host._device_plan(plan, device))
         batch = xs[0].shape[0]
         flat = [jnp.reshape(x.astype(jnp.float32), (batch, -1)) for x in xs]

@@ -27,7 +27,12 @@ _PARAMS = {
     "concatenate": ("dimension",), "broadcast_in_dim": ("shape", "broadcast_dimensions"),
     "transpose": ("permutation",), "reshape": ("new_sizes", "dimensions"), "squeeze": ("dimensions",),
 }
-_NO_RULE = ("pjit", "jit", "custom_jvp_call", "custom_vjp_call", "while", "cond", "scan")
+# call-like primitives: the reference registers a rule for `pjit` only (primitives.py:576-602): the call is ONE vertex
+# whose value is computed and whose partials are dropped (the rule returns an empty list, so core.py:405-410 writes
+# no edge).  The converter keeps that: the inner jaxpr travels in the equation's parameters and the lowering
+# evaluates it for the value.  `jit` is the same primitive under its newer name.
+_CALLS = ("pjit", "jit")
+_NO_RULE = ("custom_jvp_call", "custom_vjp_call", "while", "cond", "scan")
 
 
 def available() -> bool:
@@ -73,12 +78,18 @@ def from_jax(closed_jaxpr, out_is_sequence: bool = True) -> Jaxpr:
     for eqn in jaxpr.eqns:
         name = eqn.primitive.name
         if name in _NO_RULE or len(eqn.outvars) != 1:
-            # the reference has no elemental rule for these either (core.py:396-398) or treats them as opaque
-            raise NotImplementedError(f"{name} does not have a registered elemental partial")
+            # no elemental rule in the reference either (core.py:396-398 raises the same error), or several results
+            raise NotImplementedError(f"{name} does not have registered elemental partial.")
         ins = tuple(atom(a) for a in eqn.invars)
         out = Var(tuple(eqn.outvars[0].aval.shape), eqn_index=len(eqns))
         env[id(eqn.outvars[0])] = out
-        params = {k: _plain(eqn.params[k]) for k in _PARAMS.get(name, ()) if k in eqn.params}
+        if name in _CALLS:
+            params = {"jaxpr": from_jax(eqn.params["jaxpr"]), "name": str(eqn.params.get("name", ""))}
+            name = "pjit"
+        elif name == "iota":
+            params = {"shape": _plain(eqn.params["shape"]), "dimension": int(eqn.params["dimension"])}
+        else:
+            params = {k: _plain(eqn.params[k]) for k in _PARAMS.get(name, ()) if k in eqn.params}
         eqns.append(Eqn(name, ins, out, params))
         pads.append(_vmap_pads(name, ins, eqns))
     outvars = [atom(v) for v in jaxpr.outvars]

@@ -316,8 +316,26 @@ def lower_eqn(dag: Dag, eqn: Eqn, read, division: str = "ieee",
     def edges(out: Vec, partials: Sequence[Vec]):
         return out, [(eqn.invars[i],) + _parallel_jacobian(ops[i], out, partials[i], len(ops)) for i in traced]
 
-    if prim == "stop_gradient":    # primitives.py:458-462: value passes through, no edge
+    if prim in ("stop_gradient", "device_put"):    # primitives.py:452-462: value passes through, no edge
         return ops[0], []
+    if prim == "iota":             # primitives.py:444-449: a constant array, no operands and no edge
+        shape, dim = tuple(eqn.params["shape"]), int(eqn.params["dimension"])
+        idx = np.indices(shape)[dim].reshape(-1) if shape else np.zeros(1, dtype=np.int64)
+        return Vec(shape, [dag.const(float(i)) for i in idx]), []
+    if prim == "pjit":
+        # primitives.py:576-602: the reference evaluates the call and returns NO partials, so the call is one vertex
+        # without in-edges (core.py:405-410) - derivatives do not flow through it.  Same here: the inner jaxpr is
+        # evaluated for its value only.  (With real JAX, jnp.where / jnp.clip / jax.nn.* arrive as pjit equations.)
+        inner = eqn.params["jaxpr"]
+        warnings.warn(f"derivatives through the nested call {eqn.params.get('name') or 'pjit'!r} are dropped, as in the "
+                      "reference (graphax primitives.py:576-602): it is a vertex without in-edges", stacklevel=2)
+        env = {id(v): o for v, o in zip(inner.invars, ops)}
+
+        def read_inner(a):
+            return Vec((), [dag.const(a.val)], is_literal=True) if isinstance(a, Literal) else env[id(a)]
+        for e in inner.eqns:
+            env[id(e.outvar)], _ = lower_eqn(dag, e, read_inner, division)
+        return read_inner(inner.outvars[0]), []
 
     # ---- elementwise binary (primitives.py:180-205, 237-239) ----------------
     if prim in ("max", "min"):     # primitives.py:208-215: ties send the derivative to the second operand

@@ -127,3 +127,45 @@ def test_large_plan_interpreter(built_library):
     rev_j, _ = replay.replay(rev.blob, xs, rev.n_rows, rev.n_cols)
     assert (np.abs(ref_j - rev_j) / scale).max() <= 1e-4
     dp.close()
+
+
+@pytest.mark.gpu
+def test_large_plan_interpreter_through_the_chunked_host_path(built_library):
+    """The global-memory interpreter keeps the live values of CTA b in one per-plan scratch area.  The host pipeline
+    (`gx_jacve_host`) launches consecutive chunks on two streams, and callers may launch one plan from several streams:
+    launches of such a plan are chained through an event (gx_abi.cu), so more than two chunks - and two user streams -
+    must still reproduce the single-launch result bit for bit."""
+    import ctypes
+    import torch
+    from graphax_b200 import runtime
+    plan = _plan("Encoder", "fwd")
+    batch = 3 * 1024 + 77                                           # > 2 chunks of the (small) host chunk below
+    xs = [np.ascontiguousarray(x.astype(np.float32)) for x in _inputs("Encoder", batch)]
+    dp = runtime.DevicePlan(plan, 0)
+    assert dp.info().kernel_kind == runtime.KERNEL_INTERPRETER and dp.info().smem_bytes == 0
+    ins = [torch.from_numpy(x).cuda() for x in xs]
+    want = torch.empty((batch, plan.n_rows, plan.n_cols), device="cuda")
+    dp.launch(batch, [t.data_ptr() for t in ins], want.data_ptr(), None, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    # (1) two user streams, launched back to back on halves of the batch
+    half = batch // 2
+    got = torch.full_like(want, float("nan"))
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for rep in range(3):
+        dp.launch(half, [t[:half].contiguous().data_ptr() for t in ins], got[:half].data_ptr(), None, s1.cuda_stream)
+        dp.launch(batch - half, [t[half:].contiguous().data_ptr() for t in ins], got[half:].data_ptr(), None, s2.cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.equal(got.view(torch.int32), want.view(torch.int32))
+    # (2) the chunked host pipeline (pinned buffers: chunks go straight from / to the caller's memory)
+    import os
+    os.environ["GX_HOST_CHUNK"] = "1024"
+    try:
+        dp2 = runtime.DevicePlan(plan, 0)
+        hin = [torch.from_numpy(x).pin_memory() for x in xs]
+        hj = torch.empty((batch, plan.n_rows, plan.n_cols)).pin_memory()
+        dp2.run_host(batch, [t.data_ptr() for t in hin], hj.data_ptr(), None, True)
+        assert np.array_equal(hj.numpy().view(np.uint32), want.cpu().numpy().view(np.uint32))
+        dp2.close()
+    finally:
+        del os.environ["GX_HOST_CHUNK"]
+    dp.close()

@@ -140,3 +140,34 @@ def test_gpu_call_with_a_jax_numpy_function():
 
 
 test_gpu_call_with_a_jax_numpy_function = __import__("pytest").mark.gpu(test_gpu_call_with_a_jax_numpy_function)
+
+
+def test_nested_call_is_one_vertex_without_in_edges_like_the_reference():
+    """`pjit` (what jnp.where / jnp.clip / jax.nn.* become under real JAX): the reference's rule evaluates the call and
+    returns no partials (primitives.py:576-602), so the call is one vertex whose derivative is dropped.  Same here,
+    with a warning; `iota` and `device_put` are value-only as well (primitives.py:444-455)."""
+    import warnings
+    import numpy as np
+    from graphax_b200.plan import build_plan
+    from graphax_b200.tracer import Eqn, Jaxpr, Var, jnp, make_jaxpr
+    from oracle import replay
+    inner = make_jaxpr(lambda a: jnp.sin(a) * 2.0, [()])
+    x, y = Var((), input_index=0), Var((), input_index=1)
+    v = [Var((), eqn_index=i) for i in range(4)]
+    eqns = [Eqn("pjit", (x,), v[0], {"jaxpr": inner, "name": "g"}), Eqn("device_put", (y,), v[1], {}),
+            Eqn("mul", (v[0], y), v[2], {}), Eqn("add", (v[2], x), v[3], {})]
+    jaxpr = Jaxpr([x, y], eqns, [v[3]], [0] * 4, False)
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        plan = build_plan(jaxpr, "rev", (0, 1))
+    assert any("dropped" in str(c.message) for c in caught)
+    jac, primal = replay.replay(plan.blob, [np.array([0.5], np.float32), np.array([3.0], np.float32)], 1, 2)
+    # f = g(x) * y + x with g opaque: df/dx = 1 (not 1 + 2 cos(x) y), df/dy = g(x) = 2 sin(x)
+    np.testing.assert_allclose(jac[0, 0], [1.0, 2 * np.sin(0.5)], rtol=1e-6)
+    np.testing.assert_allclose(primal[0, 0], 2 * np.sin(0.5) * 3.0 + 0.5, rtol=1e-6)
+    ramp, scaled = Var((3,), eqn_index=0), Var((3,), eqn_index=1)
+    iota = Jaxpr([x], [Eqn("iota", (), ramp, {"shape": (3,), "dimension": 0}), Eqn("mul", (ramp, x), scaled, {})],
+                 [scaled], [0, 0], False)
+    p2 = build_plan(iota, "rev", (0,))
+    j2, _ = replay.replay(p2.blob, [np.array([2.0], np.float32)], 3, 1)
+    np.testing.assert_allclose(j2[0, :, 0], [0.0, 1.0, 2.0])
