@@ -80,12 +80,16 @@ def _reference_available() -> bool:
 def _ref_chunk(bounds):
     """One chunk through the reference's own `jax.vmap(graphax.jacve(RoeFlux, order, argnums))` (worker process)."""
     if "fun" not in _CPU_CTX:
-        sys.path[:0] = [str(ROOT / "tests" / "golden" / "jaxlite"), str(ROOT / "baseline" / "_ref")]
-        import jax
+        try:                                   # a box that has the real thing: the reference on JAX / XLA itself
+            import jax
+            sys.path.insert(0, str(ROOT / "baseline" / "_ref"))
+        except ImportError:
+            sys.path[:0] = [str(ROOT / "tests" / "golden" / "jaxlite"), str(ROOT / "baseline" / "_ref")]
+            import jax
         import jax.numpy as jnp
         import graphax
         from graphax import examples as gex
-        assert "jaxlite" in jax.__file__ and "_ref" in graphax.__file__
+        assert "_ref" in graphax.__file__
         w = WORKLOADS[WORKLOAD]
         fun = {"roe3d": gex.RoeFlux_3d, "roe1d": gex.RoeFlux_1d, "robotarm": gex.RobotArm_6DOF}[WORKLOAD]
         order = _CPU_CTX["order"]
