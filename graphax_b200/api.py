@@ -294,9 +294,8 @@ class JacveFunction:
         grads_tree = grads[0] if single else tuple(grads)
         if self.count_ops:
             if plan.stats["num_muls"] is None:
-                # matrix-valued vertices: the reference's tensor-level cost model (tensor.py:1414-1493) is not
-                # restated; report the structurally non-zero scalar products instead (equal to the reference's
-                # numbers for the NeuralNetwork test, within 0-4 % for Perceptron / Encoder / EncoderDecoder)
+                # an edge outside the reference's structure rules (the reference itself raises there, e.g. a
+                # concatenation of a replicated dimension): report the structurally non-zero scalar products instead
                 aux = {"num_muls": plan.stats["scalar_muls"], "num_adds": plan.stats["scalar_adds"],
                        "order_counts": list(plan.stats["scalar_order_counts"]), "model": "scalar products"}
                 return grads_tree, aux

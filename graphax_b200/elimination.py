@@ -28,6 +28,7 @@ from dataclasses import dataclass, field, replace
 from typing import Dict, List, Optional, Sequence, Set, Tuple, Union
 
 from . import structure as st
+from . import structure_nd as nd
 from .lowering import Dag, Entries, Vec, lower_eqn
 from .tracer import Jaxpr, Literal, Var
 
@@ -100,7 +101,8 @@ def build_graph(jaxpr: Jaxpr, division: str = "ieee", fuse: bool = True) -> Grap
                 for ij, n in entries.items():
                     merged[ij] = dag.add(n, merged[ij]) if ij in merged else n
                 both = struct is not None and old.struct is not None
-                edge = Edge(_try(st.add, struct, old.struct) if both else None, merged)
+                alg, pair = _algebra(struct, old.struct) if both else (st, [])
+                edge = Edge(_try(alg.add, *pair) if both else None, merged)
             else:
                 edge = Edge(struct, entries)
             g.fwd[src][v] = edge
@@ -144,12 +146,20 @@ def _try(fn, *structs):
     block there): the scalar entries stay exact, the descriptor is dropped (``None`` = not tracked)."""
     try:
         return fn(*structs)
-    except AssertionError:
+    except (AssertionError, NotImplementedError, IndexError, AttributeError):
         return None
 
 
-def _strip(s: st.Struct) -> st.Struct:
+def _strip(s):
     return replace(s, pre=()) if s.pre else s
+
+
+def _algebra(*structs):
+    """The structure algebra for these edges: ``structure.py`` while every vertex involved has rank <= 1,
+    ``structure_nd.py`` as soon as one descriptor is an N-dimensional one (rank <= 1 descriptors are converted)."""
+    if any(isinstance(s, nd.NStruct) for s in structs):
+        return nd, [nd.from_struct(s) for s in structs]
+    return st, list(structs)
 
 
 def _product_entries(dag: Dag, post: Entries, pre: Entries, existing: Optional[Entries]) -> Entries:
@@ -208,31 +218,34 @@ class StepStats:
 def _structured_product(g: Graph, stats: StepStats, post: Edge, pre: Edge, old: Optional[Edge], p: int, s: int) -> None:
     """One J[s,p] (+)= J[s,v] J[v,p] with the reference's SparseTensor structure rules (core.py:198-262)."""
     dag = g.dag
-    pre_s = pre.struct
-    if post.struct.pre and pre.struct.has_val:
+    alg, (post_s, pre_s) = _algebra(post.struct, pre.struct, *([old.struct] if old is not None else []))[0], \
+        _algebra(post.struct, pre.struct, *([old.struct] if old is not None else []))[1][:2]
+    pre_pending = pre_s.pre
+    if post_s.pre and pre_s.has_val:
         # unload_pre_transforms: shape-op Jacobians pending on the outgoing edge act on the incoming one
         pre_s = _strip(pre_s)
-        for t in post.struct.pre:
-            pre_s = st.apply_transform(t, pre_s)
-    if pre.struct.has_val and post.struct.has_val:
-        lhs, rhs = _strip(post.struct), _strip(pre_s)
-        cls = st.mul_class(lhs, rhs)
+        for t in post_s.pre:
+            pre_s = alg.apply_transform(t, pre_s)
+    if pre_s.has_val and post_s.has_val:
+        lhs, rhs = _strip(post_s), _strip(pre_s)
+        cls = alg.mul_class(lhs, rhs)
         key = f"{post.struct.sparsity_class()}x{pre.struct.sparsity_class()}:{cls}"
         stats.classes[key] = stats.classes.get(key, 0) + 1
-        out_s = st.mul(lhs, rhs)
-        stats.num_muls += st.num_muls(lhs, rhs)
-        pending = pre.struct.pre
-    elif pre.struct.has_val:
-        out_s, pending = _strip(pre_s), pre.struct.pre
+        out_s = alg.mul(lhs, rhs)
+        stats.num_muls += alg.num_muls(lhs, rhs)
+        pending = pre_pending
+    elif pre_s.has_val:
+        out_s, pending = _strip(pre_s), pre_pending
     else:
-        out_s, pending = _strip(post.struct), pre.struct.pre + post.struct.pre
+        out_s, pending = _strip(post_s), pre_pending + post_s.pre
     out_s = replace(out_s, pre=pending)
 
     if old is not None:
         # fill-in onto an existing edge: flush deferred transforms on both, then add
-        new_m, old_m = st.materialise(out_s), st.materialise(old.struct)
-        out_s = st.add(new_m, old_m)
-        stats.num_adds += st.num_adds(out_s, old_m)
+        old_s = nd.from_struct(old.struct) if alg is nd else old.struct
+        new_m, old_m = alg.materialise(out_s), alg.materialise(old_s)
+        out_s = alg.add(new_m, old_m)
+        stats.num_adds += alg.num_adds(out_s, old_m)
     entries = _product_entries(dag, post.entries, pre.entries, None if old is None else old.entries)
     edge = Edge(out_s, entries)
     g.fwd[p][s] = edge
@@ -262,7 +275,8 @@ def eliminate(g: Graph, vertex: int) -> StepStats:
                 continue
             try:
                 _structured_product(g, stats, post, pre, old, p, s)
-            except AssertionError:      # outside the reference's structure rules: keep the exact entries only
+            except (AssertionError, NotImplementedError, IndexError, AttributeError):
+                # outside the reference's structure rules (it raises there): keep the exact entries only
                 stats.structure_complete = False
                 entries = _product_entries(dag, post.entries, pre.entries, None if old is None else old.entries)
                 edge = Edge(None, entries)
@@ -330,5 +344,6 @@ def accumulate(jaxpr: Jaxpr, order: Order, argnums: Sequence[int], division: str
             if edge is None:
                 blocks[(oi, ai)] = (None, {})
             else:
-                blocks[(oi, ai)] = (_try(st.materialise, edge.struct) if edge.struct is not None else None, edge.entries)
+                alg = nd if isinstance(edge.struct, nd.NStruct) else st
+                blocks[(oi, ai)] = (_try(alg.materialise, edge.struct) if edge.struct is not None else None, edge.entries)
     return Accumulated(g, vertices, steps, blocks)

@@ -23,6 +23,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import structure as st
+from . import structure_nd as nd
 from .tracer import Eqn, Literal, Var
 
 # opcode table shared with csrc/gx_ops.h and oracle/replay.c (keep in sync; tests check it)
@@ -256,11 +257,13 @@ Entries = Dict[Tuple[int, int], int]
 
 
 def _parallel_jacobian(primal: Vec, out: Vec, partial: Vec, n_operands: int) -> Tuple[Optional[st.Struct], Entries]:
-    """``make_parallel_jacobian`` (reference primitives.py:42-107).  Entries are exact for any rank; the
-    structure descriptor is produced for rank <= 1 (``None`` above: no ``count_ops`` for such graphs)."""
+    """``make_parallel_jacobian`` (reference primitives.py:42-107).  Entries are exact for any rank; the structure
+    descriptor comes from ``structure.py`` for rank <= 1 and from ``structure_nd.py`` above."""
     if out.ndim > 1 or primal.ndim > 1:
         ip, iq = _bcast_index(primal, out.shape), _bcast_index(partial, out.shape)
-        return None, {(i, int(ip[i])): partial.nodes[int(iq[i])] for i in range(out.size)}
+        struct = nd.elementwise(primal.shape, out.shape, n_operands, partial.shape,
+                                partial.is_literal or partial.size == 1)
+        return struct, {(i, int(ip[i])): partial.nodes[int(iq[i])] for i in range(out.size)}
     n = out.size
     if primal.ndim == 0 and out.ndim == 0:
         return st.SCALAR, {(0, 0): partial.nodes[0]}
@@ -541,15 +544,20 @@ def lower_eqn(dag: Dag, eqn: Eqn, read, division: str = "ieee",
         idx = x.index_array()
         if prim == "transpose":
             idx = np.transpose(idx, eqn.params["permutation"])
+            t = nd.NTransform("transpose", perm=tuple(int(q) for q in eqn.params["permutation"]))
         else:
             idx = idx.reshape(eqn.outvar.shape)
+            t = nd.NTransform("squeeze", dims=tuple(int(d) for d in eqn.params["dimensions"])) \
+                if prim == "squeeze" and "dimensions" in eqn.params else \
+                nd.NTransform("reshape", in_shape=x.shape, out_shape=tuple(eqn.outvar.shape))
         out, entries = gather_edge(x, idx)
-        return out, ([(eqn.invars[0], None, entries)] if traced else [])
+        return out, ([(eqn.invars[0], nd.transform_edge(t), entries)] if traced else [])
     if prim == "slice_nd":
         (x,) = ops
         idx = x.index_array()[tuple(slice(a, b) for a, b in zip(eqn.params["start_indices"], eqn.params["limit_indices"]))]
         out, entries = gather_edge(x, idx)
-        return out, ([(eqn.invars[0], None, entries)] if traced else [])
+        t = nd.NTransform("slice", in_shape=x.shape, out_shape=tuple(idx.shape))
+        return out, ([(eqn.invars[0], nd.transform_edge(t), entries)] if traced else [])
     if prim == "concatenate_nd":
         axis, off, pieces, es = int(eqn.params["dimension"]), 0, [], []
         for o in ops:
@@ -564,7 +572,9 @@ def lower_eqn(dag: Dag, eqn: Eqn, read, division: str = "ieee",
             for i, j in zip(dst, range(o.size)):
                 nodes[int(i)] = o.nodes[j]
             if isinstance(a, Var):
-                es.append((a, None, {(int(i), j): dag.const(1.0) for i, j in zip(dst, range(o.size))}))
+                t = nd.NTransform("concat", in_shape=o.shape, out_shape=tuple(full.shape), dims=(axis,),
+                                  lo=off, hi=off + o.shape[axis])
+                es.append((a, nd.transform_edge(t), {(int(i), j): dag.const(1.0) for i, j in zip(dst, range(o.size))}))
             off += o.shape[axis]
         return Vec(full.shape, nodes), es
     if prim == "broadcast_in_dim_nd":
@@ -575,7 +585,8 @@ def lower_eqn(dag: Dag, eqn: Eqn, read, division: str = "ieee",
             view[ax] = d
         idx = np.broadcast_to(x.index_array().reshape(view) if x.ndim else np.zeros(view, dtype=np.int64), shape)
         out, entries = gather_edge(x, np.ascontiguousarray(idx))
-        return out, ([(eqn.invars[0], None, entries)] if traced else [])
+        t = nd.NTransform("broadcast", in_shape=x.shape, out_shape=shape, dims=tuple(sorted(bdims)))
+        return out, ([(eqn.invars[0], nd.transform_edge(t), entries)] if traced else [])
     if prim == "reduce_sum_nd":
         (x,) = ops
         axes = tuple(eqn.params["axes"])
@@ -589,7 +600,7 @@ def lower_eqn(dag: Dag, eqn: Eqn, read, division: str = "ieee",
             nodes.append(acc)
             for j in grp:
                 entries[(i, int(j))] = dag.const(1.0)
-        return Vec(eqn.outvar.shape, nodes), ([(eqn.invars[0], None, entries)] if traced else [])
+        return Vec(eqn.outvar.shape, nodes), ([(eqn.invars[0], nd.reduce_sum(x.shape, axes), entries)] if traced else [])
     if prim in ("reduce_max", "reduce_min"):      # primitives.py:275-346: where(x == out) / count
         (x,) = ops
         axes = tuple(eqn.params["axes"])
@@ -607,7 +618,7 @@ def lower_eqn(dag: Dag, eqn: Eqn, read, division: str = "ieee",
                 count = dag.add(count, h)
             for j, h in zip(grp, hits):
                 entries[(i, int(j))] = dag.div(h, count)
-        return Vec(eqn.outvar.shape, nodes), ([(eqn.invars[0], None, entries)] if traced else [])
+        return Vec(eqn.outvar.shape, nodes), ([(eqn.invars[0], nd.reduce_extreme(x.shape, axes), entries)] if traced else [])
     if prim == "dot_general_nd":                  # primitives.py:349-441, any rank, batch dimensions allowed
         x, y = ops
         (cx, cy), (bx, by) = eqn.params["dimension_numbers"]
@@ -631,8 +642,9 @@ def lower_eqn(dag: Dag, eqn: Eqn, read, division: str = "ieee",
                         ex[(o, int(ix[b, i, k]))] = y.nodes[int(iy[b, j, k])]
                         ey[(o, int(iy[b, j, k]))] = x.nodes[int(ix[b, i, k])]
                     o += 1
+        structs = nd.dot_general(x.shape, y.shape, eqn.params["dimension_numbers"])
         es = []
         for i in traced:
-            es.append((eqn.invars[i], None, ex if i == 0 else ey))
+            es.append((eqn.invars[i], structs[i], ex if i == 0 else ey))
         return Vec(eqn.outvar.shape, nodes), es
     raise NotImplementedError(f"{prim} does not have registered elemental partial.")   # core.py:398

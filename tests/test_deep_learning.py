@@ -169,3 +169,31 @@ def test_large_plan_interpreter_through_the_chunked_host_path(built_library):
     finally:
         del os.environ["GX_HOST_CHUNK"]
     dp.close()
+
+
+@pytest.mark.gpu
+def test_count_ops_and_sparse_representation_above_rank_one_through_the_api(built_library):
+    """`jacve(..., count_ops=True)` and `sparse_representation=True` on matrix-valued vertices: the reference's own
+    numbers (Perceptron: 7762 / 1384 forward, 312 / 21 reverse, tests/golden/reference_trace_rank_n.json.gz) and the
+    SparseTensor structure of every Jacobian block (core.py:555-581), with values equal to the dense result."""
+    import gzip
+    import json
+    import torch
+    from helpers import GOLDEN
+    trace = json.loads(gzip.open(GOLDEN / "reference_trace_rank_n.json.gz").read())["cases"]["Perceptron"]
+    fn, shapes, argnums = CASES["Perceptron"]
+    xs = [torch.from_numpy(x[0].astype(np.float32)).cuda() for x in _inputs("Perceptron", 1)]
+    for order in ("fwd", "rev"):
+        jac, aux = gx.jacve(fn, order=order, argnums=argnums, count_ops=True)(*xs)
+        ref = trace["orders"][order]
+        assert (aux["num_muls"], aux["num_adds"]) == (ref["num_muls"], ref["num_adds"]) and "model" not in aux
+        assert [list(c) for c in aux["order_counts"]] == ref["order_counts"]
+        sparse = gx.jacve(fn, order=order, argnums=argnums, sparse_representation=True)(*xs)
+        blocks = sparse if isinstance(sparse[0], gx.SparseJacobian) or sparse[0] is None else sparse[0]
+        dense = jac if not isinstance(jac[0], tuple) else jac[0]
+        for i, (b, d) in enumerate(zip(blocks, ref["blocks"])):
+            if d is None:
+                assert b is None
+                continue
+            assert (b.out_dims, b.primal_dims, b.val_shape) == (d["out"], d["primal"], d["val"]), (order, i)
+            assert torch.equal(b.dense, dense[i])

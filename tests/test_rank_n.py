@@ -109,7 +109,6 @@ def test_plan_replay_matches_oracle(name, order):
     jaxpr = make_jaxpr(fn, shapes)
     argnums = tuple(range(len(shapes)))
     plan = build_plan(jaxpr, order, argnums)
-    assert plan.stats["num_muls"] is None or all(len(s) <= 1 for s in shapes)      # no count_ops above rank 1
     xs = [x.astype(np.float32) for x in _inputs(shapes, 64)]
     jac, primal = replay.replay(plan.blob, xs, plan.n_rows, plan.n_cols)
     t64, p64 = _oracle_tile(jaxpr, order, argnums, [x.astype(np.float64) for x in xs], np.float64)

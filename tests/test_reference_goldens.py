@@ -338,22 +338,20 @@ def test_random_tensor_function_f_against_reference_run():
 
 
 @pytest.mark.parametrize("name", list(RUN["rank_n"]))
-def test_scalar_product_counts_for_matrix_valued_graphs(name):
-    """`count_ops` above rank 1 reports structurally non-zero scalar products (the reference's tensor-level cost model,
-    `tensor.py:1414-1493`, is not restated).  Against the reference run: identical for its NeuralNetwork test, within
-    5 % for Perceptron / Encoder / EncoderDecoder; on vertices of rank <= 1 the exact model is used (other tests)."""
+def test_count_ops_for_matrix_valued_graphs(name):
+    """`count_ops` above rank 1: the reference's tensor-level cost model (`tensor.py:1414-1493`) on the engine's
+    restatement of its dimension bookkeeping (`structure_nd.py`): identical to the reference run for NeuralNetwork,
+    Perceptron, Encoder and EncoderDecoder, forward and reverse (round 1 reported structurally non-zero scalar
+    products there, 0-4 % off; those remain available as `scalar_muls` / `scalar_adds`)."""
     from graphax_b200.plan import build_plan
     from graphax_b200.tracer import make_jaxpr
     rec = RUN["rank_n"][name]
     jaxpr = make_jaxpr(_rank_n_case(name), [tuple(s) for s in rec["in_shapes"]])
-    for order in ("rev",) if name == "EncoderDecoder" else ("fwd", "rev"):
+    for order in ("fwd", "rev"):
         stats = build_plan(jaxpr, order, tuple(rec["argnums"]), rounding="fma").stats     # counts do not depend on rounding
-        assert stats["num_muls"] is None                     # no tensor-level structure above rank 1
-        ref = rec["orders"][order]["num_muls"]
-        assert abs(stats["scalar_muls"] - ref) <= 0.05 * ref, (order, stats["scalar_muls"], ref)
-        if name == "NeuralNetwork":
-            assert (stats["scalar_muls"], stats["scalar_adds"]) == (ref, rec["orders"][order]["num_adds"])
-        assert sum(c for _, c in stats["scalar_order_counts"]) == stats["scalar_muls"]
+        assert (stats["num_muls"], stats["num_adds"]) == (rec["orders"][order]["num_muls"], rec["orders"][order]["num_adds"])
+        assert sum(c for _, c in stats["order_counts"]) == stats["num_muls"]
+        assert abs(stats["scalar_muls"] - stats["num_muls"]) <= 0.05 * stats["num_muls"]
 
 
 def test_reference_test_suite_on_the_stand_in():
