@@ -8,7 +8,8 @@ Same call shape as the reference (``graphax/__init__.py:2-4``)::
 from .api import jacve, vmap, tree_allclose, JacveFunction, SparseJacobian
 from .tracer import jnn, jnp, lax, make_jaxpr
 from .primitives import Primitive, defelemental, defelemental2, elemental_rules
+from .filtering import filter_jacve
 
 __version__ = "0.1.0"
 __all__ = ["jacve", "vmap", "tree_allclose", "jnn", "jnp", "lax", "make_jaxpr", "JacveFunction", "SparseJacobian",
-           "Primitive", "defelemental", "defelemental2", "elemental_rules"]
+           "Primitive", "defelemental", "defelemental2", "elemental_rules", "filter_jacve"]

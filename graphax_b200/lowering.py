@@ -364,8 +364,12 @@ def lower_eqn(dag: Dag, eqn: Eqn, read, division: str = "ieee",
         zero = Vec(shape, [dag.const(0.0)] * len(iw))
         partials = (zero, off, on)
         return out, [(eqn.invars[i],) + _parallel_jacobian(ops[i], out, partials[i], 2) for i in traced]
-    if prim == "convert_element_type":   # primitives.py:1236-1255: one floating-point type here, the value passes through
-        return edges(ops[0], (ew.ones_like(ops[0]),))
+    if prim == "convert_element_type":
+        # primitives.py:1236-1255: a transform edge that converts the neighbouring edge's values - with one
+        # floating-point type the identity, and like every transform edge it costs no multiplication
+        x = ops[0]
+        entries = {(i, i): dag.const(1.0) for i in range(x.size)}
+        return x, ([(eqn.invars[0], nd.transform_edge(nd.NTransform("convert")), entries)] if traced else [])
     if prim in ("ge", "le", "ne"):   # complements of lt / gt / eq (a NaN operand compares as true here)
         x, y = ops
         base = ew.binary({"ge": "lt", "le": "gt", "ne": "eq"}[prim], x, y)
