@@ -160,18 +160,48 @@ def build_dense_plan(jaxpr: Jaxpr, order, argnums: Sequence[int]) -> DensePlan:
         env[key(v)] = dag.input(i, in_shapes[i])
 
     def read(a) -> int:
-        return dag.const(a.val) if isinstance(a, Literal) else env[key(a)]
+        if isinstance(a, Literal):
+            return dag.const(a.val)
+        if key(a) in transposed_of:
+            raise NotImplementedError("a transposed matrix is only supported as an operand of a contraction "
+                                      "(x @ W.T) on the tensor-valued path")
+        return env[key(a)]
+
+    # `W.T` feeding a contraction (x @ W.T, how models usually write a linear layer): the transpose vertex is folded
+    # into the contraction's dimension numbers - the kernel reads either operand layout in place - and its Jacobian
+    # goes straight to the matrix it transposes
+    transposed_of: Dict[int, Var] = {}
+
+    def contraction_operands(eqn):
+        """[(underlying variable, contracted axis of it)] for both operands of a dot_general."""
+        (ca, cb), (ba, _bb) = eqn.params["dimension_numbers"]
+        if len(ca) != 1 or ba or eqn.invars[0].ndim != 2 or eqn.invars[1].ndim != 2:
+            raise NotImplementedError("dot_general: exactly one contracting dimension of two matrices")
+        out = []
+        for a, c in zip(eqn.invars, (ca[0], cb[0])):
+            if isinstance(a, Var) and key(a) in transposed_of:
+                out.append((transposed_of[key(a)], 1 - c))
+            else:
+                out.append((a, c))
+        return out
 
     # ---- forward: primal values (core.py:380-403) ------------------------------------------------
     for eqn in jaxpr.eqns:
-        p, ins = eqn.primitive, [read(a) for a in eqn.invars]
+        p = eqn.primitive
         shape = _norm(eqn.outvar.shape)
+        if p == "transpose" and eqn.invars[0].ndim == 2 and tuple(eqn.params["permutation"]) == (1, 0) \
+                and isinstance(eqn.invars[0], Var) and key(eqn.invars[0]) not in transposed_of:
+            transposed_of[key(eqn.outvar)] = eqn.invars[0]
+            continue
         if p == "dot_general":
-            (ca, cb), (ba, _bb) = eqn.params["dimension_numbers"]
-            if len(ca) != 1 or ba or eqn.invars[0].ndim != 2 or eqn.invars[1].ndim != 2:
-                raise NotImplementedError("dot_general: exactly one contracting dimension of two matrices")
-            out = dag.gemm(ins[0], ca[0] == 0, ins[1], cb[0] == 0)
-        elif p == "broadcast_in_dim":
+            (va, ca0), (vb, cb0) = contraction_operands(eqn)
+            out = dag.gemm(read(va), ca0 == 0, read(vb), cb0 == 0)
+            if dag.nodes[out].shape != shape:
+                raise AssertionError(f"shape mismatch lowering {eqn!r}")
+            env[key(eqn.outvar)] = out
+            continue
+        ins = [read(a) for a in eqn.invars]
+        if p == "broadcast_in_dim":
             if _norm(eqn.invars[0].shape) != shape:
                 raise NotImplementedError("broadcast_in_dim other than rank promotion (n,) -> (1, n)")
             out = ins[0]
@@ -211,20 +241,23 @@ def build_dense_plan(jaxpr: Jaxpr, order, argnums: Sequence[int]) -> DensePlan:
     for eqn in reversed(jaxpr.eqns):
         g = cot.pop(key(eqn.outvar), None)
         if g is None:
-            continue                                  # no path from this vertex to the output
+            continue                                  # no path from this vertex to the output (or a folded transpose)
         p = eqn.primitive
-        ins = [read(a) for a in eqn.invars]
+        if p == "dot_general":
+            (va, ca0), (vb, cb0) = contraction_operands(eqn)
+            operands, ins = [va, vb], [read(va), read(vb)]
+        else:
+            operands, ins = list(eqn.invars), [read(a) for a in eqn.invars]
         out = env[key(eqn.outvar)]
-        traced = [i for i, a in enumerate(eqn.invars) if isinstance(a, Var)]
+        traced = [i for i, a in enumerate(operands) if isinstance(a, Var)]
         oshape = _norm(eqn.outvar.shape)
         gfull = g if dag.nodes[g].shape == oshape else dag.ew("copy", g, shape=oshape)
         for i in traced:
-            a = eqn.invars[i]
+            a = operands[i]
             n_products += 1
             if p == "dot_general":
                 # out[M,N] = A[M,K] . B[N,K]^T with A = op_ta(a), B = op_tb(b); gemm(X,tx,Y,ty) = op(X) . op(Y)^T
-                (ca, cb), _ = eqn.params["dimension_numbers"]
-                ta, tb = ca[0] == 0, cb[0] == 0
+                ta, tb = ca0 == 0, cb0 == 0
                 if i == 0:      # dA = g . B, stored transposed when the operand was
                     eff = dag.gemm(gfull, False, ins[1], not tb) if not ta else dag.gemm(ins[1], not tb, gfull, False)
                 else:           # dB = g^T . A  (the batch axis is the contraction: [B,H]^T [B,H'])

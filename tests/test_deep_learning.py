@@ -182,7 +182,7 @@ def test_count_ops_and_sparse_representation_above_rank_one_through_the_api(buil
     from helpers import GOLDEN
     trace = json.loads(gzip.open(GOLDEN / "reference_trace_rank_n.json.gz").read())["cases"]["Perceptron"]
     fn, shapes, argnums = CASES["Perceptron"]
-    xs = [torch.from_numpy(x[0].astype(np.float32)).cuda() for x in _inputs("Perceptron", 1)]
+    xs = [torch.as_tensor(np.asarray(x[0], dtype=np.float32)).cuda() for x in _inputs("Perceptron", 1)]
     for order in ("fwd", "rev"):
         jac, aux = gx.jacve(fn, order=order, argnums=argnums, count_ops=True)(*xs)
         ref = trace["orders"][order]
