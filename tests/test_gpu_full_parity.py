@@ -108,3 +108,30 @@ def test_fma_rounding_against_the_stated_tolerance_over_the_full_batch(built_lib
         assert worst < 2.0 and over <= 16, (worst, over)
     else:
         assert over == 0 and worst < 0.5, (worst, over)
+
+
+@pytest.mark.parametrize("order", ["rev", "fwd", "alphagrad", "markowitz"])
+def test_roeflux_1d_reference_rounding_is_exact_over_its_full_batch(built_library, order):
+    """Config 2 (RoeFlux_1d, batch 2^16): every order of the reference's tests, the whole batch, equal values."""
+    import torch
+    from graphax_b200 import runtime
+    from oracle import ve_numpy
+    w = WORKLOADS["roe1d"]
+    batch = w.batch
+    xs = w.inputs(batch)
+    plan = w.plan(order, rounding="reference")
+    dp = runtime.DevicePlan(plan, 0, jit=False)
+    assert dp.kernel == "aot"
+    dev = [torch.from_numpy(x).cuda() for x in xs]
+    jac = torch.empty((batch, plan.n_rows, plan.n_cols), device="cuda")
+    primal = torch.empty((batch, plan.n_rows), device="cuda")
+    dp.launch(batch, [t.data_ptr() for t in dev], jac.data_ptr(), primal.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    j32, p32, _ = ve_numpy.jacve(w.jaxpr(), w.order(order), w.argnums, xs, np.float32)
+    t32 = pack_blocks(j32, batch, w.sizes)
+    got = jac.cpu().numpy()
+    assert int((got != t32).sum()) == 0
+    assert int((primal.cpu().numpy() != np.concatenate([p.reshape(batch, -1) for p in p32], axis=1)).sum()) == 0
+    _record(f"roe1d:{order}:reference", {"samples": batch, "entries": int(got.size), "value_mismatches": 0,
+                                         "zero_sign_differences": int((bits(got) != bits(t32)).sum())})
+    dp.close()
