@@ -218,8 +218,8 @@ class StepStats:
 def _structured_product(g: Graph, stats: StepStats, post: Edge, pre: Edge, old: Optional[Edge], p: int, s: int) -> None:
     """One J[s,p] (+)= J[s,v] J[v,p] with the reference's SparseTensor structure rules (core.py:198-262)."""
     dag = g.dag
-    alg, (post_s, pre_s) = _algebra(post.struct, pre.struct, *([old.struct] if old is not None else []))[0], \
-        _algebra(post.struct, pre.struct, *([old.struct] if old is not None else []))[1][:2]
+    alg, converted = _algebra(post.struct, pre.struct, *([old.struct] if old is not None else []))
+    post_s, pre_s = converted[0], converted[1]
     pre_pending = pre_s.pre
     if post_s.pre and pre_s.has_val:
         # unload_pre_transforms: shape-op Jacobians pending on the outgoing edge act on the incoming one
@@ -242,8 +242,7 @@ def _structured_product(g: Graph, stats: StepStats, post: Edge, pre: Edge, old: 
 
     if old is not None:
         # fill-in onto an existing edge: flush deferred transforms on both, then add
-        old_s = nd.from_struct(old.struct) if alg is nd else old.struct
-        new_m, old_m = alg.materialise(out_s), alg.materialise(old_s)
+        new_m, old_m = alg.materialise(out_s), alg.materialise(converted[2])
         out_s = alg.add(new_m, old_m)
         stats.num_adds += alg.num_adds(out_s, old_m)
     entries = _product_entries(dag, post.entries, pre.entries, None if old is None else old.entries)
