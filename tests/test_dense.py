@@ -229,7 +229,25 @@ def test_jacve_api_dispatches_matrix_arguments(built_library):
     for g, ti in zip(grads, (t[1], t[2], t[3], t[4])):
         assert float((g.double().cpu() - ti.grad).abs().max()) <= 3e-2 * float(ti.grad.abs().max())
     with pytest.raises(NotImplementedError):
-        gx.jacve(MLP_loss, order="fwd", argnums=(1,))(*tens)
+        gx.jacve(MLP_loss, order="fwd", argnums=(1,))(*tens)          # 65k input scalars: refused, not attempted
+
+
+@pytest.mark.gpu
+def test_dense_jacve_other_orders_on_small_problems(built_library):
+    """`dense_jacve(order="fwd")`: tensor-level elimination is reverse-only, but small problems (the reference's own
+    test sizes) run on the per-sample engine in any order - here against the reference run of the batched MLP,
+    whose forward and reverse results both exist."""
+    import torch
+    from graphax_b200.dense import dense_jacve
+    rec, args, ref = _reference_mlp()
+    tens = [torch.from_numpy(a).cuda() for a in args]
+    loss, grads = dense_jacve(MLP_loss, "fwd", (1, 2, 3, 4), *tens, has_aux=True)
+    r_grads, r_loss = ref["fwd"]
+    assert abs(float(loss) - r_loss) <= 1e-5 * abs(r_loss)
+    for g, r in zip(grads, r_grads):
+        g = g.cpu().numpy().astype(np.float64).reshape(r.shape)
+        bound = 1e-5 * np.abs(r).max() + 1e-5 * np.abs(r)
+        assert (np.abs(g - r) <= bound).all()
 
 
 @pytest.mark.gpu
