@@ -414,7 +414,10 @@ class DenseExecutor:
         self.arena_size = off
         self.arena = None
         self.input_stage: Dict[Tuple[int, str], object] = {}
-        self.concurrent = os.environ.get("GX_DENSE_STREAMS", "2") != "1" and not self.split
+        # one stream by default: the programmatic-dependent-launch chain of the five contractions (55.4 us per MLP
+        # step, B200 r02) beats running the two weight-Jacobian contractions on a side stream (57.4 us: the fork /
+        # join edges of the captured graph cost more than the overlap gains); GX_DENSE_STREAMS=2 restores the latter
+        self.concurrent = os.environ.get("GX_DENSE_STREAMS", "1") == "2" and not self.split
         self._split_bufs: Dict[int, list] = {}
         self._split_done: set = set()
         # kernels that add into the arena, and results that nothing downstream reads (side-stream candidates)
