@@ -16,7 +16,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 GEN = CSRC / "gen"
 OBJ = CSRC / "build"
-LIB = PKG / "libgraphax_b200.so"
+LIB = Path(os.environ.get("GX_LIB") or PKG / "libgraphax_b200.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-cudart", "static", f"-I{CSRC}"]

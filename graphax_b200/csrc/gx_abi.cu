@@ -848,12 +848,15 @@ int gx_plan_specialize_opts(gx_plan* p, const char* src, size_t nbytes, const ch
   if (rt.CreateProgram(&prog, src, "gx_plan.cu", 0, nullptr, nullptr) != 0)
     return fail(GX_ERR_JIT, "nvrtcCreateProgram failed");
   std::string archopt = std::string("--gpu-architecture=") + (arch && *arch ? arch : "sm_100a");
-  // two input stages per warp unless only one fits beside the output tile (same rule as codegen.input_stages)
+  // input stages per warp: same rule as codegen.input_stages
   const int tile = (int)(p->h.n_rows * p->h.n_cols + ((p->h.flags & GX_FLAG_HAS_PRIMAL) ? p->h.n_rows : 0));
   auto smem_for = [&](int in_stages) {
     return (threads / 32) * (in_stages * (int)p->h.n_in_scalars * 32 * spt + out_stages * tile * 32 * spt + 4) * 4;
   };
-  const int in_stages = smem_for(2) <= 227 * 1024 ? 2 : 1;
+  // GX_INPUT_STAGED=0: one-sample-per-thread kernels load their inputs straight into registers (no stage)
+  const char* staged_env = getenv("GX_INPUT_STAGED");
+  const bool staged = spt != 1 || !(staged_env && staged_env[0] == '0');
+  const int in_stages = !staged ? 0 : smem_for(2) <= 227 * 1024 ? 2 : 1;
   char d_threads[48], d_blocks[48], d_stages[48], d_spt[48], d_in[48];
   snprintf(d_in, sizeof d_in, "-DGX_IN_STAGES=%d", in_stages);
   snprintf(d_spt, sizeof d_spt, "-DGX_SPT=%d", spt);

@@ -34,8 +34,13 @@ typedef unsigned long long uint64_t;
 
 #define GX_TILE (GX_N_ROWS * GX_N_COLS)
 #ifndef GX_IN_STAGES
-#define GX_IN_STAGES 2 /* 1: wide tiles whose second input stage would not fit; the next tile is then requested as soon
-                          as the current one has been copied to registers */
+#define GX_IN_STAGES 2 /* 0: inputs never touch shared memory - every lane loads its own sample's scalars for the NEXT
+                             tile straight into registers from a point late in the current tile's body, where few
+                             values are live (a few dozen bytes per sample: the loads of a warp cover whole sectors
+                             of every input array, and their latency hides behind the rest of the body);
+                          2: bulk-copied (TMA) into two shared-memory stages per warp, one tile ahead;
+                          1: one such stage (wide tiles), the next tile requested as soon as the current one has
+                             been copied to registers */
 #endif
 #ifndef GX_CHECKED_FAST_MATH
 #define GX_CHECKED_FAST_MATH 1
@@ -44,6 +49,9 @@ typedef unsigned long long uint64_t;
 #define GX_SPT 1
 #endif
 #define GX_WT (32 * GX_SPT) /* samples per warp tile */
+#if GX_SPT != 1 && GX_IN_STAGES == 0
+#error "the packed two-sample kernels stage their inputs: GX_IN_STAGES must be 1 or 2"
+#endif
 #define GX_MAX_ARRAYS_K 32
 
 struct GxLaunchArgs {
@@ -148,12 +156,14 @@ GX_KERNEL_NAME(const __grid_constant__ GxLaunchArgs args) {
   const long long stride = (long long)gridDim.x * kWarps;
 
   pdl_launch_dependents();
+#if GX_IN_STAGES > 0
   if (lane == 0) {
     mbar_init(&full_bar[0], 1);
     mbar_init(&full_bar[1], 1);
     fence_mbar_init();
   }
   __syncwarp();
+#endif
   pdl_wait();  // everything above overlaps the tail of the previous kernel on the stream
 
   auto issue_loads = [&](long long tile, int stage) {
@@ -167,7 +177,22 @@ GX_KERNEL_NAME(const __grid_constant__ GxLaunchArgs args) {
   };
 
   long long tile = (long long)blockIdx.x * kWarps + warp;
+#if GX_IN_STAGES > 0
   if (tile < n_bulk && elect_one()) issue_loads(tile, 0);
+#elif GX_SPT == 1
+  // every lane reads its own sample (lanes past the end of the batch compute on 1.0 and store nothing)
+  auto load_inputs = [&](float (&dst)[GX_N_IN], long long t) {
+    const long long sample = t * GX_WT + lane;
+    const bool ok = sample < args.batch;
+#define GX_RD_DIRECT(a, size, off)                   \
+  _Pragma("unroll") for (int c = 0; c < (size); ++c) \
+      dst[(off) + c] = ok ? __ldg(args.in[a] + sample * (size) + c) : 1.0f;
+    GX_FOREACH_ARRAY(GX_RD_DIRECT)
+#undef GX_RD_DIRECT
+  };
+  float x[GX_N_IN], xn[GX_N_IN];
+  load_inputs(x, tile);
+#endif
 
   for (int it = 0; tile < n_tiles; ++it, tile += stride) {
     const int stage = GX_IN_STAGES == 2 ? (it & 1) : 0;
@@ -180,7 +205,17 @@ GX_KERNEL_NAME(const __grid_constant__ GxLaunchArgs args) {
 
     float* tile_s = out_stage + ostage * kOutStageFloats;
 #if GX_SPT == 1
+#if GX_IN_STAGES == 0
+    // x holds this tile's inputs (loaded during the previous tile, or before the loop); the body calls `prefetch`
+    // once, late, to start the loads of the next tile into xn
+    auto prefetch = [&]() { load_inputs(xn, next); };
+    auto no_prefetch = []() {};
+    bulk_wait_read<GX_OUT_STAGES - 1>();
+    __syncwarp();
+#else
     float x[GX_N_IN];
+    auto prefetch = []() {};
+    auto no_prefetch = []() {};
     const long long sample = tile * GX_WT + lane;
     if (bulk) {
       mbar_wait(&full_bar[stage], in_parity);
@@ -203,13 +238,19 @@ GX_KERNEL_NAME(const __grid_constant__ GxLaunchArgs args) {
     __syncwarp();
     // single input stage: every lane has its inputs in registers, the stage can take the next tile already
     if (GX_IN_STAGES == 1 && next < n_bulk && elect_one()) issue_loads(next, 0);
+#endif
 #if GX_CHECKED_FAST_MATH
     // branch-free reciprocals / square roots; a lane whose operand left their exact range flags the tile, which
     // is then re-evaluated with the IEEE intrinsics (identical results wherever both are defined)
-    if (__any_sync(0xffffffffu, gx_body<false>(x, tile_s + lane * GX_TILE, tile_s + GX_WT * GX_TILE + lane * GX_N_ROWS)))
-      gx_body<true>(x, tile_s + lane * GX_TILE, tile_s + GX_WT * GX_TILE + lane * GX_N_ROWS);
+    if (__any_sync(0xffffffffu, gx_body<false>(x, tile_s + lane * GX_TILE, tile_s + GX_WT * GX_TILE + lane * GX_N_ROWS,
+                                                prefetch)))
+      gx_body<true>(x, tile_s + lane * GX_TILE, tile_s + GX_WT * GX_TILE + lane * GX_N_ROWS, no_prefetch);
 #else
-    gx_body<true>(x, tile_s + lane * GX_TILE, tile_s + GX_WT * GX_TILE + lane * GX_N_ROWS);
+    gx_body<true>(x, tile_s + lane * GX_TILE, tile_s + GX_WT * GX_TILE + lane * GX_N_ROWS, prefetch);
+#endif
+#if GX_IN_STAGES == 0
+#pragma unroll
+    for (int k = 0; k < GX_N_IN; ++k) x[k] = xn[k];
 #endif
 #else
     // two samples per thread: lane and lane + 32 of the warp tile, packed as (.x, .y)

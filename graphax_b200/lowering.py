@@ -70,6 +70,7 @@ class Dag:
         self.args: List[Tuple[int, ...]] = []
         self.cval: List[Optional[np.float32]] = []     # value for const nodes
         self._memo: Dict[tuple, int] = {}
+        self._mul_twin: Dict[Tuple[int, int], Tuple[int, bool]] = {}   # sign-stripped operands -> (mul node, negated?)
 
     # ---- node construction -------------------------------------------------
     def _new(self, key: tuple, op: str, args: Tuple[int, ...], cval=None) -> int:
@@ -92,6 +93,14 @@ class Dag:
 
     def is_const(self, n: int) -> bool:
         return self.op[n] == "const"
+
+    def _strip_sign(self, n: int) -> Tuple[int, bool]:
+        """(node without its leading negation / the constant's magnitude, was it negative?)"""
+        if self.op[n] == "neg":
+            return self.args[n][0], True
+        if self.op[n] == "const" and np.signbit(self.cval[n]) and not np.isnan(self.cval[n]):
+            return self.const(-self.cval[n]), True
+        return n, False
 
     def _is(self, n: int, v: float) -> bool:
         return self.op[n] == "const" and float(self.cval[n]) == v and not (v == 0.0)
@@ -142,6 +151,15 @@ class Dag:
                 return self.emit("neg", x)
             if self._is(x, -1.0):
                 return self.emit("neg", y)
+            # (-x)*y, x*(-y) and x*y round to the same magnitude (round-to-nearest is symmetric, zeros and
+            # infinities included): a product whose sign-stripped twin already exists is that node, negated -
+            # a free operand modifier in the instruction that reads it.  The first product of each magnitude
+            # is created exactly as written.
+            sx, sy = self._strip_sign(x), self._strip_sign(y)
+            twin = self._mul_twin.get((min(sx[0], sy[0]), max(sx[0], sy[0])))
+            if twin is not None:
+                node, node_flip = twin
+                return node if node_flip == (sx[1] != sy[1]) else self.emit("neg", node)
         if op == "fma" and not self.fuse:
             return self.emit("add", self.emit("mul", a[0], a[1]), a[2])
         if op == "fma":
@@ -159,7 +177,11 @@ class Dag:
             folded = self._fold(op, [self.cval[n] for n in a])
             if folded is not None:
                 return folded
-        return self._new((op,) + tuple(a), op, tuple(a))
+        nid = self._new((op,) + tuple(a), op, tuple(a))
+        if op == "mul":
+            sx, sy = self._strip_sign(a[0]), self._strip_sign(a[1])
+            self._mul_twin.setdefault((min(sx[0], sy[0]), max(sx[0], sy[0])), (nid, sx[1] != sy[1]))
+        return nid
 
     # convenience
     def add(self, a, b): return self.emit("add", a, b)

@@ -15,7 +15,8 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 from .plan import Plan
 
-LIB_PATH = Path(__file__).resolve().parent / "libgraphax_b200.so"
+# GX_LIB: another build of the library (A/B measurements of ahead-of-time kernels); the default is the in-tree one
+LIB_PATH = Path(os.environ.get("GX_LIB") or Path(__file__).resolve().parent / "libgraphax_b200.so")
 GX_MAX_ARRAYS = 32
 KERNEL_INTERPRETER, KERNEL_AOT, KERNEL_JIT = 0, 1, 2
 KERNEL_NAMES = {0: "interpreter", 1: "aot", 2: "jit"}

@@ -3,6 +3,8 @@ import re
 import struct
 from pathlib import Path
 
+import os
+
 import numpy as np
 import pytest
 
@@ -191,6 +193,11 @@ def test_launch_shape_fits_shared_memory_and_fast_math_heuristic():
     from graphax_b200.codegen import input_stages
     t2 = launch_shape(encdec)[0]                               # [8 x 180] tile: one warp, and only one input stage fits
     assert t2 == 32 and input_stages(encdec, t2) == 1 and input_stages(enc, threads) == 2
+    os.environ["GX_INPUT_STAGED"] = "0"                        # the measured alternative: inputs prefetched into registers
+    try:
+        assert input_stages(enc, threads) == 0 and input_stages(enc, threads, 2) == 2 and launch_shape(enc)[0] == 128
+    finally:
+        del os.environ["GX_INPUT_STAGED"]
     assert checked_fast_math(WORKLOADS["roe3d"].plan("rev")) and checked_fast_math(WORKLOADS["roe1d"].plan("rev"))
     assert not checked_fast_math(WORKLOADS["readme"].plan("readme"))
 
@@ -200,7 +207,7 @@ def test_generated_source_shares_sincos_and_uses_checked_reciprocals():
     src = emit_source(WORKLOADS["robotarm"].plan("rev"), nvrtc=True)
     assert src.count("sincosf(") == 6                       # six joint angles, each needs sin and cos
     src = emit_source(WORKLOADS["roe3d"].plan("mixed", rounding="fma"), nvrtc=True)
-    body = src.split("template <bool kPrecise>\n__device__ __forceinline__ unsigned gx_body")[1].split("return (kPrecise")[0]
+    body = src.split("template <bool kPrecise, class Prefetch>\n__device__ __forceinline__ unsigned gx_body")[1].split("return (kPrecise")[0]
     assert body.count("gx_rcp<kPrecise>(") == 9 and body.count("gx_sqrt<kPrecise>(") == 3
     assert "__frcp_rn(v" not in body and "__fdiv_rn(" not in body
     # every operand of a checked operation is folded into the running range exactly once, two per instruction
@@ -209,6 +216,6 @@ def test_generated_source_shares_sincos_and_uses_checked_reciprocals():
     # the reference rounding: no FMA outside the division / square-root sequences, three divisions per x/y,
     # one shared reciprocal per denominator
     src = emit_source(WORKLOADS["roe3d"].plan("mixed", rounding="reference"), nvrtc=True)
-    body = src.split("template <bool kPrecise>\n__device__ __forceinline__ unsigned gx_body")[1].split("return (kPrecise")[0]
+    body = src.split("template <bool kPrecise, class Prefetch>\n__device__ __forceinline__ unsigned gx_body")[1].split("return (kPrecise")[0]
     assert "__fmaf_rn(" not in body and "__fdiv_rn(" not in body
     assert body.count("gx_div<kPrecise>(") == 39 and body.count("gx_rcp<kPrecise>(") == 16

@@ -1,0 +1,6 @@
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+python tools/tune.py --workloads roe3d,roe1d,robotarm,readme --divisions reference,reciprocal,ieee --threads 64,128 --min-blocks 2,3,4,5,6,8 --out-stages 1 --spt 1 --steps 200 --out gpurun_out/tune_r02b_all.json --write > gpurun_out/tune_r02b_all.log 2>&1
+echo "exit $?"
+grep best gpurun_out/tune_r02b_all.log | cut -c1-200
+cp graphax_b200/tuning.json gpurun_out/tuning_r02b.json
