@@ -165,6 +165,23 @@ __device__ __forceinline__ void load_rows_f32(float* tile, float (&y)[32], const
   }
   unstage_rows(tile, y, lane);
 }
+// load_rows_f32 in two halves: the global loads (issued early, results kept in registers) and the pass through the tile
+__device__ __forceinline__ void fetch_rows_f32(float4 (&r)[8], const float* base, int ld, int m_base, int M, int col0, int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = m_base + 4 * i + (lane >> 3);
+    r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < M) r[i] = __ldg(reinterpret_cast<const float4*>(base + (size_t)row * ld + col0 + (lane & 7) * 4));
+  }
+}
+__device__ __forceinline__ void spread_rows_f32(float* tile, float (&y)[32], const float4 (&r)[8], int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = 4 * i + (lane >> 3);
+    *reinterpret_cast<float4*>(tile + rr * 32 + (((lane & 7) ^ (rr & 7)) << 2)) = r[i];
+  }
+  unstage_rows(tile, y, lane);
+}
 __device__ __forceinline__ void load_rows_bf16(float* tile, float (&y)[32], const uint16_t* base, int ld, int m_base, int M,
                                                int col0, int lane) {
 #pragma unroll
@@ -358,16 +375,9 @@ __device__ __forceinline__ void gx_gemm_body(const CUtensorMap& map_a, const CUt
     // ===== epilogue: warp w may only touch TMEM lanes 32*(w%4) .. 32*(w%4)+31 =====
     const int quad = warp & 3;
     const int c_begin = ((warp - 2) >> 2) * (BN / 2);
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
     const int m_base = m0 + quad * 32;
-    float* tile = reinterpret_cast<float*>(smem) + (warp - 2) * 1024;   // 4 KB of the (now idle) operand ring per warp
-#ifdef GX_GEMM_FUSED
-    GxEpiState epi_state;
-    gx_epi_begin(epi_state);
-#endif
-#pragma unroll 1
-    for (int c = c_begin; c < c_begin + BN / 2; c += 32) {
+    float* tile = reinterpret_cast<float*>(smem) + (warp - 2) * 1024;   // 4 KB of the (then idle) operand ring per warp
+    auto load_acc = [&](int c, float (&acc)[32]) {
       uint32_t v[32];
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c;
       asm volatile(
@@ -381,22 +391,47 @@ __device__ __forceinline__ void gx_gemm_body(const CUtensorMap& map_a, const CUt
           : "r"(taddr)
           : "memory");
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      float acc[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
+    };
 #ifdef GX_GEMM_FUSED
-      gx_epi_chunk(epi, epi_state, tile, m_base, n0 + c, args.M, args.ldc, acc, lane);   // N parameter = row stride
+    // The memory operands of the fused expressions do not depend on this kernel's main loop: their loads are
+    // issued while the tensor core is still working (first chunk: before the accumulator is even waited for;
+    // second chunk: as well when registers allow - one CTA per SM -, else while the first chunk is evaluated).
+    static_assert(BN / 2 == 64, "two 32-column chunks per epilogue warp");
+    GxEpiState epi_state;
+    gx_epi_begin(epi_state);
+    GxEpiPre pre0, pre1;
+    gx_epi_prefetch(epi, pre0, m_base, n0 + c_begin, args.M, args.ldc, lane);
+    if (kStages > 3) gx_epi_prefetch(epi, pre1, m_base, n0 + c_begin + 32, args.M, args.ldc, lane);
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    {
+      float acc[32];
+      load_acc(c_begin, acc);
+      if (kStages <= 3) gx_epi_prefetch(epi, pre1, m_base, n0 + c_begin + 32, args.M, args.ldc, lane);
+      gx_epi_chunk(epi, epi_state, pre0, tile, m_base, n0 + c_begin, args.M, args.ldc, acc, lane);   // N parameter = row stride
+    }
+    {
+      float acc[32];
+      load_acc(c_begin + 32, acc);
+      gx_epi_chunk(epi, epi_state, pre1, tile, m_base, n0 + c_begin + 32, args.M, args.ldc, acc, lane);
+    }
+    gx_epi_finish(epi, epi_state, lane);
 #else
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = c_begin; c < c_begin + BN / 2; c += 32) {
+      float acc[32];
+      load_acc(c, acc);
       if (args.epilogue == EPI_STORE_F32)
         store_rows_f32(tile, acc, args.c_f32, args.ldc, m_base, args.M, n0 + c, lane);
       else if (args.epilogue == EPI_STORE_BF16)
         store_rows_bf16(tile, acc, args.c_bf16, args.ldc, m_base, args.M, n0 + c, lane);
       else
         red_rows_f32(tile, acc, args.c_f32, args.ldc, m_base, args.M, n0 + c, lane);
-#endif
     }
-#ifdef GX_GEMM_FUSED
-    gx_epi_finish(epi, epi_state, lane);
 #endif
     tc_fence_before();
   }

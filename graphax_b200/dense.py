@@ -606,42 +606,60 @@ class DenseExecutor:
                "struct GxEpiState { int unused; };",
                "__device__ __forceinline__ void gx_epi_begin(GxEpiState&) {}",
                "__device__ __forceinline__ void gx_epi_finish(const GxEpi&, GxEpiState&, int) {}",
-               "__device__ __forceinline__ void gx_epi_chunk(const GxEpi& e, GxEpiState&, float* tile, int m_base, int col0,",
-               "                                             int M, int N, const float (&acc)[32], int lane) {",
-               "  const int row = m_base + lane;",
-               "  const bool ok = row < M;",
-               "  const size_t off = (size_t)(ok ? row : 0) * N + col0;"]
-        csum_slots = [k for k, n in enumerate(outs) if k > 0 and n in self.fused_colsums]
-        for k in range(1, no):
-            epi.append(f"  float Y{k}[32];")
-        for i, leaf in enumerate(leaves):          # [M, N] operands: coalesced loads through the staging tile
-            if dag.nodes[leaf].shape == (M, N) and self._leaf_dtype(leaf) != "bf16":   # (bf16 rows are 64 B: direct loads win)
-                bf = False
-                epi.append(f"  float Lm{i}[32];")
-                epi.append(f"  gxg::load_rows_{'bf16' if bf else 'f32'}(tile, Lm{i}, reinterpret_cast<const "
-                           f"{'uint16_t' if bf else 'float'}*>(e.leaf[{i}]), N, m_base, M, col0, lane);")
-        epi.append("#pragma unroll")
-        epi.append("  for (int q = 0; q < 8; ++q) {")
+               ]
+        # memory operands: fetched by gx_epi_prefetch (issued while the main loop still runs), consumed by gx_epi_chunk
+        pre_fields, pre_loads, chunk_head, chunk_quad = [], [], [], []
         for i, leaf in enumerate(leaves):
             lr, lc = dag.nodes[leaf].shape
             bf = self._leaf_dtype(leaf) == "bf16"
             ptr = f"reinterpret_cast<const {'unsigned short' if bf else 'float'}*>(e.leaf[{i}])"
             if (lr, lc) == (M, N) and not bf:
-                epi.append(f"    const float L{i}_0 = Lm{i}[4 * q], L{i}_1 = Lm{i}[4 * q + 1], L{i}_2 = Lm{i}[4 * q + 2], "
-                           f"L{i}_3 = Lm{i}[4 * q + 3];")
+                # coalesced row-contiguous loads now, through the staging tile to "one row per lane" later
+                pre_fields.append(f"float4 M{i}[8];")
+                pre_loads.append(f"  gxg::fetch_rows_f32(p.M{i}, {ptr}, N, m_base, M, col0, lane);")
+                chunk_head.append(f"  float Lm{i}[32];")
+                chunk_head.append(f"  gxg::spread_rows_f32(tile, Lm{i}, p.M{i}, lane);")
+                chunk_quad.append(f"    const float L{i}_0 = Lm{i}[4 * q], L{i}_1 = Lm{i}[4 * q + 1], L{i}_2 = Lm{i}[4 * q + 2], "
+                                  f"L{i}_3 = Lm{i}[4 * q + 3];")
             elif (lr, lc) == (1, 1) or lc == 1:
                 idx = "0" if (lr, lc) == (1, 1) else "(ok ? row : 0)"
                 val = f"gxg::bf16_bits_to_f32({ptr}[{idx}])" if bf else f"__ldg({ptr} + {idx})"
-                epi.append(f"    const float L{i}_0 = {val}, L{i}_1 = L{i}_0, L{i}_2 = L{i}_0, L{i}_3 = L{i}_0;")
+                pre_fields.append(f"float S{i};")
+                pre_loads.append(f"  p.S{i} = {val};")
+                chunk_quad.append(f"    const float L{i}_0 = p.S{i}, L{i}_1 = L{i}_0, L{i}_2 = L{i}_0, L{i}_3 = L{i}_0;")
             else:
                 base = "col0 + 4 * q" if lr == 1 else "off + 4 * q"
                 if bf:
-                    epi.append(f"    const uint2 R{i} = __ldg(reinterpret_cast<const uint2*>({ptr} + {base}));")
-                    epi.append(f"    const float L{i}_0 = gxg::bf16_bits_to_f32(R{i}.x & 0xffffu), L{i}_1 = gxg::bf16_bits_to_f32(R{i}.x >> 16), "
-                               f"L{i}_2 = gxg::bf16_bits_to_f32(R{i}.y & 0xffffu), L{i}_3 = gxg::bf16_bits_to_f32(R{i}.y >> 16);")
+                    pre_fields.append(f"uint2 R{i}[8];")
+                    pre_loads.append(f"  _Pragma(\"unroll\") for (int q = 0; q < 8; ++q) p.R{i}[q] = "
+                                     f"__ldg(reinterpret_cast<const uint2*>({ptr} + {base}));")
+                    chunk_quad.append(f"    const uint2 R{i} = p.R{i}[q];")
+                    chunk_quad.append(f"    const float L{i}_0 = gxg::bf16_bits_to_f32(R{i}.x & 0xffffu), L{i}_1 = gxg::bf16_bits_to_f32(R{i}.x >> 16), "
+                                      f"L{i}_2 = gxg::bf16_bits_to_f32(R{i}.y & 0xffffu), L{i}_3 = gxg::bf16_bits_to_f32(R{i}.y >> 16);")
                 else:
-                    epi.append(f"    const float4 R{i} = __ldg(reinterpret_cast<const float4*>({ptr} + {base}));")
-                    epi.append(f"    const float L{i}_0 = R{i}.x, L{i}_1 = R{i}.y, L{i}_2 = R{i}.z, L{i}_3 = R{i}.w;")
+                    pre_fields.append(f"float4 R{i}[8];")
+                    pre_loads.append(f"  _Pragma(\"unroll\") for (int q = 0; q < 8; ++q) p.R{i}[q] = "
+                                     f"__ldg(reinterpret_cast<const float4*>({ptr} + {base}));")
+                    chunk_quad.append(f"    const float4 R{i} = p.R{i}[q];")
+                    chunk_quad.append(f"    const float L{i}_0 = R{i}.x, L{i}_1 = R{i}.y, L{i}_2 = R{i}.z, L{i}_3 = R{i}.w;")
+        epi += ["struct GxEpiPre { " + " ".join(pre_fields or ["int unused;"]) + " };",
+                "__device__ __forceinline__ void gx_epi_prefetch(const GxEpi& e, GxEpiPre& p, int m_base, int col0, int M, int N,",
+                "                                                int lane) {",
+                "  const int row = m_base + lane;",
+                "  const bool ok = row < M;",
+                "  const size_t off = (size_t)(ok ? row : 0) * N + col0;",
+                "  (void)off;"] + pre_loads + ["}",
+                "__device__ __forceinline__ void gx_epi_chunk(const GxEpi& e, GxEpiState&, const GxEpiPre& p, float* tile, int m_base,",
+                "                                             int col0, int M, int N, const float (&acc)[32], int lane) {",
+                "  const int row = m_base + lane;",
+                "  const bool ok = row < M;"]
+        csum_slots = [k for k, n in enumerate(outs) if k > 0 and n in self.fused_colsums]
+        for k in range(1, no):
+            epi.append(f"  float Y{k}[32];")
+        epi += chunk_head
+        epi.append("#pragma unroll")
+        epi.append("  for (int q = 0; q < 8; ++q) {")
+        epi += chunk_quad
         for j in range(4):
             epi.append(f"    const float acc_{j} = acc[4 * q + {j}];")
         emitted = set()                                 # temporaries are named after their node: shared by outputs
