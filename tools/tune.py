@@ -80,6 +80,7 @@ def main():
     ap.add_argument("--schedules", default="", help="comma list of plan schedules to compare (default: the plan default)")
     ap.add_argument("--contract", type=int, default=0)
     ap.add_argument("--fast", default="", help="comma list of GX_CHECKED_FAST settings to compare, e.g. 0,1")
+    ap.add_argument("--slp", default="", help="comma list of GX_SLP settings to compare (f32x2 pairing, slp.py), e.g. 0,1")
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--out", default="gpurun_out/tune.json")
@@ -120,10 +121,13 @@ def main():
                 dp.launch(nchk, [t.data_ptr() for t in chk_in], ref.data_ptr(), None,
                           torch.cuda.current_stream().cuda_stream)
                 torch.cuda.synchronize()
-                for fast in (args.fast.split(",") if args.fast else [""]):
+                for fast, slp in [(f, s) for f in (args.fast.split(",") if args.fast else [""])
+                                  for s in (args.slp.split(",") if args.slp else [""])]:
+                 import os
                  if fast:
-                    import os
                     os.environ["GX_CHECKED_FAST"] = fast
+                 if slp:
+                    os.environ["GX_SLP"] = slp
                  for spt in map(int, args.spt.split(",")):
                   for threads in map(int, args.threads.split(",")):
                     for mb in map(int, args.min_blocks.split(",")):
@@ -134,6 +138,8 @@ def main():
                                    "samples_per_thread": spt}
                             if fast:
                                 cfg["checked_fast"] = int(fast)
+                            if slp:
+                                cfg["slp"] = int(slp)
                             try:
                                 t0 = time.time()
                                 dp.specialize(threads=threads, min_blocks=mb, out_stages=st, samples_per_thread=spt)
