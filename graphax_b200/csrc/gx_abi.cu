@@ -1111,9 +1111,13 @@ int gx_gemm_fused_launch(gx_jit_kernel* k, int M, int N, int K, const void* A, i
   if (ldn == 0) ldn = N;
   if (ldn % 4 || ldn < ((N + 127) / 128) * 128)
     return fail(GX_ERR_UNSUPPORTED, "gx_gemm_fused_launch: epilogue operands must be tile padded (ldn >= ceil(N/128)*128)");
-  if (stages != 3 && stages != 6) return fail(GX_ERR_BAD_ARG, "gx_gemm_fused_launch: stages must be 3 or 6 (GX_GEMM_STAGES)");
+  if (stages != 3 && stages != 6 && stages != 4 && stages != 8)
+    return fail(GX_ERR_BAD_ARG, "gx_gemm_fused_launch: stages must be 3 / 6, or 4 / 8 for the CTA-pair kernels (GX_GEMM_STAGES)");
+  const bool pair = gxg::stages_pair(stages);
+  if (pair && ((M + 127) / 128) % 2)
+    return fail(GX_ERR_UNSUPPORTED, "gx_gemm_fused_launch: the CTA-pair kernels need an even number of 128-row tiles");
   CUtensorMap map_a, map_b;
-  if (gxg_make_maps(&map_a, &map_b, M, N, K, A, a_mn, B, b_mn, lda, ldb))
+  if (gxg_make_maps(&map_a, &map_b, M, N, K, A, a_mn, B, b_mn, lda, ldb, pair ? 1 : 0))
     return fail(GX_ERR_CUDA, "gx_gemm_fused_launch: cuTensorMapEncodeTiled failed (pointers must be 16-byte aligned)");
   if (!k->smem_set) {
     CUresult r = driver().FuncSetAttribute(k->func, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)gxg::smem_bytes(stages));
@@ -1129,6 +1133,7 @@ int gx_gemm_fused_launch(gx_jit_kernel* k, int M, int N, int K, const void* A, i
   args.k_per_split = ((K + 63) / 64) * 64;
   args.a_mn = a_mn ? 1 : 0;
   args.b_mn = b_mn ? 1 : 0;
+  args.trace = gxg_next_trace(((N + 127) / 128) * ((M + 127) / 128));
   CUlaunchConfig cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDimX = (N + 127) / 128;
@@ -1138,11 +1143,24 @@ int gx_gemm_fused_launch(gx_jit_kernel* k, int M, int N, int K, const void* A, i
   cfg.blockDimY = cfg.blockDimZ = 1;
   cfg.sharedMemBytes = gxg::smem_bytes(stages);
   cfg.hStream = (CUstream)stream;
-  CUlaunchAttribute attr[1];
-  attr[0].id = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;
-  attr[0].value.programmaticStreamSerializationAllowed = 1;
+  CUlaunchAttribute attr[2];
+  unsigned n_attr = 0;
+  if (use_pdl()) {
+    attr[n_attr].id = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;
+    attr[n_attr].value.programmaticStreamSerializationAllowed = 1;
+    ++n_attr;
+  }
+  if (pair) {   // two consecutive tile rows = one cluster = one 256 x 128 MMA tile, pairs along x (gx_gemm_kernel.cuh)
+    cfg.gridDimX = (M + 127) / 128;
+    cfg.gridDimY = (N + 127) / 128;
+    attr[n_attr].id = CU_LAUNCH_ATTRIBUTE_CLUSTER_DIMENSION;
+    attr[n_attr].value.clusterDim.x = 2;
+    attr[n_attr].value.clusterDim.y = 1;
+    attr[n_attr].value.clusterDim.z = 1;
+    ++n_attr;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = use_pdl() ? 1 : 0;
+  cfg.numAttrs = n_attr;
   void* params[] = {&map_a, &map_b, &args, const_cast<void*>(epi)};
   CUresult r = driver().LaunchKernelEx(&cfg, k->func, params, nullptr);
   if (r != CUDA_SUCCESS) return fail(GX_ERR_CUDA, "cuLaunchKernelEx(fused gemm): " + cu_err(r));

@@ -94,6 +94,20 @@ bool gemm_use_persistent() {
   return v;
 }
 
+// CTA pairs (cta_group::2: a cluster of two CTAs computes one 256 x 128 tile, each loading half of the B tile) for
+// the single-tile kernels.  Off by default: on the MLP-sized problems of config 5 the pairs move 25 % fewer operand
+// bytes but are no faster (7.4 vs 7.1 us for 4096 x 1024 x 512, B200 r02c - those launches are bound by their
+// fill / epilogue latency, not by operand traffic).  GX_GEMM_PAIR=1 or gx_gemm_set_pair(1) turns them on.
+int g_gemm_pair = [] {
+  const char* e = getenv("GX_GEMM_PAIR");
+  return (e && e[0] == '1') ? 1 : 0;
+}();
+bool gemm_use_pair() { return g_gemm_pair != 0; }
+
+// phase stamps (GemmArgs::trace): a device buffer handed out launch by launch, `g_trace_ctas` CTAs x 8 words each
+unsigned long long* g_trace = nullptr;
+int g_trace_launches = 0, g_trace_ctas = 0, g_trace_next = 0;
+
 bool gemm_use_pdl() {
   static const bool v = [] {
     const char* e = getenv("GX_PDL");
@@ -105,16 +119,42 @@ bool gemm_use_pdl() {
 }  // namespace
 
 // tensor maps of both operands (shared with the run-time compiled kernels launched from gx_abi.cu)
+// `pair`: the CTA-pair kernels load the B tile in two halves of 64 N-rows, one per CTA
 int gxg_make_maps(CUtensorMap* map_a, CUtensorMap* map_b, int M, int N, int K, const void* A, int a_mn, const void* B,
-                  int b_mn, int lda, int ldb) {
+                  int b_mn, int lda, int ldb, int pair) {
   const int ra = a_mn ? make_map(map_a, A, K, M, BK, lda) : make_map(map_a, A, M, K, BM, lda);
-  const int rb = b_mn ? make_map(map_b, B, K, N, BK, ldb) : make_map(map_b, B, N, K, BN, ldb);
+  const int rb = b_mn ? make_map(map_b, B, K, N, BK, ldb) : make_map(map_b, B, N, K, pair ? BN / 2 : BN, ldb);
   return (ra || rb) ? -1 : 0;
+}
+
+int gxg_pair_enabled(void) { return gemm_use_pair() ? 1 : 0; }
+
+unsigned long long* gxg_next_trace(int n_ctas) {
+  if (!g_trace || g_trace_next >= g_trace_launches || n_ctas > g_trace_ctas) return nullptr;
+  return g_trace + (size_t)(g_trace_next++) * g_trace_ctas * 8;
 }
 
 extern "C" {
 
 const char* gx_gemm_last_error(void) { return g_gemm_error.c_str(); }
+
+// Diagnostics: the next `max_launches` single-tile contractions (plain and fused) each write 8 x u64 phase stamps per
+// CTA (%globaltimer: entry, dependency wait passed, first stage landed, accumulator complete, epilogue done, exit)
+// into buf[launch][max_ctas][8]; launches with more CTAs than max_ctas are skipped.  NULL switches it off.
+int gx_gemm_set_trace(void* buf, int max_launches, int max_ctas) {
+  g_trace = static_cast<unsigned long long*>(buf);
+  g_trace_launches = buf ? max_launches : 0;
+  g_trace_ctas = max_ctas;
+  g_trace_next = 0;
+  return GX_OK;
+}
+
+// Use CTA pairs (cta_group::2) for single-tile contractions whose tile rows pair up?  Returns the previous setting.
+int gx_gemm_set_pair(int on) {
+  const int before = g_gemm_pair;
+  g_gemm_pair = on ? 1 : 0;
+  return before;
+}
 
 // C[M,N] (+)= A[M,K] * B[N,K]^T; A, B bf16 row-major device pointers; C fp32 (c_bf16 == 0) or bf16 row-major.
 // k_splits > 1 accumulates with fp32 atomics into C, which the caller must have zeroed (fp32 only).
@@ -219,8 +259,13 @@ static int gemm_launch(int M, int N, int K, const void* A, int lda, int a_mn, co
     g_gemm_error = "gx_gemm_bf16_tn: more K splits than 64-wide K blocks";
     return GX_ERR_UNSUPPORTED;
   }
+  // several waves of tiles: persistent CTAs (one per SM) with a double-buffered accumulator; otherwise CTA pairs
+  // when they are switched on and the tile rows pair up
+  const long long tiles = (long long)tiles_n * tiles_m;
+  const bool persistent = k_splits == 1 && !accumulate && tiles > 2LL * sm_count() && gemm_use_persistent();
+  const bool pair = !persistent && tiles_m % 2 == 0 && gemm_use_pair();
   CUtensorMap map_a, map_b;
-  if (gxg_make_maps(&map_a, &map_b, M, N, K, A, a_mn, B, b_mn, lda, ldb)) {
+  if (gxg_make_maps(&map_a, &map_b, M, N, K, A, a_mn, B, b_mn, lda, ldb, pair ? 1 : 0)) {
     g_gemm_error = "gx_gemm_bf16_tn: cuTensorMapEncodeTiled failed (pointers must be 16-byte aligned)";
     return GX_ERR_CUDA;
   }
@@ -232,6 +277,12 @@ static int gemm_launch(int M, int N, int K, const void* A, int lda, int a_mn, co
     if (attr_err == cudaSuccess)
       attr_err = cudaFuncSetAttribute(gx_gemm_tn_kernel_deep, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem_bytes(kStagesDeep));
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(gx_gemm_tn_kernel_pair, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem_bytes(kStagesPairShallow));
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(gx_gemm_tn_kernel_pair_deep, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem_bytes(kStagesPairDeep));
     if (attr_err == cudaSuccess)
       attr_err = cudaFuncSetAttribute(gx_gemm_tn_kernel_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)kSmemPersistent);
@@ -254,26 +305,38 @@ static int gemm_launch(int M, int N, int K, const void* A, int lda, int a_mn, co
   args.k_per_split = k_per_split;
   args.a_mn = a_mn ? 1 : 0;
   args.b_mn = b_mn ? 1 : 0;
+  args.trace = persistent ? nullptr : gxg_next_trace(tiles_n * tiles_m * k_splits);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = dim3(tiles_n, tiles_m, k_splits);
   cfg.blockDim = dim3(kThreads);
   // a grid that fits the GPU once gets the deep ring (twice the bytes in flight per SM)
   const bool deep = (long long)tiles_n * tiles_m * k_splits <= sm_count();
-  cfg.dynamicSmemBytes = smem_bytes(deep ? kStagesDeep : kStagesShallow);
+  const int stages = pair ? (deep ? kStagesPairDeep : kStagesPairShallow) : (deep ? kStagesDeep : kStagesShallow);
+  cfg.dynamicSmemBytes = smem_bytes(stages);
   cfg.stream = static_cast<cudaStream_t>(stream);
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // prologue overlaps the predecessor's tail
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int n_attr = 0;
+  if (gemm_use_pdl()) {
+    attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // prologue overlaps the predecessor's tail
+    attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+    ++n_attr;
+  }
+  if (pair) {   // two consecutive tile rows form a cluster = one 256 x 128 MMA tile; the pair must lie along x
+    cfg.gridDim = dim3(tiles_m, tiles_n, k_splits);
+    attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+    attr[n_attr].val.clusterDim.x = 2;
+    attr[n_attr].val.clusterDim.y = 1;
+    attr[n_attr].val.clusterDim.z = 1;
+    ++n_attr;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = gemm_use_pdl() ? 1 : 0;
+  cfg.numAttrs = n_attr;
   CUtensorMap map_b_half = map_b;              // 128-row boxes of B: the half-width items of the persistent kernel
   void* params[] = {&map_a, &map_b, &args};
   void* params_persistent[] = {&map_a, &map_b, &map_b_half, &args};
-  // several waves of tiles: persistent CTAs (one per SM) with a double-buffered accumulator
-  const long long tiles = (long long)tiles_n * tiles_m;
-  const bool persistent = k_splits == 1 && !accumulate && tiles > 2LL * sm_count() && gemm_use_persistent();
-  const void* fn = deep ? (const void*)gx_gemm_tn_kernel_deep : (const void*)gx_gemm_tn_kernel;
+  const void* fn = pair ? (deep ? (const void*)gx_gemm_tn_kernel_pair_deep : (const void*)gx_gemm_tn_kernel_pair)
+                        : (deep ? (const void*)gx_gemm_tn_kernel_deep : (const void*)gx_gemm_tn_kernel);
   if (persistent) {
     cfg.gridDim = dim3(sm_count());
     cfg.dynamicSmemBytes = kSmemPersistent;

@@ -42,11 +42,23 @@ constexpr int BM = 128, BN = 128, BK = 64, UMMA_K = 16;
 // operand ring depth: 3 stages = 96 KB, two CTAs per SM (one's epilogue overlaps the other's main loop); grids that
 // fill the GPU only once (<= one CTA per SM) use 6 stages so that twice as many bytes are in flight per SM
 constexpr int kStagesShallow = 3, kStagesDeep = 6;
+// CTA-pair variant (cta_group::2, below): a stage is 16 KB of A + 8 KB of B, so the same shared memory holds 4 / 8 stages;
+// the stage count also names the variant on the host side (3 / 6 = one CTA per tile, 4 / 8 = CTA pairs)
+constexpr int kStagesPairShallow = 4, kStagesPairDeep = 8;
+#ifdef GX_NVRTC
+#define GX_HD __device__
+#else
+#define GX_HD __host__ __device__
+#endif
+GX_HD constexpr bool stages_deep(int stages) { return stages == kStagesDeep || stages == kStagesPairDeep; }
+GX_HD constexpr bool stages_pair(int stages) { return stages == kStagesPairShallow || stages == kStagesPairDeep; }
 constexpr int kThreads = 320;   // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quadrant)
 constexpr int kTmemCols = 128;
 constexpr uint32_t kStageBytesA = BM * BK * 2, kStageBytesB = BN * BK * 2;
 #ifndef GX_NVRTC
-constexpr uint32_t smem_bytes(int stages) { return stages * (kStageBytesA + kStageBytesB) + 1024 /*align*/ + 256 /*barriers*/; }
+constexpr uint32_t smem_bytes(int stages) {
+  return stages * (kStageBytesA + (stages_pair(stages) ? kStageBytesB / 2 : kStageBytesB)) + 1024 /*align*/ + 256 /*barriers*/;
+}
 #endif
 
 enum { EPI_STORE_F32 = 0, EPI_STORE_BF16 = 1, EPI_ATOMIC_F32 = 2 };
@@ -56,7 +68,17 @@ struct GemmArgs {
   uint16_t* c_bf16;
   int M, N, K, ldc, epilogue, k_per_split;
   int a_mn, b_mn;   // operand stored [K, M] / [K, N] (MN-major) instead of [M, K] / [N, K]
+  // optional phase stamps of the single-tile kernels (tools/gemm_trace.py): 8 x u64 per CTA - %globaltimer at
+  // entry, after griddepcontrol.wait, first operand stage landed, accumulator complete, epilogue done, exit
+  unsigned long long* trace;
 };
+__device__ __forceinline__ void trace_stamp(unsigned long long* trace, int cta, int slot) {
+  if (trace) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
+    trace[(size_t)cta * 8 + slot] = t;
+  }
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -92,6 +114,46 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// ---- CTA pairs (cta_group::2): two CTAs of a cluster on the two SMs of a TPC compute one 256 x 128 tile.  Each
+// loads its own 128 rows of A and HALF of the B tile (64 of the 128 N rows); one MMA (M256 N128 K16), issued by the
+// leader CTA, reads both shared memories and writes both tensor memories: 24 KB of operands per CTA and k-block
+// instead of 32 KB.  The MLP-sized contractions are bound by exactly that traffic.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// the pair's loads complete on the LEADER's barrier (bar_cluster_addr: a shared::cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs of the pair once the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -262,6 +324,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr) {
 }
 // kind::f16: D fp32, A/B bf16, M = 128, N = 128; bit 15 / 16 select MN-major A / B
 constexpr uint32_t kInstrDescBase = (1u << 4) | (1u << 7) | (1u << 10) | ((BN >> 3) << 17) | ((BM >> 4) << 24);
+constexpr uint32_t kInstrDescPair = (1u << 4) | (1u << 7) | (1u << 10) | ((BN >> 3) << 17) | (((2 * BM) >> 4) << 24);   // M = 256
 
 }  // namespace gxg
 
@@ -289,16 +352,24 @@ __device__ __forceinline__ void gx_gemm_body(const CUtensorMap& map_a, const CUt
   using namespace gxg;
   extern __shared__ uint8_t gg_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gg_smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr bool kPair = stages_pair(kStages), kDeep = stages_deep(kStages);
+  constexpr uint32_t kBytesB = kPair ? kStageBytesB / 2 : kStageBytesB;   // a pair's CTA holds half of the B tile
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * kStageBytesA;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * (kStageBytesA + kStageBytesB));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * (kStageBytesA + kBytesB));
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  // pair: the grid is (tile rows, tile columns) and the cluster (2, 1, 1) - two consecutive tile rows (the launch is
+  // rejected as a cluster misconfiguration unless the pair lies along x); rank 0 (the leader) issues the MMAs of both
+  const int m0 = (stages_pair(kStages) ? blockIdx.x : blockIdx.y) * BM, n0 = (stages_pair(kStages) ? blockIdx.y : blockIdx.x) * BN;
+  const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int cta_linear = (int)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
+  if (threadIdx.x == 0) trace_stamp(args.trace, cta_linear, 0);
   const int k_begin = blockIdx.z * args.k_per_split;
   const int k_len = args.K - k_begin < args.k_per_split ? args.K - k_begin : args.k_per_split;   // last split may be short
   const int num_k_blocks = (k_len + BK - 1) / BK;
@@ -313,19 +384,28 @@ __device__ __forceinline__ void gx_gemm_body(const CUtensorMap& map_a, const CUt
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {  // the allocating warp also owns the deallocation
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
-                 "n"(kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (warp == 1) {  // the allocating warp also owns the deallocation (pair: warp 1 of both CTAs, collectively)
+    if (kPair) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
+                   "n"(kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)),
+                   "n"(kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();   // the peer's barriers exist before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
   // everything above overlapped the previous kernel's tail; from here on its results are needed
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (threadIdx.x == 0) trace_stamp(args.trace, cta_linear, 1);
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -333,8 +413,24 @@ __device__ __forceinline__ void gx_gemm_body(const CUtensorMap& map_a, const CUt
       for (int kb = 0; kb < num_k_blocks; ++kb) {
         const int s = kb % kStages;
         mbar_wait(&empty_bar[s], ((kb / kStages) & 1) ^ 1);  // slot free (passes immediately the first round)
-        mbar_expect_tx(&full_bar[s], kStageBytesA + kStageBytesB);
         const int k0 = k_begin + kb * BK;
+        if (kPair) {
+          // both CTAs' bytes are counted on the leader's barrier (the only one the MMA thread waits on); the peer's
+          // copies may complete before the leader has armed the phase: the pending arrival keeps it open
+          if (leader) mbar_expect_tx(&full_bar[s], 2 * (kStageBytesA + kBytesB));
+          const uint32_t bar = mapa_u32(smem_u32(&full_bar[s]), 0);
+          const int nh = n0 + (int)cta_rank * (BN / 2);          // this CTA's half of the B tile
+          if (!args.a_mn) {
+            tma_load_2d_pair(smem_a + s * kStageBytesA, &map_a, k0, m0, bar);
+          } else {
+            tma_load_2d_pair(smem_a + s * kStageBytesA, &map_a, m0, k0, bar);
+            tma_load_2d_pair(smem_a + s * kStageBytesA + 8192, &map_a, m0 + 64, k0, bar);
+          }
+          if (!args.b_mn) tma_load_2d_pair(smem_b + s * kBytesB, &map_b, k0, nh, bar);   // 64-row box (host: gxg_make_maps)
+          else tma_load_2d_pair(smem_b + s * kBytesB, &map_b, nh, k0, bar);
+          continue;
+        }
+        mbar_expect_tx(&full_bar[s], kStageBytesA + kStageBytesB);
         if (!args.a_mn) {
           tma_load_2d(smem_a + s * kStageBytesA, &map_a, k0, m0, &full_bar[s]);
         } else {   // two [64 k x 64 m] boxes
@@ -350,24 +446,34 @@ __device__ __forceinline__ void gx_gemm_body(const CUtensorMap& map_a, const CUt
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    for (int kb = 0; kb < num_k_blocks; ++kb) {
+    // ===== MMA issuer (pair: the leader's only; the peer's warp 1 just owns its half of the TMEM allocation) =====
+    for (int kb = 0; kb < (leader ? num_k_blocks : 0); ++kb) {
       const int s = kb % kStages;
       mbar_wait(&full_bar[s], (kb / kStages) & 1);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t sa = smem_u32(smem_a + s * kStageBytesA), sb = smem_u32(smem_b + s * kStageBytesB);
+        if (kb == 0) trace_stamp(args.trace, cta_linear, 2);
+        const uint32_t sa = smem_u32(smem_a + s * kStageBytesA), sb = smem_u32(smem_b + s * kBytesB);
         const uint64_t da = args.a_mn ? make_smem_desc_mn(sa) : make_smem_desc(sa);
         const uint64_t db = args.b_mn ? make_smem_desc_mn(sb) : make_smem_desc(sb);
         // one MMA consumes 16 K: K-major = 32 B inside the swizzle atom (+2 in the 16-byte address field),
         // MN-major = 16 rows of 128 B (+128)
         const uint32_t step_a = args.a_mn ? 128u : 2u, step_b = args.b_mn ? 128u : 2u;
-        const uint32_t idesc = kInstrDescBase | (args.a_mn ? (1u << 15) : 0u) | (args.b_mn ? (1u << 16) : 0u);
+        const uint32_t idesc = (kPair ? kInstrDescPair : kInstrDescBase) | (args.a_mn ? (1u << 15) : 0u) | (args.b_mn ? (1u << 16) : 0u);
+        if (kPair) {
+          // descriptors are shared-memory OFFSETS: the same stage of both CTAs; rows 128-255 of D land in the peer's TMEM
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k)
-          umma_f16(tmem_base, da + step_a * k, db + step_b * k, idesc, (kb | k) != 0 ? 1u : 0u);
-        umma_commit(&empty_bar[s]);                       // smem slot reusable once these MMAs have read it
-        if (kb == num_k_blocks - 1) umma_commit(tmem_full_bar);  // accumulator complete
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_f16_pair(tmem_base, da + step_a * k, db + step_b * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_pair(&empty_bar[s]);                       // frees the stage in both CTAs
+          if (kb == num_k_blocks - 1) umma_commit_pair(tmem_full_bar);  // both epilogues may start
+        } else {
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_f16(tmem_base, da + step_a * k, db + step_b * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[s]);                       // smem slot reusable once these MMAs have read it
+          if (kb == num_k_blocks - 1) umma_commit(tmem_full_bar);  // accumulator complete
+        }
       }
       __syncwarp();
     }
@@ -403,13 +509,14 @@ __device__ __forceinline__ void gx_gemm_body(const CUtensorMap& map_a, const CUt
     gx_epi_begin(epi_state);
     GxEpiPre pre0, pre1;
     gx_epi_prefetch(epi, pre0, m_base, n0 + c_begin, args.M, args.ldc, lane);
-    if (kStages > 3) gx_epi_prefetch(epi, pre1, m_base, n0 + c_begin + 32, args.M, args.ldc, lane);
+    if (kDeep) gx_epi_prefetch(epi, pre1, m_base, n0 + c_begin + 32, args.M, args.ldc, lane);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    if (threadIdx.x == 64) trace_stamp(args.trace, cta_linear, 3);
     {
       float acc[32];
       load_acc(c_begin, acc);
-      if (kStages <= 3) gx_epi_prefetch(epi, pre1, m_base, n0 + c_begin + 32, args.M, args.ldc, lane);
+      if (!kDeep) gx_epi_prefetch(epi, pre1, m_base, n0 + c_begin + 32, args.M, args.ldc, lane);
       gx_epi_chunk(epi, epi_state, pre0, tile, m_base, n0 + c_begin, args.M, args.ldc, acc, lane);   // N parameter = row stride
     }
     {
@@ -421,6 +528,7 @@ __device__ __forceinline__ void gx_gemm_body(const CUtensorMap& map_a, const CUt
 #else
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    if (threadIdx.x == 64) trace_stamp(args.trace, cta_linear, 3);
 #pragma unroll 1
     for (int c = c_begin; c < c_begin + BN / 2; c += 32) {
       float acc[32];
@@ -434,11 +542,17 @@ __device__ __forceinline__ void gx_gemm_body(const CUtensorMap& map_a, const CUt
     }
 #endif
     tc_fence_before();
+    if (threadIdx.x == 64) trace_stamp(args.trace, cta_linear, 4);
   }
   __syncthreads();
+  if (threadIdx.x == 0) trace_stamp(args.trace, cta_linear, 5);
+  if (kPair) cluster_sync_all();   // neither CTA may leave (or free its TMEM) while the other still reads / writes it
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    if (kPair)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
   }
 }
 
@@ -667,7 +781,7 @@ gx_gemm_tn_kernel_persistent_n256(const __grid_constant__ CUtensorMap map_a, con
 #ifndef GX_GEMM_STAGES
 #define GX_GEMM_STAGES 3
 #endif
-extern "C" __global__ void __launch_bounds__(gxg::kThreads, GX_GEMM_STAGES > 3 ? 1 : 2)
+extern "C" __global__ void __launch_bounds__(gxg::kThreads, gxg::stages_deep(GX_GEMM_STAGES) ? 1 : 2)
 GX_GEMM_KERNEL_NAME(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const gxg::GemmArgs args GX_GEMM_EPI_PARAM) {
   gx_gemm_body<GX_GEMM_STAGES>(map_a, map_b, args GX_GEMM_EPI_ARG);
@@ -678,5 +792,16 @@ extern "C" __global__ void __launch_bounds__(gxg::kThreads, 1)
 gx_gemm_tn_kernel_deep(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                        const gxg::GemmArgs args) {
   gx_gemm_body<gxg::kStagesDeep>(map_a, map_b, args);
+}
+// CTA-pair instances (grid (tile rows, tile columns, splits) in clusters of (2, 1, 1); map_b has 64-row boxes)
+extern "C" __global__ void __launch_bounds__(gxg::kThreads, 2)
+gx_gemm_tn_kernel_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                       const gxg::GemmArgs args) {
+  gx_gemm_body<gxg::kStagesPairShallow>(map_a, map_b, args);
+}
+extern "C" __global__ void __launch_bounds__(gxg::kThreads, 1)
+gx_gemm_tn_kernel_pair_deep(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                            const gxg::GemmArgs args) {
+  gx_gemm_body<gxg::kStagesPairDeep>(map_a, map_b, args);
 }
 #endif

@@ -598,7 +598,14 @@ class DenseExecutor:
                 return re.sub(r"\bl(\d+)_@", repl, text)
             bodies.append(([sub(ln) for ln in lines], sub(result)))
         nl, no = max(1, len(leaves)), len(outs)
-        stages = 6 if (M // 128) * (N // 128) <= 148 else 3      # single-wave grids: deep operand ring, one CTA per SM
+        tiles_m, tiles_n = -(-M // 128), -(-N // 128)
+        deep = tiles_m * tiles_n <= 148                          # single-wave grids: deep operand ring, one CTA per SM
+        if os.environ.get("GX_FUSED_SHALLOW") == "1":
+            deep = False
+        # CTA pairs (cta_group::2: 256 x 128 per cluster of two CTAs, 24 instead of 32 KB of operands per CTA and
+        # k-block) whenever the tile rows pair up; the stage count names the variant (gx_gemm_kernel.cuh)
+        pair = tiles_m % 2 == 0 and os.environ.get("GX_GEMM_PAIR", "0") == "1"      # off by default: measured neutral
+        stages = (8 if deep else 4) if pair else (6 if deep else 3)
         src = ["#define GX_NVRTC", "#define GX_GEMM_FUSED", "#define GX_GEMM_KERNEL_NAME gx_gemm_fused",
                f"#define GX_GEMM_STAGES {stages}"]
         epi = [_GX_TANH,
@@ -672,16 +679,29 @@ class DenseExecutor:
                         epi.append(ln)
                 epi.append(f"    Y{k}[4 * q + {j}] = {result.replace('_@', f'_{j}')};")
         epi.append("  }")
+        # GX_EPI_DEBUG (measurement only, results are wrong): leave parts of the epilogue out to see what they cost
+        debug = set(filter(None, os.environ.get("GX_EPI_DEBUG", "").split(",")))
         # row-contiguous stores through the warp's staging tile (gx_gemm_kernel.cuh: store_rows)
-        epi.append("  gxg::store_rows(tile, acc, e.o32[0], e.o16[0], N, m_base, M, col0, lane);")
-        for k in range(1, no):
-            epi.append(f"  gxg::store_rows(tile, Y{k}, e.o32[{k}], e.o16[{k}], N, m_base, M, col0, lane);")
+        if "nostore" not in debug:
+            epi.append("  gxg::store_rows(tile, acc, e.o32[0], e.o16[0], N, m_base, M, col0, lane);")
+            for k in range(1, no):
+                epi.append(f"  gxg::store_rows(tile, Y{k}, e.o32[{k}], e.o16[{k}], N, m_base, M, col0, lane);")
+        else:
+            for k in range(1, no):
+                epi.append(f"  if (Y{k}[lane] == 12345.678f) e.o32[{k}][0] = Y{k}[0];")
         for k in csum_slots:
+            if "nocsum" in debug:
+                continue
             epi.append("#pragma unroll")
             epi.append(f"  for (int j = 0; j < 32; ++j) Y{k}[j] = ok ? Y{k}[j] : 0.0f;")
             epi.append(f"  gxg::warp_transpose_reduce(Y{k}, lane);")
-            epi.append(f"  atomicAdd(e.csum[{k}] + col0 + lane, Y{k}[0]);")
+            if "noatomic" in debug:
+                epi.append(f"  if (Y{k}[0] == 12345.678f) atomicAdd(e.csum[{k}] + col0 + lane, Y{k}[0]);")
+            else:
+                epi.append(f"  atomicAdd(e.csum[{k}] + col0 + lane, Y{k}[0]);")
         epi.append("}")
+        if "notanh" in debug:
+            epi = [ln if "__device__" in ln else ln.replace("gx_tanh(", "0.5f * (") for ln in epi]
         header = (Path(__file__).resolve().parent / "csrc" / "gx_gemm_kernel.cuh").read_text().replace("#pragma once", "")
         marker = "#ifndef GX_GEMM_KERNEL_NAME"
         text = "\n".join(src) + "\n" + header.replace(marker, "\n".join(epi) + "\n" + marker, 1)

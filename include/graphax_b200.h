@@ -135,6 +135,14 @@ int gx_split3_bf16(const void* in, void* out0, void* out1, void* out2, long long
 int gx_gemm_bf16x3_ld(int M, int N, int K, const void* const* A3, int lda, int a_mn, const void* const* B3, int ldb,
                       int b_mn, void* C, int ldc, int k_splits, void* stream);
 const char* gx_gemm_last_error(void);
+/* Single-tile contractions as CTA pairs (tcgen05 cta_group::2: a cluster of two CTAs on the SMs of one TPC computes a
+ * 256 x 128 tile, each CTA loading half of the B tile)?  Process-wide; default off (or GX_GEMM_PAIR=1); returns the
+ * previous setting.  Needs an even number of 128-row tiles, otherwise the call runs one CTA per tile. */
+int gx_gemm_set_pair(int on);
+/* Diagnostics: the next `max_launches` single-tile contractions write 8 x uint64 phase stamps per CTA (%globaltimer at
+ * entry, after the dependency wait, first operand stage landed, accumulator complete, epilogue done, exit) into
+ * buf[launch][max_ctas][8] (device memory); NULL switches it off (tools/gemm_trace.py). */
+int gx_gemm_set_trace(void* buf, int max_launches, int max_ctas);
 
 /* Fused elementwise kernels of the tensor-valued path are emitted per plan (graphax_b200/dense.py) and
  * compiled at run time: the elementwise half of `_pure_broadcast_mul` / `_sparse_add` (sparse/tensor.py:
@@ -149,7 +157,8 @@ int gx_colsum_f32(const void* in, void* out, int rows, int cols, void* stream);
  * csrc/gx_gemm_kernel.cuh compiled by gx_jit_compile behind a generated `GxEpi` / `gx_epi_chunk` (dense.py) -
  * the reference's `_mixed_mul` followed by `_pure_broadcast_mul` / elemental partials (sparse/tensor.py:1062-1231,
  * 826-866) without the intermediate edge ever reaching HBM.  `epi` points to the kernel's GxEpi block; `stages` is
- * the operand-ring depth the kernel was compiled with (GX_GEMM_STAGES: 3, or 6 for grids of at most one CTA per SM);
+ * the operand-ring depth the kernel was compiled with (GX_GEMM_STAGES: 3, or 6 for grids of at most one CTA per SM;
+ * 4 / 8 name the CTA-pair variant of the same two - cta_group::2, clusters of two tile rows, M a multiple of 256 -);
  * M, N, K, lda, ldb as in gx_gemm_bf16_ld, `ldn` the row stride of every [M, N] epilogue operand and output. */
 int gx_gemm_fused_launch(gx_jit_kernel* kernel, int M, int N, int K, const void* A, int lda, int a_mn, const void* B,
                          int ldb, int b_mn, int ldn, const void* epi, int stages, void* stream);

@@ -153,6 +153,68 @@ def test_mlp_weight_jacobians(built_library, mode, sizes, monkeypatch):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("m,n,k,splits,a_mn,b_mn", [(256, 128, 64, 1, False, False), (256, 384, 1024, 1, False, True),
+                                                    (512, 256, 2048, 4, True, True), (1024, 512, 4096, 8, True, False),
+                                                    (4096, 1024, 512, 1, False, False), (384, 256, 512, 1, False, False)])
+def test_tcgen05_gemm_cta_pairs(built_library, m, n, k, splits, a_mn, b_mn):
+    """The cta_group::2 variant (clusters of two CTAs on one 256 x 128 tile, each loading half of the B tile; the
+    leader issues the MMAs of both, its commits release the stages of both) gives the results of the one-CTA kernel:
+    K-major and MN-major operands, split-K, shallow and deep rings; an odd number of tile rows (384) falls back."""
+    import torch
+    from graphax_b200 import runtime
+    torch.manual_seed(2)
+    a = (torch.randn(m, k) * 0.5).bfloat16()
+    b = (torch.randn(n, k) * 0.5).bfloat16()
+    ref = (a.double() @ b.double().T).numpy()
+    da = (a.T.contiguous() if a_mn else a).cuda()
+    db = (b.T.contiguous() if b_mn else b).cuda()
+    lib = runtime.load_library()
+    single = runtime.gemm_bf16_tn(da, db, k_splits=splits, a_mn=a_mn, b_mn=b_mn).cpu().numpy()
+    before = lib.gx_gemm_set_pair(1)
+    try:
+        paired = runtime.gemm_bf16_tn(da, db, k_splits=splits, a_mn=a_mn, b_mn=b_mn).cpu().numpy()
+        if splits == 1:
+            paired16 = runtime.gemm_bf16_tn(da, db, out_dtype=torch.bfloat16, a_mn=a_mn, b_mn=b_mn).float().cpu().numpy()
+    finally:
+        lib.gx_gemm_set_pair(before)
+    assert np.abs(paired - ref).max() <= 2e-6 * k * 0.25 + 1e-5
+    if splits == 1:
+        assert np.array_equal(paired, single)            # same products, same accumulation order per element
+        assert np.abs(paired16 - ref).max() <= 2 ** -8 * np.abs(ref).max()
+    else:
+        assert np.abs(paired - single).max() <= 1e-5 * np.abs(ref).max()    # the order of the split-K atomics differs
+
+
+@pytest.mark.gpu
+def test_mlp_weight_jacobians_cta_pairs(built_library, monkeypatch):
+    """The run-time compiled contractions with fused epilogues in their CTA-pair form (GX_GEMM_PAIR=1)."""
+    import torch
+    from graphax_b200.dense import dense_jacve
+    B, I, H, O = 2048, 256, 1024, 768
+    tens = [torch.from_numpy(a).cuda() for a in _mlp_args(B, I, H, O)]
+    tens = [t.bfloat16() if t.ndim == 2 else t for t in tens]
+    cache = dense_jacve.__kwdefaults__["_cache"]
+    cache.clear()
+    _, single = dense_jacve(MLP_loss, "rev", (1, 2, 3, 4), *tens, has_aux=True)
+    ex = list(cache.values())[-1]
+    assert ex.gemm_fused and all(meta[3] in (3, 6) for meta in ex._fused_meta.values())
+    cache.clear()
+    monkeypatch.setenv("GX_GEMM_PAIR", "1")
+    lib = ex.lib
+    before = lib.gx_gemm_set_pair(1)
+    try:
+        _, paired = dense_jacve(MLP_loss, "rev", (1, 2, 3, 4), *tens, has_aux=True)
+        torch.cuda.synchronize()
+        ex = list(cache.values())[-1]
+        assert ex.gemm_fused and all(meta[3] in (4, 8) for meta in ex._fused_meta.values())
+    finally:
+        lib.gx_gemm_set_pair(before)
+        cache.clear()
+    for g, p in zip(single, paired):
+        assert float((g - p).abs().max()) <= 1e-4 * float(g.abs().max())
+
+
+@pytest.mark.gpu
 def test_tensor_path_matches_the_reference_run(built_library):
     """The tcgen05 path against weight Jacobians computed by the reference's own code (batched MLP of the
     reference's test_vmap_NeuralNetwork at widths 6 -> 10 -> 4, batch 12): float32 arguments take the three-term
