@@ -1134,6 +1134,7 @@ int gx_gemm_fused_launch(gx_jit_kernel* k, int M, int N, int K, const void* A, i
   args.a_mn = a_mn ? 1 : 0;
   args.b_mn = b_mn ? 1 : 0;
   args.trace = gxg_next_trace(((N + 127) / 128) * ((M + 127) / 128));
+  gxg_take_zero(&args.zero_ptr, &args.zero_n);
   CUlaunchConfig cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDimX = (N + 127) / 128;

@@ -108,6 +108,10 @@ bool gemm_use_pair() { return g_gemm_pair != 0; }
 unsigned long long* g_trace = nullptr;
 int g_trace_launches = 0, g_trace_ctas = 0, g_trace_next = 0;
 
+// one-shot request of this host thread: the next single-tile launch clears [g_zero_ptr, +16 * g_zero_n)
+thread_local float4* g_zero_ptr = nullptr;
+thread_local unsigned g_zero_n = 0;
+
 bool gemm_use_pdl() {
   static const bool v = [] {
     const char* e = getenv("GX_PDL");
@@ -129,6 +133,13 @@ int gxg_make_maps(CUtensorMap* map_a, CUtensorMap* map_b, int M, int N, int K, c
 
 int gxg_pair_enabled(void) { return gemm_use_pair() ? 1 : 0; }
 
+void gxg_take_zero(float4** ptr, unsigned* n16) {
+  *ptr = g_zero_ptr;
+  *n16 = g_zero_n;
+  g_zero_ptr = nullptr;
+  g_zero_n = 0;
+}
+
 unsigned long long* gxg_next_trace(int n_ctas) {
   if (!g_trace || g_trace_next >= g_trace_launches || n_ctas > g_trace_ctas) return nullptr;
   return g_trace + (size_t)(g_trace_next++) * g_trace_ctas * 8;
@@ -146,6 +157,21 @@ int gx_gemm_set_trace(void* buf, int max_launches, int max_ctas) {
   g_trace_launches = buf ? max_launches : 0;
   g_trace_ctas = max_ctas;
   g_trace_next = 0;
+  return GX_OK;
+}
+
+// The next single-tile contraction launched by this thread (gx_gemm_bf16*, gx_gemm_fused_launch) also clears `bytes`
+// bytes at `ptr` (16-byte aligned, a multiple of 16): its epilogue warps do it while the main loop runs, after the
+// launch's dependency wait, so whatever the NEXT launch on the stream adds into the region finds it zeroed.  The
+// region must not be an output of that contraction itself.  One-shot; a launch that cannot host it (persistent
+// kernels) clears the region with a memset on its stream first.
+int gx_gemm_zero_with_next_launch(void* ptr, long long bytes) {
+  if (!ptr || bytes <= 0 || bytes % 16 || (reinterpret_cast<uintptr_t>(ptr) & 15) || bytes / 16 > 0xffffffffLL) {
+    g_gemm_error = "gx_gemm_zero_with_next_launch: region must be 16-byte aligned and a multiple of 16 bytes";
+    return GX_ERR_BAD_ARG;
+  }
+  g_zero_ptr = static_cast<float4*>(ptr);
+  g_zero_n = (unsigned)(bytes / 16);
   return GX_OK;
 }
 
@@ -306,6 +332,12 @@ static int gemm_launch(int M, int N, int K, const void* A, int lda, int a_mn, co
   args.a_mn = a_mn ? 1 : 0;
   args.b_mn = b_mn ? 1 : 0;
   args.trace = persistent ? nullptr : gxg_next_trace(tiles_n * tiles_m * k_splits);
+  gxg_take_zero(&args.zero_ptr, &args.zero_n);
+  if (persistent && args.zero_n) {
+    cudaMemsetAsync(args.zero_ptr, 0, (size_t)args.zero_n * 16, static_cast<cudaStream_t>(stream));
+    args.zero_ptr = nullptr;
+    args.zero_n = 0;
+  }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = dim3(tiles_n, tiles_m, k_splits);

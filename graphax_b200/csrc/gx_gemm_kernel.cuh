@@ -71,6 +71,11 @@ struct GemmArgs {
   // optional phase stamps of the single-tile kernels (tools/gemm_trace.py): 8 x u64 per CTA - %globaltimer at
   // entry, after griddepcontrol.wait, first operand stage landed, accumulator complete, epilogue done, exit
   unsigned long long* trace;
+  // optional: `zero_n` 16-byte words at `zero_ptr` are cleared by the (otherwise idle) epilogue warps of the single-tile
+  // kernels while the main loop runs - the step's accumulator arena, so that no separate memset has to be launched
+  // and waited for (gx_gemm_zero_with_next_launch)
+  float4* zero_ptr;
+  unsigned zero_n;
 };
 __device__ __forceinline__ void trace_stamp(unsigned long long* trace, int cta, int slot) {
   if (trace) {
@@ -479,6 +484,11 @@ __device__ __forceinline__ void gx_gemm_body(const CUtensorMap& map_a, const CUt
     }
   } else {
     // ===== epilogue: warp w may only touch TMEM lanes 32*(w%4) .. 32*(w%4)+31 =====
+    if (args.zero_n) {   // after griddepcontrol.wait: nobody adds into the region before this grid has completed
+      const unsigned n_ctas = gridDim.x * gridDim.y * gridDim.z, per_cta = kThreads - 64;
+      for (unsigned i = (unsigned)cta_linear * per_cta + (threadIdx.x - 64); i < args.zero_n; i += n_ctas * per_cta)
+        args.zero_ptr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     const int quad = warp & 3;
     const int c_begin = ((warp - 2) >> 2) * (BN / 2);
     const int m_base = m0 + quad * 32;

@@ -2,6 +2,7 @@
 // it without compiling the kernel themselves.
 #pragma once
 #include <cuda.h>
+#include <cuda_runtime.h>
 #include <stdint.h>
 namespace gxg {
 constexpr int kThreads = 320;
@@ -16,6 +17,8 @@ struct GemmArgs {
   int M, N, K, ldc, epilogue, k_per_split;
   int a_mn, b_mn;
   unsigned long long* trace;
+  float4* zero_ptr;
+  unsigned zero_n;
 };
 }  // namespace gxg
 int gxg_make_maps(CUtensorMap* map_a, CUtensorMap* map_b, int M, int N, int K, const void* A, int a_mn, const void* B,
@@ -23,3 +26,5 @@ int gxg_make_maps(CUtensorMap* map_a, CUtensorMap* map_b, int M, int N, int K, c
 int gxg_pair_enabled(void);
 // next slice of the trace buffer (gx_gemm_set_trace), or null
 unsigned long long* gxg_next_trace(int n_ctas);
+// region the next single-tile launch of this thread has been asked to clear (gx_gemm_zero_with_next_launch); one-shot
+void gxg_take_zero(float4** ptr, unsigned* n16);

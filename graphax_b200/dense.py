@@ -890,21 +890,36 @@ class DenseExecutor:
         # Jacobians themselves) run beside the critical chain forward -> cotangents; under CUDA-graph capture the
         # events become parallel branches.
         main = torch.cuda.current_stream(self.device)
-        if getattr(self, "side", None) is None:
-            self.side = torch.cuda.Stream(device=self.device)
-        side = self.side
-        fork = torch.cuda.Event()
-        fork.record(main)
-        side.wait_event(fork)
+        # The accumulator arena is cleared by the first contraction of the step itself (its epilogue warps are idle
+        # during the main loop) when that contraction does not add into the arena: no memset launch, and every later
+        # launch keeps a single, programmatic dependency (a second edge from a memset on the side stream made the
+        # first arena user start 1.8 us late: profiles/gemm_trace_r02c_mlp.txt).  Otherwise: memset beside the chain.
+        first = self.order[0] if self.order else None
+        host_zero = bool(self.arena_size and first is not None and dag.nodes[first].kind == "gemm" and not self.split
+                         and first not in self.arena_users and os.environ.get("GX_DENSE_MEMSET", "0") != "1")
+        use_side = self.concurrent or bool(self.arena_size and not host_zero)
+        side = None
+        if use_side:
+            if getattr(self, "side", None) is None:
+                self.side = torch.cuda.Stream(device=self.device)
+            side = self.side
+            fork = torch.cuda.Event()
+            fork.record(main)
+            side.wait_event(fork)
         zeroed = None
         if self.arena_size:
             for key in self.arena_keys:
                 self._buf(*key)
-            with torch.cuda.stream(side):
-                self.arena.zero_()
-                zeroed = torch.cuda.Event()
-                zeroed.record(side)
-            self.launches += 1
+            if host_zero:
+                rc = self.lib.gx_gemm_zero_with_next_launch(self.arena.data_ptr(), self.arena.numel() * 4)
+                if rc != 0:
+                    raise self.rt.GraphaxB200Error(self.lib.gx_gemm_last_error().decode())
+            else:
+                with torch.cuda.stream(side):
+                    self.arena.zero_()
+                    zeroed = torch.cuda.Event()
+                    zeroed.record(side)
+                self.launches += 1
         for n in self.order:
             if n in self.side_nodes and self.concurrent:
                 ready = torch.cuda.Event()
@@ -917,9 +932,10 @@ class DenseExecutor:
                 main.wait_event(zeroed)
                 zeroed = None
             self._launch_node(n)
-        join = torch.cuda.Event()
-        join.record(side)
-        main.wait_event(join)
+        if use_side:
+            join = torch.cuda.Event()
+            join.record(side)
+            main.wait_event(join)
         grads = []
         for a, g in zip(self.plan.argnums, self.plan.grads):
             shape = self.plan.jaxpr.invars[a].shape

@@ -143,6 +143,11 @@ int gx_gemm_set_pair(int on);
  * entry, after the dependency wait, first operand stage landed, accumulator complete, epilogue done, exit) into
  * buf[launch][max_ctas][8] (device memory); NULL switches it off (tools/gemm_trace.py). */
 int gx_gemm_set_trace(void* buf, int max_launches, int max_ctas);
+/* The next single-tile contraction launched by the calling thread also clears `bytes` bytes at `ptr` (device memory,
+ * 16-byte aligned, a multiple of 16; not an output of that contraction): the accumulator arena that split-K
+ * contractions and fused column sums of LATER launches add into (the reference's zero-initialised fill-in,
+ * core.py:555-562) - saves a memset launch and the dependency edge it brings.  One-shot. */
+int gx_gemm_zero_with_next_launch(void* ptr, long long bytes);
 
 /* Fused elementwise kernels of the tensor-valued path are emitted per plan (graphax_b200/dense.py) and
  * compiled at run time: the elementwise half of `_pure_broadcast_mul` / `_sparse_add` (sparse/tensor.py:

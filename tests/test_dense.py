@@ -215,6 +215,39 @@ def test_mlp_weight_jacobians_cta_pairs(built_library, monkeypatch):
 
 
 @pytest.mark.gpu
+def test_arena_cleared_by_the_first_contraction(built_library, monkeypatch):
+    """The step's accumulator arena (split-K outputs, bias column sums) is cleared by the epilogue warps of the first
+    contraction instead of a memset launch: repeated steps of one executor give the same Jacobians (a missed clear
+    would double them), equal to the memset variant up to the order of the atomic additions."""
+    import torch
+    from graphax_b200.dense import dense_jacve
+    B, I, H, O = 2048, 256, 1024, 768
+    tens = [torch.from_numpy(a).cuda() for a in _mlp_args(B, I, H, O)]
+    tens = [t.bfloat16() if t.ndim == 2 else t for t in tens]
+    cache = dense_jacve.__kwdefaults__["_cache"]
+    cache.clear()
+    runs = []
+    for _ in range(3):
+        _, grads = dense_jacve(MLP_loss, "rev", (1, 2, 3, 4), *tens, has_aux=True)
+        runs.append([g.clone() for g in grads])
+    def launches_per_step():
+        ex = list(cache.values())[-1]
+        l0 = ex.launches
+        ex.run(tens)
+        return ex.launches - l0
+    fused_clear = launches_per_step()
+    cache.clear()
+    monkeypatch.setenv("GX_DENSE_MEMSET", "1")
+    _, with_memset = dense_jacve(MLP_loss, "rev", (1, 2, 3, 4), *tens, has_aux=True)
+    assert launches_per_step() == fused_clear + 1      # the memset is the only launch that disappears
+    cache.clear()
+    for a, b, c, m in zip(*runs, with_memset):
+        scale = float(m.abs().max())
+        assert float((a - b).abs().max()) <= 1e-5 * scale and float((a - c).abs().max()) <= 1e-5 * scale
+        assert float((a - m).abs().max()) <= 1e-5 * scale
+
+
+@pytest.mark.gpu
 def test_tensor_path_matches_the_reference_run(built_library):
     """The tcgen05 path against weight Jacobians computed by the reference's own code (batched MLP of the
     reference's test_vmap_NeuralNetwork at widths 6 -> 10 -> 4, batch 12): float32 arguments take the three-term
