@@ -683,17 +683,23 @@ class DenseExecutor:
         debug = set(filter(None, os.environ.get("GX_EPI_DEBUG", "").split(",")))
         # row-contiguous stores through the warp's staging tile (gx_gemm_kernel.cuh: store_rows)
         if "nostore" not in debug:
-            epi.append("  gxg::store_rows(tile, acc, e.o32[0], e.o16[0], N, m_base, M, col0, lane);")
+            # only outputs somebody reads get a store: a call whose pointers are null at run time would still keep
+            # its 32 values alive (the raw accumulator next to every fused output: 200 bytes of spills at 96 registers)
+            stored = lambda o: o in self.f32_read or o in self.needs_bf16
+            if stored(g):
+                epi.append("  gxg::store_rows(tile, acc, e.o32[0], e.o16[0], N, m_base, M, col0, lane);")
             for k in range(1, no):
-                epi.append(f"  gxg::store_rows(tile, Y{k}, e.o32[{k}], e.o16[{k}], N, m_base, M, col0, lane);")
+                if stored(outs[k]):
+                    epi.append(f"  gxg::store_rows(tile, Y{k}, e.o32[{k}], e.o16[{k}], N, m_base, M, col0, lane);")
         else:
             for k in range(1, no):
                 epi.append(f"  if (Y{k}[lane] == 12345.678f) e.o32[{k}][0] = Y{k}[0];")
         for k in csum_slots:
             if "nocsum" in debug:
                 continue
-            epi.append("#pragma unroll")
-            epi.append(f"  for (int j = 0; j < 32; ++j) Y{k}[j] = ok ? Y{k}[j] : 0.0f;")
+            if M % 128:                                     # rows of the last tile beyond M stay out of the sums
+                epi.append("#pragma unroll")
+                epi.append(f"  for (int j = 0; j < 32; ++j) Y{k}[j] = ok ? Y{k}[j] : 0.0f;")
             epi.append(f"  gxg::warp_transpose_reduce(Y{k}, lane);")
             if "noatomic" in debug:
                 epi.append(f"  if (Y{k}[0] == 12345.678f) atomicAdd(e.csum[{k}] + col0 + lane, Y{k}[0]);")
