@@ -375,6 +375,12 @@ int64_t host_chunk() {
   return (int64_t)(n >= 1024 ? n : (1 << 17));
 }
 
+// small first chunks in gx_jacve_host (GX_HOST_RAMP=0: every chunk full sized)
+bool host_ramp() {
+  const char* e = getenv("GX_HOST_RAMP");
+  return !(e && e[0] == '0');
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -953,12 +959,27 @@ int gx_jacve_host(gx_plan* p, int64_t batch, const void* const* in_ptrs, void* j
     p->host_ready = true;
     p->host_staging = p->host_staging || staging;
   }
-  const int64_t n_chunks = (batch + kHostChunk - 1) / kHostChunk;
+  // Chunk schedule: the result copy (D2H, 5x the input bytes for RoeFlux_3d) is what the call waits for, so it should
+  // start as early as possible - the first chunks are small (an eighth of a full chunk, doubling) and only then full
+  // sized; every chunk still fits the slot's staging buffers.
+  std::vector<int64_t> starts, sizes;
+  {
+    int64_t b = 0, sz = std::max<int64_t>(kHostChunk / 8, std::min<int64_t>(kHostChunk, 4096));
+    if (!host_ramp()) sz = kHostChunk;
+    while (b < batch) {
+      const int64_t nb = std::min<int64_t>(sz, batch - b);
+      starts.push_back(b);
+      sizes.push_back(nb);
+      b += nb;
+      sz = std::min<int64_t>(kHostChunk, sz * 2);
+    }
+  }
+  const int64_t n_chunks = (int64_t)starts.size();
   auto drain = [&](int64_t c) -> int {  // staged results of chunk c -> caller memory
     auto& s = p->slots[c & 1];
     GX_CUDA(cudaEventSynchronize(s.done));
     if (staging) {
-      const int64_t b0 = c * kHostChunk, nb = std::min<int64_t>(kHostChunk, batch - b0);
+      const int64_t b0 = starts[c], nb = sizes[c];
       memcpy(static_cast<float*>(jac_out) + b0 * tile, s.h_jac, 4 * tile * nb);
       if (primal_out) memcpy(static_cast<float*>(primal_out) + b0 * rows, s.h_primal, 4 * rows * nb);
     }
@@ -966,7 +987,7 @@ int gx_jacve_host(gx_plan* p, int64_t batch, const void* const* in_ptrs, void* j
   };
   for (int64_t c = 0; c < n_chunks; ++c) {
     auto& s = p->slots[c & 1];
-    const int64_t b0 = c * kHostChunk, nb = std::min<int64_t>(kHostChunk, batch - b0);
+    const int64_t b0 = starts[c], nb = sizes[c];
     if (c >= 2) {
       int rc = drain(c - 2);
       if (rc) return rc;

@@ -555,7 +555,7 @@ __device__ __forceinline__ void gx_gemm_body(const CUtensorMap& map_a, const CUt
     if (threadIdx.x == 64) trace_stamp(args.trace, cta_linear, 4);
   }
   __syncthreads();
-  if (threadIdx.x == 0) trace_stamp(args.trace, cta_linear, 5);
+  if (threadIdx.x == 64) trace_stamp(args.trace, cta_linear, 5);
   if (kPair) cluster_sync_all();   // neither CTA may leave (or free its TMEM) while the other still reads / writes it
   if (warp == 1) {
     tc_fence_after();

@@ -902,7 +902,8 @@ class DenseExecutor:
         # first arena user start 1.8 us late: profiles/gemm_trace_r02c_mlp.txt).  Otherwise: memset beside the chain.
         first = self.order[0] if self.order else None
         host_zero = bool(self.arena_size and first is not None and dag.nodes[first].kind == "gemm" and not self.split
-                         and first not in self.arena_users and os.environ.get("GX_DENSE_MEMSET", "0") != "1")
+                         and not self.concurrent and first not in self.arena_users
+                         and os.environ.get("GX_DENSE_MEMSET", "0") != "1")
         use_side = self.concurrent or bool(self.arena_size and not host_zero)
         side = None
         if use_side:
