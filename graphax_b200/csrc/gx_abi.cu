@@ -440,6 +440,8 @@ struct gx_plan {
   } slots[2];
   bool host_ready = false;
   bool host_staging = false;
+  int64_t host_dev_cap = 0;     // samples the device buffers of a slot hold
+  int64_t host_stage_cap = 0;   // samples the pinned staging buffers of a slot hold
 };
 
 namespace {
@@ -940,40 +942,59 @@ int gx_jacve_host(gx_plan* p, int64_t batch, const void* const* in_ptrs, void* j
   std::lock_guard<std::mutex> lock(p->host_mu);
   GX_CUDA(cudaSetDevice(p->device));
   const size_t n_in = p->h.n_in_scalars, tile = (size_t)p->h.n_rows * p->h.n_cols, rows = p->h.n_rows;
-  if (p->host_chunk == 0) p->host_chunk = host_chunk();   // fixed at the plan's first host call (sizes the staging buffers)
-  const int64_t kHostChunk = p->host_chunk;
+  if (p->host_chunk == 0) p->host_chunk = host_chunk();   // fixed at the plan's first host call
+  const int64_t base = p->host_chunk;
   const bool staging = !pinned;
-  if (!p->host_ready || (staging && !p->host_staging)) {
-    for (auto& s : p->slots) {
-      if (!s.stream) GX_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-      if (!s.done) GX_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
-      if (!s.d_in) GX_CUDA(cudaMalloc(&s.d_in, 4 * n_in * kHostChunk));
-      if (!s.d_jac) GX_CUDA(cudaMalloc(&s.d_jac, 4 * tile * kHostChunk));
-      if (!s.d_primal) GX_CUDA(cudaMalloc(&s.d_primal, 4 * rows * kHostChunk));
-      if (staging && !s.h_in) {
-        GX_CUDA(cudaMallocHost(&s.h_in, 4 * n_in * kHostChunk));
-        GX_CUDA(cudaMallocHost(&s.h_jac, 4 * tile * kHostChunk));
-        GX_CUDA(cudaMallocHost(&s.h_primal, 4 * rows * kHostChunk));
-      }
-    }
-    p->host_ready = true;
-    p->host_staging = p->host_staging || staging;
-  }
-  // Chunk schedule: the result copy (D2H, 5x the input bytes for RoeFlux_3d) is what the call waits for, so it should
-  // start as early as possible - the first chunks are small (an eighth of a full chunk, doubling) and only then full
-  // sized; every chunk still fits the slot's staging buffers.
+  // Chunk schedule.  The result copy (D2H, 5x the input bytes for RoeFlux_3d) is what the call waits for, so the first
+  // two chunks are half sized to start it early; everything after that moves `base` samples.  (Measured on a B200,
+  // 2^20 RoeFlux_3d samples, base 2^17: 254.6 vs 254.1 M Jacobians/s with all chunks full sized, and the same with
+  // chunks growing to 4 x base - neither the fill nor the number of copies is where the last 9 % to the raw-copy floor
+  // go; a synchronous call cannot hide its first H2D copy and its last event wait the way back-to-back copies do.)
+  const int64_t chunk_cap = base;
   std::vector<int64_t> starts, sizes;
   {
-    int64_t b = 0, sz = std::max<int64_t>(kHostChunk / 8, std::min<int64_t>(kHostChunk, 4096));
-    if (!host_ramp()) sz = kHostChunk;
+    int64_t b = 0, sz = host_ramp() ? std::max<int64_t>(base / 2, std::min<int64_t>(base, 1024)) : base;
+    int n = 0;
     while (b < batch) {
       const int64_t nb = std::min<int64_t>(sz, batch - b);
       starts.push_back(b);
       sizes.push_back(nb);
       b += nb;
-      sz = std::min<int64_t>(kHostChunk, sz * 2);
+      if (++n >= 2) sz = std::min<int64_t>(chunk_cap, sz * 2);
     }
   }
+  const int64_t need_dev = *std::max_element(sizes.begin(), sizes.end());
+  if (!p->host_ready) {
+    for (auto& s : p->slots) {
+      GX_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+      GX_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    }
+    p->host_ready = true;
+  }
+  if (need_dev > p->host_dev_cap) {   // first call, or a larger batch than any before: (re)allocate the device side
+    const int64_t cap = std::min<int64_t>(chunk_cap, (need_dev + 1023) / 1024 * 1024);
+    for (auto& s : p->slots) {
+      GX_CUDA(cudaStreamSynchronize(s.stream));
+      if (s.d_in) cudaFree(s.d_in);
+      if (s.d_jac) cudaFree(s.d_jac);
+      if (s.d_primal) cudaFree(s.d_primal);
+      s.d_in = s.d_jac = s.d_primal = nullptr;
+      GX_CUDA(cudaMalloc(&s.d_in, 4 * n_in * cap));
+      GX_CUDA(cudaMalloc(&s.d_jac, 4 * tile * cap));
+      GX_CUDA(cudaMalloc(&s.d_primal, 4 * rows * cap));
+    }
+    p->host_dev_cap = cap;
+  }
+  if (staging && !p->host_staging) {
+    for (auto& s : p->slots) {
+      GX_CUDA(cudaMallocHost(&s.h_in, 4 * n_in * base));
+      GX_CUDA(cudaMallocHost(&s.h_jac, 4 * tile * base));
+      GX_CUDA(cudaMallocHost(&s.h_primal, 4 * rows * base));
+    }
+    p->host_staging = true;
+    p->host_stage_cap = base;
+  }
+  const int64_t dev_cap = p->host_dev_cap, stage_cap = p->host_stage_cap;
   const int64_t n_chunks = (int64_t)starts.size();
   auto drain = [&](int64_t c) -> int {  // staged results of chunk c -> caller memory
     auto& s = p->slots[c & 1];
@@ -997,9 +1018,9 @@ int gx_jacve_host(gx_plan* p, int64_t batch, const void* const* in_ptrs, void* j
     for (unsigned i = 0; i < p->h.n_in_arrays; ++i) {
       const size_t sz = p->in_sizes[i];
       const float* src = static_cast<const float*>(in_ptrs[i]) + b0 * sz;
-      float* dst = s.d_in + off * kHostChunk;
+      float* dst = s.d_in + off * dev_cap;
       if (staging) {
-        float* st = s.h_in + off * kHostChunk;
+        float* st = s.h_in + off * stage_cap;
         memcpy(st, src, 4 * sz * nb);
         src = st;
       }
