@@ -389,6 +389,88 @@ static int gemm_launch(int M, int N, int K, const void* A, int lda, int a_mn, co
   return GX_OK;
 }
 
+// Two independent contractions in one launch (gx_gemm_tn_kernel_dual): both as in gx_gemm_bf16_ld (index 0 / 1 of
+// every array argument).  Falls back to two launches when the pair does not fit the dual kernel (a problem large
+// enough for the persistent kernel, more than 65535 CTAs).
+int gx_gemm_bf16_dual_ld(const int* M, const int* N, const int* K, const void* const* A, const int* lda, const int* a_mn,
+                         const void* const* B, const int* ldb, const int* b_mn, void* const* C, const int* ldc_in,
+                         const int* c_is_bf16, const int* k_splits, void* stream) {
+  if (!M || !N || !K || !A || !lda || !a_mn || !B || !ldb || !b_mn || !C || !ldc_in || !c_is_bf16 || !k_splits) {
+    g_gemm_error = "gx_gemm_bf16_dual_ld: NULL argument";
+    return GX_ERR_BAD_ARG;
+  }
+  CUtensorMap maps[4];
+  GxDualArgs dual;
+  memset(&dual, 0, sizeof dual);
+  long long ctas[2];
+  bool ok = true;
+  for (int i = 0; i < 2 && ok; ++i) {
+    const int tiles_m = (M[i] + BM - 1) / BM, tiles_n = (N[i] + BN - 1) / BN;
+    const int ldc = ldc_in[i] ? ldc_in[i] : N[i];
+    const int k_blocks = (K[i] + BK - 1) / BK;
+    const int splits = k_splits[i];
+    ok = M[i] > 0 && N[i] > 0 && K[i] > 0 && A[i] && B[i] && C[i] && splits >= 1 && !(splits > 1 && c_is_bf16[i]) &&
+         ldc % 4 == 0 && ldc >= (N[i] % BN ? tiles_n * BN : N[i]);
+    if (!ok) break;
+    const int k_per_split = ((k_blocks + splits - 1) / splits) * BK;
+    ok = !((long long)k_per_split * (splits - 1) >= K[i] && splits > 1) &&
+         !(splits == 1 && (long long)tiles_m * tiles_n > 2LL * sm_count() && gemm_use_persistent());
+    if (!ok) break;
+    if (gxg_make_maps(&maps[2 * i], &maps[2 * i + 1], M[i], N[i], K[i], A[i], a_mn[i], B[i], b_mn[i], lda[i], ldb[i], 0)) {
+      g_gemm_error = "gx_gemm_bf16_dual_ld: cuTensorMapEncodeTiled failed (pointers must be 16-byte aligned)";
+      return GX_ERR_CUDA;
+    }
+    GemmArgs& a = dual.args[i];
+    a.c_f32 = c_is_bf16[i] ? nullptr : static_cast<float*>(C[i]);
+    a.c_bf16 = c_is_bf16[i] ? static_cast<uint16_t*>(C[i]) : nullptr;
+    a.M = M[i], a.N = N[i], a.K = K[i], a.ldc = ldc;
+    a.epilogue = splits > 1 ? EPI_ATOMIC_F32 : (c_is_bf16[i] ? EPI_STORE_BF16 : EPI_STORE_F32);
+    a.k_per_split = k_per_split;
+    a.a_mn = a_mn[i] ? 1 : 0, a.b_mn = b_mn[i] ? 1 : 0;
+    dual.tiles_m[i] = tiles_m, dual.tiles_n[i] = tiles_n;
+    ctas[i] = (long long)tiles_m * tiles_n * splits;
+  }
+  if (!ok || ctas[0] + ctas[1] > 65535 || g_zero_n) {   // not a pair for the dual kernel: one after the other
+    for (int i = 0; i < 2; ++i) {
+      const int rc = gx_gemm_bf16_ld(M[i], N[i], K[i], A[i], lda[i], a_mn[i], B[i], ldb[i], b_mn[i], C[i], ldc_in[i],
+                                     c_is_bf16[i], k_splits[i], stream);
+      if (rc != GX_OK) return rc;
+    }
+    return GX_OK;
+  }
+  dual.n_ctas0 = (int)ctas[0];
+  dual.args[0].trace = gxg_next_trace((int)(ctas[0] + ctas[1]));
+  dual.args[1].trace = dual.args[0].trace;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(gx_gemm_tn_kernel_dual, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem_bytes(kStagesShallow));
+  });
+  if (attr_err != cudaSuccess) {
+    g_gemm_error = std::string("cudaFuncSetAttribute(dual): ") + cudaGetErrorString(attr_err);
+    return GX_ERR_CUDA;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3((unsigned)(ctas[0] + ctas[1]));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes(kStagesShallow);
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = gemm_use_pdl() ? 1 : 0;
+  void* params[] = {&maps[0], &maps[1], &maps[2], &maps[3], &dual};
+  cudaError_t e = cudaLaunchKernelExC(&cfg, (const void*)gx_gemm_tn_kernel_dual, params);
+  if (e != cudaSuccess) {
+    g_gemm_error = std::string("gx_gemm_tn_kernel_dual launch: ") + cudaGetErrorString(e);
+    return GX_ERR_CUDA;
+  }
+  return GX_OK;
+}
+
 int gx_transpose_bf16(int rows, int cols, const void* in, void* out, void* stream) {
   if (rows <= 0 || cols <= 0 || !in || !out) {
     g_gemm_error = "gx_transpose_bf16: bad argument";

@@ -351,9 +351,24 @@ constexpr uint32_t kInstrDescPair = (1u << 4) | (1u << 7) | (1u << 10) | ((BN >>
 #define GX_GEMM_EPI_ARG
 #endif
 
+// tile_m / tile_n / split: which 128 x 128 tile (and which K split of it) this CTA computes; cta_linear / n_ctas: its
+// place among the CTAs that share args.trace / args.zero_ptr
+struct GxTileCoord {
+  int tile_m, tile_n, split, cta_linear, n_ctas;
+};
+template <int kStages>
+__device__ __forceinline__ GxTileCoord gx_tile_from_grid() {
+  GxTileCoord c;
+  c.tile_m = gxg::stages_pair(kStages) ? blockIdx.x : blockIdx.y;
+  c.tile_n = gxg::stages_pair(kStages) ? blockIdx.y : blockIdx.x;
+  c.split = blockIdx.z;
+  c.cta_linear = (int)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
+  c.n_ctas = (int)(gridDim.x * gridDim.y * gridDim.z);
+  return c;
+}
 template <int kStages>
 __device__ __forceinline__ void gx_gemm_body(const CUtensorMap& map_a, const CUtensorMap& map_b,
-                                             const gxg::GemmArgs& args GX_GEMM_EPI_PARAM_REF) {
+                                             const gxg::GemmArgs& args, const GxTileCoord& coord GX_GEMM_EPI_PARAM_REF) {
   using namespace gxg;
   extern __shared__ uint8_t gg_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gg_smem_raw) + 1023) & ~uintptr_t(1023));
@@ -370,12 +385,12 @@ __device__ __forceinline__ void gx_gemm_body(const CUtensorMap& map_a, const CUt
   const int lane = threadIdx.x & 31;
   // pair: the grid is (tile rows, tile columns) and the cluster (2, 1, 1) - two consecutive tile rows (the launch is
   // rejected as a cluster misconfiguration unless the pair lies along x); rank 0 (the leader) issues the MMAs of both
-  const int m0 = (stages_pair(kStages) ? blockIdx.x : blockIdx.y) * BM, n0 = (stages_pair(kStages) ? blockIdx.y : blockIdx.x) * BN;
+  const int m0 = coord.tile_m * BM, n0 = coord.tile_n * BN;
   const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
-  const int cta_linear = (int)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
+  const int cta_linear = coord.cta_linear;
   if (threadIdx.x == 0) trace_stamp(args.trace, cta_linear, 0);
-  const int k_begin = blockIdx.z * args.k_per_split;
+  const int k_begin = coord.split * args.k_per_split;
   const int k_len = args.K - k_begin < args.k_per_split ? args.K - k_begin : args.k_per_split;   // last split may be short
   const int num_k_blocks = (k_len + BK - 1) / BK;
 
@@ -485,7 +500,7 @@ __device__ __forceinline__ void gx_gemm_body(const CUtensorMap& map_a, const CUt
   } else {
     // ===== epilogue: warp w may only touch TMEM lanes 32*(w%4) .. 32*(w%4)+31 =====
     if (args.zero_n) {   // after griddepcontrol.wait: nobody adds into the region before this grid has completed
-      const unsigned n_ctas = gridDim.x * gridDim.y * gridDim.z, per_cta = kThreads - 64;
+      const unsigned n_ctas = (unsigned)coord.n_ctas, per_cta = kThreads - 64;
       for (unsigned i = (unsigned)cta_linear * per_cta + (threadIdx.x - 64); i < args.zero_n; i += n_ctas * per_cta)
         args.zero_ptr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -794,24 +809,48 @@ gx_gemm_tn_kernel_persistent_n256(const __grid_constant__ CUtensorMap map_a, con
 extern "C" __global__ void __launch_bounds__(gxg::kThreads, gxg::stages_deep(GX_GEMM_STAGES) ? 1 : 2)
 GX_GEMM_KERNEL_NAME(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const gxg::GemmArgs args GX_GEMM_EPI_PARAM) {
-  gx_gemm_body<GX_GEMM_STAGES>(map_a, map_b, args GX_GEMM_EPI_ARG);
+  gx_gemm_body<GX_GEMM_STAGES>(map_a, map_b, args, gx_tile_from_grid<GX_GEMM_STAGES>() GX_GEMM_EPI_ARG);
 }
 #ifndef GX_NVRTC
 // the library's second instance: deep ring, one CTA per SM
 extern "C" __global__ void __launch_bounds__(gxg::kThreads, 1)
 gx_gemm_tn_kernel_deep(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                        const gxg::GemmArgs args) {
-  gx_gemm_body<gxg::kStagesDeep>(map_a, map_b, args);
+  gx_gemm_body<gxg::kStagesDeep>(map_a, map_b, args, gx_tile_from_grid<gxg::kStagesDeep>());
 }
 // CTA-pair instances (grid (tile rows, tile columns, splits) in clusters of (2, 1, 1); map_b has 64-row boxes)
 extern "C" __global__ void __launch_bounds__(gxg::kThreads, 2)
 gx_gemm_tn_kernel_pair(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                        const gxg::GemmArgs args) {
-  gx_gemm_body<gxg::kStagesPairShallow>(map_a, map_b, args);
+  gx_gemm_body<gxg::kStagesPairShallow>(map_a, map_b, args, gx_tile_from_grid<gxg::kStagesPairShallow>());
 }
 extern "C" __global__ void __launch_bounds__(gxg::kThreads, 1)
 gx_gemm_tn_kernel_pair_deep(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                             const gxg::GemmArgs args) {
-  gx_gemm_body<gxg::kStagesPairDeep>(map_a, map_b, args);
+  gx_gemm_body<gxg::kStagesPairDeep>(map_a, map_b, args, gx_tile_from_grid<gxg::kStagesPairDeep>());
+}
+// Two independent contractions in ONE launch (1-D grid: the CTAs of the first problem, then those of the second):
+// the weight Jacobians of adjacent layers, g2^T a1 and g1^T x - each alone is half a wave of split-K tiles that pays
+// its own pipeline fill, epilogue and hand-over; together they fill the GPU with two CTAs per SM and the epilogue of
+// one CTA runs under the main loop of its neighbour.
+struct GxDualArgs {
+  gxg::GemmArgs args[2];
+  int n_ctas0;                 // CTAs of problem 0
+  int tiles_m[2], tiles_n[2];
+};
+extern "C" __global__ void __launch_bounds__(gxg::kThreads, 2)
+gx_gemm_tn_kernel_dual(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_b0,
+                       const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_b1,
+                       const __grid_constant__ GxDualArgs dual) {
+  const int which = (int)blockIdx.x >= dual.n_ctas0 ? 1 : 0;
+  const int local = (int)blockIdx.x - (which ? dual.n_ctas0 : 0);
+  GxTileCoord c;
+  c.tile_n = local % dual.tiles_n[which];
+  c.tile_m = (local / dual.tiles_n[which]) % dual.tiles_m[which];
+  c.split = local / (dual.tiles_n[which] * dual.tiles_m[which]);
+  c.cta_linear = (int)blockIdx.x;
+  c.n_ctas = (int)gridDim.x;
+  if (which) gx_gemm_body<gxg::kStagesShallow>(map_a1, map_b1, dual.args[1], c);
+  else gx_gemm_body<gxg::kStagesShallow>(map_a0, map_b0, dual.args[0], c);
 }
 #endif

@@ -851,6 +851,36 @@ class DenseExecutor:
             for extra in self.fused_colsums.get(n, [])[1:]:       # same sums requested twice: copy
                 self._buf(extra, "f32").copy_(self._buf(self.fused_colsums[n][0], "f32"))
 
+    def _plain_gemm(self, n: int) -> bool:
+        """A contraction launched by the library kernel as it is: no fused epilogue, no three-term split, and nobody
+        needs a bf16 copy of its result."""
+        return (self.plan.dag.nodes[n].kind == "gemm" and n not in self.fused_kernels and not self.split
+                and n not in self.needs_bf16)
+
+    def _launch_dual(self, n0: int, n1: int) -> None:
+        """Two independent plain contractions in one launch (gx_gemm_bf16_dual_ld): the weight Jacobians of adjacent
+        layers are each half a wave of split-K tiles; together they fill the GPU once and pay one pipeline fill, one
+        epilogue tail and one hand-over instead of two."""
+        dag = self.plan.dag
+        stream = self.torch.cuda.current_stream(self.device).cuda_stream
+        cols = {k: [] for k in ("M", "N", "K", "A", "lda", "amn", "B", "ldb", "bmn", "C", "ldc", "c16", "splits")}
+        for n in (n0, n1):
+            node = dag.nodes[n]
+            a, b = self._bf16(node.args[0]), self._bf16(node.args[1])
+            m, nn, k, splits = self._gemm_geometry(n)
+            out = self._buf(n, "f32")
+            for key, v in zip(cols, (m, nn, k, a.data_ptr(), a.shape[1], int(node.tx), b.data_ptr(), b.shape[1],
+                                     int(node.ty), out.data_ptr(), out.shape[1], 0, splits)):
+                cols[key].append(v)
+        ints = lambda key: (ctypes.c_int * 2)(*cols[key])
+        ptrs = lambda key: (ctypes.c_void_p * 2)(*cols[key])
+        rc = self.lib.gx_gemm_bf16_dual_ld(ints("M"), ints("N"), ints("K"), ptrs("A"), ints("lda"), ints("amn"), ptrs("B"),
+                                           ints("ldb"), ints("bmn"), ptrs("C"), ints("ldc"), ints("c16"), ints("splits"),
+                                           stream)
+        if rc != 0:
+            raise self.rt.GraphaxB200Error(self.lib.gx_gemm_last_error().decode())
+        self.launches += 1
+
     def run(self, inputs: Sequence) -> Tuple[List, object]:
         torch, dag = self.torch, self.plan.dag
         stream = torch.cuda.current_stream(self.device).cuda_stream
@@ -927,7 +957,20 @@ class DenseExecutor:
                     zeroed = torch.cuda.Event()
                     zeroed.record(side)
                 self.launches += 1
-        for n in self.order:
+        dual = os.environ.get("GX_DENSE_DUAL", "1") != "0" and not self.concurrent
+        skip = None
+        for pos, n in enumerate(self.order):
+            if n == skip:
+                continue
+            nxt = self.order[pos + 1] if pos + 1 < len(self.order) else None
+            if (dual and nxt is not None and self._plain_gemm(n) and self._plain_gemm(nxt)
+                    and n not in dag.nodes[nxt].args and not (host_zero and pos == 0)):
+                if zeroed is not None and (n in self.arena_users or nxt in self.arena_users):
+                    main.wait_event(zeroed)
+                    zeroed = None
+                self._launch_dual(n, nxt)
+                skip = nxt
+                continue
             if n in self.side_nodes and self.concurrent:
                 ready = torch.cuda.Event()
                 ready.record(main)

@@ -33,7 +33,7 @@ class GxInfo(ctypes.Structure):
 EXPORTS = ["gx_plan_create", "gx_plan_destroy", "gx_plan_info", "gx_plan_specialize", "gx_plan_specialize_opts",
            "gx_plan_select_kernel",
            "gx_jacve_launch", "gx_jacve_host", "gx_last_error", "gx_abi_version", "gx_aot_count", "gx_aot_key",
-           "gx_hash_bytes", "gx_gemm_bf16_tn", "gx_gemm_bf16", "gx_gemm_bf16_ld", "gx_transpose_bf16", "gx_gemm_last_error", "gx_gemm_set_pair", "gx_gemm_set_trace", "gx_gemm_zero_with_next_launch",
+           "gx_hash_bytes", "gx_gemm_bf16_tn", "gx_gemm_bf16", "gx_gemm_bf16_ld", "gx_transpose_bf16", "gx_gemm_last_error", "gx_gemm_set_pair", "gx_gemm_set_trace", "gx_gemm_zero_with_next_launch", "gx_gemm_bf16_dual_ld",
            "gx_jit_compile", "gx_jit_destroy", "gx_jit_launch", "gx_colsum_f32", "gx_gemm_fused_launch",
            "gx_split3_bf16", "gx_gemm_bf16x3_ld"]
 
@@ -95,6 +95,9 @@ def load_library() -> ctypes.CDLL:
         lib.gx_gemm_set_trace.restype = ctypes.c_int
         lib.gx_gemm_zero_with_next_launch.argtypes = [vp, ctypes.c_longlong]
         lib.gx_gemm_zero_with_next_launch.restype = ctypes.c_int
+        ip, pp = ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_void_p)
+        lib.gx_gemm_bf16_dual_ld.argtypes = [ip, ip, ip, pp, ip, ip, pp, ip, ip, pp, ip, ip, ip, vp]
+        lib.gx_gemm_bf16_dual_ld.restype = ctypes.c_int
         lib.gx_jit_compile.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(vp)]
         lib.gx_jit_compile.restype = ctypes.c_int
         lib.gx_jit_destroy.argtypes = [vp]

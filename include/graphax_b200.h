@@ -134,6 +134,12 @@ int gx_transpose_bf16(int rows, int cols, const void* in, void* out, void* strea
 int gx_split3_bf16(const void* in, void* out0, void* out1, void* out2, long long n, void* stream);
 int gx_gemm_bf16x3_ld(int M, int N, int K, const void* const* A3, int lda, int a_mn, const void* const* B3, int ldb,
                       int b_mn, void* C, int ldc, int k_splits, void* stream);
+/* Two independent contractions in ONE launch (index 0 / 1 of every array argument; each as in gx_gemm_bf16_ld): the
+ * weight Jacobians of adjacent layers, each alone half a wave of split-K tiles.  Falls back to two launches when the
+ * pair does not fit (a problem large enough for the persistent kernel). */
+int gx_gemm_bf16_dual_ld(const int* M, const int* N, const int* K, const void* const* A, const int* lda, const int* a_mn,
+                         const void* const* B, const int* ldb, const int* b_mn, void* const* C, const int* ldc,
+                         const int* c_is_bf16, const int* k_splits, void* stream);
 const char* gx_gemm_last_error(void);
 /* Single-tile contractions as CTA pairs (tcgen05 cta_group::2: a cluster of two CTAs on the SMs of one TPC computes a
  * 256 x 128 tile, each CTA loading half of the B tile)?  Process-wide; default off (or GX_GEMM_PAIR=1); returns the

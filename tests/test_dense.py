@@ -248,6 +248,58 @@ def test_arena_cleared_by_the_first_contraction(built_library, monkeypatch):
 
 
 @pytest.mark.gpu
+def test_dual_contraction_launch(built_library, monkeypatch):
+    """Two independent contractions in one launch (gx_gemm_bf16_dual_ld) give the results of two launches: different
+    shapes, operand layouts and split counts side by side; the MLP step uses it for its two weight Jacobians."""
+    import ctypes
+    import torch
+    from graphax_b200 import runtime
+    from graphax_b200.dense import dense_jacve
+    lib = runtime.load_library()
+    torch.manual_seed(3)
+    probs = [(512, 1024, 4096, 4, True, True), (1024, 512, 2048, 2, False, True)]
+    ops, refs, outs = [], [], []
+    for (m, n, k, splits, a_mn, b_mn) in probs:
+        a = (torch.randn(m, k) * 0.5).bfloat16()
+        b = (torch.randn(n, k) * 0.5).bfloat16()
+        refs.append((a.double() @ b.double().T).numpy())
+        ops.append(((a.T.contiguous() if a_mn else a).cuda(), (b.T.contiguous() if b_mn else b).cuda()))
+        outs.append(torch.zeros((m, n), dtype=torch.float32, device="cuda"))
+    I2, P2 = ctypes.c_int * 2, ctypes.c_void_p * 2
+    col = lambda i: I2(*[p[i] for p in probs])
+    rc = lib.gx_gemm_bf16_dual_ld(col(0), col(1), col(2), P2(*[o[0].data_ptr() for o in ops]),
+                                  I2(*[o[0].shape[1] for o in ops]), I2(*[int(p[4]) for p in probs]),
+                                  P2(*[o[1].data_ptr() for o in ops]), I2(*[o[1].shape[1] for o in ops]),
+                                  I2(*[int(p[5]) for p in probs]), P2(*[o.data_ptr() for o in outs]), I2(0, 0), I2(0, 0),
+                                  col(3), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, lib.gx_gemm_last_error().decode()
+    torch.cuda.synchronize()
+    for (m, n, k, *_), out, ref in zip(probs, outs, refs):
+        assert np.abs(out.cpu().numpy() - ref).max() <= 2e-6 * k * 0.25 + 1e-5
+    # and inside the MLP step: with and without the pairing of the two weight-Jacobian contractions
+    B, I, H, O = 4096, 512, 1024, 512
+    tens = [torch.from_numpy(a).cuda() for a in _mlp_args(B, I, H, O)]
+    tens = [t.bfloat16() if t.ndim == 2 else t for t in tens]
+    cache = dense_jacve.__kwdefaults__["_cache"]
+    cache.clear()
+    _, paired = dense_jacve(MLP_loss, "rev", (1, 2, 3, 4), *tens, has_aux=True)
+    ex = list(cache.values())[-1]
+    l0 = ex.launches
+    ex.run(tens)
+    n_paired = ex.launches - l0
+    cache.clear()
+    monkeypatch.setenv("GX_DENSE_DUAL", "0")
+    _, single = dense_jacve(MLP_loss, "rev", (1, 2, 3, 4), *tens, has_aux=True)
+    ex = list(cache.values())[-1]
+    l0 = ex.launches
+    ex.run(tens)
+    assert ex.launches - l0 == n_paired + 1
+    cache.clear()
+    for g, p in zip(single, paired):
+        assert float((g - p).abs().max()) <= 1e-5 * float(g.abs().max())
+
+
+@pytest.mark.gpu
 def test_tensor_path_matches_the_reference_run(built_library):
     """The tcgen05 path against weight Jacobians computed by the reference's own code (batched MLP of the
     reference's test_vmap_NeuralNetwork at widths 6 -> 10 -> 4, batch 12): float32 arguments take the three-term
