@@ -69,7 +69,7 @@ struct GemmArgs {
   int M, N, K, ldc, epilogue, k_per_split;
   int a_mn, b_mn;   // operand stored [K, M] / [K, N] (MN-major) instead of [M, K] / [N, K]
   // optional phase stamps of the single-tile kernels (tools/gemm_trace.py): 8 x u64 per CTA - %globaltimer at
-  // entry, after griddepcontrol.wait, first operand stage landed, accumulator complete, epilogue done, exit
+  // entry, after griddepcontrol.wait, first operand stage landed, accumulator complete, epilogue done, exit; slot 6: %smid
   unsigned long long* trace;
   // optional: `zero_n` 16-byte words at `zero_ptr` are cleared by the (otherwise idle) epilogue warps of the single-tile
   // kernels while the main loop runs - the step's accumulator arena, so that no separate memset has to be launched
@@ -389,7 +389,14 @@ __device__ __forceinline__ void gx_gemm_body(const CUtensorMap& map_a, const CUt
   const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
   const int cta_linear = coord.cta_linear;
-  if (threadIdx.x == 0) trace_stamp(args.trace, cta_linear, 0);
+  if (threadIdx.x == 0) {
+    trace_stamp(args.trace, cta_linear, 0);
+    if (args.trace) {   // slot 6: the SM this CTA runs on
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      args.trace[(size_t)cta_linear * 8 + 6] = smid;
+    }
+  }
   const int k_begin = coord.split * args.k_per_split;
   const int k_len = args.K - k_begin < args.k_per_split ? args.K - k_begin : args.k_per_split;   // last split may be short
   const int num_k_blocks = (k_len + BK - 1) / BK;

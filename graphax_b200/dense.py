@@ -600,8 +600,6 @@ class DenseExecutor:
         nl, no = max(1, len(leaves)), len(outs)
         tiles_m, tiles_n = -(-M // 128), -(-N // 128)
         deep = tiles_m * tiles_n <= 148                          # single-wave grids: deep operand ring, one CTA per SM
-        if os.environ.get("GX_FUSED_SHALLOW") == "1":
-            deep = False
         # CTA pairs (cta_group::2: 256 x 128 per cluster of two CTAs, 24 instead of 32 KB of operands per CTA and
         # k-block) whenever the tile rows pair up; the stage count names the variant (gx_gemm_kernel.cuh)
         pair = tiles_m % 2 == 0 and os.environ.get("GX_GEMM_PAIR", "0") == "1"      # off by default: measured neutral

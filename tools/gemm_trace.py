@@ -11,6 +11,7 @@ from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 ap = argparse.ArgumentParser()
 ap.add_argument("--pair", action="store_true")
+ap.add_argument("--smid", action="store_true", help="also print which SMs every launch used and the main-loop time by SM range")
 ap.add_argument("--batch", type=int, default=4096)
 ap.add_argument("--widths", default="512,1024,512")
 a = ap.parse_args()
@@ -72,4 +73,13 @@ for l in range(MAXL):
     print("    phases (median us): wait", round(float(np.median(d[:, 0])), 2), " fill", round(float(np.median(d[:, 1])), 2),
           " main loop", round(float(np.median(d[:, 2])), 2), " epilogue", round(float(np.median(d[:, 3])), 2),
           " drain", round(float(np.median(d[:, 4])), 2), "| span", round(float((rows[:, 5].max() - rows[:, 0].min()) / 1e3), 2))
+    if a.smid:
+        sm = rows[:, 6].astype(int)
+        ml = (rows[:, 3] - rows[:, 2]) / 1e3
+        print("    SMs used:", len(set(sm.tolist())), "of ids", sm.min(), "..", sm.max(), " idle ids:",
+              sorted(set(range(int(sm.max()) + 1)) - set(sm.tolist()))[:40])
+        for lo in range(0, int(sm.max()) + 1, 16):
+            sel = (sm >= lo) & (sm < lo + 16)
+            if sel.any():
+                print(f"      SM {lo:3d}-{lo + 15:3d}: {int(sel.sum()):3d} CTAs, main loop median {np.median(ml[sel]):.2f} us")
     prev_end = rows[:, 5].max()
