@@ -94,6 +94,7 @@ class JacveFunction:
         self._plans: Dict[Tuple, Plan] = {}
         self._device_plans: Dict[Tuple, Any] = {}
         self._elementwise_cache: Dict[Tuple, Any] = {}
+        self._package_geometry: Dict[Tuple, Any] = {}
         wraps(fun)(self)
 
     # ---- host side: trace + lower once per shape signature -------------------
@@ -274,15 +275,41 @@ class JacveFunction:
         jaxpr: Jaxpr = plan.jaxpr
         lead = (batch,) if batched else ()
         out_shapes = [v.shape for v in jaxpr.outvars]
-        rows = np.concatenate([[0], np.cumsum(plan.out_sizes)]).astype(int)
-        cols = np.concatenate([[0], np.cumsum([plan.in_sizes[a] for a in self.argnums])]).astype(int)
-        jt = jac if batched else jac[0]
+        # every block is one strided view of the packed tile: row range of the output x column range of the argument,
+        # split into the output's and the argument's own dimensions (geometry cached per plan and argument shapes: a
+        # host-array call spends more time on this packaging than on anything else it does in Python)
+        key = (id(plan), tuple(map(tuple, shapes)))
+        geom = self._package_geometry.get(key)
+        if geom is None:
+            rows = [int(v) for v in np.concatenate([[0], np.cumsum(plan.out_sizes)])]
+            cols = [int(v) for v in np.concatenate([[0], np.cumsum([plan.in_sizes[a] for a in self.argnums])])]
+
+            def dense_strides(shape, unit):
+                st, acc = [], unit
+                for d in reversed(shape):
+                    st.append(acc)
+                    acc *= int(d)
+                return tuple(reversed(st))
+            blocks = {}
+            for oi, oshape in enumerate(out_shapes):
+                for ai, a in enumerate(self.argnums):
+                    blocks[oi, ai] = (tuple(oshape) + tuple(shapes[a]),
+                                      dense_strides(oshape, plan.n_cols) + dense_strides(shapes[a], 1),
+                                      rows[oi] * plan.n_cols + cols[ai])
+            geom = self._package_geometry[key] = (rows, cols, blocks, plan)     # the plan stays alive with its id
+        rows, cols, blocks, _ = geom
+        tile = plan.n_rows * plan.n_cols
+        is_numpy = isinstance(jac, np.ndarray)              # host-side checks hand the packed tile over as an array
+        base = 0 if is_numpy else jac.storage_offset()
         grads = []
         for oi, oshape in enumerate(out_shapes):
             row = []
             for ai, a in enumerate(self.argnums):
-                block = jt[..., rows[oi]:rows[oi + 1], cols[ai]:cols[ai + 1]]
-                block = block.reshape(lead + tuple(oshape) + tuple(shapes[a]))
+                shape, strides, off = blocks[oi, ai]
+                if is_numpy:
+                    block = (jac if batched else jac[0])[..., rows[oi]:rows[oi + 1], cols[ai]:cols[ai + 1]].reshape(lead + shape)
+                else:
+                    block = jac.as_strided(lead + shape, ((tile,) if batched else ()) + strides, base + off)
                 if self.sparse_representation:
                     d = plan.structure["blocks"][f"{oi},{ai}"]
                     block = None if d is None else SparseJacobian(d["out_dims"], d["primal_dims"], d["val_shape"], block)
