@@ -1148,6 +1148,9 @@ int gx_jit_launch(gx_jit_kernel* k, unsigned grid_x, unsigned grid_y, unsigned b
 // outputs), copied by the launch.
 int gx_gemm_fused_launch(gx_jit_kernel* k, int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb,
                          int b_mn, int ldn, const void* epi, int stages, void* stream) {
+  float4* zero_ptr = nullptr;     // a pending gx_gemm_zero_with_next_launch belongs to THIS launch, also if it fails
+  unsigned zero_n = 0;
+  gxg_take_zero(&zero_ptr, &zero_n);
   if (!k || !A || !B || !epi) return fail(GX_ERR_BAD_ARG, "gx_gemm_fused_launch: NULL argument");
   if (M <= 0 || N <= 0 || K <= 0) return fail(GX_ERR_BAD_ARG, "gx_gemm_fused_launch: empty problem");
   if (ldn == 0) ldn = N;
@@ -1176,7 +1179,8 @@ int gx_gemm_fused_launch(gx_jit_kernel* k, int M, int N, int K, const void* A, i
   args.a_mn = a_mn ? 1 : 0;
   args.b_mn = b_mn ? 1 : 0;
   args.trace = gxg_next_trace(((N + 127) / 128) * ((M + 127) / 128));
-  gxg_take_zero(&args.zero_ptr, &args.zero_n);
+  args.zero_ptr = zero_ptr;
+  args.zero_n = zero_n;
   CUlaunchConfig cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDimX = (N + 127) / 128;

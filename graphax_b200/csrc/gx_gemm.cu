@@ -269,6 +269,9 @@ int gx_split3_bf16(const void* in, void* out0, void* out1, void* out2, long long
 
 static int gemm_launch(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C,
                        int ldc, int c_is_bf16, int k_splits, bool accumulate, void* stream) {
+  float4* zero_ptr = nullptr;     // a pending gx_gemm_zero_with_next_launch belongs to THIS launch, also if it fails
+  unsigned zero_n = 0;
+  gxg_take_zero(&zero_ptr, &zero_n);
   if (M <= 0 || N <= 0 || K <= 0 || !A || !B || !C) {
     g_gemm_error = "gx_gemm_bf16_tn: bad argument";
     return GX_ERR_BAD_ARG;
@@ -332,7 +335,8 @@ static int gemm_launch(int M, int N, int K, const void* A, int lda, int a_mn, co
   args.a_mn = a_mn ? 1 : 0;
   args.b_mn = b_mn ? 1 : 0;
   args.trace = persistent ? nullptr : gxg_next_trace(tiles_n * tiles_m * k_splits);
-  gxg_take_zero(&args.zero_ptr, &args.zero_n);
+  args.zero_ptr = zero_ptr;
+  args.zero_n = zero_n;
   if (persistent && args.zero_n) {
     cudaMemsetAsync(args.zero_ptr, 0, (size_t)args.zero_n * 16, static_cast<cudaStream_t>(stream));
     args.zero_ptr = nullptr;

@@ -852,8 +852,28 @@ class DenseExecutor:
     def _plain_gemm(self, n: int) -> bool:
         """A contraction launched by the library kernel as it is: no fused epilogue, no three-term split, and nobody
         needs a bf16 copy of its result."""
-        return (self.plan.dag.nodes[n].kind == "gemm" and n not in self.fused_kernels and not self.split
+        return (self.plan.dag.nodes[n].kind == "gemm" and n not in self.gemm_fused and not self.split
                 and n not in self.needs_bf16)
+
+    def launch_groups(self, host_zero: bool = False) -> List[Tuple[int, ...]]:
+        """The step's launches in order: single nodes, or pairs of consecutive plain contractions that do not depend
+        on each other and share one launch (``_launch_dual``).  ``host_zero``: the first launch also clears the arena
+        and stays single."""
+        dag = self.plan.dag
+        dual = os.environ.get("GX_DENSE_DUAL", "1") != "0" and not self.concurrent
+        groups: List[Tuple[int, ...]] = []
+        pos = 0
+        while pos < len(self.order):
+            n = self.order[pos]
+            nxt = self.order[pos + 1] if pos + 1 < len(self.order) else None
+            if (dual and nxt is not None and self._plain_gemm(n) and self._plain_gemm(nxt)
+                    and n not in dag.nodes[nxt].args and not (host_zero and pos == 0)):
+                groups.append((n, nxt))
+                pos += 2
+            else:
+                groups.append((n,))
+                pos += 1
+        return groups
 
     def _launch_dual(self, n0: int, n1: int) -> None:
         """Two independent plain contractions in one launch (gx_gemm_bf16_dual_ld): the weight Jacobians of adjacent
@@ -955,19 +975,13 @@ class DenseExecutor:
                     zeroed = torch.cuda.Event()
                     zeroed.record(side)
                 self.launches += 1
-        dual = os.environ.get("GX_DENSE_DUAL", "1") != "0" and not self.concurrent
-        skip = None
-        for pos, n in enumerate(self.order):
-            if n == skip:
-                continue
-            nxt = self.order[pos + 1] if pos + 1 < len(self.order) else None
-            if (dual and nxt is not None and self._plain_gemm(n) and self._plain_gemm(nxt)
-                    and n not in dag.nodes[nxt].args and not (host_zero and pos == 0)):
-                if zeroed is not None and (n in self.arena_users or nxt in self.arena_users):
+        for group in self.launch_groups(host_zero):
+            n = group[0]
+            if len(group) == 2:
+                if zeroed is not None and (group[0] in self.arena_users or group[1] in self.arena_users):
                     main.wait_event(zeroed)
                     zeroed = None
-                self._launch_dual(n, nxt)
-                skip = nxt
+                self._launch_dual(*group)
                 continue
             if n in self.side_nodes and self.concurrent:
                 ready = torch.cuda.Event()

@@ -75,6 +75,24 @@ def test_dense_plan_structure():
         build_dense_plan(jaxpr, "fwd", (1,))
 
 
+def test_launch_groups_of_the_mlp_step(built_library, monkeypatch):
+    """Host-side planning of config 5 (no GPU): three contractions with fused epilogues, then the two weight-Jacobian
+    contractions - independent plain split-K launches - as one pair; a pair never contains a dependent contraction."""
+    from graphax_b200.dense import DenseExecutor, build_dense_plan
+    B, I, H, O = 4096, 512, 1024, 512
+    jaxpr = make_jaxpr(MLP_loss, [(B, I), (H, I), (H,), (O, H), (O,), (B, O)])
+    plan = build_dense_plan(jaxpr, "rev", (1, 2, 3, 4))
+    ex = DenseExecutor(plan, 0)
+    groups = ex.launch_groups(host_zero=True)
+    kinds = [tuple(plan.dag.nodes[n].kind for n in g) for g in groups]
+    assert kinds == [("gemm",), ("gemm",), ("gemm",), ("gemm", "gemm")]
+    assert all(g[0] in ex.gemm_fused for g in groups[:3])
+    a, b = groups[3]
+    assert a not in plan.dag.nodes[b].args and {plan.dag.nodes[a].shape, plan.dag.nodes[b].shape} == {(O, H), (H, I)}
+    monkeypatch.setenv("GX_DENSE_DUAL", "0")
+    assert [len(g) for g in ex.launch_groups(host_zero=True)] == [1] * 5
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("m,n,k,splits", [(128, 128, 64, 1), (256, 384, 1024, 1), (512, 256, 2048, 4),
                                           (1024, 512, 4096, 8)])
