@@ -537,18 +537,23 @@ __device__ __forceinline__ void gx_gemm_body(const CUtensorMap& map_a, const CUt
     // issued while the tensor core is still working (first chunk: before the accumulator is even waited for;
     // second chunk: as well when registers allow - one CTA per SM -, else while the first chunk is evaluated).
     static_assert(BN / 2 == 64, "two 32-column chunks per epilogue warp");
+#ifdef GX_GEMM_MIN_BLOCKS
+    constexpr bool kRoomy = GX_GEMM_MIN_BLOCKS == 1;   // one CTA per SM: registers for both chunks' operands at once
+#else
+    constexpr bool kRoomy = kDeep;
+#endif
     GxEpiState epi_state;
     gx_epi_begin(epi_state);
     GxEpiPre pre0, pre1;
     gx_epi_prefetch(epi, pre0, m_base, n0 + c_begin, args.M, args.ldc, lane);
-    if (kDeep) gx_epi_prefetch(epi, pre1, m_base, n0 + c_begin + 32, args.M, args.ldc, lane);
+    if (kRoomy) gx_epi_prefetch(epi, pre1, m_base, n0 + c_begin + 32, args.M, args.ldc, lane);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     if (threadIdx.x == 64) trace_stamp(args.trace, cta_linear, 3);
     {
       float acc[32];
       load_acc(c_begin, acc);
-      if (!kDeep) gx_epi_prefetch(epi, pre1, m_base, n0 + c_begin + 32, args.M, args.ldc, lane);
+      if (!kRoomy) gx_epi_prefetch(epi, pre1, m_base, n0 + c_begin + 32, args.M, args.ldc, lane);
       gx_epi_chunk(epi, epi_state, pre0, tile, m_base, n0 + c_begin, args.M, args.ldc, acc, lane);   // N parameter = row stride
     }
     {
@@ -813,7 +818,10 @@ gx_gemm_tn_kernel_persistent_n256(const __grid_constant__ CUtensorMap map_a, con
 #ifndef GX_GEMM_STAGES
 #define GX_GEMM_STAGES 3
 #endif
-extern "C" __global__ void __launch_bounds__(gxg::kThreads, gxg::stages_deep(GX_GEMM_STAGES) ? 1 : 2)
+#ifndef GX_GEMM_MIN_BLOCKS   /* resident CTAs per SM the register budget is sized for */
+#define GX_GEMM_MIN_BLOCKS (gxg::stages_deep(GX_GEMM_STAGES) ? 1 : 2)
+#endif
+extern "C" __global__ void __launch_bounds__(gxg::kThreads, GX_GEMM_MIN_BLOCKS)
 GX_GEMM_KERNEL_NAME(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const gxg::GemmArgs args GX_GEMM_EPI_PARAM) {
   gx_gemm_body<GX_GEMM_STAGES>(map_a, map_b, args, gx_tile_from_grid<GX_GEMM_STAGES>() GX_GEMM_EPI_ARG);

@@ -604,8 +604,9 @@ class DenseExecutor:
         # k-block) whenever the tile rows pair up; the stage count names the variant (gx_gemm_kernel.cuh)
         pair = tiles_m % 2 == 0 and os.environ.get("GX_GEMM_PAIR", "0") == "1"      # off by default: measured neutral
         stages = (8 if deep else 4) if pair else (6 if deep else 3)
+        min_blocks = 1 if deep else 2
         src = ["#define GX_NVRTC", "#define GX_GEMM_FUSED", "#define GX_GEMM_KERNEL_NAME gx_gemm_fused",
-               f"#define GX_GEMM_STAGES {stages}"]
+               f"#define GX_GEMM_STAGES {stages}", f"#define GX_GEMM_MIN_BLOCKS {min_blocks}"]
         epi = [_GX_TANH,
                f"struct GxEpi {{ const void* leaf[{nl}]; float* o32[{no}]; unsigned short* o16[{no}]; float* csum[{no}]; }};",
                "struct GxEpiState { int unused; };",
