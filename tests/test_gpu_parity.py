@@ -268,6 +268,42 @@ def test_full_size_properties(built_library):
     assert (np.abs(j_rev - j_mix) / mx).max() < 3e-5
 
 
+def test_batch_with_more_than_2_31_jacobian_entries(built_library):
+    """Maximum sizes: 43 M samples = 2.15e9 Jacobian entries (8.6 GB), past the range of 32-bit element offsets; ragged.
+    The batch is a 2^20-sample block repeated, so every repetition must equal the first (all of the 8.6 GB checked
+    on the device) and windows of the first, a middle and the last repetition equal the plan replay."""
+    import torch
+    from graphax_b200 import runtime
+    from oracle import replay
+    w = WORKLOADS["roe3d"]
+    block, reps, tail = 1 << 20, 41, 19
+    batch = block * reps + tail
+    assert batch * 50 > 2 ** 31
+    if torch.cuda.mem_get_info()[0] < 20 * 2 ** 30:
+        pytest.skip("needs 20 GB of free device memory")
+    xs = w.inputs(block)
+    dev = [torch.cat([torch.from_numpy(x).cuda().repeat((reps,) + (1,) * (x.ndim - 1)), torch.from_numpy(x[:tail]).cuda()])
+           for x in xs]
+    plan = w.plan("rev", rounding="reference")
+    dp = runtime.DevicePlan(plan, 0, jit=False)
+    assert dp.kernel == "aot"
+    jac = torch.empty((batch, 5, 10), device="cuda")
+    primal = torch.empty((batch, 5), device="cuda")
+    dp.launch(batch, [t.data_ptr() for t in dev], jac.data_ptr(), primal.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    first_j, first_p = jac[:block], primal[:block]
+    for r in range(1, reps):
+        assert torch.equal(jac[r * block:(r + 1) * block], first_j), f"repetition {r} differs"
+        assert torch.equal(primal[r * block:(r + 1) * block], first_p)
+    assert torch.equal(jac[reps * block:], first_j[:tail]) and torch.equal(primal[reps * block:], first_p[:tail])
+    for lo in (0, 20 * block + 54_321, (reps - 1) * block + block - 4099):
+        sl = slice(lo % block, lo % block + 4099)
+        ref_j, ref_p = replay.replay(plan.blob, [x[sl] for x in xs], plan.n_rows, plan.n_cols)
+        assert np.array_equal(bits(jac[lo:lo + 4099].cpu().numpy()), bits(ref_j))
+        assert np.array_equal(bits(primal[lo:lo + 4099].cpu().numpy()), bits(ref_p))
+    dp.close()
+
+
 def test_host_pipeline(built_library):
     """gx_jacve_host (H2D -> kernel -> D2H, chunked) equals the device-resident launch."""
     import torch
