@@ -377,6 +377,35 @@ def _reschedule_min_pressure(dag: Dag, sched: List[int], roots: Sequence[int], r
     return best
 
 
+def _random_topological_order(dag: Dag, sched: List[int], seed: int, sigma: float = 8.0) -> List[int]:
+    """``sched`` with every operation's position jittered by a Gaussian of ``sigma`` positions, made topological
+    again (priority = jittered position)."""
+    import heapq
+    import random
+    rng = random.Random(seed)
+    nodeset = set(sched)
+    args = {n: [a for a in dict.fromkeys(dag.args[n]) if a in nodeset] for n in sched}
+    users: Dict[int, List[int]] = {n: [] for n in sched}
+    for n in sched:
+        for a in args[n]:
+            users[a].append(n)
+    prio = {n: i + rng.gauss(0.0, sigma) for i, n in enumerate(sched)}
+    indeg = {n: len(args[n]) for n in sched}
+    heap = [(prio[n], n) for n in sched if indeg[n] == 0]
+    heapq.heapify(heap)
+    out: List[int] = []
+    while heap:
+        _, n = heapq.heappop(heap)
+        out.append(n)
+        for u in users[n]:
+            indeg[u] -= 1
+            if indeg[u] == 0:
+                heapq.heappush(heap, (prio[u], u))
+    if len(out) != len(sched):
+        raise AssertionError("scheduler lost operations")
+    return out
+
+
 def _reschedule_for_ilp(dag: Dag, sched: List[int], limit: int, window: int) -> List[int]:
     """List scheduling for instruction-level parallelism under a cap on live values.
 
@@ -497,13 +526,19 @@ def build_plan(jaxpr: Jaxpr, order, argnums: Sequence[int], with_primal: bool = 
         sched = _reschedule_for_pressure(dag, sched, roots)
     elif schedule == "minpressure":
         sched = _reschedule_min_pressure(dag, sched, roots)
+    elif schedule.startswith("minpressure:"):
+        # "minpressure:<seed>[:<sigma>]": the same passes from a jittered copy of the order - their tie breaks follow the incoming
+        # order, so every seed gives another schedule of about the same pressure (tools/tune.py --schedules: how much
+        # of the kernel time is the compiler's luck with one particular order)
+        parts = schedule.split(":")
+        sched = _reschedule_min_pressure(dag, _random_topological_order(dag, sched, int(parts[1]), float(parts[2]) if len(parts) > 2 else 8.0), roots)
     elif schedule.startswith("ilp"):
         # "ilp:<live limit>:<window>"
         parts = schedule.split(":")
         sched = _reschedule_for_ilp(dag, sched, int(parts[1]) if len(parts) > 1 else 120,
                                     int(parts[2]) if len(parts) > 2 else 4)
     elif schedule != "elimination":
-        raise ValueError("schedule must be 'pressure', 'minpressure', 'ilp[:limit[:window]]' or 'elimination'")
+        raise ValueError("schedule must be 'pressure', 'minpressure[:seed]', 'ilp[:limit[:window]]' or 'elimination'")
 
     # stores directly after the value they read; constant / input / zero stores at the end
     stores_after: Dict[int, List[SsaOp]] = {}
