@@ -127,6 +127,26 @@ def test_schedule_and_division_variants_agree(name, order):
     assert p_press.n_slots <= p_elim.n_slots
 
 
+def test_jittered_schedules_compute_the_same_bits():
+    """schedule='minpressure:<seed>:<sigma>': another statement order of about the same pressure, the same results."""
+    w = WORKLOADS["roe3d"]
+    xs = w.inputs(256)
+    base = build_plan(w.jaxpr(), w.order("mixed"), w.argnums, rounding="reference", schedule="minpressure")
+    ref = replay.replay(base.blob, xs, base.n_rows, base.n_cols)
+    keys = {base.key}
+    for schedule in ("minpressure:1:8", "minpressure:2:30"):
+        p = build_plan(w.jaxpr(), w.order("mixed"), w.argnums, rounding="reference", schedule=schedule)
+        got = replay.replay(p.blob, xs, p.n_rows, p.n_cols)
+        assert np.array_equal(got[0].view(np.uint32), ref[0].view(np.uint32))
+        assert np.array_equal(got[1].view(np.uint32), ref[1].view(np.uint32))
+        assert sorted(o.op for o in p.ssa) == sorted(o.op for o in base.ssa)
+        assert abs(p.n_slots - base.n_slots) <= 12
+        keys.add(p.key)
+    assert len(keys) == 3                                    # different orders, different blobs
+    with pytest.raises(ValueError):
+        build_plan(w.jaxpr(), "rev", w.argnums, schedule="random")
+
+
 def test_argnums_subset_prunes_dead_work():
     w = WORKLOADS["roe3d"]
     full = build_plan(w.jaxpr(), "rev", w.argnums)
