@@ -62,6 +62,31 @@ class SparseJacobian:
     dense: Any
 
 
+def sparse_tensor_zeros_like(st: SparseJacobian) -> SparseJacobian:
+    """Reference ``sparse/tensor.py:190-201`` (exported from ``graphax/__init__.py:4``): the same structure with an
+    all-zero value."""
+    import torch
+    dense = torch.zeros_like(st.dense) if isinstance(st.dense, torch.Tensor) else np.zeros_like(st.dense)
+    return SparseJacobian([dict(d) if isinstance(d, dict) else d for d in st.out_dims],
+                          [dict(d) if isinstance(d, dict) else d for d in st.primal_dims],
+                          None if st.val_shape is None else list(st.val_shape), dense)
+
+
+def get_output_vertices(fun: Callable, arg_shapes: Sequence[Tuple[int, ...]], frontend: str = "auto") -> set:
+    """Reference ``utils.py:8-27``: the output vertices that feed other vertices (``vo_vertices``, core.py:335-337,
+    404-409) - outputs that may, and in a custom order must, be eliminated.  Takes the function and its per-sample
+    argument shapes where the reference takes a jaxpr."""
+    from .elimination import build_graph
+    return set(build_graph(make_jaxpr(fun, tuple(tuple(s) for s in arg_shapes), frontend)).vo_vertices)
+
+
+def get_valid_vertices(fun: Callable, arg_shapes: Sequence[Tuple[int, ...]], frontend: str = "auto") -> List[int]:
+    """Reference ``utils.py:30-36``: the vertex ids a custom elimination order has to contain (every equation that is
+    not a pure output), in ascending order = the ``"fwd"`` order (core.py:275-311)."""
+    from .elimination import build_graph, eliminable_vertices
+    return eliminable_vertices(build_graph(make_jaxpr(fun, tuple(tuple(s) for s in arg_shapes), frontend)))
+
+
 class JacveFunction:
     """The callable ``jacve`` returns. ``__call__`` = one sample, ``batched`` = leading batch axis."""
 

@@ -147,6 +147,28 @@ def test_jittered_schedules_compute_the_same_bits():
         build_plan(w.jaxpr(), "rev", w.argnums, schedule="random")
 
 
+def test_reference_helper_functions():
+    """get_valid_vertices / get_output_vertices (reference utils.py:8-36) and sparse_tensor_zeros_like
+    (sparse/tensor.py:190-201, exported at graphax/__init__.py:4)."""
+    import graphax_b200 as gx
+    from graphax_b200.examples import RoeFlux_1d, RoeFlux_3d
+    w1, w3 = WORKLOADS["roe1d"], WORKLOADS["roe3d"]
+    valid = gx.get_valid_vertices(RoeFlux_1d, w1.arg_shapes)
+    assert sorted(set(range(1, 102)) - set(valid)) == [97, 99, 101]          # SURVEY App. A.5: the three pure outputs
+    assert valid == sorted(valid) and gx.get_output_vertices(RoeFlux_1d, w1.arg_shapes) == set()
+    assert len(gx.get_valid_vertices(RoeFlux_3d, w3.arg_shapes)) == 135
+    # an output that feeds another vertex is an output vertex AND eliminable (core.py:404-409)
+    def chained(x):
+        y = gx.jnp.sin(x)
+        return y, gx.jnp.cos(y)
+    assert gx.get_output_vertices(chained, [()]) == {1}
+    assert gx.get_valid_vertices(chained, [()]) == [1]
+    st = gx.SparseJacobian([{"kind": "dense", "size": 3}], [{"kind": "dense", "size": 2}], [3, 2], np.ones((3, 2), np.float32))
+    z = gx.sparse_tensor_zeros_like(st)
+    assert z.out_dims == st.out_dims and z.primal_dims == st.primal_dims and z.val_shape == [3, 2]
+    assert z.dense.shape == (3, 2) and not z.dense.any() and st.dense.all()
+
+
 def test_argnums_subset_prunes_dead_work():
     w = WORKLOADS["roe3d"]
     full = build_plan(w.jaxpr(), "rev", w.argnums)
