@@ -152,6 +152,9 @@ def build_dense_plan(jaxpr: Jaxpr, order, argnums: Sequence[int]) -> DensePlan:
             raise NotImplementedError("the tensor-valued path implements reverse-order elimination only")
     if len(jaxpr.outvars) != 1 or _norm(jaxpr.outvars[0].shape) != (1, 1):
         raise NotImplementedError("the tensor-valued path needs a single scalar output")
+    if getattr(jaxpr, "constvars", None):
+        raise NotImplementedError("the tensor-valued path takes every array as an argument: pass the arrays the "
+                                  "function closes over as (non-differentiated) arguments")
     dag = TensorDag()
     env: Dict[int, int] = {}
     key = lambda v: -(v.input_index + 1) if v.input_index is not None else v.eqn_index + 1

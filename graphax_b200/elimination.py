@@ -29,6 +29,8 @@ from typing import Dict, List, Optional, Sequence, Set, Tuple, Union
 
 from . import structure as st
 from . import structure_nd as nd
+import numpy as np
+
 from .lowering import Dag, Entries, Vec, lower_eqn
 from .tracer import Jaxpr, Literal, Var
 
@@ -66,8 +68,11 @@ def build_graph(jaxpr: Jaxpr, division: str = "ieee", fuse: bool = True) -> Grap
     for var in jaxpr.invars:
         env[Graph.key(var)] = Vec(var.shape, [dag.input(k + i) for i in range(var.size)])
         k += var.size
+    # closed-over arrays (core.py:374): sources of edges like the inputs, their values constants of the plan
+    for var, val in zip(jaxpr.constvars, jaxpr.consts):
+        env[Graph.key(var)] = Vec(var.shape, [dag.const(x) for x in np.asarray(val, dtype=np.float32).reshape(-1)])
     g = Graph(jaxpr, dag, env, {}, {}, set())
-    for var in jaxpr.invars:
+    for var in list(jaxpr.invars) + list(jaxpr.constvars):
         g.fwd[Graph.key(var)] = {}
         g.bwd[Graph.key(var)] = {}
     out_keys = {Graph.key(v) for v in jaxpr.outvars if isinstance(v, Var)}

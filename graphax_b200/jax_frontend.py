@@ -57,14 +57,19 @@ def from_jax(closed_jaxpr, out_is_sequence: bool = True) -> Jaxpr:
     import jax
     jaxpr = closed_jaxpr.jaxpr
     literal_cls = jax.core.Literal
-    if getattr(jaxpr, "constvars", None):
-        raise NotImplementedError("functions that close over array constants are not lowered; "
-                                  "pass the arrays as arguments")
     env: Dict[int, Var] = {}
     invars = []
     for i, v in enumerate(jaxpr.invars):
         env[id(v)] = Var(tuple(v.aval.shape), input_index=i)
         invars.append(env[id(v)])
+    # arrays the function closes over (core.py:374 writes them into the environment next to the arguments)
+    constvars, consts = [], []
+    for v, val in zip(getattr(jaxpr, "constvars", ()) or (), getattr(closed_jaxpr, "consts", ()) or ()):
+        env[id(v)] = Var(tuple(v.aval.shape), input_index=len(invars) + len(constvars), name=f"const{len(constvars)}")
+        constvars.append(env[id(v)])
+        consts.append(np.ascontiguousarray(np.asarray(val), dtype=np.float32))
+    if len(constvars) != len(getattr(jaxpr, "constvars", ()) or ()):
+        raise NotImplementedError("jaxpr with constvars but without their values (pass the ClosedJaxpr)")
 
     def atom(a):
         if isinstance(a, literal_cls):
@@ -93,7 +98,7 @@ def from_jax(closed_jaxpr, out_is_sequence: bool = True) -> Jaxpr:
         eqns.append(Eqn(name, ins, out, params))
         pads.append(_vmap_pads(name, ins, eqns))
     outvars = [atom(v) for v in jaxpr.outvars]
-    return Jaxpr(invars, eqns, outvars, pads, out_is_sequence)
+    return Jaxpr(invars, eqns, outvars, pads, out_is_sequence, constvars, consts)
 
 
 def _vmap_pads(name: str, ins: Sequence, eqns: List[Eqn]) -> int:

@@ -91,6 +91,11 @@ class Jaxpr:
     # would insert immediately before equation i (0-based)
     vmap_pads: List[int] = field(default_factory=list)
     out_is_sequence: bool = True
+    # arrays the function closes over (jax: ClosedJaxpr.consts / jaxpr.constvars, reference core.py:374): variables
+    # with known values - sources of edges like the inputs (their input_index continues after the arguments), never
+    # differentiated
+    constvars: List[Var] = field(default_factory=list)
+    consts: List[np.ndarray] = field(default_factory=list)
 
     def vertex_of(self, var: Var) -> int:
         return var.eqn_index + 1
@@ -127,7 +132,7 @@ class Jaxpr:
         return out
 
     def pretty(self) -> str:
-        lines = ["{ lambda ; " + " ".join(map(repr, self.invars)) + " . let"]
+        lines = ["{ lambda " + " ".join(map(repr, self.constvars)) + " ; " + " ".join(map(repr, self.invars)) + " . let"]
         for i, e in enumerate(self.eqns, start=1):
             lines.append(f"  {i:4d}: {e!r}")
         lines.append("  in (" + ", ".join(map(repr, self.outvars)) + ") }")
@@ -135,9 +140,29 @@ class Jaxpr:
 
 
 class _Trace:
-    def __init__(self) -> None:
+    def __init__(self, n_args: int = 0) -> None:
         self.eqns: List[Eqn] = []
         self.vmap_pads: List[int] = []
+        self.n_args = n_args
+        self.constvars: List[Var] = []
+        self.consts: List[np.ndarray] = []
+        self._const_of: Dict[int, Tuple[Any, Var]] = {}     # id(object) -> (object kept alive, its variable)
+
+    def constant(self, value: Any) -> Var:
+        """The variable of an array the traced function closes over (one per object, like jax's constvars)."""
+        hit = self._const_of.get(id(value))
+        if hit is not None:
+            return hit[1]
+        arr = value.value if isinstance(value, ConstArray) else \
+            value.detach().cpu().numpy() if hasattr(value, "detach") else np.asarray(value)
+        if arr.dtype == object or not (np.issubdtype(arr.dtype, np.number) or arr.dtype == bool):
+            raise TypeError(f"cannot trace operand of type {type(value).__name__}")
+        arr = np.ascontiguousarray(arr, dtype=np.float32)
+        var = Var(arr.shape, input_index=self.n_args + len(self.constvars), name=f"const{len(self.constvars)}")
+        self.constvars.append(var)
+        self.consts.append(arr)
+        self._const_of[id(value)] = (value, var)
+        return var
 
     def emit(self, primitive: str, invars: Sequence[Atom], out_shape: Shape,
              pads: int = 0, **params) -> "Tracer":
@@ -163,8 +188,9 @@ def _atom(x: Any) -> Atom:
         return Literal(float(x))
     if isinstance(x, np.ndarray) and x.shape == ():
         return Literal(float(x))
-    raise TypeError(f"cannot trace operand of type {type(x).__name__}; "
-                    "array constants must enter the function as arguments")
+    if _ACTIVE and (isinstance(x, (np.ndarray, list, tuple, ConstArray)) or (hasattr(x, "detach") and hasattr(x, "numpy"))):
+        return _current().constant(x)       # an array the function closes over: a constvar, like under jax.make_jaxpr
+    raise TypeError(f"cannot trace operand of type {type(x).__name__}")
 
 
 def _bcast_shape(a: Shape, b: Shape) -> Shape:
@@ -310,12 +336,54 @@ class Tracer:
         return _dot(self, other)
 
 
+class ConstArray:
+    """A concrete array inside a traced function (``jnp.asarray(np_array)``): like a jax Array under ``make_jaxpr`` it
+    becomes a constant of the trace (a constvar) the first time an operation uses it, and every operation on it is
+    staged.  Outside a trace it behaves like its NumPy value."""
+    __slots__ = ("value",)
+    __array_priority__ = 1000
+
+    def __init__(self, value: Any):
+        value = value.detach().cpu().numpy() if hasattr(value, "detach") else np.asarray(value)
+        self.value = np.ascontiguousarray(value, dtype=np.float32)
+
+    shape = property(lambda self: self.value.shape)
+    ndim = property(lambda self: self.value.ndim)
+    size = property(lambda self: self.value.size)
+
+    def __array__(self, dtype=None, copy=None):
+        return self.value if dtype is None else self.value.astype(dtype)
+
+    def _operand(self):
+        return Tracer(_current(), _current().constant(self)) if _ACTIVE else self.value
+
+    def __repr__(self) -> str:
+        return f"ConstArray({self.value!r})"
+
+
+def _forward_to_operand(name: str):
+    def method(self, *args, **kwargs):
+        args = [a.value if isinstance(a, ConstArray) and not _ACTIVE else a for a in args]
+        return getattr(self._operand(), name)(*args, **kwargs)
+    method.__name__ = name
+    return method
+
+
+for _name in ("__neg__", "__add__", "__radd__", "__sub__", "__rsub__", "__mul__", "__rmul__", "__truediv__",
+              "__rtruediv__", "__pow__", "__rpow__", "__matmul__", "__rmatmul__", "__getitem__", "__gt__", "__lt__",
+              "sum", "reshape", "transpose"):
+    if hasattr(Tracer, _name):
+        setattr(ConstArray, _name, _forward_to_operand(_name))
+ConstArray.T = property(lambda self: self._operand().T)
+
+
 _CONST_UNARY = {"sqrt": np.sqrt, "abs": np.abs, "neg": np.negative, "exp": np.exp, "log": np.log, "sin": np.sin,
                 "cos": np.cos, "tan": np.tan, "tanh": np.tanh}
 
 
 def _unary(prim: str):
     def fn(x: Any) -> Tracer:
+        x = _lift(x)
         if not isinstance(x, Tracer):
             if isinstance(x, (int, float, np.floating, np.integer)):
                 if _ACTIVE:
@@ -333,6 +401,7 @@ def _unary(prim: str):
 
 def _binary_fn(prim: str):
     def fn(x: Any, y: Any) -> Tracer:
+        x = _lift(x) if not isinstance(y, Tracer) else x
         if isinstance(x, Tracer):
             return x._binary(prim, y)
         if isinstance(y, Tracer):
@@ -364,7 +433,18 @@ def _reduce_sum(x: Tracer, axis=None, keepdims: bool = False) -> Tracer:
     return x.trace.emit("reduce_sum", (x.var,), shape, axes=axes)
 
 
+def _lift(x: Any) -> Any:
+    """An array the function closes over as a traced constant (numbers and traced values pass through)."""
+    if isinstance(x, Tracer) or not _ACTIVE or isinstance(x, (bool, int, float, np.floating, np.integer)):
+        return x
+    if isinstance(x, (np.ndarray, list, tuple, ConstArray)) or (hasattr(x, "detach") and hasattr(x, "numpy")):
+        trace = _current()
+        return Tracer(trace, trace.constant(x))
+    return x
+
+
 def _dot(a: Tracer, b: Tracer) -> Tracer:
+    a, b = _lift(a), _lift(b)
     if not (isinstance(a, Tracer) and isinstance(b, Tracer)):
         raise TypeError("dot expects two traced values")
     if a.ndim > 1 or b.ndim > 1:
@@ -380,6 +460,7 @@ def _dot(a: Tracer, b: Tracer) -> Tracer:
 
 def _dot_general(a: Tracer, b: Tracer, dimension_numbers, precision=None, preferred_element_type=None) -> Tracer:
     """``lax.dot_general``: out = batch dims, then free dims of a, then free dims of b."""
+    a, b = _lift(a), _lift(b)
     (ca, cb), (ba, bb) = dimension_numbers
     ca, cb = tuple(int(c) for c in ca), tuple(int(c) for c in cb)
     ba, bb = tuple(int(c) for c in ba), tuple(int(c) for c in bb)
@@ -394,6 +475,7 @@ def _dot_general(a: Tracer, b: Tracer, dimension_numbers, precision=None, prefer
 def _matmul(a: Tracer, b: Tracer) -> Tracer:
     """``a @ b`` / ``jnp.dot`` for ranks 1 and 2: one dot_general contracting the last axis of a with the
     first (for a 1-D b: only) axis of b."""
+    a, b = _lift(a), _lift(b)
     if not (isinstance(a, Tracer) and isinstance(b, Tracer)) or not (1 <= a.ndim <= 2 and 1 <= b.ndim <= 2):
         raise NotImplementedError("matmul of ranks 1 and 2 only")
     return _dot_general(a, b, (((a.ndim - 1,), (0,)), ((), ())))
@@ -572,6 +654,14 @@ class _JnpShim:
     @staticmethod
     def reshape(x, shape):
         return x.reshape(shape)
+
+    @staticmethod
+    def asarray(x, dtype=None):
+        """A traced value as it is; numbers stay weak-typed scalars; an array becomes a constant of the trace."""
+        if isinstance(x, (Tracer, ConstArray)) or isinstance(x, (bool, int, float, np.floating, np.integer)):
+            return x
+        return ConstArray(x)
+    array = asarray
     zeros = staticmethod(_zeros)
     concatenate = staticmethod(_concatenate)
     where = staticmethod(_where)
@@ -634,7 +724,7 @@ def make_jaxpr(fun: Callable, arg_shapes: Sequence[Shape], frontend: str = "auto
 
 
 def _make_jaxpr_native(fun: Callable, arg_shapes: Sequence[Shape]) -> Jaxpr:
-    trace = _Trace()
+    trace = _Trace(len(arg_shapes))
     invars = [Var(tuple(s), input_index=i) for i, s in enumerate(arg_shapes)]
     _ACTIVE.append(trace)
     try:
@@ -649,4 +739,4 @@ def _make_jaxpr_native(fun: Callable, arg_shapes: Sequence[Shape]) -> Jaxpr:
         if not isinstance(o, Tracer):
             raise TypeError("function outputs must be traced arrays")
         outvars.append(o.var)
-    return Jaxpr(invars, trace.eqns, outvars, trace.vmap_pads, out_is_sequence)
+    return Jaxpr(invars, trace.eqns, outvars, trace.vmap_pads, out_is_sequence, trace.constvars, trace.consts)

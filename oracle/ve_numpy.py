@@ -606,6 +606,12 @@ def build_graph(jaxpr, args: Sequence[np.ndarray], dtype):
         env[_key(var)] = a
         graph[_key(var)] = {}
         transpose_graph[_key(var)] = {}
+    # closed-over arrays (core.py:374): in the environment like the arguments, the same value for every sample
+    for var, c in zip(getattr(jaxpr, "constvars", ()), getattr(jaxpr, "consts", ())):
+        c = np.asarray(c, dtype=dtype)
+        env[_key(var)] = np.ascontiguousarray(np.broadcast_to(c, (batch,) + c.shape))
+        graph[_key(var)] = {}
+        transpose_graph[_key(var)] = {}
     outkeys = {_key(v) for v in jaxpr.outvars}
     elemental = []
     for eqn in jaxpr.eqns:

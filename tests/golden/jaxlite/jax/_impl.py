@@ -210,6 +210,7 @@ class _Trace:
         self.eqns: List[JaxprEqn] = []
         self.constvars: List[Var] = []
         self.consts: List[Any] = []
+        self.const_of = {}
 
 
 _TRACES: List[_Trace] = []
@@ -268,11 +269,15 @@ class Primitive:
                 v = v.astype(_canon_dtype(v.dtype))
                 invars.append(Literal(v[()], ShapedArray((), v.dtype, weak_type=True)))
                 stand_ins.append(v)
-            else:   # a captured array constant becomes a constvar
-                c = a if isinstance(a, Array) else Array(a)
-                var = Var(c.aval)
-                trace.constvars.append(var)
-                trace.consts.append(c)
+            else:   # a captured array constant becomes a constvar: one per object, as in JAX (constants are keyed by id)
+                hit = trace.const_of.get(id(a))
+                if hit is None:
+                    c = a if isinstance(a, Array) else Array(a)
+                    var = Var(c.aval)
+                    trace.constvars.append(var)
+                    trace.consts.append(c)
+                    hit = trace.const_of[id(a)] = (a, c, var)     # `a` is kept alive so that its id stays unique
+                _, c, var = hit
                 invars.append(var)
                 stand_ins.append(c._v)
         out = np.asarray(self.impl(*stand_ins, **params))       # abstract evaluation by example

@@ -86,7 +86,7 @@ def jsonable(v):
 
 def dump_jaxpr(jaxpr):
     key = {}
-    for i, v in enumerate(jaxpr.invars):
+    for i, v in enumerate(list(jaxpr.invars) + list(jaxpr.constvars)):     # constants continue the arguments' numbering
         key[v] = -(i + 1)
     eqns = []
     for n, eqn in enumerate(jaxpr.eqns, start=1):
@@ -94,8 +94,11 @@ def dump_jaxpr(jaxpr):
         ops = [["lit", float(a.val)] if isinstance(a, jax.core.Literal) else ["var", key[a]] for a in eqn.invars]
         eqns.append({"primitive": eqn.primitive.name, "operands": ops, "shape": list(eqn.outvars[0].aval.shape),
                      "params": {k: jsonable(v) for k, v in eqn.params.items() if v is not None}})
-    return key, {"n_eqns": len(eqns), "eqns": eqns, "outvars": [key[v] for v in jaxpr.outvars],
-                 "in_shapes": [list(v.aval.shape) for v in jaxpr.invars]}
+    rec = {"n_eqns": len(eqns), "eqns": eqns, "outvars": [key[v] for v in jaxpr.outvars],
+           "in_shapes": [list(v.aval.shape) for v in jaxpr.invars]}
+    if jaxpr.constvars:
+        rec["const_shapes"] = [list(v.aval.shape) for v in jaxpr.constvars]
+    return key, rec
 
 
 def pack(out, n_rows_each, n_cols_each):
@@ -415,6 +418,62 @@ def run_examples(n_points=4):
     return out, arrays
 
 
+def run_closures(n_points=4):
+    """Functions that close over arrays (`jaxpr.constvars`, core.py:374): a least-squares residual with a scalar and a
+    vector output, and the reference's own Gaussian data fitting residual (`examples/minpack.py:fi`) on the data of
+    graphax_b200.examples.minpack (the reference draws its data with jax.random)."""
+    from graphax.examples import minpack
+    from graphax_b200.examples import minpack as mine
+    X = jnp.array((np.arange(15, dtype=np.float32).reshape(5, 3) % 7 - 3) / 4)
+    y = jnp.array(np.array([0.5, -1.0, 0.25, 2.0, -0.75], np.float32))
+    scale = jnp.array(np.array([1.0, 0.5, 2.0, -1.5, 0.25], np.float32))
+
+    def least_squares(w):
+        r = X @ w - y
+        weighted = scale * r
+        return jnp.sum(r * weighted), weighted        # (not r * r: the reference halves d(x*x), core.py:376-378)
+
+    data, tis = jnp.array(mine.FIT_DATA), jnp.array(mine.FIT_TIMES)
+
+    def gaussian_fit(x1, x2, x3, x4, x5, x6, x7, x8, x9, x10, x11):
+        return minpack.fi(x1, x2, x3, x4, x5, x6, x7, x8, x9, x10, x11, data, tis)
+
+    cases = {
+        "least_squares": (least_squares, [[0.3, -0.2, 0.5]]),
+        "GaussianDataFitting": (gaussian_fit, [1.3, 0.65, 0.65, 0.7, 0.6, 3.0, 5.0, 7.0, 2.0, 4.5, 5.5]),   # MINPACK-2 start
+    }
+    out, arrays = {}, {}
+    rng = np.random.default_rng(11)
+    for name, (fun, base) in cases.items():
+        base = [np.asarray(b, np.float32) for b in base]
+        pts = [[jnp.array(b * (1 + 0.02 * rng.uniform(-1, 1, b.shape)).astype(np.float32)) for b in base] for _ in range(n_points)]
+        closed = jax.make_jaxpr(fun)(*pts[0])
+        _, rec = dump_jaxpr(closed.jaxpr)
+        for i, c in enumerate(closed.consts):
+            arrays[f"closures/{name}/const{i}"] = np.asarray(c, dtype=np.float32)
+        argnums = tuple(range(len(base)))
+        out_sizes = [int(np.prod(v.aval.shape, dtype=np.int64)) for v in closed.jaxpr.outvars]
+        in_sizes = [int(b.size) for b in base]
+        arrays[f"closures/{name}/inputs"] = np.stack([np.concatenate([np.asarray(a).reshape(-1) for a in p]) for p in pts])
+        rec["orders"] = {}
+        for order in ("fwd", "rev"):
+            jacs = []
+            for p in pts:
+                res, aux = graphax.jacve(fun, order=order, argnums=argnums, count_ops=True)(*p)
+                if len(out_sizes) == 1:
+                    res = (res,)
+                if len(argnums) == 1:
+                    res = tuple(r if isinstance(r, tuple) else (r,) for r in res)
+                jacs.append(pack(res, out_sizes, in_sizes))
+            rec["orders"][order] = {"num_muls": int(aux["num_muls"]), "num_adds": int(aux["num_adds"]),
+                                    "order_counts": [[int(a), int(b)] for a, b in aux["order_counts"]]}
+            arrays[f"closures/{name}/jac/{order}"] = np.stack(jacs)
+        out[name] = rec
+        print(f"  {name}: {rec['n_eqns']} eqns, {len(closed.consts)} constants, "
+              f"{ {k: (v['num_muls'], v['num_adds']) for k, v in rec['orders'].items()} }")
+    return out, arrays
+
+
 PYTREE_CASES = {   # name: (source of the function over `jnp`, per-sample shapes, argnums)
     "1out_1in": ("lambda x: jnp.sin(x) * x", [(3,)], (0,)),
     "1out_2in_both": ("lambda x, y: jnp.sin(x) * y", [(3,), (3,)], (0, 1)),
@@ -595,6 +654,9 @@ def main():
     arrays.update(arr)
     print("further examples", flush=True)
     out["examples"], arr = run_examples()
+    arrays.update(arr)
+    print("closures", flush=True)
+    out["closures"], arr = run_closures()
     arrays.update(arr)
     print("pytree conventions", flush=True)
     out["pytree"] = run_pytree_cases()

@@ -130,11 +130,17 @@ def torch_eval_jaxpr(jaxpr, args):
     return tuple(env[id(o)] for o in jaxpr.outvars)
 
 
-def jaxpr_from_record(rec):
+def jaxpr_from_record(rec, consts=()):
     """Rebuild an engine jaxpr from the equations recorded by tests/golden/make_reference_goldens.py (`dump_jaxpr`):
-    the function exactly as the reference traced it, without needing its source."""
+    the function exactly as the reference traced it, without needing its source.  ``consts``: the values of the arrays
+    the function closes over (`const_shapes` in the record), numbered after the arguments."""
     from graphax_b200.tracer import Eqn, Jaxpr, Literal, Var
     env = {-(i + 1): Var(tuple(s), input_index=i) for i, s in enumerate(rec["in_shapes"])}
+    n_in = len(rec["in_shapes"])
+    const_shapes = rec.get("const_shapes", [])
+    assert len(const_shapes) == len(consts), "pass the recorded constants"
+    for i, shape in enumerate(const_shapes):
+        env[-(n_in + i + 1)] = Var(tuple(shape), input_index=n_in + i, name=f"const{i}")
     eqns = []
     for n, e in enumerate(rec["eqns"], start=1):
         ins = tuple(Literal(float(v)) if kind == "lit" else env[v] for kind, v in e["operands"])
@@ -143,5 +149,6 @@ def jaxpr_from_record(rec):
         tup = lambda v: tuple(tup(x) for x in v) if isinstance(v, list) else v
         params = {k: tup(v) for k, v in e["params"].items() if k not in ("precision", "preferred_element_type", "sharding")}
         eqns.append(Eqn(e["primitive"], ins, out, params))
-    return Jaxpr([env[-(i + 1)] for i in range(len(rec["in_shapes"]))], eqns, [env[k] for k in rec["outvars"]],
-                 [0] * len(eqns), True)
+    return Jaxpr([env[-(i + 1)] for i in range(n_in)], eqns, [env[k] for k in rec["outvars"]],
+                 [0] * len(eqns), True, [env[-(n_in + i + 1)] for i in range(len(const_shapes))],
+                 [np.asarray(c, dtype=np.float32) for c in consts])

@@ -124,6 +124,28 @@ def test_further_reference_examples_via_runtime_specialisation(built_library, na
 
 
 @pytest.mark.parametrize("order", ["fwd", "rev"])
+def test_function_closing_over_arrays_on_the_gpu(built_library, order):
+    """GaussianDataFitting closes over its 65 data points and sample times (reference `examples/minpack.py`; constants
+    of the trace, core.py:374): single calls and a vmapped batch on the GPU equal the Jacobians of the reference run
+    (tests/golden/make_reference_goldens.py::run_closures) within the parity bound, with the reference's count_ops."""
+    import json
+    import torch
+    from graphax_b200.examples import GaussianDataFitting
+    from helpers import GOLDEN, parity_bound
+    rec = json.loads((GOLDEN / "reference_run.json").read_text())["closures"]["GaussianDataFitting"]
+    arr = np.load(GOLDEN / "reference_run.npz")
+    pts, ref = arr["closures/GaussianDataFitting/inputs"], arr["closures/GaussianDataFitting/jac/" + order].astype(np.float64)
+    jf = gx.jacve(GaussianDataFitting, order=order, argnums=tuple(range(11)), count_ops=True)
+    out, aux = jf(*[float(v) for v in pts[0]])
+    assert (aux["num_muls"], aux["num_adds"]) == (rec["orders"][order]["num_muls"], rec["orders"][order]["num_adds"])
+    J = np.stack([b.cpu().numpy().reshape(65) for b in out], axis=1)             # one output: a tuple over the arguments
+    assert (np.abs(J - ref[0]) <= parity_bound(ref[:1])[0]).all()
+    batched, _ = gx.vmap(jf)(*[torch.from_numpy(np.ascontiguousarray(pts[:, k])).cuda() for k in range(11)])
+    JB = np.stack([b.cpu().numpy().reshape(len(pts), 65) for b in batched], axis=2)
+    assert (np.abs(JB - ref) <= parity_bound(ref)).all()
+
+
+@pytest.mark.parametrize("order", ["fwd", "rev"])
 def test_elementwise_function_of_matrices(built_library, order):
     """Reference test_Simple with 50x50 arguments (example_test.py:49-54): every edge is diagonal, the blocks
     come back dense as out.shape + in.shape = [50,50,50,50] (or as their diagonal values with

@@ -69,6 +69,21 @@ except NotImplementedError:
 jf = gx.jacve(scope_fun := (lambda x, y: jnp.sin(x) * y), order="rev", argnums=(0, 1))
 plan = jf.lower([(3,), (3,)])
 out["api_lowers"] = [plan.n_rows, plan.n_cols, len(plan.jaxpr.eqns)]
+# arrays the function closes over arrive as jaxpr.constvars (one per object): same plan as the native tracer
+import numpy as np
+Xn = (np.arange(15, dtype=np.float32).reshape(5, 3) % 7 - 3) / 4
+yn = np.array([0.5, -1.0, 0.25, 2.0, -0.75], np.float32)
+Xj, yj = jnp.array(Xn), jnp.array(yn)
+def closing_jax(w):
+    r = Xj @ w - yj
+    return jnp.sum(r * (yj - r)), r * yj
+def closing_native(w):
+    r = Xn @ w - yn
+    return gx.jnp.sum(r * (yn - r)), r * yn
+cj, cn = make_jaxpr(closing_jax, [(3,)], "jax"), make_jaxpr(closing_native, [(3,)], "native")
+out["closure"] = {"constvars": [list(v.shape) for v in cj.constvars], "input_index": [v.input_index for v in cj.constvars],
+                  "same_consts": all(np.array_equal(a, b) for a, b in zip(cj.consts, cn.consts)),
+                  "same_plans": all(build_plan(cj, o, (0,)).blob == build_plan(cn, o, (0,)).blob for o in ("fwd", "rev"))}
 print(json.dumps(out))
 '''
 
@@ -79,6 +94,7 @@ def test_jax_frontend_reproduces_the_native_tracer_on_a_jax_numpy_function():
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out.pop("refuses_untraceable") is True
     assert out.pop("api_lowers") == [3, 6, 2]
+    assert out.pop("closure") == {"constvars": [[5, 3], [5]], "input_index": [1, 2], "same_consts": True, "same_plans": True}
     assert out.pop("vmap_eqns") == 146 and out.pop("vmap_pads") == [24, 33, 48, 55, 59, 82, 91, 133]
     assert out["roe3d"]["n_eqns"] == 138 and out["roe1d"]["n_eqns"] == 101 and out["robotarm"]["n_eqns"] == 114
     for name, rec in out.items():

@@ -314,6 +314,88 @@ def test_further_reference_examples(name):
         assert (np.abs(rep - ref) <= parity_bound(ref)).all(), float((np.abs(rep - ref) / parity_bound(ref)).max())
 
 
+def _same_trace(jaxpr, rec):
+    from graphax_b200.tracer import Literal
+    n_in = len(jaxpr.invars)
+    assert [list(v.shape) for v in jaxpr.invars] == rec["in_shapes"]
+    assert [list(v.shape) for v in jaxpr.constvars] == rec.get("const_shapes", [])
+    assert len(jaxpr.eqns) == rec["n_eqns"]
+    key = lambda v: -(v.input_index + 1) if v.input_index is not None else v.eqn_index + 1
+    assert [key(v) for v in jaxpr.outvars] == rec["outvars"]
+    for n, (mine, ref) in enumerate(zip(jaxpr.eqns, rec["eqns"]), start=1):
+        assert mine.primitive == ref["primitive"], n
+        ops = [["lit", float(np.float32(a.val))] if isinstance(a, Literal) else ["var", key(a)] for a in mine.invars]
+        assert ops == ref["operands"], (n, mine)
+        assert list(mine.outvar.shape) == ref["shape"], n
+    assert all(v.input_index == n_in + i for i, v in enumerate(jaxpr.constvars))
+
+
+@pytest.mark.parametrize("name", list(RUN["examples"]))
+def test_further_examples_trace_like_the_reference(name):
+    """graphax_b200.examples.{KerrSenn_metric, FreeEnergy, CloudSchemes_step, PropaneCombustion, HumanHeartDipole,
+    SteadyStateCombustion, BlackScholes}: the engine's tracer turns them into the jaxprs the reference's own sources
+    gave - same equations, operands, literals and output vertices, so custom orders mean the same vertices."""
+    from graphax_b200 import examples
+    from graphax_b200.tracer import make_jaxpr
+    rec = RUN["examples"][name]
+    _same_trace(make_jaxpr(getattr(examples, name), [tuple(s) for s in rec["in_shapes"]], "native"), rec)
+
+
+def _least_squares():
+    import graphax_b200 as gx
+    X = (np.arange(15, dtype=np.float32).reshape(5, 3) % 7 - 3) / 4
+    y = np.array([0.5, -1.0, 0.25, 2.0, -0.75], np.float32)
+    scale = np.array([1.0, 0.5, 2.0, -1.5, 0.25], np.float32)
+
+    def least_squares(w):
+        r = X @ w - y
+        weighted = scale * r
+        return gx.jnp.sum(r * weighted), weighted        # (not r * r: the reference halves d(x*x), core.py:376-378)
+    return least_squares
+
+
+@pytest.mark.parametrize("name", list(RUN["closures"]))
+def test_functions_closing_over_arrays_against_reference_run(name):
+    """Closed-over arrays are constants of the trace (`jaxpr.constvars`, reference core.py:374): one variable per
+    array object, a source of edges like an argument, never differentiated.  The engine's trace equals the one the
+    reference's sources gave; `count_ops` (totals and per vertex), the oracle's Jacobians (bit for bit) and the plan
+    replay (parity bound) equal the reference run, forward and reverse."""
+    from graphax_b200 import examples
+    from graphax_b200.plan import build_plan
+    from graphax_b200.tracer import make_jaxpr
+    from helpers import jaxpr_from_record
+    rec = RUN["closures"][name]
+    consts = [ARR[f"closures/{name}/const{i}"] for i in range(len(rec["const_shapes"]))]
+    fun = examples.GaussianDataFitting if name == "GaussianDataFitting" else _least_squares()
+    jaxpr = make_jaxpr(fun, [tuple(s) for s in rec["in_shapes"]], "native")
+    _same_trace(jaxpr, rec)
+    assert all(np.array_equal(a, b) for a, b in zip(jaxpr.consts, consts))
+    recorded = jaxpr_from_record(rec, consts)
+    flat = ARR[f"closures/{name}/inputs"]
+    xs, off = [], 0
+    for shape in rec["in_shapes"]:
+        size = int(np.prod(shape, dtype=np.int64)) if shape else 1
+        xs.append(np.ascontiguousarray(flat[:, off:off + size].reshape((len(flat),) + tuple(shape))))
+        off += size
+    argnums = tuple(range(len(xs)))
+    for order in ("fwd", "rev"):
+        want = rec["orders"][order]
+        ref = ARR[f"closures/{name}/jac/{order}"]
+        for jp in (jaxpr, recorded):
+            plan = build_plan(jp, order, argnums)
+            assert (plan.stats["num_muls"], plan.stats["num_adds"]) == (want["num_muls"], want["num_adds"])
+            assert [list(c) for c in plan.stats["order_counts"]] == want["order_counts"]
+            assert plan.in_sizes == [int(np.prod(s, dtype=np.int64)) if s else 1 for s in rec["in_shapes"]]
+            rep, _ = replay.replay(plan.blob, xs, plan.n_rows, plan.n_cols)
+            assert (np.abs(rep - ref.astype(np.float64)) <= parity_bound(ref.astype(np.float64))).all()
+        if any(len(shape) > 1 for shape in rec["const_shapes"]):
+            continue                               # the NumPy restatement covers vertices of rank <= 1
+        jac, _, counts = vo.jacve(jaxpr, order, argnums, xs, np.float32)
+        got = pack_blocks(jac, len(flat), [int(np.prod(s, dtype=np.int64)) if s else 1 for s in rec["in_shapes"]])
+        assert np.array_equal(got, ref), order
+        assert (counts["num_muls"], counts["num_adds"]) == (want["num_muls"], want["num_adds"])
+
+
 def test_random_tensor_function_f_against_reference_run():
     """`examples/randoms.py:f`: 80 equations on vectors and matrices (dot_general in four layouts, transpose, reshape,
     squeeze, reduce_max / reduce_min, slice, stop_gradient), rebuilt from the jaxpr the reference traced.  Reference
