@@ -222,6 +222,8 @@ class JacveFunction:
             return None
         if len(full.eqns) != len(scalar.eqns) or len(full.outvars) != len(scalar.outvars):
             return None
+        if full.constvars or scalar.constvars:
+            return None                 # closed-over arrays are per-element data: not a function of scalars alone
         for e, f in zip(full.eqns, scalar.eqns):
             if e.primitive != f.primitive or e.primitive not in self._ELEMENTWISE or e.outvar.shape != tuple(common):
                 return None
