@@ -578,6 +578,11 @@ def _zeros(shape, dtype=None) -> Tracer:
                            shape=shape, broadcast_dimensions=())
 
 
+def _full(shape, value: float) -> Tracer:
+    shape = (int(shape),) if isinstance(shape, (int, np.integer)) else tuple(int(s) for s in shape)
+    return _current().emit("broadcast_in_dim", (Literal(float(value)),), shape, shape=shape, broadcast_dimensions=())
+
+
 def _concatenate(parts: Sequence[Tracer], axis: int = 0) -> Tracer:
     parts = list(parts)
     if not parts or not all(isinstance(p, Tracer) for p in parts):
@@ -689,7 +694,22 @@ class _JnpShim:
         """``jnp.ones(())`` folds to a literal under make_jaxpr (function g)."""
         if shape == () or shape == []:
             return 1.0
-        raise NotImplementedError("only rank-0 ones() constants are lowered")
+        return _full(shape, 1.0)
+
+    @staticmethod
+    def full(shape, fill_value, dtype=None):
+        """``jnp.full``: like ``jnp.zeros``, one ``broadcast_in_dim`` of a literal - a vertex without in-edges."""
+        if isinstance(fill_value, Tracer):
+            raise NotImplementedError("full() with a traced fill value")
+        return _full(shape, float(fill_value))
+
+    @staticmethod
+    def zeros_like(x, dtype=None):
+        return _full(tuple(np.shape(x)) if not isinstance(x, (Tracer, ConstArray)) else x.shape, 0.0)
+
+    @staticmethod
+    def ones_like(x, dtype=None):
+        return _full(tuple(np.shape(x)) if not isinstance(x, (Tracer, ConstArray)) else x.shape, 1.0)
 
 
 jnp = _JnpShim()

@@ -108,3 +108,35 @@ def test_nn_helpers_lower_to_the_expected_primitives():
     j = make_jaxpr(lambda a: jnp.sqrt(2.) * lax.stop_gradient(a), [(2,)])
     # omnistaging: an operation on constants inside a traced function is an equation too (`sqrt 2.0`)
     assert [e.primitive for e in j.eqns] == ["sqrt", "stop_gradient", "mul"]
+
+
+def test_constant_fills_and_closed_over_arrays():
+    """jnp.ones / full / zeros_like / ones_like stage one broadcast_in_dim of a literal (a vertex without in-edges, like
+    jnp.zeros); NumPy operands and jnp.asarray values become constants of the trace, one per array object, numbered
+    after the arguments in order of first use."""
+    import numpy as np
+    from graphax_b200.plan import build_plan
+    from graphax_b200.tracer import jnp, make_jaxpr
+    from oracle import replay
+    table = np.array([1.0, -2.0, 0.5], np.float32)
+    offsets = [0.25, 0.5, 0.75]
+
+    def f(x):
+        late = jnp.asarray(offsets)                       # registered when first used, not here
+        y = x * jnp.full((3,), 2.5) + jnp.ones_like(x) * x * table - jnp.zeros_like(x)
+        return jnp.sum(y * table) + jnp.sum(late * x), jnp.ones((2, 3)) * x
+
+    jaxpr = make_jaxpr(f, [(3,)], "native")
+    assert [e.primitive for e in jaxpr.eqns][:3] == ["broadcast_in_dim", "mul", "broadcast_in_dim"]
+    assert [v.shape for v in jaxpr.constvars] == [(3,), (3,)] and [v.input_index for v in jaxpr.constvars] == [1, 2]
+    assert np.array_equal(jaxpr.consts[0], table) and np.array_equal(jaxpr.consts[1], np.float32(offsets))
+    x = np.array([[0.1, 0.2, 0.3], [1.0, -1.0, 2.0]], np.float32)
+    for order in ("fwd", "rev"):
+        plan = build_plan(jaxpr, order, (0,))
+        assert plan.in_sizes == [3]                       # constants are not kernel inputs
+        jac, primal = replay.replay(plan.blob, [x], plan.n_rows, plan.n_cols)
+        want = np.broadcast_to((2.5 + table) * table + np.float32(offsets), (2, 3))
+        np.testing.assert_allclose(jac[:, 0], want, rtol=1e-6)
+        np.testing.assert_allclose(jac[:, 1:].reshape(2, 2, 3, 3), np.broadcast_to(np.eye(3, dtype=np.float32), (2, 2, 3, 3)))
+    with pytest.raises(TypeError):
+        make_jaxpr(lambda x: x * "three", [()], "native")
