@@ -1009,7 +1009,10 @@ int gx_jacve_host(gx_plan* p, int64_t batch, const void* const* in_ptrs, void* j
   for (int64_t c = 0; c < n_chunks; ++c) {
     auto& s = p->slots[c & 1];
     const int64_t b0 = starts[c], nb = sizes[c];
-    if (c >= 2) {
+    // Staged (pageable) buffers: the host copies chunk c-2 out of the slot before the slot is reused.  Pinned buffers
+    // need no host in the loop at all: a slot's stream is in order (D2H of chunk c-2, then H2D of chunk c into the same
+    // device buffers), so the whole call is enqueued ahead of the GPU and a descheduled host thread cannot stall it.
+    if (c >= 2 && staging) {
       int rc = drain(c - 2);
       if (rc) return rc;
     }
