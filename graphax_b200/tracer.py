@@ -418,6 +418,17 @@ def _keepdims(x: Tracer, reduced: Tracer, axes) -> Tracer:
     return x.trace.emit("broadcast_in_dim", (reduced.var,), shape, shape=shape, broadcast_dimensions=bdims)
 
 
+def _array_first(fn):
+    """The first argument may be an array the function closes over: it enters the trace as a constant."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(x, *args, **kwargs):
+        return fn(_lift(x), *args, **kwargs)
+    return wrapped
+
+
+@_array_first
 def _reduce_sum(x: Tracer, axis=None, keepdims: bool = False) -> Tracer:
     if keepdims:
         r = _reduce_sum(x, axis)
@@ -481,6 +492,7 @@ def _matmul(a: Tracer, b: Tracer) -> Tracer:
     return _dot_general(a, b, (((a.ndim - 1,), (0,)), ((), ())))
 
 
+@_array_first
 def _transpose(x: Tracer, axes=None) -> Tracer:
     perm = tuple(range(x.ndim))[::-1] if axes is None else tuple(int(a) for a in axes)
     if x.ndim < 2:
@@ -490,15 +502,18 @@ def _transpose(x: Tracer, axes=None) -> Tracer:
 
 def _outer(a: Tracer, b: Tracer) -> Tracer:
     """jnp.outer: ravel both, then multiply [n,1] * [1,m] (two broadcast_in_dim-free reshapes in jnp)."""
+    a, b = _lift(a), _lift(b)
     return a.reshape(a.size, 1) * b.reshape(1, b.size)
 
 
+@_array_first
 def _squeeze(x: Tracer, axis=None) -> Tracer:
     axes = tuple(i for i, s in enumerate(x.shape) if s == 1) if axis is None else \
         tuple(sorted(a % x.ndim for a in ((axis,) if isinstance(axis, int) else axis)))
     return x.trace.emit("squeeze", (x.var,), tuple(s for i, s in enumerate(x.shape) if i not in axes), dimensions=axes)
 
 
+@_array_first
 def _expand_dims(x: Tracer, axis: int) -> Tracer:
     axis = axis % (x.ndim + 1)
     shape = x.shape[:axis] + (1,) + x.shape[axis:]
@@ -508,6 +523,7 @@ def _expand_dims(x: Tracer, axis: int) -> Tracer:
 
 def _reduce_extreme(prim: str):
     def fn(x: Tracer, axis=None, keepdims: bool = False) -> Tracer:
+        x = _lift(x)
         axes = tuple(range(x.ndim)) if axis is None else tuple(sorted(a % x.ndim for a in ((axis,) if isinstance(axis, int) else axis)))
         shape = tuple(s for i, s in enumerate(x.shape) if i not in axes)
         r = x.trace.emit(prim, (x.var,), shape, axes=axes)
@@ -515,6 +531,7 @@ def _reduce_extreme(prim: str):
     return fn
 
 
+@_array_first
 def _mean(x: Tracer, axis=None) -> Tracer:
     """jnp.mean: reduce_sum, then a division by the literal element count."""
     axes = tuple(range(x.ndim)) if axis is None else tuple(a % x.ndim for a in ((axis,) if isinstance(axis, int) else axis))
@@ -568,6 +585,7 @@ class _NnShim:
 jnn = _NnShim()
 
 
+@_array_first
 def _square(x: Tracer) -> Tracer:
     return x.trace.emit("square", (x.var,), x.shape)
 
@@ -584,7 +602,7 @@ def _full(shape, value: float) -> Tracer:
 
 
 def _concatenate(parts: Sequence[Tracer], axis: int = 0) -> Tracer:
-    parts = list(parts)
+    parts = [_lift(p) for p in parts]
     if not parts or not all(isinstance(p, Tracer) for p in parts):
         raise TypeError("concatenate expects a sequence of traced values")
     if any(p.ndim != parts[0].ndim for p in parts):
