@@ -169,6 +169,23 @@ def test_reference_helper_functions():
     assert z.dense.shape == (3, 2) and not z.dense.any() and st.dense.all()
 
 
+def test_input_staging_is_chosen_per_plan(monkeypatch):
+    """tuning.json `input_staged: 0` (RobotArm_6DOF, Markowitz and forward orders: measured faster without the
+    shared-memory input stage) reaches the generated source of the ahead-of-time kernels; GX_INPUT_STAGED overrides."""
+    from graphax_b200 import codegen
+    monkeypatch.delenv("GX_INPUT_STAGED", raising=False)
+    w = WORKLOADS["robotarm"]
+    direct, staged = w.plan("markowitz", rounding="reference"), w.plan("rev", rounding="reference")
+    assert codegen.input_stages(direct, 128) == 0 and codegen.input_stages(staged, 128) == 2
+    assert "#define GX_IN_STAGES 0" in codegen.emit_source(direct, nvrtc=False)
+    assert "#define GX_IN_STAGES 2" in codegen.emit_source(staged, nvrtc=False)
+    assert codegen.input_stages(direct, 128, samples_per_thread=2) == 2      # the packed kernels always stage
+    monkeypatch.setenv("GX_INPUT_STAGED", "1")
+    assert codegen.input_stages(direct, 128) == 2
+    monkeypatch.setenv("GX_INPUT_STAGED", "0")
+    assert codegen.input_stages(staged, 128) == 0
+
+
 def test_argnums_subset_prunes_dead_work():
     w = WORKLOADS["roe3d"]
     full = build_plan(w.jaxpr(), "rev", w.argnums)
