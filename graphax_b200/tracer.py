@@ -153,6 +153,10 @@ class _Trace:
         hit = self._const_of.get(id(value))
         if hit is not None:
             return hit[1]
+        def has_tracer(v) -> bool:
+            return isinstance(v, Tracer) or (isinstance(v, (list, tuple)) and any(has_tracer(e) for e in v))
+        if has_tracer(value):     # (NumPy would index the tracers while probing the sequence and stage equations)
+            raise TypeError("a sequence of traced values is not an array: use jnp.concatenate / jnp.stack-like operations")
         arr = value.value if isinstance(value, ConstArray) else \
             value.detach().cpu().numpy() if hasattr(value, "detach") else np.asarray(value)
         if arr.dtype == object or not (np.issubdtype(arr.dtype, np.number) or arr.dtype == bool):
