@@ -177,7 +177,8 @@ def main():
     if args.write:
         path = ROOT / "graphax_b200" / "tuning.json"
         merged = json.loads(path.read_text()) if path.exists() else {}
-        merged.update(best)
+        for key, entry in best.items():           # keep what this sweep does not measure (e.g. "input_staged")
+            merged[key] = {**merged.get(key, {}), **entry}
         path.write_text(json.dumps(merged, indent=1))
 
 
