@@ -170,16 +170,22 @@ def test_reference_helper_functions():
 
 
 def test_input_staging_is_chosen_per_plan(monkeypatch):
-    """tuning.json `input_staged: 0` (RobotArm_6DOF, Markowitz and forward orders: measured faster without the
-    shared-memory input stage) reaches the generated source of the ahead-of-time kernels; GX_INPUT_STAGED overrides."""
+    """tuning.json `input_staged: 0` / `prefetch_at` (the RobotArm_6DOF plans: measured faster without the
+    shared-memory input stage, the next tile's loads issued early in the body) reach the generated source of the
+    ahead-of-time kernels; GX_INPUT_STAGED / GX_PREFETCH_AT override."""
     from graphax_b200 import codegen
     monkeypatch.delenv("GX_INPUT_STAGED", raising=False)
-    w = WORKLOADS["robotarm"]
-    direct, staged = w.plan("markowitz", rounding="reference"), w.plan("rev", rounding="reference")
+    monkeypatch.delenv("GX_PREFETCH_AT", raising=False)
+    direct = WORKLOADS["robotarm"].plan("markowitz", rounding="reference")
+    staged = WORKLOADS["roe3d"].plan("mixed", rounding="reference")
     assert codegen.input_stages(direct, 128) == 0 and codegen.input_stages(staged, 128) == 2
     assert "#define GX_IN_STAGES 0" in codegen.emit_source(direct, nvrtc=False)
     assert "#define GX_IN_STAGES 2" in codegen.emit_source(staged, nvrtc=False)
     assert codegen.input_stages(direct, 128, samples_per_thread=2) == 2      # the packed kernels always stage
+    assert codegen.prefetch_position(direct) == int(0.2 * len(direct.ssa))   # tuning.json prefetch_at
+    assert 0.45 * len(staged.ssa) <= codegen.prefetch_position(staged) <= 0.75 * len(staged.ssa)   # the automatic rule
+    monkeypatch.setenv("GX_PREFETCH_AT", "0.5")
+    assert codegen.prefetch_position(direct) == int(0.5 * len(direct.ssa))
     monkeypatch.setenv("GX_INPUT_STAGED", "1")
     assert codegen.input_stages(direct, 128) == 2
     monkeypatch.setenv("GX_INPUT_STAGED", "0")
