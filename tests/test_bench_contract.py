@@ -57,3 +57,20 @@ def test_reference_arm_line_on_the_host_cpu():
     assert d["e2e"] == {"value": d["value"], "unit": "Jacobians/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["value"] == d["value"]
     assert d["config"]["order"] == "mixed" and d["config"]["batch_per_gpu"] == 8192
+
+
+def test_committed_multi_gpu_lines_scale_and_verify_every_rank():
+    """Weak scaling of the final code (profiles/bench_r02{f,g}_roe3d_mixed_{2,4,8}gpu.json): whole-job Jacobians/s within
+    5 % of N x the one-GPU line, max-over-ranks device time, results of EVERY rank checked over the NCCL all-gather."""
+    one = json.loads(LINES[-1].read_text())
+    seen = []
+    for path in sorted((ROOT / "profiles").glob("bench_r02[f-z]_roe3d_mixed_*gpu.json")):
+        d = json.loads(path.read_text())
+        n = d["n_gpus"]
+        seen.append(n)
+        assert d["scaling"] == "weak" and d["config"]["batch_per_gpu"] == 1 << 20
+        assert 0.95 * n * one["value"] <= d["value"] <= 1.03 * n * one["value"], path.name
+        assert d["verify"]["ranks"] == n and d["verify"]["rows"] == 1024 * n and d["verify"]["bit_exact"] is True
+        assert "NCCL" in d["verify"]["collective"]
+        assert d["e2e"]["value"] <= d["e2e"]["floor"]["value"] * 1.001 and d["e2e"]["frac_of_floor"] > 0.85
+    assert {2, 4, 8} <= set(seen)
